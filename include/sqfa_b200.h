@@ -1,0 +1,175 @@
+/*
+ * sqfa_b200 -- C ABI of the B200-native (sm_100a) SQFA hot paths.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types. Every pointer is a
+ * DEVICE pointer unless the name ends in `_host`. Every function enqueues work on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream), never synchronises, never
+ * allocates or frees device memory (callers pass workspaces sized by the *_workspace_bytes
+ * queries) and returns 0 on success, a positive cudaError_t value on a CUDA failure or a negative
+ * SQFA_E_* code on invalid arguments. `sqfa_last_error()` returns a human-readable message for
+ * the last failure on the calling thread.
+ *
+ * Reference interfaces replaced (paths under /root/reference/src/sqfa/):
+ *   HP1  statistics.py:8-54   class_statistics      -> sqfa_label_max, sqfa_bucket_labels,
+ *        statistics.py:97-124 sample_covariance        sqfa_class_sums, sqfa_class_means,
+ *        statistics.py:57-94  oas_covariance           sqfa_class_gram, sqfa_stats_epilogue
+ *   HP2  linalg.py:19-45      conjugate_matrix      -> sqfa_project_fwd / sqfa_project_bwd
+ *        model.py:172-237     transform_scatters / transform -> sqfa_project_fwd / sqfa_transform
+ *        linalg.py:48-70      generalized_eigenvalues  \
+ *        distances.py:46-237  affine_invariant(_sq), fisher_rao_lower_bound(_sq),
+ *                             log_euclidean(_sq)        > sqfa_class_factor + sqfa_pair_distances
+ *        _optim.py:16-30,90-96 closure loss + guard + autograd backward /
+ */
+#ifndef SQFA_B200_H_
+#define SQFA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sqfa_stream_t; /* cudaStream_t */
+
+#define SQFA_E_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported shape) */
+#define SQFA_E_WORKSPACE (-2)   /* workspace too small */
+#define SQFA_E_UNSUPPORTED (-3) /* e.g. matrix size m > SQFA_MAX_M */
+
+#define SQFA_MAX_M 64 /* largest SPD matrix the pair kernels accept (k+1 for Fisher-Rao) */
+
+/* estimator argument of sqfa_stats_epilogue (reference: estimator="empirical" | "oas") */
+#define SQFA_EST_EMPIRICAL 0
+#define SQFA_EST_OAS 1
+
+/* distance selector of the pair kernels */
+#define SQFA_DIST_AFFINE_INVARIANT 0 /* distances.py:70-89  sqrt(sum log^2 lambda + 1e-6)      */
+#define SQFA_DIST_FISHER_RAO_LB 1    /* distances.py:210-237 sqrt(AI^2(E_i,E_j)/2 + 1e-6)       */
+#define SQFA_DIST_LOG_EUCLIDEAN 2    /* distances.py:119-138 sqrt(|logA - logB|_F^2 + 1e-6)     */
+/* add SQFA_DIST_SQUARED to get the squared variants (no sqrt, no epsilon) */
+#define SQFA_DIST_SQUARED 16
+
+int sqfa_version(void);
+const char* sqfa_last_error(void);
+/* number of SMs of the current device (grid sizing); <= 0 on failure */
+int sqfa_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * HP1: class_statistics (statistics.py:8-54)
+ * ------------------------------------------------------------------------------------------- */
+
+/* max(labels) -> *out_max (device int64; -1 when n == 0 or all labels negative).
+ * Reference: `n_classes = int(torch.max(labels) + 1)` statistics.py:29. */
+int sqfa_label_max(const int64_t* labels, int64_t n, int64_t* out_max, sqfa_stream_t stream);
+
+/* Stable bucketing of rows by label (statistics.py:37, `(labels == i).nonzero()` for every i).
+ *   perm    [n]     row ids sorted by class, ascending inside a class (== stable argsort);
+ *                   rows with label outside [0, n_classes) come last (bucket n_classes)
+ *   offsets [C+2]   offsets[c] = start of class c in perm, offsets[C] = start of dropped rows,
+ *                   offsets[C+1] = n
+ *   counts  [C+1]   class sizes, counts[C] = dropped rows
+ * n must be < 2^31. */
+size_t sqfa_bucket_workspace_bytes(int64_t n, int32_t n_classes);
+int sqfa_bucket_labels(const int64_t* labels, int64_t n, int32_t n_classes, int64_t* counts, int64_t* offsets,
+                       int32_t* perm, void* ws, size_t ws_bytes, sqfa_stream_t stream);
+
+/* Per-class column sums  sums[c][j] (+)= sum_{i in c} (X[i][j] - shift[c][j])   (shift may be NULL).
+ * X is row-major with row stride ldx (floats). ws: sqfa_class_sums_workspace_bytes. */
+size_t sqfa_class_sums_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes);
+int sqfa_class_sums(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
+                    int64_t n, int32_t n_dim, int32_t n_classes, float* sums, int accumulate, void* ws,
+                    size_t ws_bytes, sqfa_stream_t stream);
+
+/* means[c][j] = sums[c][j] / counts[c] (+ shift[c][j])   (statistics.py:40; 0/0 = NaN when empty) */
+int sqfa_class_means(const float* sums, const int64_t* counts, const float* shift, int32_t n_dim,
+                     int32_t n_classes, float* means, sqfa_stream_t stream);
+
+/* Segmented Gram on the tensor cores (tcgen05, 3xTF32):
+ *   gram[c] (+)= sum_{i in c} (x_i - shift_c)(x_i - shift_c)^T        (statistics.py:119-120)
+ * Only the upper triangle of every gram[c] (D x D, row-major) is defined on return.
+ *   ksplit     >= 1 splits every class along the sample axis into that many jobs (load balance
+ *              when C * tiles < #SMs); > 1 or accumulate != 0 requires gram to be zero-initialised
+ *              / hold the running sum, contributions are added with red.global.add.
+ *   ws         sqfa_class_gram_workspace_bytes() bytes (job counter). */
+size_t sqfa_class_gram_workspace_bytes(void);
+int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
+                    int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int ksplit, void* ws,
+                    size_t ws_bytes, sqfa_stream_t stream);
+
+/* Statistics epilogue (statistics.py:43-47, 84-93, 116, 120-122):
+ *   cov[c] = (gram[c] - n_c d d^T) / (n_c - ddof),  d = means[c] - shift[c]  (shift NULL -> d = 0)
+ *   ddof = 1: unbiased estimate; ddof = 0: `assume_centered` (statistics.py:116)
+ *   estimator == SQFA_EST_OAS applies the OAS shrinkage to cov
+ *   sm[c]  = cov[c] + means[c] means[c]^T       (sm may be NULL)
+ * Reads the upper triangle of gram, writes full symmetric cov and sm; cov may alias gram. */
+size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes);
+int sqfa_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
+                        int32_t n_dim, int32_t n_classes, int estimator, int ddof, float* cov, float* sm, void* ws,
+                        size_t ws_bytes, sqfa_stream_t stream);
+
+/* Test hook: D[128 x N] = A^T B through one tcgen05.mma chain with a caller-chosen operand
+ * layout / descriptor (pins the UMMA layout assumptions of sqfa_class_gram on hardware). */
+int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K, int32_t N, int32_t mode,
+                          uint32_t lbo, uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
+                          uint32_t kstep_bytes, sqfa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HP2: the per-iteration loss and its backward (model.py:190-220, 508-546; _optim.py:90-96)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Projection  T[c] = F S[c]  (k x D),  Psi[c] = T[c] F^T (k x k),  mu'[c] = F m[c]  (k)
+ * -- conjugate_matrix(S, F) linalg.py:41 and transform(means) model.py:236 in one pass over S.
+ *   S [C][D][D] symmetric, M [C][D] or NULL, F [k][D]
+ *   T [C][k][D] saved for the backward, Psi [C][k][k], Mu [C][k] (only if M != NULL) */
+size_t sqfa_project_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters);
+int sqfa_project_fwd(const float* S, const float* M, const float* F, int32_t n_classes, int32_t n_dim,
+                     int32_t n_filters, float* T, float* Psi, float* Mu, void* ws, size_t ws_bytes,
+                     sqfa_stream_t stream);
+
+/* dF = sum_c ( (gPsi[c] + gPsi[c]^T) T[c] + gMu[c] m[c]^T )   (gMu / M may be NULL) */
+int sqfa_project_bwd(const float* gPsi, const float* gMu, const float* T, const float* M, int32_t n_classes,
+                     int32_t n_dim, int32_t n_filters, float* dF, sqfa_stream_t stream);
+
+/* Z = X F^T  (model.py:236, transform): X [n][D] row stride ldx, F [k][D], Z [n][k] */
+int sqfa_transform(const float* X, int64_t ldx, const float* F, int64_t n, int32_t n_dim, int32_t n_filters,
+                   float* Z, sqfa_stream_t stream);
+
+/* Embedding (model.py:216-217 / 537-538 noise, distances.py:162-174 _embed_gaussian):
+ *   mode AI / LE : E[c] = Psi[c] + noise I                          (m = k)
+ *   mode FR      : E[c] = [[Psi[c] + noise I + mu mu^T, mu],[mu^T, 1]]  (m = k + 1)
+ * and its adjoint  (gPsi, gMu) <- gE. */
+int sqfa_embed_fwd(const float* Psi, const float* Mu, float noise, int32_t n_classes, int32_t n_filters,
+                   int32_t dist, float* E, sqfa_stream_t stream);
+int sqfa_embed_bwd(const float* gE, const float* Mu, int32_t n_classes, int32_t n_filters, int32_t dist,
+                   float* gPsi, float* gMu, sqfa_stream_t stream);
+
+/* Per-class factorisation of the m x m SPD matrices E[c]:
+ *   AI / FR: W[c] = [L | L^-1]  (Cholesky E = L L^T), 2 m^2 floats per class
+ *   LE     : W[c] = [V | log-eigenvalues | logE], one-sided Jacobi eigendecomposition
+ * Replaces spd_inv_sqrt (linalg.py:144-162) / spd_log (linalg.py:165-183). flag[0] is set to 1
+ * if any matrix is not positive definite / has non-finite entries. */
+size_t sqfa_class_factor_floats(int32_t m, int32_t dist);
+int sqfa_class_factor(const float* E, int32_t n_classes, int32_t m, int32_t dist, float* W, int32_t* flag,
+                      sqfa_stream_t stream);
+
+/* Pairwise distances over the strict lower triangle, pairs p in [pair_begin, pair_end) of the
+ * linearised (i > j) list p = i (i - 1) / 2 + j, one warp per pair (one-sided Jacobi on
+ * L_j^-1 L_i; replaces generalized_eigenvalues linalg.py:48-70 + distances.py:46-237):
+ *   dist_out  [C][C] or NULL: d(i,j) written to (i,j) and (j,i)  (diagonal written by
+ *             sqfa_fill_diagonal)
+ *   loss      [2] += { sum_p d_p , number of non-finite d_p }      (closure _optim.py:94, guard :16-30)
+ *   gE        [C][m][m] += d( sum_p d_p * weight ) / dE            (NULL -> forward only)
+ * weight is the scalar dLoss/dd applied to every pair (-1/P for the SQFA loss). */
+int sqfa_pair_distances(const float* E, const float* W, int32_t n_classes, int32_t m, int32_t dist,
+                        int64_t pair_begin, int64_t pair_end, float weight, float* dist_out, float* loss,
+                        float* gE, sqfa_stream_t stream);
+
+/* Adjoint of the per-class factorisation for LE (Daleckii-Krein); no-op for AI / FR whose
+ * gradients are accumulated directly on E by sqfa_pair_distances. */
+int sqfa_class_factor_bwd(const float* W, const float* gLog, int32_t n_classes, int32_t m, int32_t dist,
+                          float* gE, sqfa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQFA_B200_H_ */

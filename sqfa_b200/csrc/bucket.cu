@@ -1,0 +1,221 @@
+// K1: label bucketing. Stable LSB radix sort (8-bit digits) of (label, row id) on device.
+//
+// Replaces the C passes of `(labels == i).nonzero().squeeze(1)` in the reference
+// (/root/reference/src/sqfa/statistics.py:36-37): for every class i the reference takes the row
+// ids with that label in ascending order -- i.e. the stable bucket permutation. The result here is
+// bit-exact equal to torch.sort(labels, stable=True).indices restricted to labels in [0, C);
+// rows whose label is outside [0, C) belong to no class in the reference and are parked in a
+// trailing "dropped" bucket with key C.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sqfa_internal.h"
+
+namespace sqfa {
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int STEPS_PER_TILE = 32;
+constexpr int TILE = 32 * STEPS_PER_TILE;  // elements per warp tile
+
+__device__ __forceinline__ int32_t clip_label(int64_t y, int32_t C) { return (y < 0 || y >= C) ? C : (int32_t)y; }
+
+__global__ void label_max_kernel(const int64_t* __restrict__ labels, int64_t n, long long* out) {
+  long long m = -1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const long long v = labels[i];
+    m = v > m ? v : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = other > m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+template <bool FIRST>
+__device__ __forceinline__ int32_t load_key(const int64_t* labels, const int32_t* keys, int64_t i, int32_t C) {
+  if (FIRST) return clip_label(labels[i], C);
+  return keys[i];
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+radix_hist_kernel(const int64_t* __restrict__ labels, const int32_t* __restrict__ keys, int64_t n, int32_t C,
+                  int shift, int32_t* __restrict__ hist, int ntiles) {
+  __shared__ int32_t s_hist[WARPS_PER_BLOCK][RADIX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (tile >= ntiles) return;
+  int32_t* h = s_hist[warp];
+  for (int b = lane; b < RADIX; b += 32) h[b] = 0;
+  __syncwarp();
+  const int64_t base = (int64_t)tile * TILE;
+  for (int s = 0; s < STEPS_PER_TILE; ++s) {
+    const int64_t i = base + s * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t d = valid ? ((uint32_t)load_key<FIRST>(labels, keys, i, C) >> shift) & (RADIX - 1) : RADIX;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (__ffs(peers) - 1) == lane) h[d] += __popc(peers);
+    __syncwarp();
+  }
+  for (int b = lane; b < RADIX; b += 32) hist[(int64_t)b * ntiles + tile] = h[b];
+}
+
+// exclusive scan, one block; n is small (256 * ntiles)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int32_t* a, int64_t n) {
+  __shared__ int64_t s_sum[1024];
+  const int tid = threadIdx.x;
+  const int64_t chunk = (n + 1023) / 1024;
+  const int64_t lo = tid * chunk;
+  const int64_t hi = lo + chunk < n ? lo + chunk : n;
+  int64_t sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += a[i];
+  s_sum[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    int64_t v = tid >= o ? s_sum[tid - o] : 0;
+    __syncthreads();
+    s_sum[tid] += v;
+    __syncthreads();
+  }
+  int64_t run = s_sum[tid] - sum;
+  for (int64_t i = lo; i < hi; ++i) {
+    const int32_t t = a[i];
+    a[i] = (int32_t)run;
+    run += t;
+  }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+radix_scatter_kernel(const int64_t* __restrict__ labels, const int32_t* __restrict__ keys_in,
+                     const int32_t* __restrict__ vals_in, int64_t n, int32_t C, int shift,
+                     const int32_t* __restrict__ hist_scanned, int ntiles, int32_t* __restrict__ keys_out,
+                     int32_t* __restrict__ vals_out) {
+  __shared__ int32_t s_base[WARPS_PER_BLOCK][RADIX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * WARPS_PER_BLOCK + warp;
+  if (tile >= ntiles) return;
+  int32_t* bp = s_base[warp];
+  for (int b = lane; b < RADIX; b += 32) bp[b] = hist_scanned[(int64_t)b * ntiles + tile];
+  __syncwarp();
+  const int64_t base = (int64_t)tile * TILE;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int s = 0; s < STEPS_PER_TILE; ++s) {
+    const int64_t i = base + s * 32 + lane;
+    const bool valid = i < n;
+    int32_t key = 0, val = 0;
+    uint32_t d = RADIX;
+    if (valid) {
+      key = load_key<FIRST>(labels, keys_in, i, C);
+      val = FIRST ? (int32_t)i : vals_in[i];
+      d = ((uint32_t)key >> shift) & (RADIX - 1);
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    int32_t pos = 0;
+    if (valid) pos = bp[d] + __popc(peers & lt);  // stable: earlier lanes first
+    __syncwarp();
+    if (valid && (__ffs(peers) - 1) == lane) bp[d] += __popc(peers);
+    __syncwarp();
+    if (valid) {
+      keys_out[pos] = key;
+      vals_out[pos] = val;
+    }
+  }
+}
+
+// offsets[c] = first sorted position whose key >= c, for c in [0, C+1]; offsets[C+1] = n.
+__global__ void class_offsets_kernel(const int32_t* __restrict__ sorted_keys, int64_t n, int32_t C,
+                                     int64_t* __restrict__ offsets, int64_t* __restrict__ counts) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const int32_t prev = (i == 0) ? -1 : sorted_keys[i - 1];
+  const int32_t cur = (i == n) ? C + 1 : sorted_keys[i];
+  for (int32_t c = prev + 1; c <= cur; ++c) offsets[c] = i;
+}
+
+__global__ void class_counts_kernel(const int64_t* __restrict__ offsets, int32_t C, int64_t* __restrict__ counts) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c <= C) counts[c] = offsets[c + 1] - offsets[c];
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+cudaError_t launch_label_max(const int64_t* labels, int64_t n, int64_t* out_max, cudaStream_t stream) {
+  const long long init = -1;
+  cudaError_t e = cudaMemcpyAsync(out_max, &init, sizeof(init), cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  if (n > 0) {
+    const int threads = 256;
+    int64_t blocks = (n + threads * 8 - 1) / (threads * 8);
+    if (blocks > 1184) blocks = 1184;
+    label_max_kernel<<<(int)blocks, threads, 0, stream>>>(labels, n, reinterpret_cast<long long*>(out_max));
+  }
+  return cudaGetLastError();
+}
+
+size_t bucket_workspace_bytes(int64_t n, int32_t C) {
+  (void)C;
+  const int64_t ntiles = (n + TILE - 1) / TILE;
+  size_t b = 0;
+  b += 4 * align_up((size_t)(n > 0 ? n : 1) * sizeof(int32_t), 256);  // keys x2, vals x2
+  b += align_up((size_t)(ntiles > 0 ? ntiles : 1) * RADIX * sizeof(int32_t), 256);
+  return b;
+}
+
+cudaError_t launch_bucket_labels(const int64_t* labels, int64_t n, int32_t C, int64_t* counts, int64_t* offsets,
+                                 int32_t* perm, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (ws_bytes < bucket_workspace_bytes(n, C)) return cudaErrorInvalidValue;
+  if (n >= (int64_t)1 << 31) return cudaErrorInvalidValue;
+  const int ntiles = (int)((n + TILE - 1) / TILE);
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  const size_t nb = align_up((size_t)(n > 0 ? n : 1) * sizeof(int32_t), 256);
+  int32_t* keys[2] = {reinterpret_cast<int32_t*>(p), reinterpret_cast<int32_t*>(p + nb)};
+  int32_t* vals[2] = {reinterpret_cast<int32_t*>(p + 2 * nb), reinterpret_cast<int32_t*>(p + 3 * nb)};
+  int32_t* hist = reinterpret_cast<int32_t*>(p + 4 * nb);
+
+  int bits = 0;
+  while ((1ll << bits) < (int64_t)C + 1) ++bits;  // keys take values 0..C
+  int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+  if (passes < 1) passes = 1;
+
+  const int32_t* sorted_keys = nullptr;
+  if (n > 0) {
+    const int blocks = (ntiles + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const int threads = WARPS_PER_BLOCK * 32;
+    int cur = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+      const int shift = pass * RADIX_BITS;
+      // the last pass writes the row ids straight into the caller's perm buffer
+      int32_t* vout = (pass == passes - 1) ? perm : vals[cur ^ 1];
+      if (pass == 0) {
+        radix_hist_kernel<true><<<blocks, threads, 0, stream>>>(labels, nullptr, n, C, shift, hist, ntiles);
+        exclusive_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int64_t)ntiles * RADIX);
+        radix_scatter_kernel<true><<<blocks, threads, 0, stream>>>(labels, nullptr, nullptr, n, C, shift, hist,
+                                                                   ntiles, keys[cur ^ 1], vout);
+      } else {
+        radix_hist_kernel<false><<<blocks, threads, 0, stream>>>(nullptr, keys[cur], n, C, shift, hist, ntiles);
+        exclusive_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int64_t)ntiles * RADIX);
+        radix_scatter_kernel<false><<<blocks, threads, 0, stream>>>(nullptr, keys[cur], vals[cur], n, C, shift,
+                                                                    hist, ntiles, keys[cur ^ 1], vout);
+      }
+      cur ^= 1;
+    }
+    sorted_keys = keys[cur];
+  }
+  {
+    const int threads = 256;
+    const int64_t blocks = (n + 1 + threads - 1) / threads;
+    class_offsets_kernel<<<(int)blocks, threads, 0, stream>>>(sorted_keys, n, C, offsets, counts);
+    class_counts_kernel<<<(C + 1 + threads - 1) / threads, threads, 0, stream>>>(offsets, C, counts);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace sqfa

@@ -1,0 +1,135 @@
+// extern "C" boundary of libsqfa_b200.so -- see include/sqfa_b200.h for the contract.
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#include "../../include/sqfa_b200.h"
+#include "sqfa_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail_arg(const char* fn, const char* what, int code = SQFA_E_INVALID) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", fn, what);
+  return code;
+}
+
+int wrap(const char* fn, cudaError_t e) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", fn, (int)e, cudaGetErrorString(e));
+  return (int)e;
+}
+
+inline cudaStream_t S(sqfa_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+int sm_count_cached() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+
+}  // namespace
+
+extern "C" {
+
+int sqfa_version(void) { return 100; }
+const char* sqfa_last_error(void) { return g_err; }
+int sqfa_device_sm_count(void) { return sm_count_cached(); }
+
+// --------------------------------------------------------------------------------------------- HP1
+int sqfa_label_max(const int64_t* labels, int64_t n, int64_t* out_max, sqfa_stream_t stream) {
+  if (n < 0 || out_max == nullptr || (n > 0 && labels == nullptr)) return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_label_max(labels, n, out_max, S(stream)));
+}
+
+size_t sqfa_bucket_workspace_bytes(int64_t n, int32_t n_classes) {
+  return sqfa::bucket_workspace_bytes(n < 0 ? 0 : n, n_classes);
+}
+
+int sqfa_bucket_labels(const int64_t* labels, int64_t n, int32_t n_classes, int64_t* counts, int64_t* offsets,
+                       int32_t* perm, void* ws, size_t ws_bytes, sqfa_stream_t stream) {
+  if (n < 0 || n_classes < 0 || counts == nullptr || offsets == nullptr || ws == nullptr ||
+      (n > 0 && (labels == nullptr || perm == nullptr)))
+    return fail_arg(__func__, "bad argument");
+  if (n >= ((int64_t)1 << 31)) return fail_arg(__func__, "n must be < 2^31", SQFA_E_UNSUPPORTED);
+  if (ws_bytes < sqfa::bucket_workspace_bytes(n, n_classes))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_bucket_labels(labels, n, n_classes, counts, offsets, perm, ws, ws_bytes, S(stream)));
+}
+
+size_t sqfa_class_sums_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes) {
+  const int sms = sm_count_cached();
+  const int ns = sqfa::class_sums_splits(n, n_classes, n_dim, sms > 0 ? sms : 148);
+  return (size_t)ns * (size_t)(n_classes > 0 ? n_classes : 1) * (size_t)(n_dim > 0 ? n_dim : 1) * sizeof(float);
+}
+
+int sqfa_class_sums(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
+                    int64_t n, int32_t n_dim, int32_t n_classes, float* sums, int accumulate, void* ws,
+                    size_t ws_bytes, sqfa_stream_t stream) {
+  if (n < 0 || n_dim <= 0 || n_classes < 0 || offsets == nullptr || sums == nullptr || ws == nullptr ||
+      (n > 0 && (X == nullptr || perm == nullptr)) || ldx < n_dim)
+    return fail_arg(__func__, "bad argument");
+  const int sms = sm_count_cached();
+  const int ns = sqfa::class_sums_splits(n, n_classes, n_dim, sms > 0 ? sms : 148);
+  if (ws_bytes < (size_t)ns * (size_t)n_classes * (size_t)n_dim * sizeof(float))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_class_sums(X, ldx, perm, offsets, shift, n, n_dim, n_classes, sums, accumulate,
+                                                static_cast<float*>(ws), ns, S(stream)));
+}
+
+int sqfa_class_means(const float* sums, const int64_t* counts, const float* shift, int32_t n_dim,
+                     int32_t n_classes, float* means, sqfa_stream_t stream) {
+  if (sums == nullptr || counts == nullptr || means == nullptr || n_dim <= 0 || n_classes < 0)
+    return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_class_means(sums, counts, shift, n_dim, n_classes, means, S(stream)));
+}
+
+size_t sqfa_class_gram_workspace_bytes(void) { return 256; }
+
+int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
+                    int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int ksplit, void* ws,
+                    size_t ws_bytes, sqfa_stream_t stream) {
+  if (n_dim <= 0 || n_classes < 0 || offsets == nullptr || gram == nullptr || ws == nullptr || ldx < n_dim ||
+      X == nullptr || perm == nullptr)
+    return fail_arg(__func__, "bad argument");
+  if (ws_bytes < sqfa_class_gram_workspace_bytes()) return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail_arg(__func__, "no CUDA device");
+  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n_dim, n_classes, gram, accumulate,
+                                                ksplit, static_cast<int*>(ws), sms, S(stream)));
+}
+
+size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes) {
+  return sqfa::stats_epilogue_workspace_bytes(n_classes);
+}
+
+int sqfa_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
+                        int32_t n_dim, int32_t n_classes, int estimator, int ddof, float* cov, float* sm, void* ws,
+                        size_t ws_bytes, sqfa_stream_t stream) {
+  if (gram == nullptr || means == nullptr || counts == nullptr || cov == nullptr || n_dim <= 0 || n_classes < 0 ||
+      (estimator != SQFA_EST_EMPIRICAL && estimator != SQFA_EST_OAS) || (ddof != 0 && ddof != 1))
+    return fail_arg(__func__, "bad argument");
+  if (estimator == SQFA_EST_OAS && (ws == nullptr || ws_bytes < sqfa::stats_epilogue_workspace_bytes(n_classes)))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_stats_epilogue(gram, means, shift, counts, n_dim, n_classes, estimator, ddof, cov,
+                                                    sm, ws, S(stream)));
+}
+
+int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K, int32_t N, int32_t mode,
+                          uint32_t lbo, uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
+                          uint32_t kstep_bytes, sqfa_stream_t stream) {
+  if (A == nullptr || B == nullptr || Dout == nullptr || K <= 0 || K % 8 != 0 || K > 64 || N < 16 || N > 256 ||
+      N % 32 != 0)
+    return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_umma_probe(A, B, Dout, K, N, mode, lbo, sbo, layout_type, a_major, b_major,
+                                                kstep_bytes, S(stream)));
+}
+
+}  // extern "C"

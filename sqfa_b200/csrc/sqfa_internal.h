@@ -1,0 +1,36 @@
+// Internal launcher declarations shared by the .cu translation units and the C-ABI (capi.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sqfa {
+
+// ---- bucket.cu (K1) ----
+cudaError_t launch_label_max(const int64_t* labels, int64_t n, int64_t* out_max, cudaStream_t stream);
+size_t bucket_workspace_bytes(int64_t n, int32_t C);
+cudaError_t launch_bucket_labels(const int64_t* labels, int64_t n, int32_t C, int64_t* counts, int64_t* offsets,
+                                 int32_t* perm, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// ---- stats.cu (K2a, K3) ----
+int class_sums_splits(int64_t n, int C, int D, int num_sms);
+cudaError_t launch_class_sums(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                              const float* shift, int64_t n, int D, int C, float* sums, int accumulate,
+                              float* partial_ws, int nsplit, cudaStream_t stream);
+cudaError_t launch_class_means(const float* sums, const int64_t* counts, const float* shift, int D, int C,
+                               float* means, cudaStream_t stream);
+size_t stats_epilogue_workspace_bytes(int C);
+cudaError_t launch_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
+                                  int D, int C, int estimator, int ddof, float* cov, float* sm, void* ws,
+                                  cudaStream_t stream);
+
+// ---- gram.cu (K2) ----
+int gram_tiles_per_class(int D, int* TM_out, int* TN_out);
+cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                              const float* shift, int D, int C, float* gram, int accumulate, int ksplit,
+                              int* job_counter, int num_sms, cudaStream_t stream);
+cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K, int N, int mode, uint32_t lbo,
+                              uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
+                              uint32_t kstep_bytes, cudaStream_t stream);
+
+}  // namespace sqfa

@@ -1,0 +1,131 @@
+"""GPU parity of hot path 1 (class_statistics) against the CPU oracle, through the C ABI."""
+
+import pytest
+import torch
+
+from conftest import make_class_data, rel_err
+from oracle import sqfa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star: class means and second moments within 1e-5 relative (fp32)
+
+
+def _probe(K, N):
+    from sqfa_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    A = torch.randint(-4, 5, (K, 128), generator=g).float().cuda()
+    B = torch.randint(-4, 5, (K, N), generator=g).float().cuda()
+    D = torch.full((128, N), float("nan"), device="cuda")
+    rc = lib.sqfa_debug_umma_probe(
+        _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), K, N, 0, K * 128, 1024, 2, 1, 1, 1024, _lib.stream_ptr()
+    )
+    torch.cuda.synchronize()
+    assert rc == 0
+    return (D.double() - A.double().T @ B.double()).abs().max().item()
+
+
+@pytest.mark.parametrize("K,N", [(8, 32), (16, 256), (32, 128)])
+def test_umma_operand_layout(K, N):
+    """Small-integer operands: products are exact in tf32, any error is a layout bug."""
+    assert _probe(K, N) == 0.0
+
+
+@pytest.mark.parametrize("n,c", [(1000, 3), (5000, 10), (4099, 300), (70000, 1000)])
+def test_bucket_labels_bit_exact(n, c):
+    from sqfa_b200.statistics import bucket_labels
+
+    g = torch.Generator().manual_seed(n + c)
+    y = torch.randint(0, c, (n,), generator=g)
+    perm, offsets, counts = bucket_labels(y.cuda())
+    ref = torch.sort(y, stable=True).indices
+    assert torch.equal(perm.cpu().long(), ref)
+    ref_counts = torch.bincount(y, minlength=int(y.max()) + 1)
+    assert torch.equal(counts.cpu()[:-1], ref_counts)
+    assert int(counts[-1]) == 0
+    assert torch.equal(offsets.cpu()[1:-1], torch.cumsum(ref_counts, 0))
+
+
+def test_bucket_labels_out_of_range_rows_dropped():
+    from sqfa_b200.statistics import bucket_labels
+
+    y = torch.tensor([2, -1, 0, 7, 1, 0, -5, 2, 1, 9])
+    perm, offsets, counts = bucket_labels(y.cuda(), n_classes=3)
+    assert perm.cpu().tolist() == [2, 5, 4, 8, 0, 7, 1, 3, 6, 9]
+    assert counts.cpu().tolist() == [2, 2, 2, 4]
+    assert offsets.cpu().tolist() == [0, 2, 4, 6, 10]
+
+
+@pytest.mark.parametrize(
+    "n,d,c,kw",
+    [
+        (1000, 4, 3, {}),                       # reference's own test shape (tests/test_statistics.py:24)
+        (3000, 104, 19, {}),                    # stereo-disparity D
+        (6000, 784, 10, {}),                    # MNIST D (ragged tiles: 784 = 3*256 + 16)
+        (4000, 512, 40, {"skew": True}),        # ragged class sizes
+        (2500, 300, 5, {"offset": 3.0}),        # uncentred data: cancellation stress
+        (1500, 1027, 4, {}),                    # D not a multiple of 4 -> scalar load path
+        (5000, 3072, 2, {}),                    # CIFAR D, full 128x256 tiles
+    ],
+)
+def test_class_statistics_matches_oracle(n, d, c, kw):
+    from sqfa_b200.statistics import class_statistics
+
+    X, y = make_class_data(n, d, c, seed=d, **kw)
+    got = class_statistics(X.cuda(), y.cuda())
+    ref32 = O.class_statistics(X, y)
+    ref64 = O.class_statistics(X.double(), y)
+    for key in ("means", "covariances", "second_moments"):
+        assert got[key].shape == ref32[key].shape
+        assert rel_err(got[key], ref64[key]) < TOL, key
+        assert rel_err(got[key], ref32[key]) < TOL, key
+    # symmetric output, both triangles written
+    cov = got["covariances"]
+    assert torch.equal(cov, cov.transpose(1, 2))
+
+
+def test_class_statistics_constant_data():
+    """Known-answer test of the reference: tests/test_statistics.py:24-50."""
+    from sqfa_b200.statistics import class_statistics
+
+    X = torch.ones(1000, 4)
+    y = torch.randint(0, 3, (1000,))
+    s = class_statistics(X, y)  # CPU in -> CPU out
+    assert s["means"].device.type == "cpu"
+    assert s["means"].shape == (3, 4) and s["covariances"].shape == (3, 4, 4)
+    assert torch.allclose(s["means"], torch.ones(3, 4), atol=1e-6)
+    assert torch.allclose(s["covariances"], torch.zeros(3, 4, 4), atol=1e-5)
+    assert torch.allclose(s["second_moments"], torch.ones(3, 4, 4), atol=1e-5)
+
+
+def test_class_statistics_oas_and_edge_classes():
+    from sqfa_b200.statistics import class_statistics
+
+    X, y = make_class_data(2000, 64, 6, seed=3)
+    y[y == 4] = 5          # class 4: a single row
+    y[0] = 4
+    y[y == 2] = 1          # class 2: empty
+    got = class_statistics(X.cuda(), y.cuda(), estimator="oas")
+    ref = O.class_statistics(X, y, estimator="oas")
+    for key in ("means", "covariances", "second_moments"):
+        g, r = got[key].cpu(), ref[key]
+        assert torch.equal(torch.isnan(g), torch.isnan(r)), key
+        ok = ~torch.isnan(r)
+        assert rel_err(g[ok], r[ok]) < TOL, key
+
+
+def test_sample_covariance_and_pca():
+    from sqfa_b200 import statistics as S
+
+    X, _ = make_class_data(3000, 96, 1, seed=5)
+    assert rel_err(S.sample_covariance(X.cuda()), O.sample_covariance(X.double())) < TOL
+    assert rel_err(S.sample_covariance(X.cuda(), assume_centered=True),
+                   O.sample_covariance(X.double(), assume_centered=True)) < TOL
+    assert rel_err(S.oas_covariance(X.cuda()), O.oas_covariance(X.double())) < TOL
+    comp = S.pca(X.cuda(), 4).cpu()
+    assert comp.shape == (4, 96)
+    assert O.subspace_angle(comp, O.pca(X.double(), 4).float()) < 1e-3
+    with pytest.raises(ValueError):
+        S.pca(X.cuda(), 97)

@@ -1,0 +1,74 @@
+"""Pin the tcgen05 operand-layout assumptions on hardware (run on a B200 through gpurun).
+
+Every hypothesis (smem writer mode, LBO, SBO, swizzle type, major-ness bits, K-step stride) runs
+in its own subprocess, so a trap in one does not poison the CUDA context of the others. Results go
+to gpurun_out/umma_probe.json: max |D - A^T B| for each hypothesis (exact products: the inputs
+are small integers, so any mismatch is a layout error, not rounding).
+"""
+
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run_one(cfg):
+    import torch
+
+    from sqfa_b200 import _lib
+
+    lib = _lib.load()
+    K, N = cfg["K"], cfg["N"]
+    g = torch.Generator().manual_seed(1)
+    A = torch.randint(-4, 5, (K, 128), generator=g).float().cuda()
+    B = torch.randint(-4, 5, (K, N), generator=g).float().cuda()
+    D = torch.full((128, N), float("nan"), device="cuda")
+    rc = lib.sqfa_debug_umma_probe(
+        _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), K, N, cfg["mode"], cfg["lbo"], cfg["sbo"], cfg["layout"],
+        cfg["a_major"], cfg["b_major"], cfg["kstep"], _lib.stream_ptr(),
+    )
+    torch.cuda.synchronize()
+    ref = A.double().T @ B.double()
+    err = (D.double() - ref).abs().max().item()
+    print(json.dumps({"rc": rc, "max_err": err}))
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--one":
+        run_one(json.loads(sys.argv[2]))
+        return
+    hyps = []
+    for K in (8, 16, 32):
+        for N in (32, 128, 256):
+            # what gram.cu assumes: MN-major, 128B swizzle, chunk stride = LBO, 8-row atom stride = SBO
+            hyps.append(dict(name="mn_sw128", K=K, N=N, mode=0, lbo=K * 128, sbo=1024, layout=2, a_major=1,
+                             b_major=1, kstep=1024))
+    K, N = 16, 128
+    hyps.append(dict(name="mn_sw128_swapped", K=K, N=N, mode=0, lbo=1024, sbo=K * 128, layout=2, a_major=1,
+                     b_major=1, kstep=1024))
+    hyps.append(dict(name="k_major_noswz", K=K, N=N, mode=1, lbo=128 * 16, sbo=128, layout=0, a_major=0, b_major=0,
+                     kstep=2 * 128 * 16))
+    hyps.append(dict(name="k_major_noswz_swapped", K=K, N=N, mode=1, lbo=128, sbo=128 * 16, layout=0, a_major=0,
+                     b_major=0, kstep=2 * 128 * 16))
+    out = []
+    for h in hyps:
+        try:
+            res = subprocess.run([sys.executable, __file__, "--one", json.dumps(h)], capture_output=True, text=True,
+                                 timeout=120)
+            line = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else ""
+            r = json.loads(line) if line.startswith("{") else {"rc": res.returncode, "stderr": res.stderr[-400:]}
+        except subprocess.TimeoutExpired:
+            r = {"timeout": True}
+        r.update(h)
+        out.append(r)
+        print(r, flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "umma_probe.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
