@@ -87,13 +87,15 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
 /* Segmented Gram on the tensor cores (tcgen05, 3xTF32):
  *   gram[c] (+)= sum_{i in c} (x_i - shift_c)(x_i - shift_c)^T        (statistics.py:119-120)
  * Only the upper triangle of every gram[c] (D x D, row-major) is defined on return.
- *   ksplit     >= 1 splits every class along the sample axis into that many jobs (load balance
- *              when C * tiles < #SMs); > 1 or accumulate != 0 requires gram to be zero-initialised
- *              / hold the running sum, contributions are added with red.global.add.
- *   ws         sqfa_class_gram_workspace_bytes() bytes (job counter). */
-size_t sqfa_class_gram_workspace_bytes(void);
+ *   accumulate 0: gram is overwritten (zeroed, then summed); 1: added to the existing content
+ *              (streaming / chunked input).
+ *   chain_rows samples per tensor-core accumulation chain (0 = default 512). Every chain starts
+ *              from a zero accumulator and is added to gram with fp32 red.global.add, which bounds
+ *              the accumulator truncation bias of the tensor core.
+ *   ws         sqfa_class_gram_workspace_bytes(n_classes) bytes (job counter + job plan). */
+size_t sqfa_class_gram_workspace_bytes(int32_t n_classes);
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
-                    int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int ksplit, void* ws,
+                    int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows, void* ws,
                     size_t ws_bytes, sqfa_stream_t stream);
 
 /* Statistics epilogue (statistics.py:43-47, 84-93, 116, 120-122):

@@ -91,19 +91,24 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
   return wrap(__func__, sqfa::launch_class_means(sums, counts, shift, n_dim, n_classes, means, S(stream)));
 }
 
-size_t sqfa_class_gram_workspace_bytes(void) { return 256; }
+size_t sqfa_class_gram_workspace_bytes(int32_t n_classes) {
+  return sqfa::gram_workspace_bytes(n_classes < 0 ? 0 : n_classes);
+}
 
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
-                    int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int ksplit, void* ws,
+                    int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows, void* ws,
                     size_t ws_bytes, sqfa_stream_t stream) {
   if (n_dim <= 0 || n_classes < 0 || offsets == nullptr || gram == nullptr || ws == nullptr || ldx < n_dim ||
       X == nullptr || perm == nullptr)
     return fail_arg(__func__, "bad argument");
-  if (ws_bytes < sqfa_class_gram_workspace_bytes()) return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  if (ws_bytes < sqfa_class_gram_workspace_bytes(n_classes))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  if ((int64_t)n_classes * sqfa::gram_tiles_per_class(n_dim, nullptr, nullptr) > (1ll << 30) / 4096)
+    return fail_arg(__func__, "too many (class, tile) jobs", SQFA_E_UNSUPPORTED);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail_arg(__func__, "no CUDA device");
   return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n_dim, n_classes, gram, accumulate,
-                                                ksplit, static_cast<int*>(ws), sms, S(stream)));
+                                                chain_rows, static_cast<int*>(ws), sms, S(stream)));
 }
 
 size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes) {

@@ -1,0 +1,527 @@
+// K5: per-class factorisation and the pairwise SPD distances with their analytic gradient.
+//
+// Reference path replaced (/root/reference/src/sqfa/):
+//   spd_inv_sqrt            linalg.py:144-162   eigh-based whitening of every class matrix
+//   generalized_eigenvalues linalg.py:48-70     C x C conjugations + C*C LAPACK eigvalsh calls
+//   affine_invariant(_sq)   distances.py:46-89  sum log^2(lambda), sqrt(. + 1e-6)
+//   fisher_rao_lower_bound(_sq) distances.py:177-237  AI^2 of the embedded matrices / 2
+//   log_euclidean(_sq), spd_log  distances.py:92-138, linalg.py:165-183
+//   closure loss + NaN/inf guard + autograd backward   _optim.py:16-30, 90-96
+//
+// Formulation. For a pair (i, j) the generalized eigenvalues of (E_i, E_j) are the squared singular
+// values of B = L_j^-1 L_i (E = L L^T Cholesky). One warp runs a one-sided (Hestenes) Jacobi on
+// the columns of A = B^T held in shared memory, one column per lane (two for 32 < m <= 64),
+// round-robin pairing, until all columns are mutually orthogonal: A_f = A V, |a_q|^2 = lambda_q.
+// The generalized eigenvectors come for free as Y = L_i^-T A_f (y_q^T E_j y_q = 1), so
+//   d(d^2)/dE_i =  sum_q (2 log(lambda_q) / lambda_q) y_q y_q^T
+//   d(d^2)/dE_j = -sum_q (2 log(lambda_q))            y_q y_q^T
+// -- no 1/(lambda_a - lambda_b) terms (the eigh backward of the reference has them and NaNs on
+// repeated eigenvalues). Only the strict lower triangle (i > j) is evaluated: the reference
+// computes all C*C pairs and then reads the lower triangle (_optim.py:94).
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/sqfa_b200.h"
+#include "sqfa_internal.h"
+
+namespace sqfa {
+
+namespace {
+
+constexpr int PAIR_WARPS = 4;
+constexpr float JACOBI_TOL = 1e-6f;  // |a_p . a_q| <= tol |a_p||a_q| counts as orthogonal
+constexpr int JACOBI_MAX_SWEEPS = 24;
+constexpr float DIST_EPS = 1e-6f;    // distances.py:29 EPSILON
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// round-robin (circle method) partner of player p in round r, mp players (mp even)
+__device__ __forceinline__ int rr_partner(int p, int r, int mp) {
+  const int n1 = mp - 1;
+  if (p == n1) {
+    // the fixed player meets the p' with 2 p' == 2 r (mod n1)  ->  p' = r * (mp/2) mod n1
+    return (int)(((long long)r * (mp >> 1)) % n1);
+  }
+  int q = (2 * r - p) % n1;
+  if (q < 0) q += n1;
+  return q == p ? n1 : q;
+}
+
+// Cholesky E = L L^T and L^-1 of an m x m SPD matrix, one warp. La / Li: shared, row stride ld.
+// Returns false (all lanes) if a pivot is not positive / finite.
+__device__ bool warp_cholesky_inverse(const float* __restrict__ E, float* La, float* Li, int m, int ld, int lane) {
+  for (int idx = lane; idx < m * m; idx += 32) {
+    const int r = idx / m, c = idx % m;
+    La[r * ld + c] = E[idx];
+    Li[r * ld + c] = 0.f;
+  }
+  __syncwarp();
+  bool ok = true;
+  for (int j = 0; j < m; ++j) {
+    float d = La[j * ld + j];
+    for (int k = 0; k < j; ++k) d -= La[j * ld + k] * La[j * ld + k];
+    if (!(d > 0.f) || !isfinite(d)) ok = false;
+    const float ljj = sqrtf(d);
+    __syncwarp();
+    for (int i = j + 1 + lane; i < m; i += 32) {
+      float v = La[i * ld + j];
+      for (int k = 0; k < j; ++k) v -= La[i * ld + k] * La[j * ld + k];
+      La[i * ld + j] = v / ljj;
+    }
+    if (lane == 0) La[j * ld + j] = ljj;
+    __syncwarp();
+  }
+  // inverse by forward substitution, one column per lane
+  for (int c = lane; c < m; c += 32) {
+    for (int i = 0; i < m; ++i) {
+      float s = (i == c) ? 1.f : 0.f;
+      for (int k = 0; k < i; ++k) s -= La[i * ld + k] * Li[k * ld + c];
+      Li[i * ld + c] = (i < c) ? 0.f : s / La[i * ld + i];
+    }
+  }
+  __syncwarp();
+  return ok;
+}
+
+// One-sided Jacobi on the columns of the m x mp matrix in `cur` (row stride ld, column q of slot
+// t = lane + 32 t). Double-buffered between cur and nxt; returns the buffer holding the result.
+__device__ float* warp_jacobi(float* cur, float* nxt, int m, int mp, int ld, int lane) {
+  const int nslot = (mp + 31) >> 5;
+  for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+    bool rotated = false;
+    for (int r = 0; r < mp - 1; ++r) {
+      for (int t = 0; t < nslot; ++t) {
+        const int p = lane + 32 * t;
+        if (p < mp) {
+          const int q = rr_partner(p, r, mp);
+          float aa = 0.f, bb = 0.f, ab = 0.f;
+          for (int s = 0; s < m; ++s) {
+            const float x = cur[s * ld + p], y = cur[s * ld + q];
+            aa += x * x; bb += y * y; ab += x * y;
+          }
+          // rotation for the ordered pair (lo, hi): x_lo' = c x_lo - s x_hi, x_hi' = s x_lo + c x_hi
+          const bool is_lo = p < q;
+          const float alpha = is_lo ? aa : bb, beta = is_lo ? bb : aa;
+          float cs = 1.f, sn = 0.f;
+          if (fabsf(ab) > JACOBI_TOL * sqrtf(alpha * beta) && alpha > 0.f && beta > 0.f) {
+            const float zeta = (beta - alpha) / (2.f * ab);
+            const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+            cs = rsqrtf(1.f + tt * tt);
+            sn = cs * tt;
+            rotated = true;
+          }
+          const float mine = cs, other = is_lo ? -sn : sn;
+          for (int s = 0; s < m; ++s) nxt[s * ld + p] = mine * cur[s * ld + p] + other * cur[s * ld + q];
+        }
+      }
+      __syncwarp();
+      float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (!__any_sync(0xffffffffu, rotated)) break;
+  }
+  return cur;
+}
+
+__device__ __forceinline__ void decode_pair(int64_t p, int& i, int& j) {
+  long long ii = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
+  while (ii * (ii - 1) / 2 > p) --ii;
+  while ((ii + 1) * ii / 2 <= p) ++ii;
+  i = (int)ii;
+  j = (int)(p - ii * (ii - 1) / 2);
+}
+
+__device__ __forceinline__ float finish_distance(float d2, int dist, float* dd_dd2) {
+  const int base = dist & 15;
+  const float cfac = (base == SQFA_DIST_FISHER_RAO_LB) ? 0.5f : 1.f;
+  if (dist & SQFA_DIST_SQUARED) {
+    *dd_dd2 = cfac;
+    return cfac * d2;
+  }
+  const float d = sqrtf(cfac * d2 + DIST_EPS);
+  *dd_dd2 = cfac / (2.f * d);
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-class factorisation
+//   AI / FR: W[c] = [L (m*m) | L^-1 (m*m)]
+//   LE     : W[c] = [V (m*m) | lambda (m) | log lambda (m) | logE (m*m)]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+class_factor_kernel(const float* __restrict__ E, int C, int m, int dist, float* __restrict__ W,
+                    int32_t* __restrict__ flag) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * PAIR_WARPS + warp;
+  if (c >= C) return;
+  const int mp = (m + 1) & ~1;
+  const int ld = (mp > 32 ? 64 : 32) + 1;
+  const int per_warp = 4 * m * ld + 2 * m;
+  float* La = smem + (size_t)warp * per_warp;
+  float* Li = La + m * ld;
+  float* bufA = Li + m * ld;
+  float* bufB = bufA + m * ld;
+  float* lam = bufB + m * ld;
+  float* loglam = lam + m;
+  const bool ok = warp_cholesky_inverse(E + (int64_t)c * m * m, La, Li, m, ld, lane);
+  if (!ok && lane == 0) atomicOr(flag, 1);
+  const bool le = (dist & 15) == SQFA_DIST_LOG_EUCLIDEAN;
+  if (!le) {
+    float* Wc = W + (int64_t)c * 2 * m * m;
+    for (int idx = lane; idx < m * m; idx += 32) {
+      const int r = idx / m, q = idx % m;
+      Wc[idx] = (q <= r) ? La[r * ld + q] : 0.f;
+      Wc[m * m + idx] = Li[r * ld + q];
+    }
+    return;
+  }
+  // LE: eigendecomposition of E = L L^T through Jacobi on the columns of A0 = L^T
+  for (int s = 0; s < m; ++s)
+    for (int q = lane; q < (ld - 1); q += 32) bufA[s * ld + q] = (q < m && s <= q) ? La[q * ld + s] : 0.f;
+  __syncwarp();
+  float* Af = warp_jacobi(bufA, bufB, m, mp, ld, lane);
+  float* Vb = (Af == bufA) ? bufB : bufA;
+  for (int q = lane; q < m; q += 32) {
+    float n2 = 0.f;
+    for (int s = 0; s < m; ++s) n2 += Af[s * ld + q] * Af[s * ld + q];
+    lam[q] = n2;
+    loglam[q] = logf(n2);
+    // V[:, q] = L^-T a_q / |a_q|   (orthonormal eigenvectors of E)
+    const float inv = rsqrtf(n2);
+    for (int r = 0; r < m; ++r) {
+      float v = 0.f;
+      for (int s = r; s < m; ++s) v += Li[s * ld + r] * Af[s * ld + q];
+      Vb[r * ld + q] = v * inv;
+    }
+  }
+  __syncwarp();
+  float* Wc = W + (int64_t)c * (2 * m * m + 2 * m);
+  for (int idx = lane; idx < m * m; idx += 32) {
+    const int r = idx / m, s = idx % m;
+    Wc[idx] = Vb[r * ld + s];
+    float a = 0.f;
+    for (int q = 0; q < m; ++q) a += loglam[q] * Vb[r * ld + q] * Vb[s * ld + q];
+    Wc[m * m + 2 * m + idx] = a;
+  }
+  for (int q = lane; q < m; q += 32) {
+    Wc[m * m + q] = lam[q];
+    Wc[m * m + m + q] = loglam[q];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair kernel, affine-invariant family (AI, FR lower bound): one warp per pair
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+pair_ai_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair_begin, int64_t pair_end,
+               float weight, float* __restrict__ dist_out, float* __restrict__ loss, float* __restrict__ gE) {
+  extern __shared__ float smem[];
+  __shared__ float s_d[PAIR_WARPS];
+  __shared__ float s_bad[PAIR_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t p = pair_begin + (int64_t)blockIdx.x * PAIR_WARPS + warp;
+  const bool active = p < pair_end;
+  const int mp = (m + 1) & ~1;
+  const int ld = (mp > 32 ? 64 : 32) + 1;
+  const int nslot = (mp + 31) >> 5;
+  const int per_warp = 2 * m * ld + m * m + 2 * m;
+  float* bufA = smem + (size_t)warp * per_warp;
+  float* bufB = bufA + m * ld;
+  float* Ls = bufB + m * ld;   // m x m, row stride m: L_i, later L_i^-1, later Zj
+  float* ci = Ls + m * m;      // per-eigenvalue coefficients
+  float* cj = ci + m;
+  float dval = 0.f, bad = 0.f;
+  if (active) {
+    int i, j;
+    decode_pair(p, i, j);
+    const float* Wi = W + (int64_t)i * 2 * m * m;
+    const float* Wj = W + (int64_t)j * 2 * m * m;
+    // stage L_i (row-major) and L_j^-1 transposed: bufB[r][q] = Linv_j[q][r]
+    for (int idx = lane; idx < m * m; idx += 32) {
+      Ls[idx] = Wi[idx];
+      const int q = idx / m, r = idx % m;
+      bufB[r * ld + q] = Wj[m * m + idx];
+    }
+    __syncwarp();
+    // A[s][q] = B[q][s] = sum_{r >= s} Linv_j[q][r] L_i[r][s];  columns >= m are zero (dummy players)
+    for (int t = 0; t < nslot; ++t) {
+      const int q = lane + 32 * t;
+      if (q < ld - 1) {
+        for (int s = 0; s < m; ++s) {
+          float a = 0.f;
+          if (q < m)
+            for (int r = s; r < m; ++r) a += bufB[r * ld + q] * Ls[r * m + s];
+          bufA[s * ld + q] = a;
+        }
+      }
+    }
+    __syncwarp();
+    float* Af = warp_jacobi(bufA, bufB, m, mp, ld, lane);
+    float* Yb = (Af == bufA) ? bufB : bufA;
+    // eigenvalues and the distance
+    float d2 = 0.f;
+    for (int t = 0; t < nslot; ++t) {
+      const int q = lane + 32 * t;
+      if (q < m) {
+        float n2 = 0.f;
+        for (int s = 0; s < m; ++s) n2 += Af[s * ld + q] * Af[s * ld + q];
+        const float ll = logf(n2);
+        d2 += ll * ll;
+        ci[q] = 2.f * ll / n2;
+        cj[q] = -2.f * ll;
+      }
+    }
+    d2 = warp_sum(d2);
+    float dd_dd2;
+    dval = finish_distance(d2, dist, &dd_dd2);
+    if (!isfinite(dval)) bad = 1.f;
+    if (dist_out != nullptr && lane == 0) {
+      dist_out[(int64_t)i * C + j] = dval;
+      dist_out[(int64_t)j * C + i] = dval;
+    }
+    if (gE != nullptr) {
+      const float w = weight * dd_dd2;
+      __syncwarp();
+      // Y = L_i^-T A_f : Y[r][q] = sum_{s >= r} Linv_i[s][r] A_f[s][q]
+      for (int idx = lane; idx < m * m; idx += 32) Ls[idx] = Wi[m * m + idx];
+      __syncwarp();
+      for (int t = 0; t < nslot; ++t) {
+        const int q = lane + 32 * t;
+        if (q < m) {
+          for (int r = 0; r < m; ++r) {
+            float v = 0.f;
+            for (int s = r; s < m; ++s) v += Ls[s * m + r] * Af[s * ld + q];
+            Yb[r * ld + q] = v;
+          }
+        }
+      }
+      __syncwarp();
+      // Zi = Y diag(w ci) -> over A_f's buffer, Zj = Y diag(w cj) -> Ls (row stride m)
+      for (int t = 0; t < nslot; ++t) {
+        const int q = lane + 32 * t;
+        if (q < m) {
+          const float a = w * ci[q], b = w * cj[q];
+          for (int r = 0; r < m; ++r) {
+            const float y = Yb[r * ld + q];
+            Af[r * ld + q] = a * y;
+            Ls[r * m + q] = b * y;
+          }
+        }
+      }
+      __syncwarp();
+      // G_i[r][s] = sum_q Zi[r][q] Y[s][q],  G_j[r][s] = sum_q Zj[r][q] Y[s][q];  lane <-> column s
+      float* gi = gE + (int64_t)i * m * m;
+      float* gj = gE + (int64_t)j * m * m;
+      for (int t = 0; t < nslot; ++t) {
+        const int s = lane + 32 * t;
+        if (s < m) {
+          for (int r = 0; r < m; ++r) {
+            float a = 0.f, b = 0.f;
+            for (int q = 0; q < m; ++q) {
+              const float y = Yb[s * ld + q];
+              a += Af[r * ld + q] * y;
+              b += Ls[r * m + q] * y;
+            }
+            atomicAdd(gi + r * m + s, a);
+            atomicAdd(gj + r * m + s, b);
+          }
+        }
+      }
+    }
+  }
+  if (loss != nullptr) {
+    if (lane == 0) { s_d[warp] = dval; s_bad[warp] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < PAIR_WARPS; ++w) { a += s_d[w]; b += s_bad[w]; }
+      atomicAdd(loss, a);
+      if (b != 0.f) atomicAdd(loss + 1, b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair kernel, log-Euclidean: d^2 = |logE_i - logE_j|_F^2; gradient w.r.t. the matrix logarithms
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+pair_le_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair_begin, int64_t pair_end,
+               float weight, float* __restrict__ dist_out, float* __restrict__ loss, float* __restrict__ gLog) {
+  __shared__ float s_d[PAIR_WARPS];
+  __shared__ float s_bad[PAIR_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t p = pair_begin + (int64_t)blockIdx.x * PAIR_WARPS + warp;
+  const int stride = 2 * m * m + 2 * m;
+  float dval = 0.f, bad = 0.f;
+  if (p < pair_end) {
+    int i, j;
+    decode_pair(p, i, j);
+    const float* Li = W + (int64_t)i * stride + m * m + 2 * m;
+    const float* Lj = W + (int64_t)j * stride + m * m + 2 * m;
+    float d2 = 0.f;
+    for (int idx = lane; idx < m * m; idx += 32) {
+      const float t = Li[idx] - Lj[idx];
+      d2 += t * t;
+    }
+    d2 = warp_sum(d2);
+    float dd_dd2;
+    dval = finish_distance(d2, dist, &dd_dd2);
+    if (!isfinite(dval)) bad = 1.f;
+    if (dist_out != nullptr && lane == 0) {
+      dist_out[(int64_t)i * C + j] = dval;
+      dist_out[(int64_t)j * C + i] = dval;
+    }
+    if (gLog != nullptr) {
+      const float w = 2.f * weight * dd_dd2;
+      for (int idx = lane; idx < m * m; idx += 32) {
+        const float t = w * (Li[idx] - Lj[idx]);
+        atomicAdd(gLog + (int64_t)i * m * m + idx, t);
+        atomicAdd(gLog + (int64_t)j * m * m + idx, -t);
+      }
+    }
+  }
+  if (loss != nullptr) {
+    if (lane == 0) { s_d[warp] = dval; s_bad[warp] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < PAIR_WARPS; ++w) { a += s_d[w]; b += s_bad[w]; }
+      atomicAdd(loss, a);
+      if (b != 0.f) atomicAdd(loss + 1, b);
+    }
+  }
+}
+
+// Daleckii-Krein adjoint of logE = V log(Lambda) V^T:  gE += V [ (V^T gLog V) o Gamma ] V^T,
+// Gamma_ab = (log l_a - log l_b) / (l_a - l_b), Gamma_aa = 1 / l_a. One warp per class.
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+le_factor_bwd_kernel(const float* __restrict__ W, const float* __restrict__ gLog, int C, int m,
+                     float* __restrict__ gE) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * PAIR_WARPS + warp;
+  if (c >= C) return;
+  const int per_warp = 3 * m * m;
+  float* V = smem + (size_t)warp * per_warp;
+  float* G = V + m * m;
+  float* H = G + m * m;
+  const float* Wc = W + (int64_t)c * (2 * m * m + 2 * m);
+  const float* lam = Wc + m * m;
+  const float* ll = Wc + m * m + m;
+  for (int idx = lane; idx < m * m; idx += 32) {
+    V[idx] = Wc[idx];
+    const int r = idx / m, s = idx % m;  // symmetrise the incoming gradient
+    G[idx] = 0.5f * (gLog[(int64_t)c * m * m + idx] + gLog[(int64_t)c * m * m + s * m + r]);
+  }
+  __syncwarp();
+  // H = G V
+  for (int idx = lane; idx < m * m; idx += 32) {
+    const int r = idx / m, b = idx % m;
+    float a = 0.f;
+    for (int s = 0; s < m; ++s) a += G[r * m + s] * V[s * m + b];
+    H[idx] = a;
+  }
+  __syncwarp();
+  // G = (V^T H) o Gamma
+  for (int idx = lane; idx < m * m; idx += 32) {
+    const int a_ = idx / m, b = idx % m;
+    float a = 0.f;
+    for (int r = 0; r < m; ++r) a += V[r * m + a_] * H[r * m + b];
+    const float la = lam[a_], lb = lam[b];
+    const float dl = la - lb;
+    float gam;
+    if (fabsf(dl) > 1e-4f * fmaxf(la, lb)) gam = (ll[a_] - ll[b]) / dl;
+    else gam = 2.f / (la + lb);  // limit of the divided difference of log
+    G[idx] = a * gam;
+  }
+  __syncwarp();
+  // H = V G ; gE = H V^T
+  for (int idx = lane; idx < m * m; idx += 32) {
+    const int r = idx / m, b = idx % m;
+    float a = 0.f;
+    for (int a_ = 0; a_ < m; ++a_) a += V[r * m + a_] * G[a_ * m + b];
+    H[idx] = a;
+  }
+  __syncwarp();
+  for (int idx = lane; idx < m * m; idx += 32) {
+    const int r = idx / m, s = idx % m;
+    float a = 0.f;
+    for (int b = 0; b < m; ++b) a += H[r * m + b] * V[s * m + b];
+    gE[(int64_t)c * m * m + idx] += a;
+  }
+}
+
+__global__ void fill_diagonal_kernel(float* dist_out, int C, float v) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) dist_out[(int64_t)c * C + c] = v;
+}
+
+}  // namespace
+
+size_t class_factor_floats(int m, int dist) {
+  return ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) ? (size_t)(2 * m * m + 2 * m) : (size_t)(2 * m * m);
+}
+
+cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W, int32_t* flag, cudaStream_t st) {
+  if (C <= 0) return cudaSuccess;
+  const int mp = (m + 1) & ~1;
+  const int ld = (mp > 32 ? 64 : 32) + 1;
+  const int smem = PAIR_WARPS * (4 * m * ld + 2 * m) * (int)sizeof(float);
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(class_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
+  if (e != cudaSuccess) return e;
+  class_factor_kernel<<<(C + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, smem, st>>>(E, C, m, dist, W, flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pair_distances(const float* W, int C, int m, int dist, int64_t pair_begin, int64_t pair_end,
+                                  float weight, float* dist_out, float* loss, float* gE, cudaStream_t st) {
+  const int64_t npairs = pair_end - pair_begin;
+  if (dist_out != nullptr && C > 0) {
+    const float dv = (dist & SQFA_DIST_SQUARED) ? 0.f : sqrtf(DIST_EPS);  // d(i,i): lambda = 1 exactly
+    fill_diagonal_kernel<<<(C + 255) / 256, 256, 0, st>>>(dist_out, C, dv);
+  }
+  if (npairs <= 0) return cudaGetLastError();
+  const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
+  if ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) {
+    pair_le_kernel<<<blocks, PAIR_WARPS * 32, 0, st>>>(W, C, m, dist, pair_begin, pair_end, weight, dist_out, loss,
+                                                       gE);
+    return cudaGetLastError();
+  }
+  const int mp = (m + 1) & ~1;
+  const int ld = (mp > 32 ? 64 : 32) + 1;
+  const int smem = PAIR_WARPS * (2 * m * ld + m * m + 2 * m) * (int)sizeof(float);
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(pair_ai_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  pair_ai_kernel<<<blocks, PAIR_WARPS * 32, smem, st>>>(W, C, m, dist, pair_begin, pair_end, weight, dist_out, loss,
+                                                        gE);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_class_factor_bwd(const float* W, const float* gLog, int C, int m, int dist, float* gE,
+                                    cudaStream_t st) {
+  if ((dist & 15) != SQFA_DIST_LOG_EUCLIDEAN || C <= 0) return cudaSuccess;
+  const int smem = PAIR_WARPS * 3 * m * m * (int)sizeof(float);
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(le_factor_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  le_factor_bwd_kernel<<<(C + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, smem, st>>>(W, gLog, C, m, gE);
+  return cudaGetLastError();
+}
+
+}  // namespace sqfa

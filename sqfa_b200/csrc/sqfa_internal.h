@@ -26,9 +26,10 @@ cudaError_t launch_stats_epilogue(const float* gram, const float* means, const f
 
 // ---- gram.cu (K2) ----
 int gram_tiles_per_class(int D, int* TM_out, int* TN_out);
+size_t gram_workspace_bytes(int C);
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                              const float* shift, int D, int C, float* gram, int accumulate, int ksplit,
-                              int* job_counter, int num_sms, cudaStream_t stream);
+                              const float* shift, int D, int C, float* gram, int accumulate, int chain_rows,
+                              int* ws, int num_sms, cudaStream_t stream);
 cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K, int N, int mode, uint32_t lbo,
                               uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
                               uint32_t kstep_bytes, cudaStream_t stream);

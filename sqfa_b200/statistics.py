@@ -77,20 +77,6 @@ def bucket_labels(labels, n_classes=None):
     return perm[:n], offsets, counts
 
 
-def _gram_ksplit(lib, n, C, D):
-    """K-splits per tile so that small problems still fill the SMs (jobs >= ~2 x #SMs)."""
-    sms = max(lib.sqfa_device_sm_count(), 1)
-    tm, tn = (D + 127) // 128, (D + 255) // 256
-    tiles = sum(tn - (i >> 1) for i in range(tm))
-    jobs = max(C * tiles, 1)
-    ks = 1
-    if jobs < 2 * sms:
-        ks = -(-2 * sms // jobs)
-        avg = max(n // max(C, 1), 1)
-        ks = max(1, min(ks, avg // 256))  # keep >= 256 samples per split
-    return ks
-
-
 def _device_statistics(X, perm, offsets, counts, C, estimator_id, ddof=1, shift=None, want_sm=True):
     """means / covariances / second moments of the bucketed rows of X (all on X.device).
 
@@ -121,15 +107,14 @@ def _device_statistics(X, perm, offsets, counts, C, estimator_id, ddof=1, shift=
     )
 
     centre = means if shift is None else shift
-    ks = _gram_ksplit(lib, n, C, D)
     # the Gram lands directly in the covariance buffer; the epilogue rescales / mirrors it in place
-    cov = (torch.zeros if ks > 1 else torch.empty)(C, D, D, dtype=torch.float32, device=dev)
+    cov = torch.empty(C, D, D, dtype=torch.float32, device=dev)
     sm = torch.empty(C, D, D, dtype=torch.float32, device=dev) if want_sm else None
-    gws_bytes = lib.sqfa_class_gram_workspace_bytes()
+    gws_bytes = lib.sqfa_class_gram_workspace_bytes(C)
     gws = torch.empty(gws_bytes, dtype=torch.uint8, device=dev)
     _lib.check(
         lib.sqfa_class_gram(
-            _lib.ptr(X), ldx, _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), D, C, _lib.ptr(cov), 0, ks,
+            _lib.ptr(X), ldx, _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), D, C, _lib.ptr(cov), 0, 0,
             _lib.ptr(gws), gws_bytes, st,
         ),
         "sqfa_class_gram",

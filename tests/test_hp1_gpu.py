@@ -20,7 +20,7 @@ def _probe(K, N):
     B = torch.randint(-4, 5, (K, N), generator=g).float().cuda()
     D = torch.full((128, N), float("nan"), device="cuda")
     rc = lib.sqfa_debug_umma_probe(
-        _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), K, N, 0, K * 128, 1024, 2, 1, 1, 1024, _lib.stream_ptr()
+        _lib.ptr(A), _lib.ptr(B), _lib.ptr(D), K, N, 1, 128 * 16, 128, 0, 0, 0, 2 * 128 * 16, _lib.stream_ptr()
     )
     torch.cuda.synchronize()
     assert rc == 0

@@ -31,6 +31,10 @@ def run_one(cfg):
         cfg["a_major"], cfg["b_major"], cfg["kstep"], _lib.stream_ptr(),
     )
     torch.cuda.synchronize()
+    if cfg["mode"] >= 2:
+        tab = D[:, :8] if cfg["mode"] == 2 else D[:8, :].T  # [mn][k] -> word index fetched
+        print(json.dumps({"rc": rc, "table": tab.long().cpu().tolist()}))
+        return
     ref = A.double().T @ B.double()
     err = (D.double() - ref).abs().max().item()
     print(json.dumps({"rc": rc, "max_err": err}))
@@ -41,18 +45,19 @@ def main():
         run_one(json.loads(sys.argv[2]))
         return
     hyps = []
+    # what gram.cu uses: K-major, no swizzle, LBO = next 4 samples, SBO = next 8 columns
     for K in (8, 16, 32):
         for N in (32, 128, 256):
-            # what gram.cu assumes: MN-major, 128B swizzle, chunk stride = LBO, 8-row atom stride = SBO
-            hyps.append(dict(name="mn_sw128", K=K, N=N, mode=0, lbo=K * 128, sbo=1024, layout=2, a_major=1,
-                             b_major=1, kstep=1024))
-    K, N = 16, 128
-    hyps.append(dict(name="mn_sw128_swapped", K=K, N=N, mode=0, lbo=1024, sbo=K * 128, layout=2, a_major=1,
-                     b_major=1, kstep=1024))
-    hyps.append(dict(name="k_major_noswz", K=K, N=N, mode=1, lbo=128 * 16, sbo=128, layout=0, a_major=0, b_major=0,
-                     kstep=2 * 128 * 16))
-    hyps.append(dict(name="k_major_noswz_swapped", K=K, N=N, mode=1, lbo=128, sbo=128 * 16, layout=0, a_major=0,
-                     b_major=0, kstep=2 * 128 * 16))
+            hyps.append(dict(name="k_major_noswz", K=K, N=N, mode=1, lbo=128 * 16, sbo=128, layout=0, a_major=0,
+                             b_major=0, kstep=2 * 128 * 16))
+    # decode probes: which smem word does the hardware fetch for A(k, m) / B(k, n)?
+    for layout in (0, 2, 4, 6):
+        for major in (1, 0):
+            for lbo, sbo in ((2048, 1024), (1024, 2048), (4096, 512), (256, 4096)):
+                hyps.append(dict(name=f"decodeA_l{layout}_mj{major}_lbo{lbo}_sbo{sbo}", K=8, N=16, mode=2, lbo=lbo,
+                                 sbo=sbo, layout=layout, a_major=major, b_major=0, kstep=0))
+    hyps.append(dict(name="decodeB_l2_mj1_lbo2048_sbo1024", K=8, N=256, mode=3, lbo=2048, sbo=1024, layout=2,
+                     a_major=0, b_major=1, kstep=0))
     out = []
     for h in hyps:
         try:
@@ -64,7 +69,7 @@ def main():
             r = {"timeout": True}
         r.update(h)
         out.append(r)
-        print(r, flush=True)
+        print({k: v for k, v in r.items() if k != "table"}, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "umma_probe.json"), "w") as f:
         json.dump(out, f, indent=1)
