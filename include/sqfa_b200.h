@@ -121,53 +121,65 @@ int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K
 
 /* Projection  T[c] = F S[c]  (k x D),  Psi[c] = T[c] F^T (k x k),  mu'[c] = F m[c]  (k)
  * -- conjugate_matrix(S, F) linalg.py:41 and transform(means) model.py:236 in one pass over S.
- *   S [C][D][D] symmetric, M [C][D] or NULL, F [k][D]
- *   T [C][k][D] saved for the backward, Psi [C][k][k], Mu [C][k] (only if M != NULL) */
+ *   S [C][D][D] symmetric, M [C][D] or NULL, F [k][D], k <= 32
+ *   T [C][k][D] saved for the backward, Psi [C][k][k], Mu [C][k] (only if M != NULL)
+ *   ws: sqfa_project_workspace_bytes (shared by fwd and bwd) */
 size_t sqfa_project_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters);
 int sqfa_project_fwd(const float* S, const float* M, const float* F, int32_t n_classes, int32_t n_dim,
                      int32_t n_filters, float* T, float* Psi, float* Mu, void* ws, size_t ws_bytes,
                      sqfa_stream_t stream);
 
-/* dF = sum_c ( (gPsi[c] + gPsi[c]^T) T[c] + gMu[c] m[c]^T )   (gMu / M may be NULL) */
+/* dF = sum_c ( (gPsi[c] + gPsi[c]^T) T[c] + gMu[c] m[c]^T )   (gMu and M may both be NULL):
+ * analytic adjoint of sqfa_project_fwd w.r.t. F, replaces autograd through linalg.py:41 */
 int sqfa_project_bwd(const float* gPsi, const float* gMu, const float* T, const float* M, int32_t n_classes,
-                     int32_t n_dim, int32_t n_filters, float* dF, sqfa_stream_t stream);
+                     int32_t n_dim, int32_t n_filters, float* dF, void* ws, size_t ws_bytes,
+                     sqfa_stream_t stream);
 
 /* Z = X F^T  (model.py:236, transform): X [n][D] row stride ldx, F [k][D], Z [n][k] */
 int sqfa_transform(const float* X, int64_t ldx, const float* F, int64_t n, int32_t n_dim, int32_t n_filters,
                    float* Z, sqfa_stream_t stream);
 
 /* Embedding (model.py:216-217 / 537-538 noise, distances.py:162-174 _embed_gaussian):
- *   mode AI / LE : E[c] = Psi[c] + noise I                          (m = k)
- *   mode FR      : E[c] = [[Psi[c] + noise I + mu mu^T, mu],[mu^T, 1]]  (m = k + 1)
- * and its adjoint  (gPsi, gMu) <- gE. */
+ *   dist AI / LE : E[c] = Psi[c] + noise I                              (m = k,  Mu unused)
+ *   dist FR      : E[c] = [[Psi[c] + noise I + mu mu^T, mu],[mu^T, 1]]  (m = k + 1)
+ * and its adjoint  (gPsi, gMu) <- gE  (gMu written only for FR). */
 int sqfa_embed_fwd(const float* Psi, const float* Mu, float noise, int32_t n_classes, int32_t n_filters,
                    int32_t dist, float* E, sqfa_stream_t stream);
 int sqfa_embed_bwd(const float* gE, const float* Mu, int32_t n_classes, int32_t n_filters, int32_t dist,
                    float* gPsi, float* gMu, sqfa_stream_t stream);
 
-/* Per-class factorisation of the m x m SPD matrices E[c]:
+/* Per-class factorisation of the m x m SPD matrices E[c] (m <= SQFA_MAX_M), one warp per class:
  *   AI / FR: W[c] = [L | L^-1]  (Cholesky E = L L^T), 2 m^2 floats per class
- *   LE     : W[c] = [V | log-eigenvalues | logE], one-sided Jacobi eigendecomposition
+ *   LE     : W[c] = [V | lambda | log lambda | logE] (2 m^2 + 2 m floats), one-sided Jacobi
  * Replaces spd_inv_sqrt (linalg.py:144-162) / spd_log (linalg.py:165-183). flag[0] is set to 1
- * if any matrix is not positive definite / has non-finite entries. */
+ * if any matrix is not positive definite / has non-finite entries (0 otherwise). */
 size_t sqfa_class_factor_floats(int32_t m, int32_t dist);
 int sqfa_class_factor(const float* E, int32_t n_classes, int32_t m, int32_t dist, float* W, int32_t* flag,
                       sqfa_stream_t stream);
 
-/* Pairwise distances over the strict lower triangle, pairs p in [pair_begin, pair_end) of the
- * linearised (i > j) list p = i (i - 1) / 2 + j, one warp per pair (one-sided Jacobi on
- * L_j^-1 L_i; replaces generalized_eigenvalues linalg.py:48-70 + distances.py:46-237):
- *   dist_out  [C][C] or NULL: d(i,j) written to (i,j) and (j,i)  (diagonal written by
- *             sqfa_fill_diagonal)
- *   loss      [2] += { sum_p d_p , number of non-finite d_p }      (closure _optim.py:94, guard :16-30)
- *   gE        [C][m][m] += d( sum_p d_p * weight ) / dE            (NULL -> forward only)
- * weight is the scalar dLoss/dd applied to every pair (-1/P for the SQFA loss). */
-int sqfa_pair_distances(const float* E, const float* W, int32_t n_classes, int32_t m, int32_t dist,
-                        int64_t pair_begin, int64_t pair_end, float weight, float* dist_out, float* loss,
-                        float* gE, sqfa_stream_t stream);
+/* Pairwise distances d(A_a, B_b), one warp per pair (one-sided Jacobi on L_b^-1 L_a; replaces
+ * generalized_eigenvalues linalg.py:48-70 + distances.py:46-237).
+ *   Wa, Wb     outputs of sqfa_class_factor (same dist) for the n_a / n_b matrices
+ *   triangular 1: self distances (n_a == n_b, Wa == Wb): only the strict lower triangle is
+ *              evaluated, pairs p = i (i - 1) / 2 + j (i > j) for p in [pair_begin, pair_end);
+ *              d(i,j) is written to (i,j) and (j,i) and the diagonal is set to d(i,i)
+ *              (sqrt(1e-6), or 0 for the squared variants). The reference evaluates all C*C pairs
+ *              and reads the lower triangle (_optim.py:94).
+ *              0: all n_a * n_b pairs, p = a * n_b + b.
+ *   dist_out   [n_a][n_b] or NULL
+ *   loss       [2] or NULL: += { sum_p d_p , number of non-finite d_p }  (_optim.py:94, guard :16-30)
+ *   gEa, gEb   [n][m][m] or both NULL: += w_p * d(d_p)/dE, w_p = weight * (gD ? gD[a][b] (+ gD[b][a]
+ *              when triangular) : 1). For LE these are gradients w.r.t. the matrix logarithms
+ *              (feed them to sqfa_class_factor_bwd). gEa == gEb is allowed.
+ *   eig_out    [n_a][n_b][m] or NULL (AI / FR, triangular == 0 only): the generalized eigenvalues
+ *              of (A_a, B_b) in descending order (generalized_eigenvalues, linalg.py:48-70) */
+int sqfa_pair_distances(const float* Wa, const float* Wb, int32_t n_a, int32_t n_b, int32_t m, int32_t dist,
+                        int32_t triangular, int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
+                        float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
+                        sqfa_stream_t stream);
 
-/* Adjoint of the per-class factorisation for LE (Daleckii-Krein); no-op for AI / FR whose
- * gradients are accumulated directly on E by sqfa_pair_distances. */
+/* LE only: gE[c] += adjoint of logE = V log(Lambda) V^T applied to gLog[c] (Daleckii-Krein).
+ * No-op for AI / FR, whose gradients sqfa_pair_distances accumulates directly on E. */
 int sqfa_class_factor_bwd(const float* W, const float* gLog, int32_t n_classes, int32_t m, int32_t dist,
                           float* gE, sqfa_stream_t stream);
 

@@ -56,7 +56,10 @@ SIGNATURES = {
         c_int,
         [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
     ),
-    "sqfa_project_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
+    "sqfa_project_bwd": (
+        c_int,
+        [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_size, c_ptr],
+    ),
     "sqfa_transform": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "sqfa_embed_fwd": (c_int, [c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     "sqfa_embed_bwd": (c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
@@ -64,7 +67,8 @@ SIGNATURES = {
     "sqfa_class_factor": (c_int, [c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "sqfa_pair_distances": (
         c_int,
-        [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
+        [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+         c_ptr, c_ptr],
     ),
     "sqfa_class_factor_bwd": (c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
 }

@@ -138,3 +138,104 @@ int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K
 }
 
 }  // extern "C"
+
+// --------------------------------------------------------------------------------------------- HP2
+extern "C" {
+
+size_t sqfa_project_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters) {
+  if (n_classes <= 0 || n_dim <= 0 || n_filters <= 0) return 256;
+  return sqfa::project_workspace_bytes(n_classes, n_dim, n_filters);
+}
+
+int sqfa_project_fwd(const float* S_, const float* M, const float* F, int32_t n_classes, int32_t n_dim,
+                     int32_t n_filters, float* T, float* Psi, float* Mu, void* ws, size_t ws_bytes,
+                     sqfa_stream_t stream) {
+  if (S_ == nullptr || F == nullptr || T == nullptr || Psi == nullptr || ws == nullptr || n_classes < 0 ||
+      n_dim <= 0 || n_filters <= 0 || (M != nullptr && Mu == nullptr))
+    return fail_arg(__func__, "bad argument");
+  if (n_filters > 32) return fail_arg(__func__, "n_filters must be <= 32", SQFA_E_UNSUPPORTED);
+  if (ws_bytes < sqfa_project_workspace_bytes(n_classes, n_dim, n_filters))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_project_fwd(S_, M, F, n_classes, n_dim, n_filters, T, Psi, Mu,
+                                                 static_cast<float*>(ws), S(stream)));
+}
+
+int sqfa_project_bwd(const float* gPsi, const float* gMu, const float* T, const float* M, int32_t n_classes,
+                     int32_t n_dim, int32_t n_filters, float* dF, void* ws, size_t ws_bytes,
+                     sqfa_stream_t stream) {
+  if (gPsi == nullptr || T == nullptr || dF == nullptr || ws == nullptr || n_classes < 0 || n_dim <= 0 ||
+      n_filters <= 0 || ((gMu == nullptr) != (M == nullptr)))
+    return fail_arg(__func__, "bad argument");
+  if (n_filters > 32) return fail_arg(__func__, "n_filters must be <= 32", SQFA_E_UNSUPPORTED);
+  if (ws_bytes < sqfa_project_workspace_bytes(n_classes, n_dim, n_filters))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_project_bwd(gPsi, gMu, T, M, n_classes, n_dim, n_filters, dF,
+                                                 static_cast<float*>(ws), S(stream)));
+}
+
+int sqfa_transform(const float* X, int64_t ldx, const float* F, int64_t n, int32_t n_dim, int32_t n_filters,
+                   float* Z, sqfa_stream_t stream) {
+  if (n < 0 || n_dim <= 0 || n_filters <= 0 || F == nullptr || (n > 0 && (X == nullptr || Z == nullptr)) ||
+      ldx < n_dim)
+    return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_transform(X, ldx, F, n, n_dim, n_filters, Z, S(stream)));
+}
+
+static int dist_ok(int32_t dist) {
+  const int b = dist & 15;
+  return (dist & ~(15 | SQFA_DIST_SQUARED)) == 0 &&
+         (b == SQFA_DIST_AFFINE_INVARIANT || b == SQFA_DIST_FISHER_RAO_LB || b == SQFA_DIST_LOG_EUCLIDEAN);
+}
+
+int sqfa_embed_fwd(const float* Psi, const float* Mu, float noise, int32_t n_classes, int32_t n_filters,
+                   int32_t dist, float* E, sqfa_stream_t stream) {
+  const int fr = (dist & 15) == SQFA_DIST_FISHER_RAO_LB;
+  if (!dist_ok(dist) || Psi == nullptr || E == nullptr || n_classes < 0 || n_filters <= 0 || (fr && Mu == nullptr))
+    return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_embed_fwd(Psi, Mu, noise, n_classes, n_filters, fr, E, S(stream)));
+}
+
+int sqfa_embed_bwd(const float* gE, const float* Mu, int32_t n_classes, int32_t n_filters, int32_t dist,
+                   float* gPsi, float* gMu, sqfa_stream_t stream) {
+  const int fr = (dist & 15) == SQFA_DIST_FISHER_RAO_LB;
+  if (!dist_ok(dist) || gE == nullptr || gPsi == nullptr || n_classes < 0 || n_filters <= 0 ||
+      (fr && (Mu == nullptr || gMu == nullptr)))
+    return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_embed_bwd(gE, Mu, n_classes, n_filters, fr, gPsi, gMu, S(stream)));
+}
+
+size_t sqfa_class_factor_floats(int32_t m, int32_t dist) { return sqfa::class_factor_floats(m, dist); }
+
+int sqfa_class_factor(const float* E, int32_t n_classes, int32_t m, int32_t dist, float* W, int32_t* flag,
+                      sqfa_stream_t stream) {
+  if (!dist_ok(dist) || E == nullptr || W == nullptr || flag == nullptr || n_classes < 0 || m <= 0)
+    return fail_arg(__func__, "bad argument");
+  if (m > SQFA_MAX_M) return fail_arg(__func__, "m exceeds SQFA_MAX_M", SQFA_E_UNSUPPORTED);
+  return wrap(__func__, sqfa::launch_class_factor(E, n_classes, m, dist, W, flag, S(stream)));
+}
+
+int sqfa_pair_distances(const float* Wa, const float* Wb, int32_t n_a, int32_t n_b, int32_t m, int32_t dist,
+                        int32_t triangular, int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
+                        float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
+                        sqfa_stream_t stream) {
+  if (!dist_ok(dist) || Wa == nullptr || Wb == nullptr || n_a < 0 || n_b < 0 || m <= 0 ||
+      (triangular && (n_a != n_b || Wa != Wb)) || ((gEa == nullptr) != (gEb == nullptr)) ||
+      (eig_out != nullptr && (triangular || (dist & 15) == SQFA_DIST_LOG_EUCLIDEAN)))
+    return fail_arg(__func__, "bad argument");
+  const int64_t P = triangular ? (int64_t)n_a * (n_a - 1) / 2 : (int64_t)n_a * n_b;
+  if (pair_begin < 0 || pair_end > P || pair_begin > pair_end) return fail_arg(__func__, "bad pair range");
+  if (m > SQFA_MAX_M) return fail_arg(__func__, "m exceeds SQFA_MAX_M", SQFA_E_UNSUPPORTED);
+  return wrap(__func__, sqfa::launch_pair_distances(Wa, Wb, n_a, n_b, m, dist, triangular ? 1 : 0, pair_begin,
+                                                    pair_end, weight, gD, dist_out, loss, gEa, gEb, eig_out,
+                                                    S(stream)));
+}
+
+int sqfa_class_factor_bwd(const float* W, const float* gLog, int32_t n_classes, int32_t m, int32_t dist,
+                          float* gE, sqfa_stream_t stream) {
+  if (!dist_ok(dist) || W == nullptr || gLog == nullptr || gE == nullptr || n_classes < 0 || m <= 0)
+    return fail_arg(__func__, "bad argument");
+  if (m > SQFA_MAX_M) return fail_arg(__func__, "m exceeds SQFA_MAX_M", SQFA_E_UNSUPPORTED);
+  return wrap(__func__, sqfa::launch_class_factor_bwd(W, gLog, n_classes, m, dist, gE, S(stream)));
+}
+
+}  // extern "C"

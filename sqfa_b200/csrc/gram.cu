@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_tf32x3_kernel(const Gram
       const uint32_t c_off = (uint32_t)((cw >> 3) * 128 + (cw & 7) * 16);
       const float* xcol = P.X + col;
 
-      float buf[2][BK];
+      float buf[3][BK];  // three stages of loads in flight per thread (registers)
       // row ids of the next stage are fetched one stage ahead (lane r < 16 holds sample r's row)
       auto load_row = [&](int kb) -> int32_t {
         const int64_t k = (int64_t)kb * BK + (lane & (BK - 1));
@@ -212,18 +212,26 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_tf32x3_kernel(const Gram
 #pragma unroll
         for (int r = 0; r < BK; ++r) {
           const int32_t row = __shfl_sync(0xffffffffu, myrow, r);
-          // raw value; the shift is subtracted in consume() so the loads stay in flight across
-          // the previous stage. Padded rows / columns read as `sh` -> exactly 0 after centring.
-          b[r] = (row >= 0 && col_ok) ? __ldg(xcol + (int64_t)row * P.ldx) : sh;
+          // UNCONDITIONAL load (a select on the loaded value would make the thread wait for it
+          // right here and serialise the pipeline): padded rows / columns read X[0][0] and are
+          // zeroed in consume() from the validity computed there.
+          const float* ptr = (row >= 0 && col_ok) ? xcol + (int64_t)row * P.ldx : P.X;
+          b[r] = __ldg(ptr);
         }
       };
-      auto consume = [&](float(&b)[BK]) {
+      auto consume = [&](int kb, float(&b)[BK]) {
+        int64_t nv = n_c - (int64_t)kb * BK;  // valid rows of this stage
+        nv = nv > BK ? BK : nv;
+        const uint32_t vmask = col_ok ? ((1u << (int)nv) - 1u) : 0u;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * STAGE_BYTES;
 #pragma unroll
         for (int kc = 0; kc < BK / 4; ++kc) {
           float4 x, h, l;
-          x.x = b[4 * kc + 0] - sh; x.y = b[4 * kc + 1] - sh; x.z = b[4 * kc + 2] - sh; x.w = b[4 * kc + 3] - sh;
+          x.x = (vmask >> (4 * kc + 0)) & 1u ? b[4 * kc + 0] - sh : 0.f;
+          x.y = (vmask >> (4 * kc + 1)) & 1u ? b[4 * kc + 1] - sh : 0.f;
+          x.z = (vmask >> (4 * kc + 2)) & 1u ? b[4 * kc + 2] - sh : 0.f;
+          x.w = (vmask >> (4 * kc + 3)) & 1u ? b[4 * kc + 3] - sh : 0.f;
           h.x = to_tf32(x.x); l.x = x.x - h.x;
           h.y = to_tf32(x.y); l.y = x.y - h.y;
           h.z = to_tf32(x.z); l.z = x.z - h.z;
@@ -239,12 +247,17 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_tf32x3_kernel(const Gram
 
       if (nkb > 0) issue(kb0, buf[0]);
       if (nkb > 1) issue(kb0 + 1, buf[1]);
-      for (int kb = kb0; kb < kb1; kb += 2) {
-        consume(buf[0]);
-        if (kb + 2 < kb1) issue(kb + 2, buf[0]);
+      if (nkb > 2) issue(kb0 + 2, buf[2]);
+      for (int kb = kb0; kb < kb1; kb += 3) {
+        consume(kb, buf[0]);
+        if (kb + 3 < kb1) issue(kb + 3, buf[0]);
         if (kb + 1 < kb1) {
-          consume(buf[1]);
-          if (kb + 3 < kb1) issue(kb + 3, buf[1]);
+          consume(kb + 1, buf[1]);
+          if (kb + 4 < kb1) issue(kb + 4, buf[1]);
+        }
+        if (kb + 2 < kb1) {
+          consume(kb + 2, buf[2]);
+          if (kb + 5 < kb1) issue(kb + 5, buf[2]);
         }
       }
 

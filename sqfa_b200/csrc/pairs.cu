@@ -216,8 +216,10 @@ class_factor_kernel(const float* __restrict__ E, int C, int m, int dist, float* 
 // pair kernel, affine-invariant family (AI, FR lower bound): one warp per pair
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
-pair_ai_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair_begin, int64_t pair_end,
-               float weight, float* __restrict__ dist_out, float* __restrict__ loss, float* __restrict__ gE) {
+pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int nA, int nB, int m, int dist, int tri,
+               int64_t pair_begin, int64_t pair_end, float weight, const float* __restrict__ gD,
+               float* __restrict__ dist_out, float* __restrict__ loss, float* gEa, float* gEb,
+               float* __restrict__ eig_out) {
   extern __shared__ float smem[];
   __shared__ float s_d[PAIR_WARPS];
   __shared__ float s_bad[PAIR_WARPS];
@@ -227,18 +229,20 @@ pair_ai_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
   const int nslot = (mp + 31) >> 5;
-  const int per_warp = 2 * m * ld + m * m + 2 * m;
+  const int per_warp = 2 * m * ld + m * m + 3 * m;
   float* bufA = smem + (size_t)warp * per_warp;
   float* bufB = bufA + m * ld;
   float* Ls = bufB + m * ld;   // m x m, row stride m: L_i, later L_i^-1, later Zj
   float* ci = Ls + m * m;      // per-eigenvalue coefficients
   float* cj = ci + m;
+  float* lamv = cj + m;
   float dval = 0.f, bad = 0.f;
   if (active) {
     int i, j;
-    decode_pair(p, i, j);
-    const float* Wi = W + (int64_t)i * 2 * m * m;
-    const float* Wj = W + (int64_t)j * 2 * m * m;
+    if (tri) decode_pair(p, i, j);
+    else { i = (int)(p / nB); j = (int)(p % nB); }
+    const float* Wi = Wa + (int64_t)i * 2 * m * m;
+    const float* Wj = Wb + (int64_t)j * 2 * m * m;
     // stage L_i (row-major) and L_j^-1 transposed: bufB[r][q] = Linv_j[q][r]
     for (int idx = lane; idx < m * m; idx += 32) {
       Ls[idx] = Wi[idx];
@@ -272,18 +276,33 @@ pair_ai_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair
         d2 += ll * ll;
         ci[q] = 2.f * ll / n2;
         cj[q] = -2.f * ll;
+        lamv[q] = n2;
       }
     }
     d2 = warp_sum(d2);
+    if (eig_out != nullptr) {  // generalized eigenvalues, descending (linalg.py:69-70)
+      __syncwarp();
+      float* eo = eig_out + ((int64_t)i * nB + j) * m;
+      for (int t = 0; t < nslot; ++t) {
+        const int q = lane + 32 * t;
+        if (q < m) {
+          const float v = lamv[q];
+          int rank = 0;
+          for (int u = 0; u < m; ++u) rank += (lamv[u] > v || (lamv[u] == v && u < q)) ? 1 : 0;
+          eo[rank] = v;
+        }
+      }
+    }
     float dd_dd2;
     dval = finish_distance(d2, dist, &dd_dd2);
     if (!isfinite(dval)) bad = 1.f;
     if (dist_out != nullptr && lane == 0) {
-      dist_out[(int64_t)i * C + j] = dval;
-      dist_out[(int64_t)j * C + i] = dval;
+      dist_out[(int64_t)i * nB + j] = dval;
+      if (tri) dist_out[(int64_t)j * nB + i] = dval;
     }
-    if (gE != nullptr) {
-      const float w = weight * dd_dd2;
+    if (gEa != nullptr) {
+      float w = weight * dd_dd2;
+      if (gD != nullptr) w *= tri ? (gD[(int64_t)i * nB + j] + gD[(int64_t)j * nB + i]) : gD[(int64_t)i * nB + j];
       __syncwarp();
       // Y = L_i^-T A_f : Y[r][q] = sum_{s >= r} Linv_i[s][r] A_f[s][q]
       for (int idx = lane; idx < m * m; idx += 32) Ls[idx] = Wi[m * m + idx];
@@ -313,8 +332,8 @@ pair_ai_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair
       }
       __syncwarp();
       // G_i[r][s] = sum_q Zi[r][q] Y[s][q],  G_j[r][s] = sum_q Zj[r][q] Y[s][q];  lane <-> column s
-      float* gi = gE + (int64_t)i * m * m;
-      float* gj = gE + (int64_t)j * m * m;
+      float* gi = gEa + (int64_t)i * m * m;
+      float* gj = gEb + (int64_t)j * m * m;
       for (int t = 0; t < nslot; ++t) {
         const int s = lane + 32 * t;
         if (s < m) {
@@ -348,8 +367,9 @@ pair_ai_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair
 // pair kernel, log-Euclidean: d^2 = |logE_i - logE_j|_F^2; gradient w.r.t. the matrix logarithms
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
-pair_le_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair_begin, int64_t pair_end,
-               float weight, float* __restrict__ dist_out, float* __restrict__ loss, float* __restrict__ gLog) {
+pair_le_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int nA, int nB, int m, int dist, int tri,
+               int64_t pair_begin, int64_t pair_end, float weight, const float* __restrict__ gD,
+               float* __restrict__ dist_out, float* __restrict__ loss, float* gLa, float* gLb) {
   __shared__ float s_d[PAIR_WARPS];
   __shared__ float s_bad[PAIR_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -358,9 +378,10 @@ pair_le_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair
   float dval = 0.f, bad = 0.f;
   if (p < pair_end) {
     int i, j;
-    decode_pair(p, i, j);
-    const float* Li = W + (int64_t)i * stride + m * m + 2 * m;
-    const float* Lj = W + (int64_t)j * stride + m * m + 2 * m;
+    if (tri) decode_pair(p, i, j);
+    else { i = (int)(p / nB); j = (int)(p % nB); }
+    const float* Li = Wa + (int64_t)i * stride + m * m + 2 * m;
+    const float* Lj = Wb + (int64_t)j * stride + m * m + 2 * m;
     float d2 = 0.f;
     for (int idx = lane; idx < m * m; idx += 32) {
       const float t = Li[idx] - Lj[idx];
@@ -371,15 +392,16 @@ pair_le_kernel(const float* __restrict__ W, int C, int m, int dist, int64_t pair
     dval = finish_distance(d2, dist, &dd_dd2);
     if (!isfinite(dval)) bad = 1.f;
     if (dist_out != nullptr && lane == 0) {
-      dist_out[(int64_t)i * C + j] = dval;
-      dist_out[(int64_t)j * C + i] = dval;
+      dist_out[(int64_t)i * nB + j] = dval;
+      if (tri) dist_out[(int64_t)j * nB + i] = dval;
     }
-    if (gLog != nullptr) {
-      const float w = 2.f * weight * dd_dd2;
+    if (gLa != nullptr) {
+      float w = 2.f * weight * dd_dd2;
+      if (gD != nullptr) w *= tri ? (gD[(int64_t)i * nB + j] + gD[(int64_t)j * nB + i]) : gD[(int64_t)i * nB + j];
       for (int idx = lane; idx < m * m; idx += 32) {
         const float t = w * (Li[idx] - Lj[idx]);
-        atomicAdd(gLog + (int64_t)i * m * m + idx, t);
-        atomicAdd(gLog + (int64_t)j * m * m + idx, -t);
+        atomicAdd(gLa + (int64_t)i * m * m + idx, t);
+        atomicAdd(gLb + (int64_t)j * m * m + idx, -t);
       }
     }
   }
@@ -482,31 +504,33 @@ cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W
   return cudaGetLastError();
 }
 
-cudaError_t launch_pair_distances(const float* W, int C, int m, int dist, int64_t pair_begin, int64_t pair_end,
-                                  float weight, float* dist_out, float* loss, float* gE, cudaStream_t st) {
+cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
+                                  int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
+                                  float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
+                                  cudaStream_t st) {
   const int64_t npairs = pair_end - pair_begin;
-  if (dist_out != nullptr && C > 0) {
+  if (tri && dist_out != nullptr && nA > 0) {
     const float dv = (dist & SQFA_DIST_SQUARED) ? 0.f : sqrtf(DIST_EPS);  // d(i,i): lambda = 1 exactly
-    fill_diagonal_kernel<<<(C + 255) / 256, 256, 0, st>>>(dist_out, C, dv);
+    fill_diagonal_kernel<<<(nA + 255) / 256, 256, 0, st>>>(dist_out, nA, dv);
   }
   if (npairs <= 0) return cudaGetLastError();
   const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
   if ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) {
-    pair_le_kernel<<<blocks, PAIR_WARPS * 32, 0, st>>>(W, C, m, dist, pair_begin, pair_end, weight, dist_out, loss,
-                                                       gE);
+    pair_le_kernel<<<blocks, PAIR_WARPS * 32, 0, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
+                                                       dist_out, loss, gEa, gEb);
     return cudaGetLastError();
   }
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
-  const int smem = PAIR_WARPS * (2 * m * ld + m * m + 2 * m) * (int)sizeof(float);
+  const int smem = PAIR_WARPS * (2 * m * ld + m * m + 3 * m) * (int)sizeof(float);
   static int configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(pair_ai_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  pair_ai_kernel<<<blocks, PAIR_WARPS * 32, smem, st>>>(W, C, m, dist, pair_begin, pair_end, weight, dist_out, loss,
-                                                        gE);
+  pair_ai_kernel<<<blocks, PAIR_WARPS * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
+                                                        dist_out, loss, gEa, gEb, eig_out);
   return cudaGetLastError();
 }
 

@@ -35,3 +35,29 @@ cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K
                               uint32_t kstep_bytes, cudaStream_t stream);
 
 }  // namespace sqfa
+
+namespace sqfa {
+// ---- project.cu (K4, K6, transform, embedding) ----
+int project_nsplit(int D);
+size_t project_workspace_bytes(int C, int D, int k);
+cudaError_t launch_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
+                               float* Psi, float* Mu, float* ws, cudaStream_t st);
+cudaError_t launch_project_bwd(const float* gPsi, const float* gMu, const float* T, const float* M, int C, int D,
+                               int k, float* dF, float* ws, cudaStream_t st);
+cudaError_t launch_transform(const float* X, int64_t ldx, const float* F, int64_t n, int D, int k, float* Z,
+                             cudaStream_t st);
+cudaError_t launch_embed_fwd(const float* Psi, const float* Mu, float noise, int C, int k, int fr, float* E,
+                             cudaStream_t st);
+cudaError_t launch_embed_bwd(const float* gE, const float* Mu, int C, int k, int fr, float* gPsi, float* gMu,
+                             cudaStream_t st);
+
+// ---- pairs.cu (K5) ----
+size_t class_factor_floats(int m, int dist);
+cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W, int32_t* flag, cudaStream_t st);
+cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
+                                  int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
+                                  float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
+                                  cudaStream_t st);
+cudaError_t launch_class_factor_bwd(const float* W, const float* gLog, int C, int m, int dist, float* gE,
+                                    cudaStream_t st);
+}  // namespace sqfa

@@ -1,0 +1,150 @@
+"""Distances between Symmetric Positive Definite matrices -- B200-native drop-in for
+`sqfa.distances`.
+
+The three distance families SQFA optimises (affine-invariant, its Calvo-Oller / Fisher-Rao
+lower-bound use on embedded Gaussians, log-Euclidean; reference distances.py:46-237) run in the
+warp-per-pair Jacobi kernels and are differentiable through analytic backward passes. The other
+distances of the reference (Bhattacharyya, Mahalanobis, Hellinger, Fisher-Rao with shared
+covariance) are alternative `distance_fun` plug-ins outside the hot path;
+they are provided as plain device-side torch compositions so the namespace stays complete.
+"""
+
+import torch
+
+from . import _lib, _ops
+
+__all__ = [
+    "affine_invariant_sq",
+    "affine_invariant",
+    "log_euclidean_sq",
+    "log_euclidean",
+    "fisher_rao_lower_bound",
+    "fisher_rao_lower_bound_sq",
+    "bhattacharyya",
+    "mahalanobis_sq",
+    "mahalanobis",
+    "hellinger",
+    "fisher_rao_same_cov",
+]
+
+
+def __dir__():
+    return __all__
+
+
+EPSILON = 1e-6  # Value added inside of square roots
+
+
+def _batch3(A):
+    return A.unsqueeze(0) if A.dim() == 2 else A
+
+
+def _pairwise(A, B, dist):
+    """D[a, b] = d(A_a, B_b) through the native pair kernels; squeezes like the reference."""
+    same = A is B
+    a3, b3 = _batch3(A), _batch3(B)
+    if a3.shape[-1] != a3.shape[-2] or b3.shape[-1] != a3.shape[-1]:
+        raise ValueError("expected SPD matrices of equal size, shapes (n, m, m)")
+    dev = _lib.compute_device(A, B)
+    with torch.cuda.device(dev):
+        D = _ops.PairDistance.apply(a3.to(dev), None if same else b3.to(dev), dist, same)
+    return torch.squeeze(D).to(device=A.device, dtype=A.dtype)
+
+
+def affine_invariant_sq(A, B):
+    """Squared affine invariant distance between SPD matrices, shape (n_batch_A, n_batch_B)
+    (reference distances.py:46-67): sum of squared logs of the generalized eigenvalues."""
+    return _pairwise(A, B, _ops.DIST_AI | _ops.SQUARED)
+
+
+def affine_invariant(A, B):
+    """Affine invariant distance, sqrt(d^2 + 1e-6) (reference distances.py:70-89)."""
+    return _pairwise(A, B, _ops.DIST_AI)
+
+
+def log_euclidean_sq(A, B):
+    """Squared log-Euclidean distance ||log A - log B||_F^2 (reference distances.py:92-116)."""
+    return _pairwise(A, B, _ops.DIST_LE | _ops.SQUARED)
+
+
+def log_euclidean(A, B):
+    """Log-Euclidean distance, sqrt(d^2 + 1e-6) (reference distances.py:119-138)."""
+    return _pairwise(A, B, _ops.DIST_LE)
+
+
+def _embed_gaussian(statistics):
+    """Calvo-Oller embedding [[cov + mu mu^T, mu], [mu^T, 1]] of Gaussians into SPD(k+1)
+    (reference distances.py:141-174), native kernel with an analytic adjoint."""
+    means = statistics["means"]
+    covariances = statistics["covariances"]
+    if means.dim() == 1:
+        means = means.unsqueeze(0)
+    covariances = _batch3(covariances)
+    dev = _lib.compute_device(means, covariances)
+    with torch.cuda.device(dev):
+        return _ops.Embed.apply(covariances.to(dev), means.to(dev), 0.0, _ops.DIST_FR)
+
+
+def _fisher_rao(statistics_A, statistics_B, dist):
+    EA = _embed_gaussian(statistics_A)
+    EB = EA if statistics_B is statistics_A else _embed_gaussian(statistics_B)
+    ref = statistics_A["means"]
+    with torch.cuda.device(EA.device):
+        D = _ops.PairDistance.apply(EA, None if EB is EA else EB, dist, EB is EA)
+    return torch.squeeze(D).to(device=ref.device, dtype=ref.dtype)
+
+
+def fisher_rao_lower_bound_sq(statistics_A, statistics_B):
+    """Calvo & Oller lower bound of the squared Fisher-Rao distance between Gaussians given as
+    dicts with "means" (n, k) and "covariances" (n, k, k) (reference distances.py:177-207)."""
+    return _fisher_rao(statistics_A, statistics_B, _ops.DIST_FR | _ops.SQUARED)
+
+
+def fisher_rao_lower_bound(statistics_A, statistics_B):
+    """sqrt(lower bound^2 + 1e-6) (reference distances.py:210-237)."""
+    return _fisher_rao(statistics_A, statistics_B, _ops.DIST_FR)
+
+
+# ------------------------------------------------------------------------------------------------
+# Plug-in distances outside the hot path (reference distances.py:240-432): device-side torch.
+# ------------------------------------------------------------------------------------------------
+def _unsq_mean(x):
+    return x.unsqueeze(0) if x.dim() == 1 else x
+
+
+def bhattacharyya(statistics_A, statistics_B):
+    """Bhattacharyya distance between Gaussians (reference distances.py:240-280)."""
+    mu_a, mu_b = _unsq_mean(statistics_A["means"]), _unsq_mean(statistics_B["means"])
+    cov_a, cov_b = _batch3(statistics_A["covariances"]), _batch3(statistics_B["covariances"])
+    mean_cov = 0.5 * (cov_a[:, None] + cov_b[None])
+    diff = mu_a[:, None] - mu_b[None]
+    maha = torch.einsum("abi,abij,abj->ab", diff, torch.linalg.inv(mean_cov), diff)
+    logdet = torch.logdet(mean_cov) - 0.5 * (torch.logdet(cov_a)[:, None] + torch.logdet(cov_b)[None])
+    return torch.squeeze(0.125 * maha + 0.5 * logdet)
+
+
+def mahalanobis_sq(statistics_A, statistics_B):
+    """Squared Mahalanobis distance under the pairwise mean covariance (reference
+    distances.py:283-330)."""
+    mu_a, mu_b = _unsq_mean(statistics_A["means"]), _unsq_mean(statistics_B["means"])
+    cov_a, cov_b = _batch3(statistics_A["covariances"]), _batch3(statistics_B["covariances"])
+    mean_cov_inv = torch.linalg.inv(0.5 * (cov_a[:, None] + cov_b[None]))
+    diff = mu_a[:, None] - mu_b[None]
+    return torch.squeeze(torch.einsum("abi,abij,abj->ab", diff, mean_cov_inv, diff))
+
+
+def mahalanobis(statistics_A, statistics_B):
+    """Mahalanobis distance (reference distances.py:333-361)."""
+    return torch.sqrt(mahalanobis_sq(statistics_A, statistics_B) + EPSILON)
+
+
+def hellinger(statistics_A, statistics_B):
+    """Hellinger distance between Gaussians (reference distances.py:364-393)."""
+    return torch.sqrt(1 - torch.exp(-bhattacharyya(statistics_A, statistics_B)) + EPSILON)
+
+
+def fisher_rao_same_cov(statistics_A, statistics_B):
+    """Fisher-Rao distance between Gaussians assumed to share a covariance (reference
+    distances.py:396-432)."""
+    m_sq = mahalanobis_sq(statistics_A, statistics_B)
+    return 2.0**0.5 * torch.acosh(1 + m_sq / 4)

@@ -1,0 +1,467 @@
+"""Supervised Quadratic Feature Analysis models -- B200-native drop-in for `sqfa.model`.
+
+`SecondMomentsSQFA` and `SQFA` keep the constructor, method names, defaults, module state names
+(`parametrizations.filters.original`, `noise_mat`) and error behaviour of the reference
+(/root/reference/src/sqfa/model.py); `fit`, `fit_pca`, `transform`, `transform_scatters` and
+`get_class_distances` dispatch to the sm_100a kernels. Models and data may live on the CPU: `fit`
+moves the model to the CUDA device for the duration of the optimisation and back afterwards, and
+every method returns results on the device of its inputs.
+"""
+
+import torch
+import torch.nn as nn
+from torch.nn.utils.parametrizations import orthogonal
+from torch.nn.utils.parametrize import register_parametrization, remove_parametrizations
+
+from . import _lib, _ops, distances
+from ._optim import fitting_loop
+from .constraints import FixedFilters, Identity, Sphere
+from .distances import affine_invariant, fisher_rao_lower_bound
+from .linalg import conjugate_matrix
+from .statistics import class_statistics, pca, pca_from_scatter
+
+__all__ = ["SecondMomentsSQFA", "SQFA"]
+
+
+def __dir__():
+    return __all__
+
+
+# built-in distance callables -> native distance selector (SecondMoments models: tensors in)
+_TENSOR_DISTANCES = {
+    distances.affine_invariant: _ops.DIST_AI,
+    distances.affine_invariant_sq: _ops.DIST_AI | _ops.SQUARED,
+    distances.log_euclidean: _ops.DIST_LE,
+    distances.log_euclidean_sq: _ops.DIST_LE | _ops.SQUARED,
+}
+# full models: dicts {"means", "covariances"} in
+_DICT_DISTANCES = {
+    distances.fisher_rao_lower_bound: _ops.DIST_FR,
+    distances.fisher_rao_lower_bound_sq: _ops.DIST_FR | _ops.SQUARED,
+}
+
+
+def _stats_to_scatter(statistics):
+    """Scatter (second-moment) matrices from either input format (reference model.py:24-53):
+    a dict gives covariances + mean outer products, a tensor is passed through."""
+    if isinstance(statistics, dict):
+        _check_statistics(statistics)
+        means = statistics["means"]
+        return statistics["covariances"] + torch.einsum("ni,nj->nij", means, means)
+    return statistics
+
+
+def _check_statistics(data_statistics, needs_dict=False):
+    """Validate `data_statistics` (reference model.py:56-94): a dict needs the keys 'means' and
+    'covariances' (ValueError otherwise); anything that is neither a dict nor tensor-like, or a
+    tensor when a dict is required, is a TypeError."""
+    if isinstance(data_statistics, dict):
+        required_keys = {"means", "covariances"}
+        missing_keys = required_keys - set(data_statistics.keys())
+        if missing_keys:
+            raise ValueError(
+                f"`data_statistics` dictionary must contain the keys {required_keys}. "
+                f"Missing keys: {missing_keys}"
+            )
+    elif not hasattr(data_statistics, "shape"):
+        raise TypeError(
+            "`data_statistics` must be either a dict with 'means' and 'covariances' "
+            "or a torch.Tensor of shape (n_classes, n_dim, n_dim)."
+        )
+    elif needs_dict:
+        raise TypeError(
+            "`data_statistics` must be a dictionary with 'means' and 'covariances' "
+            "when `needs_dict` is True."
+        )
+
+
+def _statistics_to(data_statistics, dev):
+    """float32 copy of the statistics on the compute device (no copy if already there)."""
+    if isinstance(data_statistics, dict):
+        return {k: _ops.f32c(v, dev) for k, v in data_statistics.items() if isinstance(v, torch.Tensor)}
+    return _ops.f32c(torch.as_tensor(data_statistics), dev)
+
+
+class _Transform(torch.autograd.Function):
+    """Z = X F^T with the native skinny-GEMM kernel (reference model.py:236)."""
+
+    @staticmethod
+    def forward(ctx, F, X):
+        Fc = _ops.f32c(F, X.device)
+        ctx.save_for_backward(Fc, X)
+        return _ops.transform_raw(X, Fc)
+
+    @staticmethod
+    def backward(ctx, gZ):
+        Fc, X = ctx.saved_tensors
+        dF = gZ.t() @ X if ctx.needs_input_grad[0] else None
+        dX = gZ @ Fc if ctx.needs_input_grad[1] else None
+        return dF, dX
+
+
+class SecondMomentsSQFA(nn.Module):
+    """
+    Second-moments Supervised Quadratic Feature Analysis (SQFA) model: uses only the second
+    moment matrices of the classes and distances in the SPD manifold.
+    """
+
+    def __init__(
+        self,
+        n_dim,
+        feature_noise=0,
+        n_filters=2,
+        filters=None,
+        distance_fun=None,
+        constraint="sphere",
+    ):
+        """
+        Parameters
+        ----------
+        n_dim : int
+            Dimension of the input data space.
+        feature_noise : float
+            Diagonal term added to the feature covariances (regularisation). Default 0.
+        n_filters : int
+            Number of filters, used when `filters` is None (random initialisation). Default 2.
+        filters : torch.Tensor
+            Initial filters of shape (n_filters, n_dim). Default None.
+        distance_fun : callable
+            Takes two tensors (n_classes, n_filters, n_filters) and returns the (n_classes,
+            n_classes) matrix of pairwise distances. Default: affine invariant distance.
+        constraint : str
+            'none', 'sphere' or 'orthogonal'. Default 'sphere'.
+        """
+        super().__init__()
+
+        if filters is None:
+            filters = torch.randn(n_filters, n_dim)
+        else:
+            filters = torch.as_tensor(filters, dtype=torch.float32)
+
+        self.filters = nn.Parameter(filters)
+
+        if self.filters.shape[0] > self.filters.shape[1]:
+            raise ValueError("Number of filters must be less than or equal to the data dimension.")
+
+        # built from the n_filters ARGUMENT, like the reference (model.py:159-161)
+        feature_noise_mat = torch.as_tensor(feature_noise, dtype=torch.float32) * torch.eye(n_filters)
+        self.register_buffer("noise_mat", feature_noise_mat)
+
+        self.distance_fun = affine_invariant if distance_fun is None else distance_fun
+        self.constraint = constraint
+        self._add_constraint(constraint=self.constraint)
+        self._process_group = None
+
+    # ------------------------------------------------------------------ feature space maps
+    def transform_scatters(self, data_scatters):
+        """Feature-space scatter matrices F S_c F^T, shape (n_classes, n_filters, n_filters)
+        (reference model.py:172-188). Native projection kernel, differentiable w.r.t. filters."""
+        return conjugate_matrix(data_scatters, self.filters)
+
+    def transform(self, data_points):
+        """Project data points (n_samples, n_dim) to feature space (n_samples, n_filters)
+        (reference model.py:222-237)."""
+        dev = _lib.compute_device(data_points, self.filters)
+        if data_points.dim() != 2 or data_points.dtype != torch.float32:
+            return torch.einsum("ij,nj->ni", self.filters.to(dev), data_points.to(dev)).to(data_points.device)
+        with torch.cuda.device(dev):
+            X = data_points.to(dev)
+            if X.stride(1) != 1:
+                X = X.contiguous()
+            Z = _Transform.apply(self.filters.to(dev), X)
+        return Z.to(data_points.device)
+
+    def get_class_distances(self, data_statistics, regularized=False):
+        """Pairwise distances (n_classes, n_classes) between the feature scatter matrices of the
+        classes (reference model.py:190-220)."""
+        data_scatters = _stats_to_scatter(data_statistics)
+        feature_scatters = self.transform_scatters(data_scatters)
+        if regularized:
+            feature_scatters = feature_scatters + self.noise_mat.to(feature_scatters.device)[None, :, :]
+        return self.distance_fun(feature_scatters, feature_scatters)
+
+    # ------------------------------------------------------------------ fused closure
+    def _noise_scalar(self):
+        nm = self.noise_mat
+        val = float(nm[0, 0]) if nm.numel() > 0 else 0.0
+        if not torch.equal(nm, val * torch.eye(nm.shape[0], device=nm.device, dtype=nm.dtype)):
+            return None  # not a multiple of the identity: use the generic path
+        if nm.shape[0] != self.filters.shape[0]:
+            raise RuntimeError(
+                f"noise_mat is {tuple(nm.shape)} but the model has {self.filters.shape[0]} filters"
+            )
+        return val
+
+    def _fused_inputs(self, data_statistics):
+        """(S, M, dist) for the fused native loss, or None if distance_fun is not built in."""
+        dist = _TENSOR_DISTANCES.get(self.distance_fun)
+        if dist is None:
+            return None
+        return _stats_to_scatter(data_statistics).contiguous(), None, dist
+
+    def _fused_loss_plan(self, data_statistics):
+        """Callable evaluating [loss, #non-finite] natively at the current filters, or None."""
+        if not self.filters.is_cuda or self.filters.shape[0] > _ops.MAX_FILTERS:
+            return None
+        plan = self._fused_inputs(data_statistics)
+        noise = self._noise_scalar()
+        if plan is None or noise is None:
+            return None
+        S, M, dist = plan
+        group = self._process_group
+        return lambda: _ops.FusedLoss.apply(self.filters, S, M, noise, dist, group)
+
+    # ------------------------------------------------------------------ training
+    def fit_pca(self, X=None, data_statistics=None):
+        """Set the filters to the leading principal components of the data (or of the mean
+        scatter matrix, with the reference's `pca_from_scatter` semantics); reference
+        model.py:239-268."""
+        if X is None and data_statistics is None:
+            raise ValueError("Either X or data_statistics must be provided.")
+
+        n_components = self.filters.shape[0]
+        if data_statistics is None:
+            pca_filters = pca(X, n_components)
+        else:
+            pca_filters = pca_from_scatter(_stats_to_scatter(data_statistics), n_components)
+
+        device = self.filters.device
+        remove_parametrizations(self, "filters")
+        self.filters = nn.Parameter(pca_filters.detach().to(device=device, dtype=torch.float32).contiguous())
+        self._add_constraint(constraint=self.constraint)
+
+    def fit(
+        self,
+        X=None,
+        y=None,
+        data_statistics=None,
+        max_epochs=300,
+        lr=0.1,
+        estimator="empirical",
+        pairwise=False,
+        show_progress=True,
+        return_loss=False,
+        atol=1e-6,
+        process_group=None,
+        **kwargs,
+    ):
+        """
+        Fit the model with the LBFGS optimizer (reference model.py:270-414).
+
+        Parameters are those of the reference; `process_group` (optional, extension) shards the
+        class-pair list of every loss evaluation over the ranks of a torch.distributed group.
+        Extra keyword arguments go to `torch.optim.LBFGS`.
+        """
+        if data_statistics is None:
+            if X is None or y is None:
+                raise ValueError("Either data_statistics or X and y must be provided.")
+            data_statistics = class_statistics(X, y, estimator=estimator, keep_on_device=True)
+
+        _check_statistics(data_statistics)
+
+        dev = _lib.compute_device(
+            *(data_statistics.values() if isinstance(data_statistics, dict) else [data_statistics])
+        )
+        home = self.filters.device
+        self._process_group = process_group
+        with torch.cuda.device(dev):
+            stats_dev = _statistics_to(data_statistics, dev)
+            self.to(dev)
+            try:
+                loss, training_time = self._fit_on_device(
+                    stats_dev, max_epochs, lr, pairwise, show_progress, atol, **kwargs
+                )
+            finally:
+                self._process_group = None
+                self.to(home)
+
+        if return_loss:
+            return loss, training_time
+        return None
+
+    def _fit_on_device(self, data_statistics, max_epochs, lr, pairwise, show_progress, atol, **kwargs):
+        if not pairwise:
+            return fitting_loop(
+                model=self,
+                data_statistics=data_statistics,
+                max_epochs=max_epochs,
+                lr=lr,
+                show_progress=show_progress,
+                return_loss=True,
+                atol=atol,
+                **kwargs,
+            )
+
+        # pairwise curriculum (reference model.py:349-409): train filters two at a time, keeping
+        # the already trained ones fixed
+        n_pairs = self.filters.shape[0] // 2
+        filters_original = self.filters.detach().clone()
+        noise_original = self.noise_mat.detach().clone()[0, 0]
+        if self.filters.shape[0] % 2 != 0:
+            raise ValueError("Number of filters must be even for pairwise training.")
+
+        device = filters_original.device
+        loss = torch.tensor([])
+        training_time = torch.tensor([])
+        for i in range(n_pairs):
+            filters_last_trained = self.filters.detach().clone()
+            if i == 0:
+                filters_new_init = filters_original[:2].contiguous()
+            else:
+                filters_new_init = torch.cat((filters_last_trained, filters_original[2 * i : 2 * (i + 1)]))
+            remove_parametrizations(self, "filters")
+            self.filters = nn.Parameter(filters_new_init)
+            self._add_constraint(constraint=self.constraint)
+
+            self.register_buffer("noise_mat", noise_original * torch.eye(2 * (i + 1), device=device))
+
+            if i > 0:
+                register_parametrization(self, "filters", FixedFilters(n_row_fixed=i * 2))
+
+            loss_pair, training_time_pair = fitting_loop(
+                model=self,
+                data_statistics=data_statistics,
+                max_epochs=max_epochs,
+                lr=lr,
+                show_progress=show_progress,
+                return_loss=True,
+                atol=atol,
+                **kwargs,
+            )
+
+            remove_parametrizations(self, "filters")
+            self._add_constraint(constraint=self.constraint)
+            loss = torch.cat((loss, loss_pair))
+            if training_time.numel() > 0:
+                training_time_pair = training_time_pair + training_time[-1]
+            training_time = torch.cat((training_time, training_time_pair))
+        return loss, training_time
+
+    def _add_constraint(self, constraint="none"):
+        """Register the filter parametrization: 'none', 'sphere' or 'orthogonal'
+        (reference model.py:416-431)."""
+        if constraint == "none":
+            register_parametrization(self, "filters", Identity())
+        elif constraint == "sphere":
+            register_parametrization(self, "filters", Sphere())
+        elif constraint == "orthogonal":
+            orthogonal(self, "filters")
+
+    def __dir__(self):
+        return [
+            "filters",
+            "noise_mat",
+            "distance_fun",
+            "constraint",
+            "transform_scatters",
+            "get_class_distances",
+            "transform",
+            "fit_pca",
+        ]
+
+
+class SQFA(SecondMomentsSQFA):
+    """
+    Supervised Quadratic Feature Analysis (SQFA) model: uses the class means and covariances and
+    distances (or bounds) in the manifold of normal distributions.
+    """
+
+    def __init__(
+        self,
+        n_dim,
+        feature_noise=0,
+        n_filters=2,
+        filters=None,
+        distance_fun=None,
+        constraint="sphere",
+    ):
+        """Same parameters as `SecondMomentsSQFA`; `distance_fun` takes two dicts with 'means'
+        (n_classes, n_filters) and 'covariances' (n_classes, n_filters, n_filters). Default: the
+        Calvo-Oller lower bound of the Fisher-Rao distance."""
+        if distance_fun is None:
+            distance_fun = fisher_rao_lower_bound
+        super().__init__(
+            n_dim=n_dim,
+            feature_noise=feature_noise,
+            n_filters=n_filters,
+            filters=filters,
+            distance_fun=distance_fun,
+            constraint=constraint,
+        )
+
+    def get_class_distances(self, data_statistics, regularized=False):
+        """Pairwise distances between the feature-space class Gaussians (reference
+        model.py:508-546). `data_statistics` must be a dict with 'means' and 'covariances'."""
+        if not isinstance(data_statistics, dict):
+            raise TypeError("data_statistics must be a dictionary with 'means' and 'covariances' keys.")
+        means, covs = data_statistics["means"], data_statistics["covariances"]
+        native = (
+            covs.dim() == 3 and covs.dtype == torch.float32 and means.dtype == torch.float32
+            and self.filters.shape[0] <= _ops.MAX_FILTERS
+        )
+        if native:
+            # one pass over the covariances gives both F S F^T and F m
+            dev = _lib.compute_device(covs, means, self.filters)
+            with torch.cuda.device(dev):
+                feature_covariances, feature_means = _ops.Project.apply(
+                    self.filters.to(dev), covs.to(dev).contiguous(), means.to(dev).contiguous()
+                )
+            feature_covariances = feature_covariances.to(covs.device)
+            feature_means = feature_means.to(means.device)
+        else:
+            feature_means = self.transform(means)
+            feature_covariances = self.transform_scatters(covs)
+
+        if regularized:
+            feature_covariances = feature_covariances + self.noise_mat.to(feature_covariances.device)[None, :, :]
+
+        feature_statistics = {"means": feature_means, "covariances": feature_covariances}
+        return self.distance_fun(feature_statistics, feature_statistics)
+
+    def _fused_inputs(self, data_statistics):
+        dist = _DICT_DISTANCES.get(self.distance_fun)
+        if dist is None or not isinstance(data_statistics, dict):
+            return None
+        return data_statistics["covariances"].contiguous(), data_statistics["means"].contiguous(), dist
+
+    def fit(
+        self,
+        X=None,
+        y=None,
+        data_statistics=None,
+        max_epochs=300,
+        lr=0.1,
+        estimator="empirical",
+        pairwise=False,
+        show_progress=True,
+        return_loss=False,
+        atol=1e-6,
+        process_group=None,
+        **kwargs,
+    ):
+        """Fit the SQFA model with the LBFGS optimizer (reference model.py:548-630);
+        `data_statistics`, when given, must be a dict with 'means' and 'covariances'."""
+        if data_statistics is None:
+            if X is None or y is None:
+                raise ValueError("Either data_statistics or X and y must be provided.")
+            data_statistics = class_statistics(X, y, estimator=estimator, keep_on_device=True)
+        else:
+            _check_statistics(data_statistics, needs_dict=True)
+
+        loss, training_time = super().fit(
+            X=None,
+            y=None,
+            data_statistics=data_statistics,
+            max_epochs=max_epochs,
+            lr=lr,
+            estimator=estimator,
+            pairwise=pairwise,
+            show_progress=show_progress,
+            return_loss=True,
+            atol=atol,
+            process_group=process_group,
+            **kwargs,
+        )
+        if return_loss:
+            return loss, training_time
+        return None

@@ -131,7 +131,7 @@ def _device_statistics(X, perm, offsets, counts, C, estimator_id, ddof=1, shift=
     return means, cov, sm
 
 
-def class_statistics(points, labels, estimator="empirical"):
+def class_statistics(points, labels, estimator="empirical", keep_on_device=False):
     """
     Compute the mean, covariance and second moment matrix of each class.
 
@@ -167,7 +167,7 @@ def class_statistics(points, labels, estimator="empirical"):
         C = counts.numel() - 1
         means, cov, sm = _device_statistics(X, perm, offsets, counts, C, _ESTIMATORS[estimator])
     stats = {"means": means, "covariances": cov, "second_moments": sm}
-    if out_dev != dev:
+    if out_dev != dev and not keep_on_device:
         stats = {k: v.to(out_dev) for k, v in stats.items()}
     return stats
 

@@ -1,0 +1,232 @@
+"""GPU parity of hot path 2 (projection, pairwise SPD distances, fused loss + analytic backward, fit)
+against the CPU oracle, through the Python host API that sits on the C ABI."""
+
+import pytest
+import torch
+
+from conftest import make_class_data, rel_err
+from oracle import sqfa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DIST_TOL = 1e-4   # north_star: pairwise distances and loss within 1e-4 relative
+GRAD_TOL = 2e-3   # gradient of the loss w.r.t. the raw filters, relative Frobenius vs fp64 oracle
+ANGLE_TOL = 1e-3  # north_star: learned filters within 1e-3 in subspace angle
+
+
+def sample_spd(n, m, seed=0, dtype=torch.float64):
+    """Random SPD matrices like the reference fixture tests/make_examples.py:15-20."""
+    g = torch.Generator().manual_seed(seed)
+    ev = 2 * torch.rand(n, m, generator=g, dtype=dtype) ** 2 + 0.01
+    low = torch.tril(torch.randn(n, m, m, generator=g, dtype=dtype), diagonal=-1)
+    Q = torch.matrix_exp(low - low.transpose(1, 2))
+    return torch.einsum("ijk,ik,ilk->ijl", Q, ev, Q)
+
+
+def stats_for(n, d, c, seed=0):
+    X, y = make_class_data(n, d, c, seed=seed)
+    X = X / (X.std() * d**0.5)
+    return O.class_statistics(X.double(), y)
+
+
+def to_f32_cuda(stats):
+    return {k: v.float().cuda() for k, v in stats.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c,d,k", [(1, 16, 2), (4, 33, 3), (10, 784, 4), (19, 104, 8), (3, 1027, 16), (2, 300, 32)])
+def test_conjugate_matrix_matches_oracle(c, d, k):
+    from sqfa_b200.linalg import conjugate_matrix
+
+    S = sample_spd(c, d, seed=d) if d <= 128 else stats_for(40 * c + 200, d, c, seed=d)["second_moments"]
+    F = torch.randn(k, d, generator=torch.Generator().manual_seed(k), dtype=torch.float64)
+    ref = O.conjugate_matrix(S, F)
+    got = conjugate_matrix(S.float().cuda(), F.float().cuda())
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 1e-5
+    with pytest.raises(ValueError):
+        conjugate_matrix(S.float().cuda(), F[0].float().cuda())
+
+
+@pytest.mark.parametrize("n,m", [(1, 2), (4, 4), (8, 6), (12, 9), (20, 17), (6, 32), (5, 33), (3, 64)])
+def test_distances_match_oracle(n, m):
+    from sqfa_b200 import distances as Dn
+
+    A = sample_spd(n, m, seed=m)
+    B = sample_spd(max(n - 1, 1), m, seed=m + 100)
+    Ac, Bc = A.float().cuda(), B.float().cuda()
+    for name in ("affine_invariant_sq", "affine_invariant", "log_euclidean_sq", "log_euclidean"):
+        ref_self = getattr(O, name)(A, A)
+        got_self = getattr(Dn, name)(Ac, Ac)
+        assert got_self.shape == ref_self.shape, name
+        ref_cross = getattr(O, name)(A, B)
+        got_cross = getattr(Dn, name)(Ac, Bc)
+        assert got_cross.shape == ref_cross.shape, name
+        if n > 1:
+            i, j = torch.tril_indices(n, n, -1)
+            assert rel_err(got_self[i, j], ref_self[i, j]) < DIST_TOL, name
+            assert torch.equal(got_self, got_self.T)
+        assert rel_err(got_cross, ref_cross) < DIST_TOL, name
+    # Fisher-Rao lower bound on Gaussians
+    mu = torch.randn(n, m, generator=torch.Generator().manual_seed(7), dtype=torch.float64)
+    if m + 1 <= 64:
+        sd = {"means": mu, "covariances": A}
+        sc = {"means": mu.float().cuda(), "covariances": Ac}
+        for name in ("fisher_rao_lower_bound_sq", "fisher_rao_lower_bound"):
+            ref = getattr(O, name)(sd, sd)
+            got = getattr(Dn, name)(sc, sc)
+            assert got.shape == ref.shape
+            if n > 1:
+                i, j = torch.tril_indices(n, n, -1)
+                assert rel_err(got[i, j], ref[i, j]) < DIST_TOL, name
+
+
+@pytest.mark.parametrize("n", [1, 4, 8])
+@pytest.mark.parametrize("m", [2, 4, 6])
+def test_distance_properties(n, m):
+    """Property tests of the reference: tests/test_distances.py:40-124."""
+    from sqfa_b200 import distances as Dn
+
+    A = sample_spd(n, m, seed=10 * n + m).float().cuda()
+    ai = Dn.affine_invariant_sq(A, A)
+    le = Dn.log_euclidean_sq(A, A)
+    assert ai.shape == ((n, n) if n != 1 else ())
+    assert le.shape == ((n, n) if n != 1 else ())
+    if n > 1:
+        assert torch.allclose(ai, ai.T, atol=1e-5) and torch.allclose(le, le.T, atol=1e-5)
+        assert torch.allclose(torch.diagonal(ai), torch.zeros(n, device="cuda"), atol=1e-5)
+    Ainv = torch.linalg.inv(A.double()).float()
+    assert torch.allclose(ai, Dn.affine_invariant_sq(Ainv, Ainv), rtol=2e-4, atol=1e-4)
+    assert torch.allclose(le, Dn.log_euclidean_sq(Ainv, Ainv), rtol=2e-4, atol=1e-4)
+    eye = torch.eye(m, device="cuda")
+    assert torch.allclose(Dn.affine_invariant_sq(A, eye), Dn.log_euclidean_sq(A, eye), rtol=2e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("na,nb,m", [(1, 1, 2), (4, 1, 4), (4, 8, 6), (8, 4, 17)])
+def test_generalized_eigenvalues_and_spd_functions(na, nb, m):
+    """vs the oracle (itself pinned to scipy by the reference's tests/test_linalg.py:182-245)."""
+    from sqfa_b200 import linalg as Ln
+
+    A = sample_spd(na, m, seed=1)
+    B = sample_spd(nb, m, seed=2)
+    ref = O.generalized_eigenvalues(A, B)
+    got = Ln.generalized_eigenvalues(A.float().cuda(), B.float().cuda())
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 1e-4
+    assert rel_err(Ln.spd_log(A.float().cuda()), O.spd_log(A)) < 1e-4
+    W = Ln.spd_inv_sqrt(B.float().cuda()).double().cpu()
+    eye = torch.eye(m, dtype=torch.float64).expand(nb, m, m)
+    assert torch.allclose(W @ B @ W.transpose(-2, -1), eye, atol=1e-4)
+    R = Ln.spd_sqrt(A.float().cuda()).double().cpu()
+    assert rel_err(R @ R, A) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+CASES = [
+    # kind, n, d, c, k, distance name
+    ("second_moments", 3000, 64, 10, 4, None),
+    ("full", 3000, 64, 10, 4, None),
+    ("full", 4000, 104, 19, 8, None),
+    ("second_moments", 3000, 48, 6, 8, "log_euclidean"),
+    ("full", 3000, 40, 5, 32, None),      # m = 33: two Jacobi columns per lane
+    ("second_moments", 2000, 784, 10, 4, None),
+]
+
+
+def _models(kind, d, k, F0, distance=None, noise=0.01):
+    from sqfa_b200 import distances as Dn
+    from sqfa_b200.model import SQFA, SecondMomentsSQFA
+
+    cls = SecondMomentsSQFA if kind == "second_moments" else SQFA
+    dfun = getattr(Dn, distance) if distance else None
+    return cls(n_dim=d, feature_noise=noise, n_filters=k, filters=F0.clone(), distance_fun=dfun)
+
+
+@pytest.mark.parametrize("kind,n,d,c,k,distance", CASES)
+def test_fused_loss_and_gradient_match_oracle(kind, n, d, c, k, distance):
+    stats = stats_for(n, d, c, seed=k)
+    F0 = torch.randn(k, d, generator=torch.Generator().manual_seed(3))
+    odist = getattr(O, distance) if distance else None
+    loss64, grad64, d64 = O.loss_and_grad(kind, stats, F0.double(), noise=0.01, distance=odist)
+
+    model = _models(kind, d, k, F0, distance).cuda()
+    sc = to_f32_cuda(stats)
+    # fused native closure
+    plan = model._fused_loss_plan(sc)
+    assert plan is not None
+    out = plan()
+    out[0].backward()
+    g = model.parametrizations.filters.original.grad
+    assert float(out[1]) == 0.0
+    assert abs(float(out[0]) - float(loss64)) <= DIST_TOL * abs(float(loss64))
+    assert rel_err(g, grad64) < GRAD_TOL
+    # generic path: get_class_distances + autograd through the native ops
+    model.zero_grad()
+    dmat = model.get_class_distances(sc, regularized=True)
+    i, j = torch.tril_indices(c, c, -1)
+    assert rel_err(dmat[i, j], d64[i, j]) < DIST_TOL
+    (-dmat[i, j].mean()).backward()
+    g2 = model.parametrizations.filters.original.grad
+    assert rel_err(g2, grad64) < GRAD_TOL
+
+
+def test_fit_matches_oracle_trajectory():
+    """Filters after ONE epoch (well conditioned) and the converged loss."""
+    n, d, c, k = 4000, 32, 6, 4
+    stats = stats_for(n, d, c, seed=11)
+    stats32 = {kk: v.float() for kk, v in stats.items()}
+    F0 = O.pca_from_scatter(stats32["second_moments"], k)
+    for kind in ("second_moments", "full"):
+        Fo, losses_o, _ = O.fit_lbfgs(kind, stats32, F0, noise=0.01, max_epochs=1)
+        model = _models(kind, d, k, F0)
+        loss, _ = model.fit(data_statistics=stats32, max_epochs=1, show_progress=False, return_loss=True)
+        assert model.filters.device.type == "cpu"  # the model returns to where it lived
+        assert O.subspace_angle(model.filters.detach(), Fo) < ANGLE_TOL
+        assert abs(float(loss[0]) - float(losses_o[0])) < DIST_TOL * abs(float(losses_o[0]))
+        # converged
+        Fo, losses_o, _ = O.fit_lbfgs(kind, stats32, F0, noise=0.01, max_epochs=60)
+        model = _models(kind, d, k, F0)
+        loss, _ = model.fit(data_statistics=stats32, max_epochs=60, show_progress=False, return_loss=True)
+        assert abs(float(loss[-1]) - float(losses_o[-1])) < 1e-3 * abs(float(losses_o[-1]))
+
+
+def test_fit_from_points_pairwise_and_transform():
+    from sqfa_b200.model import SQFA
+
+    X, y = make_class_data(3000, 24, 5, seed=2)
+    X = X / (X.std() * 24**0.5)
+    model = SQFA(n_dim=24, feature_noise=0.01, n_filters=4)
+    model.fit_pca(X)
+    assert O.subspace_angle(model.filters.detach(), O.pca(X.double(), 4).float()) < 1e-3
+    loss, t = model.fit(X, y, max_epochs=5, show_progress=False, return_loss=True, pairwise=True)
+    assert torch.isfinite(loss).all() and loss.numel() > 0
+    Z = model.transform(X)
+    assert Z.shape == (3000, 4)
+    assert rel_err(Z, X.double() @ model.filters.detach().double().T) < 1e-5
+    cov = model.transform_scatters(O.class_statistics(X, y)["covariances"])
+    assert cov.shape == (5, 4, 4)
+
+
+def test_error_types_match_reference():
+    """Error matrix of the reference: tests/test_training.py:90-101, 201-259."""
+    from sqfa_b200.model import SQFA, SecondMomentsSQFA
+
+    stats = {k: v.float() for k, v in stats_for(500, 8, 3).items()}
+    with pytest.raises(ValueError):
+        SQFA(n_dim=4, n_filters=6)
+    with pytest.raises(ValueError):
+        SQFA(n_dim=8, n_filters=2).fit()
+    with pytest.raises(ValueError):
+        SQFA(n_dim=8, n_filters=2).fit_pca()
+    with pytest.raises(TypeError):
+        SQFA(n_dim=8, n_filters=2).fit(data_statistics=stats["second_moments"], show_progress=False)
+    with pytest.raises(TypeError):
+        SecondMomentsSQFA(n_dim=8, n_filters=2).fit(data_statistics=[1, 2, 3], show_progress=False)
+    with pytest.raises(ValueError):
+        SecondMomentsSQFA(n_dim=8, n_filters=2).fit(data_statistics={"means": stats["means"]}, show_progress=False)
+    with pytest.raises(ValueError):
+        SecondMomentsSQFA(n_dim=8, n_filters=3).fit(
+            data_statistics=stats, pairwise=True, show_progress=False, max_epochs=2
+        )
+    with pytest.raises(TypeError):
+        SQFA(n_dim=8, n_filters=2).get_class_distances(stats["second_moments"])
