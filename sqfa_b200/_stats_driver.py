@@ -1,0 +1,150 @@
+"""Driver of hot path 1 (class_statistics): the sequence of local compute steps and -- when the
+samples are sharded over the ranks of a process group -- the collectives between them.
+
+Per-class (count, sum x, sum (x - mu)(x - mu)^T) are additive over samples, so every rank
+processes its own rows and three all-reduces make the result global:
+max label -> n_classes, [class sums | class counts] -> global means, Gram partials -> global
+covariances. The local steps are supplied by an `ops` object: `CudaStatsOps` (the sm_100a kernels
+through the C ABI) in the product; the CPU test-suite injects oracle-backed ops to exercise this
+host logic under the gloo backend.
+"""
+
+import torch
+
+from . import _lib
+
+
+class CudaStatsOps:
+    """Local steps of class_statistics on the current CUDA device (kernels K1, K2a, K2, K3)."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.gram_events = None  # set to a list to record (start, end) CUDA events around K2
+
+    def label_max(self, y):
+        mx = torch.empty(1, dtype=torch.int64, device=y.device)
+        _lib.check(
+            self.lib.sqfa_label_max(_lib.ptr(y), y.numel(), _lib.ptr(mx), _lib.stream_ptr(y.device)),
+            "sqfa_label_max",
+        )
+        return mx
+
+    def bucket(self, y, C):
+        lib, dev, n = self.lib, y.device, y.numel()
+        counts = torch.empty(C + 1, dtype=torch.int64, device=dev)
+        offsets = torch.empty(C + 2, dtype=torch.int64, device=dev)
+        perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        ws_bytes = lib.sqfa_bucket_workspace_bytes(n, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.sqfa_bucket_labels(
+                _lib.ptr(y), n, C, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(perm), _lib.ptr(ws), ws_bytes,
+                _lib.stream_ptr(dev),
+            ),
+            "sqfa_bucket_labels",
+        )
+        return perm[:n], offsets, counts
+
+    def class_sums(self, X, perm, offsets, C):
+        lib, dev = self.lib, X.device
+        n, D = X.shape
+        sums = torch.empty(C, D, dtype=torch.float32, device=dev)
+        ws_bytes = lib.sqfa_class_sums_workspace_bytes(n, D, C)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.sqfa_class_sums(
+                _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), None, n, D, C, _lib.ptr(sums), 0,
+                _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+            ),
+            "sqfa_class_sums",
+        )
+        return sums
+
+    def class_means(self, sums, counts):
+        C, D = sums.shape
+        means = torch.empty_like(sums)
+        _lib.check(
+            self.lib.sqfa_class_means(
+                _lib.ptr(sums), _lib.ptr(counts), None, D, C, _lib.ptr(means), _lib.stream_ptr(sums.device)
+            ),
+            "sqfa_class_means",
+        )
+        return means
+
+    def class_gram(self, X, perm, offsets, centre, C):
+        """Upper triangle of sum_{i in c} (x_i - centre_c)(x_i - centre_c)^T per class (tcgen05)."""
+        lib, dev = self.lib, X.device
+        n, D = X.shape
+        gram = torch.empty(C, D, D, dtype=torch.float32, device=dev)
+        ws_bytes = lib.sqfa_class_gram_workspace_bytes(C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if self.gram_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _lib.check(
+            lib.sqfa_class_gram(
+                _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), D, C, _lib.ptr(gram),
+                0, 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+            ),
+            "sqfa_class_gram",
+        )
+        if self.gram_events is not None:
+            ev[1].record()
+            self.gram_events.append(ev)
+        return gram
+
+    def finalize(self, gram, means, counts, estimator_id, ddof, want_sm):
+        """cov (in place over gram, mirrored), optional OAS shrinkage, second moments."""
+        lib, dev = self.lib, gram.device
+        C, D, _ = gram.shape
+        sm = torch.empty(C, D, D, dtype=torch.float32, device=dev) if want_sm else None
+        ws_bytes = lib.sqfa_stats_epilogue_workspace_bytes(C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.sqfa_stats_epilogue(
+                _lib.ptr(gram), _lib.ptr(means), None, _lib.ptr(counts), D, C, estimator_id, ddof, _lib.ptr(gram),
+                _lib.ptr(sm), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+            ),
+            "sqfa_stats_epilogue",
+        )
+        return gram, sm
+
+
+def _all_reduce(t, group, op=None):
+    import torch.distributed as dist
+
+    dist.all_reduce(t, op=op if op is not None else dist.ReduceOp.SUM, group=group)
+
+
+def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, ddof=1, centre=None, want_sm=True):
+    """means, covariances, second moments of the labeled rows; with `group`, of the union of the
+    rows held by all ranks (every rank returns the full global result).
+
+    Two passes over the local rows, like the reference (mean first, then the Gram of the centred
+    rows, statistics.py:118-120). `centre` (C, D) overrides the centring vectors.
+    """
+    if n_classes is None:
+        mx = ops.label_max(y)
+        if group is not None:
+            import torch.distributed as dist
+
+            _all_reduce(mx, group, dist.ReduceOp.MAX)
+        n_classes = int(mx.item()) + 1  # the one host read the reference also does (statistics.py:29)
+    C = n_classes
+    perm, offsets, counts = ops.bucket(y, C)
+    sums = ops.class_sums(X, perm, offsets, C)
+    class_counts = counts[:C].clone()
+    if group is not None:
+        _all_reduce(sums, group)
+        _all_reduce(class_counts, group)
+    means = ops.class_means(sums, class_counts)
+    gram = ops.class_gram(X, perm, offsets, means if centre is None else centre, C)
+    if group is not None:
+        _all_reduce(gram, group)  # the one large collective: C x D x D partial sums over NVLink
+    cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm)
+    return means, cov, sm, (perm, offsets, counts)
+
+
+def pair_range(n_pairs, rank, world):
+    """Contiguous slice [begin, end) of the linearised class-pair list owned by `rank`."""
+    return (n_pairs * rank) // world, (n_pairs * (rank + 1)) // world

@@ -41,10 +41,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // round-robin (circle method) partner of player p in round r, mp players (mp even)
 __device__ __forceinline__ int rr_partner(int p, int r, int mp) {
   const int n1 = mp - 1;
-  if (p == n1) {
-    // the fixed player meets the p' with 2 p' == 2 r (mod n1)  ->  p' = r * (mp/2) mod n1
-    return (int)(((long long)r * (mp >> 1)) % n1);
-  }
+  // players i, j < n1 meet in the round with i + j == 2 r (mod n1); the one left over (2 i == 2 r,
+  // i.e. i == r because n1 is odd) meets the fixed player n1
+  if (p == n1) return r;
   int q = (2 * r - p) % n1;
   if (q < 0) q += n1;
   return q == p ? n1 : q;
@@ -155,7 +154,7 @@ class_factor_kernel(const float* __restrict__ E, int C, int m, int dist, float* 
                     int32_t* __restrict__ flag) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * PAIR_WARPS + warp;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
   if (c >= C) return;
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
@@ -189,12 +188,11 @@ class_factor_kernel(const float* __restrict__ E, int C, int m, int dist, float* 
     for (int s = 0; s < m; ++s) n2 += Af[s * ld + q] * Af[s * ld + q];
     lam[q] = n2;
     loglam[q] = logf(n2);
-    // V[:, q] = L^-T a_q / |a_q|   (orthonormal eigenvectors of E)
-    const float inv = rsqrtf(n2);
+    // V[:, q] = L^-T a_q : A_f = L^T V with V orthogonal, so this is already a unit eigenvector
     for (int r = 0; r < m; ++r) {
       float v = 0.f;
       for (int s = r; s < m; ++s) v += Li[s * ld + r] * Af[s * ld + q];
-      Vb[r * ld + q] = v * inv;
+      Vb[r * ld + q] = v;
     }
   }
   __syncwarp();
@@ -224,7 +222,7 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
   __shared__ float s_d[PAIR_WARPS];
   __shared__ float s_bad[PAIR_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t p = pair_begin + (int64_t)blockIdx.x * PAIR_WARPS + warp;
+  const int64_t p = pair_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const bool active = p < pair_end;
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
@@ -356,7 +354,7 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
     __syncthreads();
     if (threadIdx.x == 0) {
       float a = 0.f, b = 0.f;
-      for (int w = 0; w < PAIR_WARPS; ++w) { a += s_d[w]; b += s_bad[w]; }
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_d[w]; b += s_bad[w]; }
       atomicAdd(loss, a);
       if (b != 0.f) atomicAdd(loss + 1, b);
     }
@@ -373,7 +371,7 @@ pair_le_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
   __shared__ float s_d[PAIR_WARPS];
   __shared__ float s_bad[PAIR_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t p = pair_begin + (int64_t)blockIdx.x * PAIR_WARPS + warp;
+  const int64_t p = pair_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const int stride = 2 * m * m + 2 * m;
   float dval = 0.f, bad = 0.f;
   if (p < pair_end) {
@@ -410,7 +408,7 @@ pair_le_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
     __syncthreads();
     if (threadIdx.x == 0) {
       float a = 0.f, b = 0.f;
-      for (int w = 0; w < PAIR_WARPS; ++w) { a += s_d[w]; b += s_bad[w]; }
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_d[w]; b += s_bad[w]; }
       atomicAdd(loss, a);
       if (b != 0.f) atomicAdd(loss + 1, b);
     }
@@ -424,7 +422,7 @@ le_factor_bwd_kernel(const float* __restrict__ W, const float* __restrict__ gLog
                      float* __restrict__ gE) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * PAIR_WARPS + warp;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
   if (c >= C) return;
   const int per_warp = 3 * m * m;
   float* V = smem + (size_t)warp * per_warp;
@@ -483,6 +481,12 @@ __global__ void fill_diagonal_kernel(float* dist_out, int C, float v) {
 
 }  // namespace
 
+// warps per block so that the per-warp shared-memory scratch fits (large m -> fewer warps)
+static int warps_for(int per_warp_bytes) {
+  int nw = (200 * 1024) / (per_warp_bytes > 0 ? per_warp_bytes : 1);
+  return nw > PAIR_WARPS ? PAIR_WARPS : (nw < 1 ? 1 : nw);
+}
+
 size_t class_factor_floats(int m, int dist) {
   return ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) ? (size_t)(2 * m * m + 2 * m) : (size_t)(2 * m * m);
 }
@@ -491,7 +495,9 @@ cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W
   if (C <= 0) return cudaSuccess;
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
-  const int smem = PAIR_WARPS * (4 * m * ld + 2 * m) * (int)sizeof(float);
+  const int per_warp = (4 * m * ld + 2 * m) * (int)sizeof(float);
+  const int nw = warps_for(per_warp);
+  const int smem = nw * per_warp;
   static int configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(class_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -500,7 +506,7 @@ cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W
   }
   cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
-  class_factor_kernel<<<(C + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, smem, st>>>(E, C, m, dist, W, flag);
+  class_factor_kernel<<<(C + nw - 1) / nw, nw * 32, smem, st>>>(E, C, m, dist, W, flag);
   return cudaGetLastError();
 }
 
@@ -514,37 +520,42 @@ cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int 
     fill_diagonal_kernel<<<(nA + 255) / 256, 256, 0, st>>>(dist_out, nA, dv);
   }
   if (npairs <= 0) return cudaGetLastError();
-  const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
   if ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) {
+    const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
     pair_le_kernel<<<blocks, PAIR_WARPS * 32, 0, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
                                                        dist_out, loss, gEa, gEb);
     return cudaGetLastError();
   }
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
-  const int smem = PAIR_WARPS * (2 * m * ld + m * m + 3 * m) * (int)sizeof(float);
+  const int per_warp = (2 * m * ld + m * m + 3 * m) * (int)sizeof(float);
+  const int nw = warps_for(per_warp);
+  const int smem = nw * per_warp;
+  const unsigned blocks = (unsigned)((npairs + nw - 1) / nw);
   static int configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(pair_ai_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  pair_ai_kernel<<<blocks, PAIR_WARPS * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
-                                                        dist_out, loss, gEa, gEb, eig_out);
+  pair_ai_kernel<<<blocks, nw * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
+                                                dist_out, loss, gEa, gEb, eig_out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_class_factor_bwd(const float* W, const float* gLog, int C, int m, int dist, float* gE,
                                     cudaStream_t st) {
   if ((dist & 15) != SQFA_DIST_LOG_EUCLIDEAN || C <= 0) return cudaSuccess;
-  const int smem = PAIR_WARPS * 3 * m * m * (int)sizeof(float);
+  const int per_warp = 3 * m * m * (int)sizeof(float);
+  const int nw = warps_for(per_warp);
+  const int smem = nw * per_warp;
   static int configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(le_factor_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  le_factor_bwd_kernel<<<(C + PAIR_WARPS - 1) / PAIR_WARPS, PAIR_WARPS * 32, smem, st>>>(W, gLog, C, m, gE);
+  le_factor_bwd_kernel<<<(C + nw - 1) / nw, nw * 32, smem, st>>>(W, gLog, C, m, gE);
   return cudaGetLastError();
 }
 

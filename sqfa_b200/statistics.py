@@ -10,10 +10,19 @@ device of `points`. There is no CPU compute path.
 import torch
 
 from . import _lib
+from ._stats_driver import CudaStatsOps, run_class_statistics
 
 __all__ = ["class_statistics", "oas_covariance", "pca", "pca_from_scatter"]
 
 _ESTIMATORS = {"empirical": 0, "oas": 1}
+_ops_singleton = None
+
+
+def _cuda_ops():
+    global _ops_singleton
+    if _ops_singleton is None:
+        _ops_singleton = CudaStatsOps()
+    return _ops_singleton
 
 
 def _as_device_points(points, dev):
@@ -22,9 +31,7 @@ def _as_device_points(points, dev):
     if points.dim() != 2:
         raise ValueError("points must have shape (n_points, n_dim)")
     if points.dtype != torch.float32:
-        raise TypeError(
-            f"sqfa_b200 kernels compute in float32; got points of dtype {points.dtype}"
-        )
+        raise TypeError(f"sqfa_b200 kernels compute in float32; got points of dtype {points.dtype}")
     X = points.detach().to(dev, non_blocking=True)
     if X.stride(1) != 1 or X.stride(0) < X.shape[1]:
         X = X.contiguous()
@@ -52,86 +59,16 @@ def bucket_labels(labels, n_classes=None):
     counts / offsets is the bucket of rows whose label is outside [0, C). `perm[:offsets[C]]`
     equals `torch.sort(labels, stable=True).indices` for in-range labels (bit-exact).
     """
-    lib = _lib.load()
     dev = _lib.compute_device(labels)
     y = _as_device_labels(labels, dev)
-    n = y.numel()
+    ops = _cuda_ops()
     with torch.cuda.device(dev):
-        st = _lib.stream_ptr(dev)
         if n_classes is None:
-            mx = torch.empty(1, dtype=torch.int64, device=dev)
-            _lib.check(lib.sqfa_label_max(_lib.ptr(y), n, _lib.ptr(mx), st), "sqfa_label_max")
-            n_classes = int(mx.item()) + 1
-        C = int(n_classes)
-        counts = torch.empty(C + 1, dtype=torch.int64, device=dev)
-        offsets = torch.empty(C + 2, dtype=torch.int64, device=dev)
-        perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        ws_bytes = lib.sqfa_bucket_workspace_bytes(n, C)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(
-            lib.sqfa_bucket_labels(
-                _lib.ptr(y), n, C, _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(perm), _lib.ptr(ws), ws_bytes, st
-            ),
-            "sqfa_bucket_labels",
-        )
-    return perm[:n], offsets, counts
+            n_classes = int(ops.label_max(y).item()) + 1
+        return ops.bucket(y, int(n_classes))
 
 
-def _device_statistics(X, perm, offsets, counts, C, estimator_id, ddof=1, shift=None, want_sm=True):
-    """means / covariances / second moments of the bucketed rows of X (all on X.device).
-
-    Two passes over X, exactly like the reference (mean, then Gram of the centred rows,
-    statistics.py:118-120): pass 1 = per-class column sums -> means, pass 2 = tensor-core Gram of
-    (x - mean_c). `shift` overrides the centring vector (used with ddof=0 for assume_centered).
-    """
-    lib = _lib.load()
-    dev = X.device
-    n, D = X.shape
-    st = _lib.stream_ptr(dev)
-    ldx = X.stride(0)
-
-    sums = torch.empty(C, D, dtype=torch.float32, device=dev)
-    means = torch.empty(C, D, dtype=torch.float32, device=dev)
-    ws_bytes = lib.sqfa_class_sums_workspace_bytes(n, D, C)
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-    _lib.check(
-        lib.sqfa_class_sums(
-            _lib.ptr(X), ldx, _lib.ptr(perm), _lib.ptr(offsets), None, n, D, C, _lib.ptr(sums), 0,
-            _lib.ptr(ws), ws_bytes, st,
-        ),
-        "sqfa_class_sums",
-    )
-    _lib.check(
-        lib.sqfa_class_means(_lib.ptr(sums), _lib.ptr(counts), None, D, C, _lib.ptr(means), st),
-        "sqfa_class_means",
-    )
-
-    centre = means if shift is None else shift
-    # the Gram lands directly in the covariance buffer; the epilogue rescales / mirrors it in place
-    cov = torch.empty(C, D, D, dtype=torch.float32, device=dev)
-    sm = torch.empty(C, D, D, dtype=torch.float32, device=dev) if want_sm else None
-    gws_bytes = lib.sqfa_class_gram_workspace_bytes(C)
-    gws = torch.empty(gws_bytes, dtype=torch.uint8, device=dev)
-    _lib.check(
-        lib.sqfa_class_gram(
-            _lib.ptr(X), ldx, _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), D, C, _lib.ptr(cov), 0, 0,
-            _lib.ptr(gws), gws_bytes, st,
-        ),
-        "sqfa_class_gram",
-    )
-    ews_bytes = lib.sqfa_stats_epilogue_workspace_bytes(C)
-    ews = torch.empty(ews_bytes, dtype=torch.uint8, device=dev)
-    _lib.check(
-        lib.sqfa_stats_epilogue(
-            _lib.ptr(cov), _lib.ptr(means), None, _lib.ptr(counts), D, C, estimator_id, ddof, _lib.ptr(cov),
-            _lib.ptr(sm), _lib.ptr(ews), ews_bytes, st,
-        ),
-        "sqfa_stats_epilogue",
-    )
-    return means, cov, sm
-
-
-def class_statistics(points, labels, estimator="empirical", keep_on_device=False):
+def class_statistics(points, labels, estimator="empirical", keep_on_device=False, group=None):
     """
     Compute the mean, covariance and second moment matrix of each class.
 
@@ -145,6 +82,11 @@ def class_statistics(points, labels, estimator="empirical", keep_on_device=False
         Class labels of each point with shape (n_points).
     estimator:
         Covariance estimator to use. Options are "empirical" and "oas". Default is "empirical".
+    keep_on_device : bool
+        (extension) leave the result on the CUDA device even if `points` lives on the CPU.
+    group : torch.distributed process group
+        (extension) `points` / `labels` are this rank's shard of the samples; the statistics of the
+        union over all ranks are returned on every rank (three all-reduces, see _stats_driver).
 
     Returns
     -------
@@ -160,12 +102,10 @@ def class_statistics(points, labels, estimator="empirical", keep_on_device=False
     y = _as_device_labels(labels, dev)
     if y.numel() != X.shape[0]:
         raise ValueError("labels must have one entry per row of points")
-    if y.numel() == 0:
+    if y.numel() == 0 and group is None:
         raise RuntimeError("class_statistics: empty input (max() of an empty labels tensor)")
     with torch.cuda.device(dev):
-        perm, offsets, counts = bucket_labels(y)
-        C = counts.numel() - 1
-        means, cov, sm = _device_statistics(X, perm, offsets, counts, C, _ESTIMATORS[estimator])
+        means, cov, sm, _ = run_class_statistics(_cuda_ops(), X, y, _ESTIMATORS[estimator], group=group)
     stats = {"means": means, "covariances": cov, "second_moments": sm}
     if out_dev != dev and not keep_on_device:
         stats = {k: v.to(out_dev) for k, v in stats.items()}
@@ -177,12 +117,11 @@ def _single_class(points, estimator_id, assume_centered):
     X = _as_device_points(points, dev)
     n, D = X.shape
     with torch.cuda.device(dev):
-        perm = torch.arange(n, dtype=torch.int32, device=dev)
-        offsets = torch.tensor([0, n, n], dtype=torch.int64, device=dev)
-        counts = torch.tensor([n, 0], dtype=torch.int64, device=dev)
-        shift = torch.zeros(1, D, dtype=torch.float32, device=dev) if assume_centered else None
-        _, cov, _ = _device_statistics(
-            X, perm, offsets, counts, 1, estimator_id, ddof=0 if assume_centered else 1, shift=shift, want_sm=False
+        y = torch.zeros(n, dtype=torch.int64, device=dev)
+        centre = torch.zeros(1, D, dtype=torch.float32, device=dev) if assume_centered else None
+        _, cov, _, _ = run_class_statistics(
+            _cuda_ops(), X, y, estimator_id, n_classes=1, ddof=0 if assume_centered else 1, centre=centre,
+            want_sm=False,
         )
     cov = cov[0]
     return cov if points.device == dev else cov.to(points.device)

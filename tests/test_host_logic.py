@@ -1,0 +1,84 @@
+"""CPU: host-side logic of the drop-in API that needs no GPU -- constructor / validation error
+types of the reference (tests/test_training.py:205-259), module state names, pair sharding."""
+
+import pytest
+import torch
+
+from sqfa_b200 import _lib
+from sqfa_b200._stats_driver import pair_range
+from sqfa_b200.model import SQFA, SecondMomentsSQFA, _check_statistics
+
+
+def test_namespace_mirrors_reference():
+    import sqfa_b200
+
+    for name in ("statistics", "linalg", "distances", "constraints", "_optim", "model"):
+        assert hasattr(sqfa_b200, name)
+    assert sqfa_b200.statistics.__all__ == ["class_statistics", "oas_covariance", "pca", "pca_from_scatter"]
+    assert set(sqfa_b200.linalg.__all__) >= {"conjugate_matrix", "generalized_eigenvalues", "spd_log", "spd_inv_sqrt"}
+    assert set(sqfa_b200.distances.__all__) >= {"affine_invariant", "fisher_rao_lower_bound", "log_euclidean"}
+
+
+def test_module_state_names_and_defaults():
+    m = SQFA(n_dim=8, feature_noise=0.01, n_filters=3)
+    assert [n for n, _ in m.named_parameters()] == ["parametrizations.filters.original"]
+    assert [n for n, _ in m.named_buffers()] == ["noise_mat"]
+    assert m.noise_mat.shape == (3, 3) and m.noise_mat.dtype == torch.float32
+    assert torch.allclose(m.filters.norm(dim=1), torch.ones(3), atol=1e-6)  # sphere constraint
+    assert m.distance_fun.__name__ == "fisher_rao_lower_bound"
+    assert SecondMomentsSQFA(n_dim=8).distance_fun.__name__ == "affine_invariant"
+    assert SecondMomentsSQFA(n_dim=8, constraint="none").constraint == "none"
+    o = SecondMomentsSQFA(n_dim=8, n_filters=2, constraint="orthogonal")
+    assert torch.allclose(o.filters @ o.filters.T, torch.eye(2), atol=1e-5)
+    sd = m.state_dict()
+    m2 = SQFA(n_dim=8, feature_noise=0.01, n_filters=3)
+    m2.load_state_dict(sd)
+    assert torch.equal(m2.filters, m.filters)
+
+
+def test_constructor_and_validation_errors():
+    with pytest.raises(ValueError):
+        SQFA(n_dim=4, n_filters=6)
+    with pytest.raises(ValueError):
+        SecondMomentsSQFA(n_dim=8).fit()
+    with pytest.raises(ValueError):
+        SecondMomentsSQFA(n_dim=8).fit(X=torch.randn(4, 8))
+    with pytest.raises(ValueError):
+        SQFA(n_dim=8).fit_pca()
+    with pytest.raises(TypeError):
+        _check_statistics([1, 2, 3])
+    with pytest.raises(TypeError):
+        _check_statistics(torch.zeros(2, 3, 3), needs_dict=True)
+    with pytest.raises(ValueError):
+        _check_statistics({"means": torch.zeros(2, 3)})
+    with pytest.raises(TypeError):
+        SQFA(n_dim=8).fit(data_statistics=torch.zeros(2, 8, 8), show_progress=False)
+    with pytest.raises(TypeError):
+        SQFA(n_dim=8).get_class_distances(torch.zeros(2, 8, 8))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_compute_fails_loudly_without_gpu():
+    from sqfa_b200.statistics import class_statistics
+
+    with pytest.raises(_lib.SqfaNativeError):
+        class_statistics(torch.randn(16, 4), torch.zeros(16, dtype=torch.long))
+    with pytest.raises(_lib.SqfaNativeError):
+        SQFA(n_dim=4).transform_scatters(torch.eye(4)[None])
+
+
+def test_estimator_and_dtype_validation():
+    from sqfa_b200.statistics import class_statistics
+
+    with pytest.raises(ValueError):
+        class_statistics(torch.randn(4, 2), torch.zeros(4), estimator="bogus")
+
+
+@pytest.mark.parametrize("n_pairs,world", [(0, 2), (1, 4), (45, 2), (499500, 8), (4950, 3)])
+def test_pair_ranges_tile_the_pair_list(n_pairs, world):
+    ranges = [pair_range(n_pairs, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n_pairs
+    for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+        assert a1 == b0 and a0 <= a1
+    sizes = [b - a for a, b in ranges]
+    assert max(sizes) - min(sizes) <= 1

@@ -176,18 +176,23 @@ def test_fit_matches_oracle_trajectory():
     stats = stats_for(n, d, c, seed=11)
     stats32 = {kk: v.float() for kk, v in stats.items()}
     F0 = O.pca_from_scatter(stats32["second_moments"], k)
+    stats64 = {kk: v.double() for kk, v in stats.items()}
     for kind in ("second_moments", "full"):
-        Fo, losses_o, _ = O.fit_lbfgs(kind, stats32, F0, noise=0.01, max_epochs=1)
+        # fixed iteration count: one LBFGS epoch of 6 inner iterations. (A full 20-iteration epoch
+        # amplifies fp32 rounding differences beyond 1e-3 in the REFERENCE itself: its own
+        # fp32 and fp64 runs differ by more)
+        Fo, losses_o, _ = O.fit_lbfgs(kind, stats64, F0.double(), noise=0.01, max_epochs=1, max_iter=6)
         model = _models(kind, d, k, F0)
-        loss, _ = model.fit(data_statistics=stats32, max_epochs=1, show_progress=False, return_loss=True)
+        loss, _ = model.fit(data_statistics=stats32, max_epochs=1, show_progress=False, return_loss=True, max_iter=6)
         assert model.filters.device.type == "cpu"  # the model returns to where it lived
         assert O.subspace_angle(model.filters.detach(), Fo) < ANGLE_TOL
         assert abs(float(loss[0]) - float(losses_o[0])) < DIST_TOL * abs(float(losses_o[0]))
         # converged
-        Fo, losses_o, _ = O.fit_lbfgs(kind, stats32, F0, noise=0.01, max_epochs=60)
+        Fo, losses_o, _ = O.fit_lbfgs(kind, stats64, F0.double(), noise=0.01, max_epochs=100)
         model = _models(kind, d, k, F0)
-        loss, _ = model.fit(data_statistics=stats32, max_epochs=60, show_progress=False, return_loss=True)
-        assert abs(float(loss[-1]) - float(losses_o[-1])) < 1e-3 * abs(float(losses_o[-1]))
+        loss, _ = model.fit(data_statistics=stats32, max_epochs=100, show_progress=False, return_loss=True)
+        assert abs(float(loss[-1]) - float(losses_o[-1])) < 1e-4 * abs(float(losses_o[-1]))
+        print(kind, "converged angle", O.subspace_angle(model.filters.detach(), Fo))
 
 
 def test_fit_from_points_pairwise_and_transform():
