@@ -183,6 +183,18 @@ int sqfa_pair_distances(const float* Wa, const float* Wb, int32_t n_a, int32_t n
 int sqfa_class_factor_bwd(const float* W, const float* gLog, int32_t n_classes, int32_t m, int32_t dist,
                           float* gE, sqfa_stream_t stream);
 
+/* The whole closure body of the fitting loop (_optim.py:90-96) in one call, at fixed filters F:
+ *   out[0] = -mean_{i>j} d(E_i, E_j) over pairs [pair_begin, pair_end) (scaled by 1/P of ALL pairs,
+ *            so partial results of a sharded pair list add up), out[1] = # non-finite distances,
+ *   dF     = d out[0] / dF   (k x D),
+ * with E_c = F S_c F^T + noise I (AI, LE) or its Calvo-Oller embedding with mu'_c = F m_c (FR).
+ * Sequences sqfa_project_fwd, sqfa_embed_fwd, sqfa_class_factor, sqfa_pair_distances,
+ * (sqfa_class_factor_bwd,) sqfa_embed_bwd and sqfa_project_bwd on `stream` inside `ws`. */
+size_t sqfa_fused_loss_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters, int32_t dist);
+int sqfa_fused_loss(const float* S, const float* M, const float* F, int32_t n_classes, int32_t n_dim,
+                    int32_t n_filters, float noise, int32_t dist, int64_t pair_begin, int64_t pair_end, float* out,
+                    float* dF, void* ws, size_t ws_bytes, sqfa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,8 @@ below give the kernels analytic backward passes so that filter constraints (para
 `torch.optim.LBFGS` stay ordinary torch code above this boundary.
 """
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -261,16 +263,12 @@ class FusedLoss(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, F, S, M, noise, dist, group):
+    def forward(ctx, F, S, M, noise, dist, group, ws=None):
+        lib = _lib.load()
         dev = S.device
         Fc = f32c(F, dev)
-        C = S.shape[0]
+        C, D, _ = S.shape
         k = Fc.shape[0]
-        fr = (dist & 15) == DIST_FR
-        T, Psi, Mu = project_fwd_raw(S, M if fr else None, Fc)
-        E = embed_fwd_raw(Psi, Mu, noise, dist)
-        m = E.shape[-1]
-        W, _ = class_factor_raw(E, dist)
         P = C * (C - 1) // 2
         rank, world = 0, 1
         if group is not None:
@@ -278,26 +276,26 @@ class FusedLoss(torch.autograd.Function):
 
             rank, world = dist_mod.get_rank(group), dist_mod.get_world_size(group)
         p0, p1 = (P * rank) // world, (P * (rank + 1)) // world
-        out = torch.zeros(2, dtype=torch.float32, device=dev)
-        gE = torch.zeros(C, m, m, dtype=torch.float32, device=dev)
-        weight = -1.0 / max(P, 1)
-        pair_raw(W, W, C, C, m, dist, True, weight=weight, loss=out, gEa=gE, gEb=gE, pair_range=(p0, p1))
-        if (dist & 15) == DIST_LE:
-            gLog, gE = gE, torch.zeros_like(gE)
-            class_factor_bwd_raw(W, gLog, m, dist, gE)
-        gPsi, gMu = embed_bwd_raw(gE, Mu, k, dist)
-        dF = project_bwd_raw(gPsi, gMu, T, M if fr else None)
-        out[0] *= weight  # sum of distances -> minus their mean
+        nbytes = lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist)
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            ws = _ws(nbytes, dev)
+        # [loss, #non-finite, dF...] in one buffer: one all-reduce when the pair list is sharded
+        packed = torch.empty(2 + k * D, dtype=torch.float32, device=dev)
+        _lib.check(
+            lib.sqfa_fused_loss(
+                _lib.ptr(S), _lib.ptr(M), _lib.ptr(Fc), C, D, k, float(noise), dist, p0, p1, _lib.ptr(packed),
+                ctypes.c_void_p(packed.data_ptr() + 8), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
+            ),
+            "sqfa_fused_loss",
+        )
         if world > 1:
             import torch.distributed as dist_mod
 
-            packed = torch.cat([out, dF.reshape(-1)])
             dist_mod.all_reduce(packed, group=group)
-            out, dF = packed[:2], packed[2:].reshape(k, -1)
-        ctx.save_for_backward(dF)
-        return out
+        ctx.save_for_backward(packed[2:].view(k, D))
+        return packed[:2]
 
     @staticmethod
     def backward(ctx, g):
         (dF,) = ctx.saved_tensors
-        return g[0] * dF, None, None, None, None, None
+        return g[0] * dF, None, None, None, None, None, None

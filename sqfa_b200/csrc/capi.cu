@@ -239,3 +239,29 @@ int sqfa_class_factor_bwd(const float* W, const float* gLog, int32_t n_classes, 
 }
 
 }  // extern "C"
+
+extern "C" {
+
+size_t sqfa_fused_loss_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters, int32_t dist) {
+  if (n_classes <= 0 || n_dim <= 0 || n_filters <= 0 || !dist_ok(dist)) return 256;
+  return sqfa::fused_loss_workspace_bytes(n_classes, n_dim, n_filters, dist);
+}
+
+int sqfa_fused_loss(const float* S_, const float* M, const float* F, int32_t n_classes, int32_t n_dim,
+                    int32_t n_filters, float noise, int32_t dist, int64_t pair_begin, int64_t pair_end, float* out,
+                    float* dF, void* ws, size_t ws_bytes, sqfa_stream_t stream) {
+  const int base = dist & 15;
+  if (!dist_ok(dist) || S_ == nullptr || F == nullptr || out == nullptr || dF == nullptr || ws == nullptr ||
+      n_classes <= 0 || n_dim <= 0 || n_filters <= 0 || (base == SQFA_DIST_FISHER_RAO_LB && M == nullptr))
+    return fail_arg(__func__, "bad argument");
+  const int m = base == SQFA_DIST_FISHER_RAO_LB ? n_filters + 1 : n_filters;
+  if (n_filters > 32 || m > SQFA_MAX_M) return fail_arg(__func__, "n_filters must be <= 32", SQFA_E_UNSUPPORTED);
+  const int64_t P = (int64_t)n_classes * (n_classes - 1) / 2;
+  if (pair_begin < 0 || pair_end > P || pair_begin > pair_end) return fail_arg(__func__, "bad pair range");
+  if (ws_bytes < sqfa_fused_loss_workspace_bytes(n_classes, n_dim, n_filters, dist))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_fused_loss(S_, M, F, n_classes, n_dim, n_filters, noise, dist, pair_begin,
+                                                pair_end, out, dF, static_cast<float*>(ws), S(stream)));
+}
+
+}  // extern "C"

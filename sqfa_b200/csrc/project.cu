@@ -29,7 +29,7 @@ constexpr int PJ_ROWS = 256;  // rows of S per block
 template <int KT>
 __global__ void __launch_bounds__(PJ_THREADS)
 project_partial_kernel(const float* __restrict__ S, const float* __restrict__ F, int C, int D, int k, int f0,
-                       int nsplit, float* __restrict__ partial) {
+                       int nsplit, float* __restrict__ partial, float* __restrict__ psi_partial) {
   __shared__ __align__(16) float Fs[PJ_ROWS][KT];      // F^T tile: [row i][filter]
   __shared__ __align__(16) float red[KT][PJ_COLS];     // cross-warp reduction buffer
   const int c = blockIdx.z, split = blockIdx.y;
@@ -47,32 +47,57 @@ project_partial_kernel(const float* __restrict__ S, const float* __restrict__ F,
 
   const int col = j0 + 4 * lane;
   const bool vec = (D % 4 == 0) && (col + 4 <= D);
-  float acc[KT][4];
+  // accumulators packed over filter pairs: acc2[f/2][col] = (acc of filter f, acc of filter f+1)
+  // so every update is ONE Blackwell packed-fp32 FMA (fma.rn.f32x2 / FFMA2): this kernel is
+  // FMA-issue-bound, not HBM-bound, once k >= 8.
+  float2 acc2[KT / 2][4];
 #pragma unroll
-  for (int f = 0; f < KT; ++f) acc[f][0] = acc[f][1] = acc[f][2] = acc[f][3] = 0.f;
+  for (int f = 0; f < KT / 2; ++f)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc2[f][q] = make_float2(0.f, 0.f);
 
   const float* Sc = S + (int64_t)c * D * D;
   if (col < D) {
-#pragma unroll 2
-    for (int i = i0 + warp; i < i1; i += PJ_WARPS) {
-      float4 v;
-      const float* p = Sc + (int64_t)i * D + col;
-      if (vec) {
-        v = __ldg(reinterpret_cast<const float4*>(p));
-      } else {
-        v.x = __ldg(p);
-        v.y = col + 1 < D ? __ldg(p + 1) : 0.f;
-        v.z = col + 2 < D ? __ldg(p + 2) : 0.f;
-        v.w = col + 3 < D ? __ldg(p + 3) : 0.f;
-      }
-      const float* fr = Fs[i - i0];
+    // R independent 16-byte loads in flight per thread before the FMAs that consume them
+    constexpr int R = (KT >= 32) ? 4 : 8;
+    for (int ib = i0 + warp * R; ib < i1; ib += PJ_WARPS * R) {
+      float4 v[R];
 #pragma unroll
-      for (int f = 0; f < KT; f += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(fr + f);
-        acc[f + 0][0] += w.x * v.x; acc[f + 0][1] += w.x * v.y; acc[f + 0][2] += w.x * v.z; acc[f + 0][3] += w.x * v.w;
-        if (KT > 1) { acc[f + 1][0] += w.y * v.x; acc[f + 1][1] += w.y * v.y; acc[f + 1][2] += w.y * v.z; acc[f + 1][3] += w.y * v.w; }
-        if (KT > 2) { acc[f + 2][0] += w.z * v.x; acc[f + 2][1] += w.z * v.y; acc[f + 2][2] += w.z * v.z; acc[f + 2][3] += w.z * v.w; }
-        if (KT > 3) { acc[f + 3][0] += w.w * v.x; acc[f + 3][1] += w.w * v.y; acc[f + 3][2] += w.w * v.z; acc[f + 3][3] += w.w * v.w; }
+      for (int u = 0; u < R; ++u) {
+        const int i = ib + u;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < i1) {
+          const float* p = Sc + (int64_t)i * D + col;
+          if (vec) {
+            v[u] = __ldg(reinterpret_cast<const float4*>(p));
+          } else {
+            v[u].x = __ldg(p);
+            v[u].y = col + 1 < D ? __ldg(p + 1) : 0.f;
+            v[u].z = col + 2 < D ? __ldg(p + 2) : 0.f;
+            v[u].w = col + 3 < D ? __ldg(p + 3) : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const int i = ib + u < i1 ? ib + u : i0;  // rows past the end carry v = 0
+        const float* fr = Fs[i - i0];
+#pragma unroll
+        const float2 vx = make_float2(v[u].x, v[u].x), vy = make_float2(v[u].y, v[u].y);
+        const float2 vz = make_float2(v[u].z, v[u].z), vw = make_float2(v[u].w, v[u].w);
+#pragma unroll
+        for (int f = 0; f < KT; f += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(fr + f);
+          const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+          acc2[f / 2][0] = __ffma2_rn(w01, vx, acc2[f / 2][0]);
+          acc2[f / 2][1] = __ffma2_rn(w01, vy, acc2[f / 2][1]);
+          acc2[f / 2][2] = __ffma2_rn(w01, vz, acc2[f / 2][2]);
+          acc2[f / 2][3] = __ffma2_rn(w01, vw, acc2[f / 2][3]);
+          acc2[f / 2 + 1][0] = __ffma2_rn(w23, vx, acc2[f / 2 + 1][0]);
+          acc2[f / 2 + 1][1] = __ffma2_rn(w23, vy, acc2[f / 2 + 1][1]);
+          acc2[f / 2 + 1][2] = __ffma2_rn(w23, vz, acc2[f / 2 + 1][2]);
+          acc2[f / 2 + 1][3] = __ffma2_rn(w23, vw, acc2[f / 2 + 1][3]);
+        }
       }
     }
   }
@@ -83,7 +108,9 @@ project_partial_kernel(const float* __restrict__ S, const float* __restrict__ F,
       for (int f = 0; f < KT; ++f) {
         float4* r = reinterpret_cast<float4*>(&red[f][4 * lane]);
         float4 t = *r;
-        t.x += acc[f][0]; t.y += acc[f][1]; t.z += acc[f][2]; t.w += acc[f][3];
+        const float2* a = acc2[f / 2];
+        if (f & 1) { t.x += a[0].y; t.y += a[1].y; t.z += a[2].y; t.w += a[3].y; }
+        else       { t.x += a[0].x; t.y += a[1].x; t.z += a[2].x; t.w += a[3].x; }
         *r = t;
       }
     }
@@ -94,61 +121,60 @@ project_partial_kernel(const float* __restrict__ S, const float* __restrict__ F,
     if (f0 + f < k && j0 + jj < D)
       partial[(((int64_t)split * C + c) * k + f0 + f) * D + j0 + jj] = red[f][jj];
   }
+  // Psi = T F^T is linear in T: this block adds  sum_{j in its 128 columns} Tpart[f][j] F[g][j].
+  // The F^T tile of the main loop is dead now; its memory holds F[:, j0:j0+128].
+  float* Fj = &Fs[0][0];  // [KT][128]
+  for (int idx = tid; idx < KT * PJ_COLS; idx += PJ_THREADS) {
+    const int g = idx / PJ_COLS, jj = idx % PJ_COLS;
+    Fj[idx] = (g < k && j0 + jj < D) ? F[(int64_t)g * D + j0 + jj] : 0.f;
+  }
+  __syncthreads();
+  const int nblk = nsplit * gridDim.x;
+  const int blk = split * gridDim.x + blockIdx.x;
+  float* pp = psi_partial + (int64_t)c * k * k * nblk + blk;  // layout [c][o][blk]
+  for (int o = tid; o < k * k; o += PJ_THREADS) {
+    const int f = o / k, g = o % k;
+    float a = 0.f;
+#pragma unroll 8
+    for (int jj = 0; jj < PJ_COLS; ++jj) {
+      const int j = (jj + lane) & (PJ_COLS - 1);  // per-lane rotation: conflict-free without padding
+      a += red[f][j] * Fj[g * PJ_COLS + j];
+    }
+    pp[(int64_t)o * nblk] = a;
+  }
 }
 
-// Per class: T = sum_split partial, Psi = T F^T, mu' = F m.
+// T = sum over row splits of the partial products (elementwise, fully parallel)
+__global__ void project_reduce_T_kernel(const float* __restrict__ partial, int64_t total, int nsplit,
+                                        float* __restrict__ T) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float a = 0.f;
+  for (int s = 0; s < nsplit; ++s) a += partial[(int64_t)s * total + idx];
+  T[idx] = a;
+}
+
+// Per class: Psi = sum of the per-block partial Psi, mu' = F m (one warp per filter).
 __global__ void __launch_bounds__(256)
-project_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ F, const float* __restrict__ M,
-                        int C, int D, int k, int nsplit, float* __restrict__ T, float* __restrict__ Psi,
-                        float* __restrict__ Mu) {
-  extern __shared__ float sm[];  // Ts[64][k+1], Fs[64][k+1], Ms[64]
+project_reduce_psi_kernel(const float* __restrict__ psi_partial, const float* __restrict__ F,
+                          const float* __restrict__ M, int D, int k, int nblk, float* __restrict__ Psi,
+                          float* __restrict__ Mu) {
   const int c = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int ld = k + 1;
-  float* Ts = sm;
-  float* Fs = sm + 64 * ld;
-  float* Ms = Fs + 64 * ld;
-  // each thread owns outputs o = tid, tid+256, ... of the k*k (+k) results
-  const int nout = k * k + (M != nullptr ? k : 0);
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // k <= 32 -> nout <= 1056 -> <= 5 per thread
-  for (int j0 = 0; j0 < D; j0 += 64) {
-    __syncthreads();
-    for (int idx = tid; idx < 64 * k; idx += 256) {
-      const int f = idx / 64, jj = idx % 64;
-      const int j = j0 + jj;
-      float t = 0.f, fv = 0.f;
-      if (j < D) {
-        for (int s = 0; s < nsplit; ++s) t += partial[(((int64_t)s * C + c) * k + f) * D + j];
-        T[((int64_t)c * k + f) * D + j] = t;
-        fv = F[(int64_t)f * D + j];
-      }
-      Ts[jj * ld + f] = t;
-      Fs[jj * ld + f] = fv;
-    }
-    if (M != nullptr)
-      for (int jj = tid; jj < 64; jj += 256) Ms[jj] = (j0 + jj < D) ? M[(int64_t)c * D + j0 + jj] : 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 5; ++u) {
-      const int o = tid + u * 256;
-      if (o < k * k) {
-        const int f = o / k, g = o % k;
-        float a = acc[u];
-        for (int jj = 0; jj < 64; ++jj) a += Ts[jj * ld + f] * Fs[jj * ld + g];
-        acc[u] = a;
-      } else if (o < nout) {
-        const int f = o - k * k;
-        float a = acc[u];
-        for (int jj = 0; jj < 64; ++jj) a += Fs[jj * ld + f] * Ms[jj];
-        acc[u] = a;
-      }
-    }
+  const float* pp = psi_partial + (int64_t)c * nblk * k * k;  // [o][blk]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < k * k; o += 8) {  // one warp per output, lanes stride the blocks
+    float a = 0.f;
+    for (int b = lane; b < nblk; b += 32) a += pp[(int64_t)o * nblk + b];
+    for (int sh = 16; sh > 0; sh >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);
+    if (lane == 0) Psi[(int64_t)c * k * k + o] = a;
   }
-#pragma unroll
-  for (int u = 0; u < 5; ++u) {
-    const int o = tid + u * 256;
-    if (o < k * k) Psi[(int64_t)c * k * k + o] = acc[u];
-    else if (o < nout) Mu[(int64_t)c * k + (o - k * k)] = acc[u];
+  if (M != nullptr) {
+    for (int f = warp; f < k; f += 8) {
+      float a = 0.f;
+      for (int j = lane; j < D; j += 32) a += F[(int64_t)f * D + j] * M[(int64_t)c * D + j];
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) Mu[(int64_t)c * k + f] = a;
+    }
   }
 }
 
@@ -290,10 +316,9 @@ __global__ void embed_bwd_kernel(const float* __restrict__ gE, const float* __re
 
 template <int KT>
 cudaError_t run_partial(const float* S, const float* F, int C, int D, int k, int nsplit, float* partial,
-                        cudaStream_t st) {
-  dim3 grid((D + PJ_COLS - 1) / PJ_COLS, nsplit, C);
-  for (int f0 = 0; f0 < k; f0 += KT)
-    project_partial_kernel<KT><<<grid, PJ_THREADS, 0, st>>>(S, F, C, D, k, f0, nsplit, partial);
+                        float* psi_partial, cudaStream_t st) {
+  dim3 grid((D + PJ_COLS - 1) / PJ_COLS, nsplit, C);  // k <= KT: a single filter chunk
+  project_partial_kernel<KT><<<grid, PJ_THREADS, 0, st>>>(S, F, C, D, k, 0, nsplit, partial, psi_partial);
   return cudaGetLastError();
 }
 
@@ -317,8 +342,11 @@ cudaError_t run_transform(const float* X, int64_t ldx, const float* F, int64_t n
 
 int project_nsplit(int D) { return (D + PJ_ROWS - 1) / PJ_ROWS; }
 
+static size_t project_partial_floats(int C, int D, int k) { return (size_t)project_nsplit(D) * C * k * D; }
+
 size_t project_workspace_bytes(int C, int D, int k) {
-  const size_t fwd = (size_t)project_nsplit(D) * C * k * D * sizeof(float);
+  const size_t nblk = (size_t)project_nsplit(D) * ((D + PJ_COLS - 1) / PJ_COLS);
+  const size_t fwd = (project_partial_floats(C, D, k) + (size_t)C * nblk * k * k) * sizeof(float);
   const size_t bwd = (size_t)64 * k * D * sizeof(float);
   return fwd > bwd ? fwd : bwd;
 }
@@ -327,14 +355,17 @@ cudaError_t launch_project_fwd(const float* S, const float* M, const float* F, i
                                float* Psi, float* Mu, float* ws, cudaStream_t st) {
   if (C <= 0) return cudaSuccess;
   const int nsplit = project_nsplit(D);
+  float* psi_partial = ws + project_partial_floats(C, D, k);
+  const int nblk = nsplit * ((D + PJ_COLS - 1) / PJ_COLS);
   cudaError_t e;
-  if (k <= 4) e = run_partial<4>(S, F, C, D, k, nsplit, ws, st);
-  else if (k <= 8) e = run_partial<8>(S, F, C, D, k, nsplit, ws, st);
-  else if (k <= 16) e = run_partial<16>(S, F, C, D, k, nsplit, ws, st);
-  else e = run_partial<32>(S, F, C, D, k, nsplit, ws, st);
+  if (k <= 4) e = run_partial<4>(S, F, C, D, k, nsplit, ws, psi_partial, st);
+  else if (k <= 8) e = run_partial<8>(S, F, C, D, k, nsplit, ws, psi_partial, st);
+  else if (k <= 16) e = run_partial<16>(S, F, C, D, k, nsplit, ws, psi_partial, st);
+  else e = run_partial<32>(S, F, C, D, k, nsplit, ws, psi_partial, st);
   if (e != cudaSuccess) return e;
-  const int smem = (2 * 64 * (k + 1) + 64) * (int)sizeof(float);
-  project_finalize_kernel<<<C, 256, smem, st>>>(ws, F, M, C, D, k, nsplit, T, Psi, Mu);
+  const int64_t total = (int64_t)C * k * D;
+  project_reduce_T_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, total, nsplit, T);
+  project_reduce_psi_kernel<<<C, 256, 0, st>>>(psi_partial, F, M, D, k, nblk, Psi, Mu);
   return cudaGetLastError();
 }
 

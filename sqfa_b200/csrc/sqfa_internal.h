@@ -61,3 +61,11 @@ cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int 
 cudaError_t launch_class_factor_bwd(const float* W, const float* gLog, int C, int m, int dist, float* gE,
                                     cudaStream_t st);
 }  // namespace sqfa
+
+namespace sqfa {
+// ---- closure.cu ----
+size_t fused_loss_workspace_bytes(int C, int D, int k, int dist);
+cudaError_t launch_fused_loss(const float* S, const float* M, const float* F, int C, int D, int k, float noise,
+                              int dist, int64_t pair_begin, int64_t pair_end, float* out, float* dF, float* ws,
+                              cudaStream_t st);
+}  // namespace sqfa

@@ -209,7 +209,10 @@ class SecondMomentsSQFA(nn.Module):
             return None
         S, M, dist = plan
         group = self._process_group
-        return lambda: _ops.FusedLoss.apply(self.filters, S, M, noise, dist, group)
+        lib = _lib.load()
+        nbytes = lib.sqfa_fused_loss_workspace_bytes(S.shape[0], S.shape[1], self.filters.shape[0], dist)
+        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=S.device)  # reused by every evaluation
+        return lambda: _ops.FusedLoss.apply(self.filters, S, M, noise, dist, group, ws)
 
     # ------------------------------------------------------------------ training
     def fit_pca(self, X=None, data_statistics=None):
