@@ -92,11 +92,17 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
  *   chain_rows samples per tensor-core accumulation chain (0 = default 512). Every chain starts
  *              from a zero accumulator and is added to gram with fp32 red.global.add, which bounds
  *              the accumulator truncation bias of the tensor core.
- *   ws         sqfa_class_gram_workspace_bytes(n_classes) bytes (job counter + job plan). */
-size_t sqfa_class_gram_workspace_bytes(int32_t n_classes);
+ *   n          number of rows of X (sizes the K split of small problems; no rows beyond the
+ *              class offsets are read)
+ *   ws         sqfa_class_gram_workspace_bytes(n, n_dim, n_classes) bytes (device-side job plan). */
+size_t sqfa_class_gram_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes);
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
-                    int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows, void* ws,
-                    size_t ws_bytes, sqfa_stream_t stream);
+                    int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
+                    void* ws, size_t ws_bytes, sqfa_stream_t stream);
+
+/* Bring-up switch between the two tensor-core schedules of sqfa_class_gram: 1 = one CTA per
+ * 128 x 256 tile, 2 = CTA pairs on 256 x 256 tiles (tcgen05 cta_group::2). Same results. */
+int sqfa_debug_set_gram_variant(int variant);
 
 /* Statistics epilogue (statistics.py:43-47, 84-93, 116, 120-122):
  *   cov[c] = (gram[c] - n_c d d^T) / (n_c - ddof),  d = means[c] - shift[c]  (shift NULL -> d = 0)

@@ -37,11 +37,12 @@ SIGNATURES = {
         [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_ptr, c_size, c_ptr],
     ),
     "sqfa_class_means": (c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
-    "sqfa_class_gram_workspace_bytes": (c_size, [c_i32]),
+    "sqfa_class_gram_workspace_bytes": (c_size, [c_i64, c_i32, c_i32]),
     "sqfa_class_gram": (
         c_int,
-        [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_size, c_ptr],
+        [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_size, c_ptr],
     ),
+    "sqfa_debug_set_gram_variant": (c_int, [c_int]),
     "sqfa_stats_epilogue_workspace_bytes": (c_size, [c_i32]),
     "sqfa_stats_epilogue": (
         c_int,

@@ -76,15 +76,15 @@ class CudaStatsOps:
         lib, dev = self.lib, X.device
         n, D = X.shape
         gram = torch.empty(C, D, D, dtype=torch.float32, device=dev)
-        ws_bytes = lib.sqfa_class_gram_workspace_bytes(C)
+        ws_bytes = lib.sqfa_class_gram_workspace_bytes(n, D, C)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         if self.gram_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         _lib.check(
             lib.sqfa_class_gram(
-                _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), D, C, _lib.ptr(gram),
-                0, 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+                _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), n, D, C,
+                _lib.ptr(gram), 0, 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
             ),
             "sqfa_class_gram",
         )

@@ -58,6 +58,8 @@ constexpr int CHAIN_ROWS = 512;        // samples per accumulation chain (64 acc
 constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, OP_SBO = 128;
 constexpr uint32_t LAYOUT_NONE = 0;
 
+__device__ float g_zero[4] = {0.f, 0.f, 0.f, 0.f};  // what out-of-range operand columns read
+
 struct GramParams {
   const float* X;
   int64_t ldx;
@@ -192,57 +194,67 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_tf32x3_kernel(const Gram
       const int cw = isA ? (warp * 32 + lane) : (warp * 32 + lane - BM);  // column inside the operand
       const int col = (isA ? m0 : n0) + cw;                               // column of X
       const bool col_ok = col < D && (isA || cw < n_eff);
+      // The inner loops are instruction-issue bound, so everything per-thread is folded into three
+      // values: a column base pointer, a row stride in bytes and the centring shift. Columns
+      // outside the matrix read a device zero with stride 0 and shift 0 -> exact zeros, no selects.
+      const char* xcol = col_ok ? reinterpret_cast<const char*>(P.X + col) : reinterpret_cast<const char*>(g_zero);
+      const uint32_t ldb = col_ok ? (uint32_t)(P.ldx * 4) : 0u;
       const float sh = (P.shift != nullptr && col_ok) ? __ldg(P.shift + (int64_t)c * D + col) : 0.f;
       const uint32_t op_lbo = isA ? A_LBO : B_LBO;
-      const uint32_t hi_off = isA ? 0u : 2u * A_BYTES;
-      const uint32_t lo_off = isA ? (uint32_t)A_BYTES : 2u * A_BYTES + B_BYTES;
-      const uint32_t c_off = (uint32_t)((cw >> 3) * 128 + (cw & 7) * 16);
-      const float* xcol = P.X + col;
+      uint8_t* const hi_base = smem + (isA ? 0u : 2u * A_BYTES) + (uint32_t)((cw >> 3) * 128 + (cw & 7) * 16);
+      uint8_t* const lo_base = hi_base + (isA ? A_BYTES : B_BYTES);
+      const int32_t* const permc = P.perm + row_begin;
+      const int lane16 = lane & (BK - 1);
 
       float buf[3][BK];  // three stages of loads in flight per thread (registers)
-      // row ids of the next stage are fetched one stage ahead (lane r < 16 holds sample r's row)
-      auto load_row = [&](int kb) -> int32_t {
-        const int64_t k = (int64_t)kb * BK + (lane & (BK - 1));
-        return (kb < kb1 && k < n_c) ? __ldg(P.perm + row_begin + k) : -1;
+      // lane r < 16 holds the row id of sample r of the NEXT stage to issue (fetched a stage ahead);
+      // samples past the end of the chain's class read row 0 and are masked in consume_tail().
+      auto load_row = [&](int kb) -> uint32_t {
+        const int64_t k = (int64_t)kb * BK + lane16;
+        return (kb < kb1 && k < n_c) ? (uint32_t)__ldg(permc + k) : 0u;
       };
-      int32_t nextrow = load_row(kb0);
+      uint32_t nextrow = load_row(kb0);
       auto issue = [&](int kb, float(&b)[BK]) {
-        const int32_t myrow = nextrow;
+        const uint32_t myrow = nextrow;
         nextrow = load_row(kb + 1);
 #pragma unroll
-        for (int r = 0; r < BK; ++r) {
-          const int32_t row = __shfl_sync(0xffffffffu, myrow, r);
-          // UNCONDITIONAL load (a select on the loaded value would make the thread wait for it
-          // right here and serialise the pipeline): padded rows / columns read X[0][0] and are
-          // zeroed in consume() from the validity computed there.
-          const float* ptr = (row >= 0 && col_ok) ? xcol + (int64_t)row * P.ldx : P.X;
-          b[r] = __ldg(ptr);
+        for (int r = 0; r < BK; ++r) {  // SHFL + IMAD.WIDE.U32 + LDG per element, nothing else
+          const uint32_t row = __shfl_sync(0xffffffffu, myrow, r);
+          uint64_t addr;  // one IMAD.WIDE.U32: base + row * stride
+          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(ldb), "l"(xcol));
+          b[r] = __ldg(reinterpret_cast<const float*>(addr));
         }
       };
-      auto consume = [&](int kb, float(&b)[BK]) {
-        int64_t nv = n_c - (int64_t)kb * BK;  // valid rows of this stage
-        nv = nv > BK ? BK : nv;
-        const uint32_t vmask = col_ok ? ((1u << (int)nv) - 1u) : 0u;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = smem + stage * STAGE_BYTES;
+      auto store_stage = [&](const float(&x)[BK]) {
+        uint8_t* hp = hi_base + stage * STAGE_BYTES;
+        uint8_t* lp = lo_base + stage * STAGE_BYTES;
 #pragma unroll
         for (int kc = 0; kc < BK / 4; ++kc) {
-          float4 x, h, l;
-          x.x = (vmask >> (4 * kc + 0)) & 1u ? b[4 * kc + 0] - sh : 0.f;
-          x.y = (vmask >> (4 * kc + 1)) & 1u ? b[4 * kc + 1] - sh : 0.f;
-          x.z = (vmask >> (4 * kc + 2)) & 1u ? b[4 * kc + 2] - sh : 0.f;
-          x.w = (vmask >> (4 * kc + 3)) & 1u ? b[4 * kc + 3] - sh : 0.f;
-          h.x = to_tf32(x.x); l.x = x.x - h.x;
-          h.y = to_tf32(x.y); l.y = x.y - h.y;
-          h.z = to_tf32(x.z); l.z = x.z - h.z;
-          h.w = to_tf32(x.w); l.w = x.w - h.w;
-          *reinterpret_cast<float4*>(st + hi_off + kc * op_lbo + c_off) = h;
-          *reinterpret_cast<float4*>(st + lo_off + kc * op_lbo + c_off) = l;
+          float4 h, l;
+          h.x = to_tf32(x[4 * kc + 0]); l.x = x[4 * kc + 0] - h.x;
+          h.y = to_tf32(x[4 * kc + 1]); l.y = x[4 * kc + 1] - h.y;
+          h.z = to_tf32(x[4 * kc + 2]); l.z = x[4 * kc + 2] - h.z;
+          h.w = to_tf32(x[4 * kc + 3]); l.w = x[4 * kc + 3] - h.w;
+          *reinterpret_cast<float4*>(hp + kc * op_lbo) = h;
+          *reinterpret_cast<float4*>(lp + kc * op_lbo) = l;
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      auto consume = [&](int kb, float(&b)[BK]) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int64_t nv = n_c - (int64_t)kb * BK;  // valid rows of this stage
+        float x[BK];
+        if (nv >= BK) {  // full stage (all but the last of a class): FADD, CVT, FADD per element
+#pragma unroll
+          for (int r = 0; r < BK; ++r) x[r] = b[r] - sh;
+        } else {
+#pragma unroll
+          for (int r = 0; r < BK; ++r) x[r] = (r < (int)nv) ? b[r] - sh : 0.f;
+        }
+        store_stage(x);
       };
 
       if (nkb > 0) issue(kb0, buf[0]);

@@ -1,0 +1,425 @@
+// K2 (production schedule): segmented per-class Gram accumulation on CTA PAIRS.
+//
+//   G_c[256 x 256 tile] = sum_{i in class c} (x_i - s_c)(x_i - s_c)^T      as 3xTF32 (see gram.cu)
+//
+// Two CTAs of a cluster (one SM each) share one tcgen05.mma.cta_group::2 with M = 256, N = 256:
+// CTA r supplies the 128 operand columns m0 + 128 r .. of A and HALF of B (n0 + (N/2) r ..) from its
+// own shared memory, the tensor cores of both SMs compute 128 x 256 accumulators each (TMEM of
+// each SM). Relative to one CTA per 128 x 256 tile this cuts, per SM and per MMA cycle, the operand
+// bytes read from shared memory and the transform work (gather + centre + hi/lo split + store) by
+// 1/3 -- shared-memory bandwidth and instruction issue are what bound 3xTF32.
+//
+// Warp roles per CTA (13 warps):
+//   0-15  producers : a thread owns one operand column and half of a stage's 16 samples; it gathers
+//                     them through the bucket permutation straight into registers (4 stages of
+//                     loads in flight), centres, splits hi/lo, stores K-major UMMA operands and
+//                     its warp arrives on the LEADER's full[s]
+//   16    MMA       : leader CTA only; per K=8 step 3 tcgen05.mma.cta_group::2 (cross terms into
+//                     their own TMEM accumulator, hi*hi into the main one), multicast commits
+//   17-20 epilogue  : the tensor core truncates when it adds into its fp32 accumulator (bias
+//                     ~ -2^-25 per MMA, measured), so the main accumulator only ever holds a CHAIN
+//                     of <= chain_rows samples: at every chain end these warps add it (fp32,
+//                     round-to-nearest) to a 128 x 256 running sum in shared memory and hand the
+//                     accumulator back; at the end of the tile they add the cross-term accumulator
+//                     and store the tile (red.global.add only when a tile is split along K).
+// Jobs (class, tile, K part) are listed by a device-side plan (largest classes first) and dealt
+// round-robin to the CTA pairs: no atomics, no host sync, no cluster barrier per job.
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+#include "sqfa_internal.h"
+
+namespace sqfa {
+
+namespace {
+
+constexpr int TM2 = 256;  // tile rows    (UMMA M over the CTA pair)
+constexpr int TN2 = 256;  // tile columns (UMMA N)
+constexpr int BK = 16;    // samples per stage
+constexpr int STAGES2 = 3;
+constexpr int PROD_WARPS2 = 16;  // per 32-column group two warps: samples 0-7 and 8-15 of a stage
+constexpr int HR = BK / 2;       // samples per producer thread and stage
+constexpr int PREFETCH = 4;      // stages of loads in flight per producer thread (registers)
+constexpr int EPI_WARPS2 = 4;   // one per TMEM lane quarter
+constexpr int MMA_WARP2 = PROD_WARPS2;
+constexpr int GRAM2_THREADS = (PROD_WARPS2 + 1 + EPI_WARPS2) * 32;
+constexpr int OP_BYTES = 128 * BK * 4;                    // 8 KB: 128 columns x 16 samples
+constexpr int STAGE2_BYTES = 4 * OP_BYTES;                // A_hi, A_lo, B_hi, B_lo = 32 KB
+constexpr int RUN_BYTES = 128 * TN2 * 4;                  // 128 KB running sum [col][row]
+constexpr int GRAM2_SMEM = STAGES2 * STAGE2_BYTES + RUN_BYTES + 1024;
+constexpr uint32_t OP_LBO = 128 * 16, OP_SBO2 = 128;      // K-major, no swizzle (see gram.cu)
+constexpr uint32_t TMEM_COLS2 = 512, TMEM_SMALL2 = 256;
+
+__device__ float g_zero2[4] = {0.f, 0.f, 0.f, 0.f};
+
+struct Gram2Params {
+  const float* X;
+  int64_t ldx;
+  const int32_t* perm;
+  const int64_t* offsets;
+  const float* shift;
+  float* gram;
+  const int4* jobs;  // (class, tile row, tile col, K part)
+  int njobs;
+  int D, C, KS;
+  int chain_kb;      // stages per accumulation chain
+  int atomic_out;    // KS > 1 or accumulate: red.add into gram, else plain store
+  int vec_ok;
+};
+
+// Job list: classes in descending size, tiles of a class adjacent (they share the gathered rows
+// in L2), K parts innermost.  job = ((rank * T) + t) * KS + ks
+__global__ void __launch_bounds__(1024) gram2_plan_kernel(const int64_t* __restrict__ offsets, int C, int TT, int KS,
+                                                          int4* __restrict__ jobs) {
+  const int T = TT * (TT + 1) / 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int64_t n_c = offsets[c + 1] - offsets[c];
+    int rank = 0;
+    for (int o = 0; o < C; ++o) {
+      const int64_t n_o = offsets[o + 1] - offsets[o];
+      rank += (n_o > n_c || (n_o == n_c && o < c)) ? 1 : 0;
+    }
+    int t = 0;
+    for (int tm = 0; tm < TT; ++tm)
+      for (int tn = tm; tn < TT; ++tn, ++t)
+        for (int ks = 0; ks < KS; ++ks) jobs[((int64_t)rank * T + t) * KS + ks] = make_int4(c, tm, tn, ks);
+  }
+}
+
+struct JobGeom {
+  int c, m0, n0, n_eff, nh;
+  int64_t row_begin, n_c;
+  int kb0, kb1;
+};
+
+__device__ __forceinline__ JobGeom decode_job(const Gram2Params& P, int j) {
+  const int4 jb = __ldg(P.jobs + j);
+  JobGeom g;
+  g.c = jb.x;
+  g.m0 = jb.y * TM2;
+  g.n0 = jb.z * TN2;
+  int n_eff = P.D - g.n0;
+  n_eff = n_eff > TN2 ? TN2 : ((n_eff + 31) & ~31);  // multiple of 32: each CTA holds n_eff / 2 columns of B
+  g.n_eff = n_eff;
+  g.nh = n_eff >> 1;
+  g.row_begin = P.offsets[g.c];
+  g.n_c = P.offsets[g.c + 1] - g.row_begin;
+  const int nkb_total = (int)((g.n_c + BK - 1) / BK);
+  g.kb0 = (int)(((int64_t)jb.w * nkb_total) / P.KS);
+  g.kb1 = (int)(((int64_t)(jb.w + 1) * nkb_total) / P.KS);
+  return g;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GRAM2_THREADS, 1)
+gram2_tf32x3_kernel(const Gram2Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* run = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES);  // [256 cols][128 rows]
+
+  __shared__ __align__(8) uint64_t full_bar[STAGES2];   // leader: 16 producer-warp arrivals (both CTAs)
+  __shared__ __align__(8) uint64_t empty_bar[STAGES2];  // per CTA: multicast tcgen05.commit
+  __shared__ __align__(8) uint64_t acc_full_bar;        // per CTA: chain finished (multicast commit)
+  __shared__ __align__(8) uint64_t acc_empty_bar;       // leader: 8 epilogue-warp arrivals (both CTAs)
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 2 * PROD_WARPS2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full_bar, 1);
+    mbar_init(&acc_empty_bar, 2 * EPI_WARPS2);
+    mbar_fence_init();
+  }
+  if (warp == MMA_WARP2) tmem_alloc_2cta<TMEM_COLS2>(&s_tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives remotely
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int D = P.D;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp < PROD_WARPS2) {
+    // =========================== producers (both CTAs) ===========================
+    uint32_t stage = 0, phase = 0;
+    const int grp = warp & 7, half = warp >> 3;  // 32-column group (0-3: A, 4-7: B) and sample half
+    const bool isA = grp < 4;
+    const int cw = (grp & 3) * 32 + lane;  // column inside this CTA's 128-wide operand
+    // K-major chunk (4 samples x 16 B) of this column; this thread's samples are chunks 2*half, 2*half+1
+    uint8_t* const hi_base = smem + (isA ? 0 : 2 * OP_BYTES) + ((cw >> 3) * 128 + (cw & 7) * 16) + 2 * half * OP_LBO;
+    uint8_t* const lo_base = hi_base + OP_BYTES;
+    const int lane16 = lane & (BK - 1);
+    const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's barriers, cluster window
+    for (int j = pair; j < P.njobs; j += npairs) {
+      const JobGeom g = decode_job(P, j);
+      const int kb0 = g.kb0, kb1 = g.kb1;
+      const int64_t n_c = g.n_c;
+      const int col = isA ? (g.m0 + 128 * (int)rank + cw) : (g.n0 + g.nh * (int)rank + cw);
+      const bool col_ok = col < D && (isA || cw < g.nh);
+      // Instruction issue is a bottleneck of these loops, so everything per-thread is folded into a
+      // column base pointer, a row stride in bytes and the centring shift. Columns outside the
+      // matrix read a device zero with stride 0 and shift 0 -> exact zeros without selects.
+      const char* xcol = col_ok ? reinterpret_cast<const char*>(P.X + col) : reinterpret_cast<const char*>(g_zero2);
+      const uint32_t ldb = col_ok ? (uint32_t)(P.ldx * 4) : 0u;
+      const float sh = (P.shift != nullptr && col_ok) ? __ldg(P.shift + (int64_t)g.c * D + col) : 0.f;
+      const int32_t* const permc = P.perm + g.row_begin;
+
+      float buf[PREFETCH][HR];
+      auto load_row = [&](int kb) -> uint32_t {  // lane r < 16: row id of sample r of stage kb
+        const int64_t k = (int64_t)kb * BK + lane16;
+        return (kb < kb1 && k < n_c) ? (uint32_t)__ldg(permc + k) : 0u;
+      };
+      uint32_t nextrow = load_row(kb0);
+      auto issue = [&](int kb, float(&b)[HR]) {
+        const uint32_t myrow = nextrow;
+        nextrow = load_row(kb + 1);
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {  // SHFL + IMAD.WIDE.U32 + LDG per element
+          const uint32_t row = __shfl_sync(0xffffffffu, myrow, HR * half + r);
+          uint64_t addr;
+          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(ldb), "l"(xcol));
+          b[r] = __ldg(reinterpret_cast<const float*>(addr));
+        }
+      };
+      auto consume = [&](int kb, float(&b)[HR]) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int64_t nv = n_c - (int64_t)kb * BK - HR * half;  // valid samples among this thread's
+        float x[HR];
+        if (nv >= HR) {  // full: FADD, CVT, FADD per element
+#pragma unroll
+          for (int r = 0; r < HR; ++r) x[r] = b[r] - sh;
+        } else {         // ragged last stage of the class: padded samples are exact zeros
+#pragma unroll
+          for (int r = 0; r < HR; ++r) x[r] = (r < (int)nv) ? b[r] - sh : 0.f;
+        }
+        uint8_t* hp = hi_base + stage * STAGE2_BYTES;
+        uint8_t* lp = lo_base + stage * STAGE2_BYTES;
+#pragma unroll
+        for (int kc = 0; kc < HR / 4; ++kc) {
+          float4 h, l;
+          h.x = to_tf32(x[4 * kc + 0]); l.x = x[4 * kc + 0] - h.x;
+          h.y = to_tf32(x[4 * kc + 1]); l.y = x[4 * kc + 1] - h.y;
+          h.z = to_tf32(x[4 * kc + 2]); l.z = x[4 * kc + 2] - h.z;
+          h.w = to_tf32(x[4 * kc + 3]); l.w = x[4 * kc + 3] - h.w;
+          *reinterpret_cast<float4*>(hp + kc * OP_LBO) = h;
+          *reinterpret_cast<float4*>(lp + kc * OP_LBO) = l;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+      };
+#pragma unroll
+      for (int u = 0; u < PREFETCH; ++u)
+        if (kb0 + u < kb1) issue(kb0 + u, buf[u]);
+      for (int kb = kb0; kb < kb1; kb += PREFETCH) {
+#pragma unroll
+        for (int u = 0; u < PREFETCH; ++u) {
+          if (kb + u < kb1) {
+            consume(kb + u, buf[u]);
+            if (kb + u + PREFETCH < kb1) issue(kb + u + PREFETCH, buf[u]);
+          }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP2) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (leader) {
+      uint32_t stage = 0, phase = 0, chain_phase = 0;
+      for (int j = pair; j < P.njobs; j += npairs) {
+        const JobGeom g = decode_job(P, j);
+        const uint32_t idesc = make_idesc_tf32(TM2, (uint32_t)g.n_eff, 0, 0);
+        for (int cb = g.kb0; cb < g.kb1; cb += P.chain_kb) {
+          const int ce = min(g.kb1, cb + P.chain_kb);
+          // the epilogue warps of both CTAs must have drained the previous chain
+          mbar_wait_cluster(&acc_empty_bar, chain_phase ^ 1);
+          chain_phase ^= 1;
+          tc_fence_after_sync();
+          for (int kb = cb; kb < ce; ++kb) {
+            mbar_wait_cluster(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t st = smem_u32(smem + stage * STAGE2_BYTES);
+              const uint32_t a_hi = st, a_lo = st + OP_BYTES, b_hi = st + 2 * OP_BYTES, b_lo = st + 3 * OP_BYTES;
+#pragma unroll
+              for (int k8 = 0; k8 < BK / 8; ++k8) {
+                const uint32_t ko = k8 * 2 * OP_LBO;
+                const uint64_t dA_hi = make_smem_desc(a_hi + ko, OP_LBO, OP_SBO2, 0);
+                const uint64_t dA_lo = make_smem_desc(a_lo + ko, OP_LBO, OP_SBO2, 0);
+                const uint64_t dB_hi = make_smem_desc(b_hi + ko, OP_LBO, OP_SBO2, 0);
+                const uint64_t dB_lo = make_smem_desc(b_lo + ko, OP_LBO, OP_SBO2, 0);
+                const uint32_t acc_small = (kb > g.kb0 || k8 > 0) ? 1u : 0u;  // zeroed once per job
+                const uint32_t acc_main = (kb > cb || k8 > 0) ? 1u : 0u;      // zeroed at every chain start
+                umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_lo, dB_hi, idesc, acc_small);
+                umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_hi, dB_lo, idesc, 1u);
+                umma_tf32_ss_2cta(tmem_base, dA_hi, dB_hi, idesc, acc_main);
+              }
+              umma_commit_2cta(&empty_bar[stage], 3);
+              if (kb == ce - 1) umma_commit_2cta(&acc_full_bar, 3);
+            }
+            __syncwarp();
+            if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue warps (both CTAs) ===========================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int lrow = 32 * q + lane;
+    const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty_bar), 0);
+    uint32_t acc_phase = 0;
+    for (int j = pair; j < P.njobs; j += npairs) {
+      const JobGeom g = decode_job(P, j);
+      const int row = g.m0 + 128 * (int)rank + lrow;
+      float* grow = P.gram + ((int64_t)g.c * D + row) * D;
+      if (g.kb1 <= g.kb0) {  // empty class / empty K part: the tile contribution is exactly zero
+        if (!P.atomic_out && row < D)
+          for (int cc = 0; cc < g.n_eff; ++cc)
+            if (g.n0 + cc < D) grow[g.n0 + cc] = 0.f;
+        continue;
+      }
+      bool first = true;
+      for (int cb = g.kb0; cb < g.kb1; cb += P.chain_kb) {
+        const bool last = cb + P.chain_kb >= g.kb1;
+        mbar_wait(&acc_full_bar, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int col0 = 0; col0 < g.n_eff; col0 += 16) {  // 16 columns at a time: the role fits 80 registers
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tq + (uint32_t)col0, v);
+          float* rp = run + col0 * 128 + lrow;
+          if (!last) {
+            tmem_ld_wait();
+            if (col0 + 16 >= g.n_eff) {  // main accumulator fully read: hand it back to the MMA warp
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(acc_empty0);
+            }
+            if (first) {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) rp[jj * 128] = __uint_as_float(v[jj]);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) rp[jj * 128] += __uint_as_float(v[jj]);
+            }
+          } else {
+            uint32_t w[16];
+            tmem_ld_32x32b_x16(tq + TMEM_SMALL2 + (uint32_t)col0, w);
+            tmem_ld_wait();
+            if (col0 + 16 >= g.n_eff) {  // both accumulators read: the next job may start
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(acc_empty0);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              float a = __uint_as_float(v[jj]);
+              if (!first) a += rp[jj * 128];
+              v[jj] = __float_as_uint(a + __uint_as_float(w[jj]));
+            }
+            if (row < D) {
+              const int gc = g.n0 + col0;
+              if (P.vec_ok && gc + 16 <= D) {
+                if (P.atomic_out) {
+#pragma unroll
+                  for (int jj = 0; jj < 16; jj += 4)
+                    atomicAdd(reinterpret_cast<float4*>(grow + gc + jj),
+                              make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]),
+                                          __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3])));
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 16; jj += 4)
+                    *reinterpret_cast<uint4*>(grow + gc + jj) = make_uint4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj)
+                  if (gc + jj < D) {
+                    if (P.atomic_out) atomicAdd(grow + gc + jj, __uint_as_float(v[jj]));
+                    else grow[gc + jj] = __uint_as_float(v[jj]);
+                  }
+              }
+            }
+          }
+        }
+        first = false;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == MMA_WARP2) tmem_dealloc_2cta<TMEM_COLS2>(tmem_base);
+}
+
+}  // namespace
+
+int gram2_tiles_per_class(int D, int* TT_out) {
+  const int TT = (D + TM2 - 1) / TM2;
+  if (TT_out) *TT_out = TT;
+  return TT * (TT + 1) / 2;
+}
+
+// K parts per tile so that small problems still fill the CTA pairs
+int gram2_ksplit(int64_t n, int C, int D, int num_sms) {
+  const int64_t tiles = (int64_t)C * gram2_tiles_per_class(D, nullptr);
+  const int pairs = num_sms / 2 > 0 ? num_sms / 2 : 1;
+  if (tiles >= 6 * (int64_t)pairs || tiles <= 0) return 1;
+  int64_t ks = (4 * (int64_t)pairs + tiles - 1) / tiles;
+  const int64_t avg = C > 0 ? n / C : n;
+  const int64_t cap = avg / 512 > 1 ? avg / 512 : 1;  // keep >= 512 samples per part
+  if (ks > cap) ks = cap;
+  if (ks > 64) ks = 64;
+  return (int)(ks < 1 ? 1 : ks);
+}
+
+size_t gram2_workspace_bytes(int C, int D, int ksplit_max) {
+  return (size_t)C * gram2_tiles_per_class(D, nullptr) * (ksplit_max > 0 ? ksplit_max : 1) * sizeof(int4) + 256;
+}
+
+cudaError_t launch_class_gram2(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate,
+                               int chain_rows, void* ws, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gram2_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM2_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (C <= 0) return cudaSuccess;
+  Gram2Params P;
+  int TT = 0;
+  const int T = gram2_tiles_per_class(D, &TT);
+  P.X = X; P.ldx = ldx; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram;
+  P.jobs = reinterpret_cast<const int4*>(ws);
+  P.D = D; P.C = C;
+  P.KS = gram2_ksplit(n, C, D, num_sms);
+  P.njobs = C * T * P.KS;
+  const int cr = chain_rows > 0 ? chain_rows : 512;
+  P.chain_kb = (cr + BK - 1) / BK;
+  P.atomic_out = (accumulate || P.KS > 1) ? 1 : 0;
+  P.vec_ok = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(gram) & 15) == 0);
+  if (P.atomic_out && !accumulate) {  // K parts are summed with red.add -> start from zero
+    cudaError_t e = cudaMemsetAsync(gram, 0, (size_t)C * D * D * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+  }
+  gram2_plan_kernel<<<1, 1024, 0, stream>>>(offsets, C, TT, P.KS, reinterpret_cast<int4*>(ws));
+  int grid = (num_sms / 2) * 2;
+  if (grid > 2 * P.njobs) grid = 2 * P.njobs;
+  gram2_tf32x3_kernel<<<grid, GRAM2_THREADS, GRAM2_SMEM, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace sqfa

@@ -69,3 +69,13 @@ cudaError_t launch_fused_loss(const float* S, const float* M, const float* F, in
                               int dist, int64_t pair_begin, int64_t pair_end, float* out, float* dF, float* ws,
                               cudaStream_t st);
 }  // namespace sqfa
+
+namespace sqfa {
+// ---- gram2.cu (K2 on CTA pairs, cta_group::2) ----
+int gram2_tiles_per_class(int D, int* TT_out);
+int gram2_ksplit(int64_t n, int C, int D, int num_sms);
+size_t gram2_workspace_bytes(int C, int D, int ksplit_max);
+cudaError_t launch_class_gram2(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate,
+                               int chain_rows, void* ws, int num_sms, cudaStream_t stream);
+}  // namespace sqfa

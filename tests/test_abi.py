@@ -44,7 +44,7 @@ def test_ctypes_prototypes_match_header(lib):
 def test_version_and_pure_queries(lib):
     assert lib.sqfa_version() >= 100
     assert lib.sqfa_bucket_workspace_bytes(1000, 10) > 0
-    assert lib.sqfa_class_gram_workspace_bytes(10) >= (10 + 5) * 4
+    assert lib.sqfa_class_gram_workspace_bytes(50000, 3072, 10) >= 10 * 78 * 16
     assert lib.sqfa_class_factor_floats(5, 0) == 50
     assert lib.sqfa_class_factor_floats(5, 2) == 60
     assert isinstance(lib.sqfa_last_error(), bytes)

@@ -8,16 +8,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import make_class_data
 
 lib = _lib.load()
+if len(sys.argv) > 1: lib.sqfa_debug_set_gram_variant(int(sys.argv[1]))
 dev = torch.device("cuda")
 
 def gram_with(X, perm, offsets, means, C, ks):
     n, D = X.shape
     g = torch.empty(C, D, D, device=dev)
-    wsb = lib.sqfa_class_gram_workspace_bytes(C)
+    wsb = lib.sqfa_class_gram_workspace_bytes(n, D, C)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     st = _lib.stream_ptr()
     _lib.check(lib.sqfa_class_gram(_lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(means),
-                                   D, C, _lib.ptr(g), 0, ks, _lib.ptr(ws), wsb, st), "gram")
+                                   n, D, C, _lib.ptr(g), 0, ks, _lib.ptr(ws), wsb, st), "gram")
     return g
 
 def time_it(fn, reps=5):
