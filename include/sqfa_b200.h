@@ -100,10 +100,6 @@ int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int6
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
                     void* ws, size_t ws_bytes, sqfa_stream_t stream);
 
-/* Bring-up switch between the two tensor-core schedules of sqfa_class_gram: 1 = one CTA per
- * 128 x 256 tile, 2 = CTA pairs on 256 x 256 tiles (tcgen05 cta_group::2). Same results. */
-int sqfa_debug_set_gram_variant(int variant);
-
 /* Statistics epilogue (statistics.py:43-47, 84-93, 116, 120-122):
  *   cov[c] = (gram[c] - n_c d d^T) / (n_c - ddof),  d = means[c] - shift[c]  (shift NULL -> d = 0)
  *   ddof = 1: unbiased estimate; ddof = 0: `assume_centered` (statistics.py:116)

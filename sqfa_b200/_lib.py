@@ -42,7 +42,6 @@ SIGNATURES = {
         c_int,
         [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_size, c_ptr],
     ),
-    "sqfa_debug_set_gram_variant": (c_int, [c_int]),
     "sqfa_stats_epilogue_workspace_bytes": (c_size, [c_i32]),
     "sqfa_stats_epilogue": (
         c_int,

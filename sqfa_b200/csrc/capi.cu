@@ -9,7 +9,6 @@
 namespace {
 
 thread_local char g_err[512] = "";
-int g_gram_variant = 2;  // 1: one CTA per tile (gram.cu), 2: CTA pairs / cta_group::2 (gram2.cu)
 
 int fail_arg(const char* fn, const char* what, int code = SQFA_E_INVALID) {
   snprintf(g_err, sizeof(g_err), "%s: %s", fn, what);
@@ -95,10 +94,8 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
 size_t sqfa_class_gram_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes) {
   if (n_classes <= 0 || n_dim <= 0) return 256;
   const int sms = sm_count_cached();
-  const size_t v1 = sqfa::gram_workspace_bytes(n_classes);
-  const size_t v2 = sqfa::gram2_workspace_bytes(n_classes, n_dim,
-                                                sqfa::gram2_ksplit(n < 0 ? 0 : n, n_classes, n_dim, sms > 0 ? sms : 148));
-  return v1 > v2 ? v1 : v2;
+  return sqfa::gram_workspace_bytes(n_classes, n_dim,
+                                    sqfa::gram_ksplit(n < 0 ? 0 : n, n_classes, n_dim, sms > 0 ? sms : 148));
 }
 
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
@@ -110,21 +107,12 @@ int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int6
   if (n < 0) return fail_arg(__func__, "bad argument");
   if (ws_bytes < sqfa_class_gram_workspace_bytes(n, n_dim, n_classes))
     return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
-  if ((int64_t)n_classes * sqfa::gram_tiles_per_class(n_dim, nullptr, nullptr) > (1ll << 30) / 4096)
+  if ((int64_t)n_classes * sqfa::gram_tiles_per_class(n_dim, nullptr) > (1ll << 30) / 4096)
     return fail_arg(__func__, "too many (class, tile) jobs", SQFA_E_UNSUPPORTED);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail_arg(__func__, "no CUDA device");
-  if (g_gram_variant == 2)
-    return wrap(__func__, sqfa::launch_class_gram2(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram,
-                                                   accumulate, chain_rows, ws, sms, S(stream)));
-  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n_dim, n_classes, gram, accumulate,
-                                                chain_rows, static_cast<int*>(ws), sms, S(stream)));
-}
-
-int sqfa_debug_set_gram_variant(int variant) {
-  if (variant != 1 && variant != 2) return fail_arg(__func__, "variant must be 1 (single CTA) or 2 (CTA pair)");
-  g_gram_variant = variant;
-  return 0;
+  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram, accumulate,
+                                                chain_rows, ws, sms, S(stream)));
 }
 
 size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes) {

@@ -4,29 +4,33 @@
 //
 // Replaces the per-class loop of the reference (gather `points[indices]`, centre, einsum
 // "ij,ik->jk"):  /root/reference/src/sqfa/statistics.py:36-47 and :113-122.
+// Only the 256 x 256 tiles that intersect the upper triangle are computed; K3 mirrors them.
 //
-// Data flow per CTA (persistent, one CTA per SM, dynamic job counter):
-//   12 producer warps: one thread per operand column gathers the class rows through the bucket
-//                      permutation (coalesced 128 B per warp and row) straight into registers
-//                      (no raw staging in smem -- shared-memory bandwidth is the binding resource
-//                      for 3xTF32), subtracts the class shift, splits hi/lo and
-//                      stores both as 16-byte chunks of the K-major UMMA operand layout,
-//                      fence.proxy.async, arrive on full[stage].
-//   1 MMA warp       : one elected lane issues 3 tcgen05.mma per K=8 step (lo*hi, hi*lo, hi*hi),
-//                      tcgen05.commit -> empty[stage]; after the last K block commit -> tmem_full.
-//   epilogue         : the producer warps read the 128 x N accumulator with tcgen05.ld and store
-//                      (or red.add when the class is split along K / accumulating) to gram.
+// Two CTAs of a cluster (one SM each) share one tcgen05.mma.cta_group::2 with M = 256, N = 256:
+// CTA r supplies the 128 operand columns m0 + 128 r .. of A and HALF of B (n0 + (N/2) r ..) from its
+// own shared memory, the tensor cores of both SMs compute 128 x 256 accumulators each (TMEM of
+// each SM). Relative to one CTA per 128 x 256 tile this cuts, per SM and per MMA cycle, the operand
+// bytes read from shared memory and the transform work (gather + centre + hi/lo split + store) by
+// 1/3 -- shared-memory bandwidth and instruction issue are what bound 3xTF32.
 //
-// Only tiles that intersect the upper triangle are computed; K3 mirrors them.
-//
-// Accuracy note (measured on B200, tools/exp_gram.py): the tensor core truncates when it adds
-// into the fp32 accumulator, a bias of about -2^-25 of the accumulator per tcgen05.mma. Two
-// counter-measures keep the Gram at fp32 level: (1) the tiny cross terms (lo*hi, hi*lo) go to their
-// OWN accumulator (TMEM columns 256..511) so only one accumulate per K=8 step hits the large
-// one; (2) a class is cut into chains of at most CHAIN_ROWS samples (device-side job plan), every
-// chain accumulates from zero and is added to `gram` with fp32 round-to-nearest red.global.add.
+// Warp roles per CTA (21 warps, 80 registers each):
+//   0-15  producers : a thread owns one operand column and half of a stage's 16 samples; it gathers
+//                     them through the bucket permutation straight into registers (4 stages of
+//                     loads in flight), centres, splits hi/lo, stores K-major UMMA operands and
+//                     its warp arrives on the LEADER's full[s]
+//   16    MMA       : leader CTA only; per K=8 step 3 tcgen05.mma.cta_group::2 (cross terms into
+//                     their own TMEM accumulator, hi*hi into the main one), multicast commits
+//   17-20 epilogue  : the tensor core truncates when it adds into its fp32 accumulator (bias
+//                     ~ -2^-25 per MMA, measured), so the main accumulator only ever holds a CHAIN
+//                     of <= chain_rows samples: at every chain end these warps add it (fp32,
+//                     round-to-nearest) to a 128 x 256 running sum in shared memory and hand the
+//                     accumulator back; at the end of the tile they add the cross-term accumulator
+//                     and store the tile (red.global.add only when a tile is split along K).
+// Jobs (class, tile, K part) are listed by a device-side plan (largest classes first) and dealt
+// round-robin to the CTA pairs: no atomics, no host sync, no cluster barrier per job.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "ptx.cuh"
@@ -36,481 +40,439 @@ namespace sqfa {
 
 namespace {
 
-constexpr int BM = 128;  // output rows per tile  (A operand width, UMMA M)
-constexpr int BN = 256;  // output cols per tile  (B operand width, UMMA N max)
-constexpr int BK = 16;   // samples per pipeline stage (2 UMMA K-steps of 8)
-constexpr int STAGES = 4;
-constexpr int PROD_WARPS = (BM + BN) / 32;  // 12: one producer thread per operand column
-constexpr int GRAM_THREADS = (PROD_WARPS + 1) * 32;
-
+constexpr int TM2 = 256;  // tile rows    (UMMA M over the CTA pair)
+constexpr int TN2 = 256;  // tile columns (UMMA N)
+constexpr int BK = 16;    // samples per stage
+constexpr int STAGES2 = 3;
+constexpr int PROD_WARPS2 = 16;  // per 32-column group two warps: samples 0-7 and 8-15 of a stage
+constexpr int HR = BK / 2;       // samples per producer thread and stage
+constexpr int PREFETCH = 4;      // stages of loads in flight per producer thread (registers)
+constexpr int EPI_WARPS2 = 4;   // one per TMEM lane quarter
+constexpr int MMA_WARP2 = PROD_WARPS2;
+constexpr int GRAM2_THREADS = (PROD_WARPS2 + 1 + EPI_WARPS2) * 32;
+constexpr int OP_BYTES = 128 * BK * 4;                    // 8 KB: 128 columns x 16 samples
+constexpr int STAGE2_BYTES = 4 * OP_BYTES;                // A_hi, A_lo, B_hi, B_lo = 32 KB
+constexpr int RUN_BYTES = 128 * TN2 * 4;                  // 128 KB running sum [col][row]
+constexpr int GRAM2_SMEM = STAGES2 * STAGE2_BYTES + RUN_BYTES + 1024;
 // Operand layout in shared memory: K-major, no swizzle ("interleaved" core matrices), pinned on
-// hardware by tools/umma_probe.py:  element (column c, sample k) of an operand of width W lives at
-//   (k/4) * (W*16)  +  (c/8) * 128  +  (c%8) * 16  +  (k%4) * 4      bytes,
-// i.e. 8x(4 samples) core matrices of 128 contiguous bytes; LBO = W*16 (next 4 samples),
+// hardware by tools/umma_probe.py: element (column c, sample k) of a 128-column operand lives at
+//   (k/4) * 2048 + (c/8) * 128 + (c%8) * 16 + (k%4) * 4   bytes,
+// i.e. 8 x (4 samples) core matrices of 128 contiguous bytes; LBO = 2048 (next 4 samples),
 // SBO = 128 (next 8 columns). One tcgen05.mma (K = 8 tf32) consumes two k-chunks.
-constexpr int A_BYTES = BM * BK * 4;                    //  8 KB
-constexpr int B_BYTES = BN * BK * 4;                    // 16 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi+lo for A and B = 48 KB
-constexpr int GRAM_SMEM = STAGES * STAGE_BYTES + 1024;  // + alignment slack
-constexpr uint32_t TMEM_COLS = 512;   // [0,256): hi*hi accumulator, [256,512): cross-term accumulator
-constexpr uint32_t TMEM_SMALL = 256;
-constexpr int CHAIN_ROWS = 512;        // samples per accumulation chain (64 accumulates -> bias < 2e-6)
-constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, OP_SBO = 128;
-constexpr uint32_t LAYOUT_NONE = 0;
+constexpr uint32_t OP_LBO = 128 * 16, OP_SBO2 = 128;
+constexpr uint32_t TMEM_COLS2 = 512, TMEM_SMALL2 = 256;
 
-__device__ float g_zero[4] = {0.f, 0.f, 0.f, 0.f};  // what out-of-range operand columns read
+__device__ float g_zero[4] = {0.f, 0.f, 0.f, 0.f};
 
 struct GramParams {
   const float* X;
   int64_t ldx;
-  const int32_t* perm;       // rows sorted by class (stable)
-  const int64_t* offsets;    // C+1 class offsets into perm
-  const float* shift;        // C x D (or nullptr -> 0)
-  float* gram;               // C x D x D
-  int* job_counter;          // [0] dynamic job counter
-  const int* job_base;       // C+1 prefix sums of jobs per class (built by gram_plan_kernel)
-  int D;
-  int C;
-  int TM, TN, T;             // tile grid and tiles per class
-  int chain_rows;            // samples per accumulation chain
-  int vec_ok;                // gram rows 16-byte aligned -> red.global.add.v4.f32 in the epilogue
+  const int32_t* perm;
+  const int64_t* offsets;
+  const float* shift;
+  float* gram;
+  const int4* jobs;  // (class, tile row, tile col, K part)
+  int njobs;
+  int D, C, KS;
+  int chain_kb;      // stages per accumulation chain
+  int atomic_out;    // KS > 1 or accumulate: red.add into gram, else plain store
+  int vec_ok;
+  int idx32;         // every element index row * ldx + col fits 32 bits
+  int flags;         // tuning switches (env SQFA_GRAM_FLAGS): bit 0 = no A-as-B reuse on diagonal tiles
 };
 
-// jobs of class c = chains_c * T, chains_c = max(1, ceil(n_c / chain_rows));  job_base = exclusive scan
-__global__ void __launch_bounds__(1024) gram_plan_kernel(const int64_t* __restrict__ offsets, int C, int T,
-                                                         int chain_rows, int* __restrict__ job_base) {
-  __shared__ int s_sum[1024];
-  const int tid = threadIdx.x;
-  const int per = (C + 1023) / 1024;
-  const int lo = tid * per, hi = min(C, lo + per);
-  int sum = 0;
-  for (int c = lo; c < hi; ++c) {
+// Job list: classes in descending size, tiles of a class adjacent (they share the gathered rows
+// in L2), K parts innermost.  job = ((rank * T) + t) * KS + ks
+__global__ void __launch_bounds__(1024) gram_plan_kernel(const int64_t* __restrict__ offsets, int C, int TT, int KS,
+                                                          int4* __restrict__ jobs) {
+  const int T = TT * (TT + 1) / 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int64_t n_c = offsets[c + 1] - offsets[c];
-    const int chains = n_c > 0 ? (int)((n_c + chain_rows - 1) / chain_rows) : 1;
-    sum += chains * T;
+    int rank = 0;
+    for (int o = 0; o < C; ++o) {
+      const int64_t n_o = offsets[o + 1] - offsets[o];
+      rank += (n_o > n_c || (n_o == n_c && o < c)) ? 1 : 0;
+    }
+    int t = 0;
+    for (int tm = 0; tm < TT; ++tm)
+      for (int tn = tm; tn < TT; ++tn, ++t)
+        for (int ks = 0; ks < KS; ++ks) jobs[((int64_t)rank * T + t) * KS + ks] = make_int4(c, tm, tn, ks);
   }
-  s_sum[tid] = sum;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int v = tid >= o ? s_sum[tid - o] : 0;
-    __syncthreads();
-    s_sum[tid] += v;
-    __syncthreads();
-  }
-  int run = s_sum[tid] - sum;
-  for (int c = lo; c < hi; ++c) {
-    const int64_t n_c = offsets[c + 1] - offsets[c];
-    const int chains = n_c > 0 ? (int)((n_c + chain_rows - 1) / chain_rows) : 1;
-    job_base[c] = run;
-    run += chains * T;
-  }
-  if (tid == 1023) job_base[C] = s_sum[1023];
 }
 
-__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_tf32x3_kernel(const GramParams P) {
+struct JobGeom {
+  int c, m0, n0, n_eff, nh;
+  bool diag;  // full diagonal tile: each CTA's B half is the same data as its A operand
+  int64_t row_begin, n_c;
+  int kb0, kb1;
+};
+
+__device__ __forceinline__ JobGeom decode_job(const GramParams& P, int j) {
+  const int4 jb = __ldg(P.jobs + j);
+  JobGeom g;
+  g.c = jb.x;
+  g.m0 = jb.y * TM2;
+  g.n0 = jb.z * TN2;
+  int n_eff = P.D - g.n0;
+  n_eff = n_eff > TN2 ? TN2 : ((n_eff + 31) & ~31);  // multiple of 32: each CTA holds n_eff / 2 columns of B
+  g.n_eff = n_eff;
+  g.nh = n_eff >> 1;
+  g.diag = (jb.y == jb.z) && n_eff == TN2 && !(P.flags & 1);
+  g.row_begin = P.offsets[g.c];
+  g.n_c = P.offsets[g.c + 1] - g.row_begin;
+  const int nkb_total = (int)((g.n_c + BK - 1) / BK);
+  g.kb0 = (int)(((int64_t)jb.w * nkb_total) / P.KS);
+  g.kb1 = (int)(((int64_t)(jb.w + 1) * nkb_total) / P.KS);
+  return g;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GRAM2_THREADS, 1)
+gram_tf32x3_kernel(const GramParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* run = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES);  // [256 cols][128 rows]
 
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[STAGES2];   // leader: 16 producer-warp arrivals (both CTAs)
+  __shared__ __align__(8) uint64_t empty_bar[STAGES2];  // per CTA: multicast tcgen05.commit
+  __shared__ __align__(8) uint64_t acc_full_bar;        // per CTA: chain finished (multicast commit)
+  __shared__ __align__(8) uint64_t acc_empty_bar;       // leader: 8 epilogue-warp arrivals (both CTAs)
   __shared__ uint32_t s_tmem_base;
-  __shared__ int s_job[4];  // class, tile, chain, chains of the class  (class < 0: no more work)
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  const bool is_mma_warp = (warp == PROD_WARPS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], PROD_WARPS);  // one arrive per producer warp
-      mbar_init(&empty_bar[s], 1);          // one tcgen05.commit
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 2 * PROD_WARPS2);
+      mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&acc_full_bar, 1);
+    mbar_init(&acc_empty_bar, 2 * EPI_WARPS2);
     mbar_fence_init();
   }
-  if (is_mma_warp) tmem_alloc<TMEM_COLS>(&s_tmem_base);
+  if (warp == MMA_WARP2) tmem_alloc_2cta<TMEM_COLS2>(&s_tmem_base);
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives remotely
   tc_fence_after_sync();
   const uint32_t tmem_base = s_tmem_base;
 
-  uint32_t stage = 0, phase = 0;  // identical evolution in producers and the MMA warp
-  uint32_t acc_phase = 0;
-
   const int D = P.D;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
-  for (;;) {
-    if (tid == 0) {
-      // ---- fetch and decode job -> (class, chain, tile); tiles of one chain are adjacent jobs so
-      //      concurrently running CTAs share the gathered rows in L2 ----
-      const int job = atomicAdd(P.job_counter, 1);
-      if (job >= __ldg(P.job_base + P.C)) {
-        s_job[0] = -1;
-      } else {
-        int lo = 0, hi = P.C;  // largest c with job_base[c] <= job
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(P.job_base + mid) <= job) lo = mid; else hi = mid;
-        }
-        const int rem = job - __ldg(P.job_base + lo);
-        s_job[0] = lo;
-        s_job[1] = rem % P.T;
-        s_job[2] = rem / P.T;
-        s_job[3] = (__ldg(P.job_base + lo + 1) - __ldg(P.job_base + lo)) / P.T;
-      }
-    }
-    __syncthreads();
-    const int c = s_job[0];
-    if (c < 0) break;
-    int t = s_job[1];
-    const int chain = s_job[2], chains = s_job[3];
-    int tm = 0;
-    for (;; ++tm) {  // tiles of row-block tm: tn in [tm/2, TN)
-      const int cnt = P.TN - (tm >> 1);
-      if (t < cnt) break;
-      t -= cnt;
-    }
-    const int tn = (tm >> 1) + t;
-    const int m0 = tm * BM;
-    const int n0 = tn * BN;
-    int n_eff = D - n0;
-    n_eff = n_eff > BN ? BN : ((n_eff + 15) & ~15);
-
-    const int64_t row_begin = P.offsets[c];
-    const int64_t n_c = P.offsets[c + 1] - row_begin;
-    const int nkb_total = (int)((n_c + BK - 1) / BK);
-    const int kb0 = (int)(((int64_t)chain * nkb_total) / chains);
-    const int kb1 = (int)(((int64_t)(chain + 1) * nkb_total) / chains);
-    const int nkb = kb1 - kb0;
-
-    if (!is_mma_warp) {
-      // =========================== producers ===========================
-      // thread <-> one operand column: warps 0-3 the 128 A columns, warps 4-11 the 256 B columns.
-      // Per stage it gathers that column of the 16 sample rows (coalesced 128 B per warp and row),
-      // centres, splits hi/lo and writes 4+4 16-byte chunks (4 consecutive samples each).
-      const bool isA = warp < BM / 32;
-      const int cw = isA ? (warp * 32 + lane) : (warp * 32 + lane - BM);  // column inside the operand
-      const int col = (isA ? m0 : n0) + cw;                               // column of X
-      const bool col_ok = col < D && (isA || cw < n_eff);
-      // The inner loops are instruction-issue bound, so everything per-thread is folded into three
-      // values: a column base pointer, a row stride in bytes and the centring shift. Columns
-      // outside the matrix read a device zero with stride 0 and shift 0 -> exact zeros, no selects.
+  if (warp < PROD_WARPS2) {
+    // =========================== producers (both CTAs) ===========================
+    uint32_t stage = 0, phase = 0;
+    const int grp = warp & 7, half = warp >> 3;  // 32-column group (0-3: A, 4-7: B) and sample half
+    const bool isA = grp < 4;
+    const int cw = (grp & 3) * 32 + lane;  // column inside this CTA's 128-wide operand
+    // K-major chunk (4 samples x 16 B) of this column; this thread's samples are chunks 2*half, 2*half+1
+    const uint32_t hi_base =
+        smem_u32(smem) + (isA ? 0 : 2 * OP_BYTES) + ((cw >> 3) * 128 + (cw & 7) * 16) + 2 * half * OP_LBO;
+    const uint32_t lo_base = hi_base + OP_BYTES;  // 32-bit shared addresses: no 64-bit math in the loop
+    const int lane8 = lane & (HR - 1);
+    const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's barriers, cluster window
+    for (int j = pair; j < P.njobs; j += npairs) {
+      const JobGeom g = decode_job(P, j);
+      const int kb0 = g.kb0, kb1 = g.kb1;
+      const int64_t n_c = g.n_c;
+      const int col = isA ? (g.m0 + 128 * (int)rank + cw) : (g.n0 + g.nh * (int)rank + cw);
+      const bool col_ok = col < D && (isA || cw < g.nh);
+      // Instruction issue is a bottleneck of these loops, so everything per-thread is folded into a
+      // column base pointer, a row stride in bytes and the centring shift. Columns outside the
+      // matrix read a device zero with stride 0 and shift 0 -> exact zeros without selects.
       const char* xcol = col_ok ? reinterpret_cast<const char*>(P.X + col) : reinterpret_cast<const char*>(g_zero);
       const uint32_t ldb = col_ok ? (uint32_t)(P.ldx * 4) : 0u;
-      const float sh = (P.shift != nullptr && col_ok) ? __ldg(P.shift + (int64_t)c * D + col) : 0.f;
-      const uint32_t op_lbo = isA ? A_LBO : B_LBO;
-      uint8_t* const hi_base = smem + (isA ? 0u : 2u * A_BYTES) + (uint32_t)((cw >> 3) * 128 + (cw & 7) * 16);
-      uint8_t* const lo_base = hi_base + (isA ? A_BYTES : B_BYTES);
-      const int32_t* const permc = P.perm + row_begin;
-      const int lane16 = lane & (BK - 1);
+      const bool idx32 = P.idx32 != 0;
+      // idx32 path: columns outside the matrix read X[0][0] with stride 0 and use it as their
+      // shift -> exact zeros again, and the base pointer stays the (uniform) kernel argument
+      const float sh = col_ok ? (P.shift != nullptr ? __ldg(P.shift + (int64_t)g.c * D + col) : 0.f)
+                              : (idx32 ? __ldg(P.X) : 0.f);
+      const int32_t* const permc = P.perm + g.row_begin;
+      if (g.diag && !isA) {
+        // diagonal tile: the MMA reads this CTA's A buffers as its B half; the B warps only keep
+        // the barrier protocol going (arrival counts are fixed)
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
 
-      float buf[3][BK];  // three stages of loads in flight per thread (registers)
-      // lane r < 16 holds the row id of sample r of the NEXT stage to issue (fetched a stage ahead);
-      // samples past the end of the chain's class read row 0 and are masked in consume_tail().
+      float buf[PREFETCH][HR];
+      // lane r < 8 holds sample (8 * half + r) of a stage: its row id times the row stride, so the
+      // per-element address is one shuffle, one add and one widening multiply-add away.
+      // idx32: element indices fit 32 bits (always, unless a shard holds more than 2^32 floats).
+      const uint32_t ldx32 = (uint32_t)P.ldx;       // applied by the lane that HOLDS the row id
+      const uint32_t rmul = col_ok ? 1u : 0u;       // applied by the lane that READS it
+      const uint32_t col32 = col_ok ? (uint32_t)col : 0u;
+      const float* const xb = P.X;
       auto load_row = [&](int kb) -> uint32_t {
-        const int64_t k = (int64_t)kb * BK + lane16;
-        return (kb < kb1 && k < n_c) ? (uint32_t)__ldg(permc + k) : 0u;
+        const int64_t k = (int64_t)kb * BK + HR * half + lane8;
+        const uint32_t row = (kb < kb1 && k < n_c) ? (uint32_t)__ldg(permc + k) : 0u;
+        return idx32 ? row * ldx32 : row;
       };
-      uint32_t nextrow = load_row(kb0);
-      auto issue = [&](int kb, float(&b)[BK]) {
+      // row ids travel two issue() calls ahead of their use, so their load latency is never waited on
+      uint32_t nextrow = load_row(kb0), nextrow2 = load_row(kb0 + 1);
+      auto issue = [&](int kb, float(&b)[HR]) {
         const uint32_t myrow = nextrow;
-        nextrow = load_row(kb + 1);
+        if (P.flags & 2) { nextrow = load_row(kb + 1); }
+        else { nextrow = nextrow2; nextrow2 = load_row(kb + 2); }
+        if (idx32) {
 #pragma unroll
-        for (int r = 0; r < BK; ++r) {  // SHFL + IMAD.WIDE.U32 + LDG per element, nothing else
-          const uint32_t row = __shfl_sync(0xffffffffu, myrow, r);
-          uint64_t addr;  // one IMAD.WIDE.U32: base + row * stride
-          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(ldb), "l"(xcol));
-          b[r] = __ldg(reinterpret_cast<const float*>(addr));
+          for (int r = 0; r < HR; ++r) {  // SHFL + IADD + IMAD.WIDE.U32 (uniform base) + LDG per element
+            const uint32_t e = __shfl_sync(0xffffffffu, myrow, r) * rmul + col32;
+            uint64_t addr;
+            asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(e), "l"(xb));
+            b[r] = __ldg(reinterpret_cast<const float*>(addr));
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < HR; ++r) {
+            const uint32_t row = __shfl_sync(0xffffffffu, myrow, r);
+            uint64_t addr;
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(ldb), "l"(xcol));
+            b[r] = __ldg(reinterpret_cast<const float*>(addr));
+          }
         }
       };
-      auto store_stage = [&](const float(&x)[BK]) {
-        uint8_t* hp = hi_base + stage * STAGE_BYTES;
-        uint8_t* lp = lo_base + stage * STAGE_BYTES;
+      auto consume = [&](int kb, float(&b)[HR]) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int64_t nv = n_c - (int64_t)kb * BK - HR * half;  // valid samples among this thread's
+        float x[HR];
+        if (nv >= HR) {  // full: FADD, CVT, FADD per element
 #pragma unroll
-        for (int kc = 0; kc < BK / 4; ++kc) {
+          for (int r = 0; r < HR; ++r) x[r] = b[r] - sh;
+        } else {         // ragged last stage of the class: padded samples are exact zeros
+#pragma unroll
+          for (int r = 0; r < HR; ++r) x[r] = (r < (int)nv) ? b[r] - sh : 0.f;
+        }
+        const uint32_t hp = hi_base + stage * STAGE2_BYTES;
+        const uint32_t lp = lo_base + stage * STAGE2_BYTES;
+#pragma unroll
+        for (int kc = 0; kc < HR / 4; ++kc) {
           float4 h, l;
           h.x = to_tf32(x[4 * kc + 0]); l.x = x[4 * kc + 0] - h.x;
           h.y = to_tf32(x[4 * kc + 1]); l.y = x[4 * kc + 1] - h.y;
           h.z = to_tf32(x[4 * kc + 2]); l.z = x[4 * kc + 2] - h.z;
           h.w = to_tf32(x[4 * kc + 3]); l.w = x[4 * kc + 3] - h.w;
-          *reinterpret_cast<float4*>(hp + kc * op_lbo) = h;
-          *reinterpret_cast<float4*>(lp + kc * op_lbo) = l;
+          st_shared_v4(hp + kc * OP_LBO, h);
+          st_shared_v4(lp + kc * OP_LBO, l);
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
       };
-      auto consume = [&](int kb, float(&b)[BK]) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int64_t nv = n_c - (int64_t)kb * BK;  // valid rows of this stage
-        float x[BK];
-        if (nv >= BK) {  // full stage (all but the last of a class): FADD, CVT, FADD per element
 #pragma unroll
-          for (int r = 0; r < BK; ++r) x[r] = b[r] - sh;
-        } else {
+      for (int u = 0; u < PREFETCH; ++u)
+        if (kb0 + u < kb1) issue(kb0 + u, buf[u]);
+      for (int kb = kb0; kb < kb1; kb += PREFETCH) {
 #pragma unroll
-          for (int r = 0; r < BK; ++r) x[r] = (r < (int)nv) ? b[r] - sh : 0.f;
-        }
-        store_stage(x);
-      };
-
-      if (nkb > 0) issue(kb0, buf[0]);
-      if (nkb > 1) issue(kb0 + 1, buf[1]);
-      if (nkb > 2) issue(kb0 + 2, buf[2]);
-      for (int kb = kb0; kb < kb1; kb += 3) {
-        consume(kb, buf[0]);
-        if (kb + 3 < kb1) issue(kb + 3, buf[0]);
-        if (kb + 1 < kb1) {
-          consume(kb + 1, buf[1]);
-          if (kb + 4 < kb1) issue(kb + 4, buf[1]);
-        }
-        if (kb + 2 < kb1) {
-          consume(kb + 2, buf[2]);
-          if (kb + 5 < kb1) issue(kb + 5, buf[2]);
+        for (int u = 0; u < PREFETCH; ++u) {
+          if (kb + u < kb1) {
+            consume(kb + u, buf[u]);
+            if (kb + u + PREFETCH < kb1) issue(kb + u + PREFETCH, buf[u]);
+          }
         }
       }
-
-      // =========================== epilogue ===========================
-      // warp w may read TMEM lanes [32*(w%4), +32); the three warps of a lane quarter take the
-      // 32-column chunks cc = w/4, w/4 + 3, w/4 + 6.
-      const int q = warp & 3;
-      const int row = m0 + 32 * q + lane;
-      float* grow = P.gram + ((int64_t)c * D + row) * D;
-      if (nkb > 0) {
-        mbar_wait(&tmem_full_bar, acc_phase);
+    }
+  } else if (warp == MMA_WARP2) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (leader) {
+      uint32_t stage = 0, phase = 0, chain_phase = 0;
+      for (int j = pair; j < P.njobs; j += npairs) {
+        const JobGeom g = decode_job(P, j);
+        const uint32_t idesc = make_idesc_tf32(TM2, (uint32_t)g.n_eff, 0, 0);
+        for (int cb = g.kb0; cb < g.kb1; cb += P.chain_kb) {
+          const int ce = min(g.kb1, cb + P.chain_kb);
+          // the epilogue warps of both CTAs must have drained the previous chain
+          mbar_wait_cluster(&acc_empty_bar, chain_phase ^ 1);
+          chain_phase ^= 1;
+          tc_fence_after_sync();
+          for (int kb = cb; kb < ce; ++kb) {
+            mbar_wait_cluster(&full_bar[stage], phase);
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t st = smem_u32(smem + stage * STAGE2_BYTES);
+              const uint32_t a_hi = st, a_lo = st + OP_BYTES;
+              const uint32_t b_hi = g.diag ? a_hi : st + 2 * OP_BYTES, b_lo = g.diag ? a_lo : st + 3 * OP_BYTES;
+#pragma unroll
+              for (int k8 = 0; k8 < BK / 8; ++k8) {
+                const uint32_t ko = k8 * 2 * OP_LBO;
+                const uint64_t dA_hi = make_smem_desc(a_hi + ko, OP_LBO, OP_SBO2, 0);
+                const uint64_t dA_lo = make_smem_desc(a_lo + ko, OP_LBO, OP_SBO2, 0);
+                const uint64_t dB_hi = make_smem_desc(b_hi + ko, OP_LBO, OP_SBO2, 0);
+                const uint64_t dB_lo = make_smem_desc(b_lo + ko, OP_LBO, OP_SBO2, 0);
+                const uint32_t acc_small = (kb > g.kb0 || k8 > 0) ? 1u : 0u;  // zeroed once per job
+                const uint32_t acc_main = (kb > cb || k8 > 0) ? 1u : 0u;      // zeroed at every chain start
+                umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_lo, dB_hi, idesc, acc_small);
+                umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_hi, dB_lo, idesc, 1u);
+                umma_tf32_ss_2cta(tmem_base, dA_hi, dB_hi, idesc, acc_main);
+              }
+              umma_commit_2cta(&empty_bar[stage], 3);
+              if (kb == ce - 1) umma_commit_2cta(&acc_full_bar, 3);
+            }
+            __syncwarp();
+            if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue warps (both CTAs) ===========================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int lrow = 32 * q + lane;
+    const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty_bar), 0);
+    uint32_t acc_phase = 0;
+    for (int j = pair; j < P.njobs; j += npairs) {
+      const JobGeom g = decode_job(P, j);
+      const int row = g.m0 + 128 * (int)rank + lrow;
+      float* grow = P.gram + ((int64_t)g.c * D + row) * D;
+      if (g.kb1 <= g.kb0) {  // empty class / empty K part: the tile contribution is exactly zero
+        if (!P.atomic_out && row < D)
+          for (int cc = 0; cc < g.n_eff; ++cc)
+            if (g.n0 + cc < D) grow[g.n0 + cc] = 0.f;
+        continue;
+      }
+      bool first = true;
+      for (int cb = g.kb0; cb < g.kb1; cb += P.chain_kb) {
+        const bool last = cb + P.chain_kb >= g.kb1;
+        mbar_wait(&acc_full_bar, acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
 #pragma unroll 1
-        for (int cc = warp >> 2; cc < BN / 32; cc += PROD_WARPS / 4) {
-          const int col0 = cc * 32;
-          if (col0 >= n_eff) break;  // warp-uniform
-          uint32_t v[32], w[32];
-          const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col0;
-          tmem_ld_32x32b_x32(ta, v);
-          tmem_ld_32x32b_x32(ta + TMEM_SMALL, w);
-          tmem_ld_wait();
-          if (row < D) {
-            const int gc = n0 + col0;
-            if (P.vec_ok && gc + 32 <= D) {
+        for (int col0 = 0; col0 < g.n_eff; col0 += 16) {  // 16 columns at a time: the role fits 80 registers
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tq + (uint32_t)col0, v);
+          float* rp = run + col0 * 128 + lrow;
+          if (!last) {
+            tmem_ld_wait();
+            if (col0 + 16 >= g.n_eff) {  // main accumulator fully read: hand it back to the MMA warp
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(acc_empty0);
+            }
+            if (first) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                atomicAdd(reinterpret_cast<float4*>(grow + gc + j),
-                          make_float4(__uint_as_float(v[j]) + __uint_as_float(w[j]),
-                                      __uint_as_float(v[j + 1]) + __uint_as_float(w[j + 1]),
-                                      __uint_as_float(v[j + 2]) + __uint_as_float(w[j + 2]),
-                                      __uint_as_float(v[j + 3]) + __uint_as_float(w[j + 3])));
+              for (int jj = 0; jj < 16; ++jj) rp[jj * 128] = __uint_as_float(v[jj]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (gc + j < D) atomicAdd(grow + gc + j, __uint_as_float(v[j]) + __uint_as_float(w[j]));
+              for (int jj = 0; jj < 16; ++jj) rp[jj * 128] += __uint_as_float(v[jj]);
+            }
+          } else {
+            uint32_t w[16];
+            tmem_ld_32x32b_x16(tq + TMEM_SMALL2 + (uint32_t)col0, w);
+            tmem_ld_wait();
+            if (col0 + 16 >= g.n_eff) {  // both accumulators read: the next job may start
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(acc_empty0);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              float a = __uint_as_float(v[jj]);
+              if (!first) a += rp[jj * 128];
+              v[jj] = __float_as_uint(a + __uint_as_float(w[jj]));
+            }
+            if (row < D) {
+              const int gc = g.n0 + col0;
+              if (P.vec_ok && gc + 16 <= D) {
+                if (P.atomic_out) {
+#pragma unroll
+                  for (int jj = 0; jj < 16; jj += 4)
+                    atomicAdd(reinterpret_cast<float4*>(grow + gc + jj),
+                              make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]),
+                                          __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3])));
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 16; jj += 4)
+                    *reinterpret_cast<uint4*>(grow + gc + jj) = make_uint4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj)
+                  if (gc + jj < D) {
+                    if (P.atomic_out) atomicAdd(grow + gc + jj, __uint_as_float(v[jj]));
+                    else grow[gc + jj] = __uint_as_float(v[jj]);
+                  }
+              }
             }
           }
         }
-        tc_fence_before_sync();
-      }
-    } else {
-      // =========================== MMA issuer ===========================
-      const uint32_t idesc = make_idesc_tf32(BM, (uint32_t)n_eff, /*a K-major*/ 0, /*b K-major*/ 0);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = st + 2 * A_BYTES + B_BYTES;
-#pragma unroll
-          for (int k8 = 0; k8 < BK / 8; ++k8) {
-            const uint32_t ka = k8 * 2 * A_LBO, kbo = k8 * 2 * B_LBO;  // 8 samples = two k-chunks
-            const uint64_t dA_hi = make_smem_desc(a_hi + ka, A_LBO, OP_SBO, LAYOUT_NONE);
-            const uint64_t dA_lo = make_smem_desc(a_lo + ka, A_LBO, OP_SBO, LAYOUT_NONE);
-            const uint64_t dB_hi = make_smem_desc(b_hi + kbo, B_LBO, OP_SBO, LAYOUT_NONE);
-            const uint64_t dB_lo = make_smem_desc(b_lo + kbo, B_LBO, OP_SBO, LAYOUT_NONE);
-            const uint32_t acc = (kb > kb0 || k8 > 0) ? 1u : 0u;
-            umma_tf32_ss(tmem_base + TMEM_SMALL, dA_lo, dB_hi, idesc, acc);  // cross terms: own accumulator
-            umma_tf32_ss(tmem_base + TMEM_SMALL, dA_hi, dB_lo, idesc, 1u);
-            umma_tf32_ss(tmem_base, dA_hi, dB_hi, idesc, acc);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the stage when these MMAs have read it
-          if (kb == kb1 - 1) umma_commit(&tmem_full_bar);
-        }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        first = false;
       }
     }
-    // accumulator drained, every stage consumed -> safe to start the next job
-    __syncthreads();
   }
 
   tc_fence_before_sync();
-  __syncthreads();
-  if (is_mma_warp) tmem_dealloc<TMEM_COLS>(tmem_base);
-}
-
-// ------------------------------------------------------------------------------------------------
-// UMMA probe: one CTA, D[128 x N] = A^T B for A [K x 128], B [K x N] row-major fp32 in global,
-// staged into shared memory with a caller-chosen canonical layout / descriptor. Used by
-// tests/ and tools/ to pin the operand layout assumptions of gram_tf32x3_kernel on hardware.
-//   mode 0: MN-major, 128B swizzle, [chunk][k][128B]      (what the Gram kernel uses)
-//   mode 1: K-major, no swizzle, core matrices 8(mn) x 16B, [k/4][mn/8][8][16B]
-//   mode 2: DECODE A: A's smem is filled with its own word index (mod 2048, exact in tf32) and
-//           read through the caller's descriptor; B is a K-major selector B[k][n] = (n == k), so
-//           Dout[m][n<8] = word index the hardware fetched for A(k = n, m). K must be 8.
-//   mode 3: DECODE B: the same with the roles swapped: Dout[m<8][n] = word index of B(k = m, n).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1)
-umma_probe_kernel(const float* A, const float* B, float* Dout, int K, int N, int mode, uint32_t lbo, uint32_t sbo,
-                  uint32_t layout_type, uint32_t a_major, uint32_t b_major, uint32_t kstep_bytes) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t done_bar;
-  __shared__ uint32_t s_tmem_base;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* sA = smem;                       // up to 128 cols x K
-  uint8_t* sB = smem + 128 * K * 4;         // N cols x K
-  if (mode >= 2) {
-    // raw-filled operand: 8192 words; selector operand after it
-    float* raw = reinterpret_cast<float*>(smem);
-    for (int w = tid; w < 8192; w += blockDim.x) raw[w] = (float)(w & 2047);
-    float* sel = raw + 8192;  // K-major no-swizzle selector of width W: [k/4][W/8][8][4]
-    const int W = (mode == 2) ? N : 128;
-    for (int idx = tid; idx < 8 * W; idx += blockDim.x) {
-      const int k = idx / W, x = idx % W;
-      sel[(k / 4) * (W * 4) + (x / 8) * 32 + (x % 8) * 4 + (k % 4)] = (x == k) ? 1.f : 0.f;
-    }
-    if (tid == 0) { mbar_init(&done_bar, 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc<256>(&s_tmem_base);
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tb = s_tmem_base;
-    if (warp == 0) {
-      if (elect_one()) {
-        const uint64_t dRaw = make_smem_desc(smem_u32(raw), lbo, sbo, layout_type);
-        const uint64_t dSel = make_smem_desc(smem_u32(sel), (uint32_t)W * 16, 128, 0);
-        if (mode == 2)
-          umma_tf32_ss(tb, dRaw, dSel, make_idesc_tf32(128, (uint32_t)N, a_major, 0), 0u);
-        else
-          umma_tf32_ss(tb, dSel, dRaw, make_idesc_tf32(128, (uint32_t)N, 0, b_major), 0u);
-        umma_commit(&done_bar);
-      }
-      __syncwarp();
-    }
-    mbar_wait(&done_bar, 0);
-    tc_fence_after_sync();
-    for (int col0 = 0; col0 < N; col0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tb + ((uint32_t)(32 * warp) << 16) + (uint32_t)col0, v);
-      tmem_ld_wait();
-      const int row = 32 * warp + lane;
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < N) Dout[row * N + col0 + j] = __uint_as_float(v[j]);
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tb);
-    return;
-  }
-  // stage operands
-  for (int idx = tid; idx < K * 128; idx += blockDim.x) {
-    const int k = idx / 128, m = idx % 128;
-    uint32_t off;
-    if (mode == 0) off = (m / 32) * (K * 128) + k * 128 + ((((m % 32) / 4) ^ (k & 7)) << 4) + (m % 4) * 4;
-    else off = (k / 4) * (128 * 16) + (m / 8) * 128 + (m % 8) * 16 + (k % 4) * 4;
-    *reinterpret_cast<float*>(sA + off) = A[idx];
-  }
-  for (int idx = tid; idx < K * N; idx += blockDim.x) {
-    const int k = idx / N, n = idx % N;
-    uint32_t off;
-    if (mode == 0) off = (n / 32) * (K * 128) + k * 128 + ((((n % 32) / 4) ^ (k & 7)) << 4) + (n % 4) * 4;
-    else off = (k / 4) * (N * 16) + (n / 8) * 128 + (n % 8) * 16 + (k % 4) * 4;
-    *reinterpret_cast<float*>(sB + off) = B[idx];
-  }
-  if (tid == 0) { mbar_init(&done_bar, 1); mbar_fence_init(); }
-  if (warp == 0) tmem_alloc<256>(&s_tmem_base);
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = s_tmem_base;
-  if (warp == 0) {
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_tf32(128, (uint32_t)N, a_major, b_major);
-      for (int k8 = 0; k8 < K / 8; ++k8) {
-        const uint64_t dA = make_smem_desc(smem_u32(sA) + k8 * kstep_bytes, lbo, sbo, layout_type);
-        const uint64_t dB = make_smem_desc(smem_u32(sB) + k8 * (mode == 0 ? kstep_bytes : (kstep_bytes / 128) * N),
-                                           mode == 0 ? lbo : (lbo / 128) * N, sbo, layout_type);
-        umma_tf32_ss(tmem_base, dA, dB, idesc, k8 > 0 ? 1u : 0u);
-      }
-      umma_commit(&done_bar);
-    }
-    __syncwarp();
-  }
-  mbar_wait(&done_bar, 0);
-  tc_fence_after_sync();
-  for (int col0 = 0; col0 < N; col0 += 32) {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)col0, v);
-    tmem_ld_wait();
-    const int row = 32 * warp + lane;
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < N) Dout[row * N + col0 + j] = __uint_as_float(v[j]);
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem_base);
+  cluster_sync_all();
+  if (warp == MMA_WARP2) tmem_dealloc_2cta<TMEM_COLS2>(tmem_base);
 }
 
 }  // namespace
 
-int gram_tiles_per_class(int D, int* TM_out, int* TN_out) {
-  const int TM = (D + BM - 1) / BM, TN = (D + BN - 1) / BN;
-  int T = 0;
-  for (int tm = 0; tm < TM; ++tm) T += TN - (tm >> 1);
-  if (TM_out) *TM_out = TM;
-  if (TN_out) *TN_out = TN;
-  return T;
+int gram_tiles_per_class(int D, int* TT_out) {
+  const int TT = (D + TM2 - 1) / TM2;
+  if (TT_out) *TT_out = TT;
+  return TT * (TT + 1) / 2;
+}
+
+// K parts per tile so that small problems still fill the CTA pairs
+int gram_ksplit(int64_t n, int C, int D, int num_sms) {
+  const int64_t tiles = (int64_t)C * gram_tiles_per_class(D, nullptr);
+  const int pairs = num_sms / 2 > 0 ? num_sms / 2 : 1;
+  if (tiles >= 6 * (int64_t)pairs || tiles <= 0) return 1;
+  int64_t ks = (4 * (int64_t)pairs + tiles - 1) / tiles;
+  const int64_t avg = C > 0 ? n / C : n;
+  const int64_t cap = avg / 512 > 1 ? avg / 512 : 1;  // keep >= 512 samples per part
+  if (ks > cap) ks = cap;
+  if (ks > 64) ks = 64;
+  return (int)(ks < 1 ? 1 : ks);
+}
+
+size_t gram_workspace_bytes(int C, int D, int ksplit_max) {
+  return (size_t)C * gram_tiles_per_class(D, nullptr) * (ksplit_max > 0 ? ksplit_max : 1) * sizeof(int4) + 256;
 }
 
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                              const float* shift, int D, int C, float* gram, int accumulate, int chain_rows,
-                              int* ws, int num_sms, cudaStream_t stream) {
+                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate,
+                               int chain_rows, void* ws, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gram_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM);
+    cudaError_t e =
+        cudaFuncSetAttribute(gram_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM2_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   if (C <= 0) return cudaSuccess;
   GramParams P;
+  int TT = 0;
+  const int T = gram_tiles_per_class(D, &TT);
   P.X = X; P.ldx = ldx; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram;
-  P.job_counter = ws; P.job_base = ws + 4; P.D = D; P.C = C;
-  P.T = gram_tiles_per_class(D, &P.TM, &P.TN);
-  P.chain_rows = chain_rows > 0 ? ((chain_rows + BK - 1) / BK) * BK : CHAIN_ROWS;
+  P.jobs = reinterpret_cast<const int4*>(ws);
+  P.D = D; P.C = C;
+  P.KS = gram_ksplit(n, C, D, num_sms);
+  P.njobs = C * T * P.KS;
+  const int cr = chain_rows > 0 ? chain_rows : 512;
+  P.chain_kb = (cr + BK - 1) / BK;
+  P.atomic_out = (accumulate || P.KS > 1) ? 1 : 0;
   P.vec_ok = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(gram) & 15) == 0);
-  cudaError_t e = cudaMemsetAsync(ws, 0, 4 * sizeof(int), stream);
-  if (e != cudaSuccess) return e;
-  if (!accumulate) {  // chains are summed into gram with red.add -> start from zero
-    e = cudaMemsetAsync(gram, 0, (size_t)C * D * D * sizeof(float), stream);
+  static const int env_flags = [] { const char* e = getenv("SQFA_GRAM_FLAGS"); return e ? atoi(e) : 0; }();
+  P.flags = env_flags;
+  P.idx32 = ((double)n * (double)ldx + (double)D < 4.0e9 && !(env_flags & 4)) ? 1 : 0;
+  if (P.atomic_out && !accumulate) {  // K parts are summed with red.add -> start from zero
+    cudaError_t e = cudaMemsetAsync(gram, 0, (size_t)C * D * D * sizeof(float), stream);
     if (e != cudaSuccess) return e;
   }
-  gram_plan_kernel<<<1, 1024, 0, stream>>>(offsets, C, P.T, P.chain_rows, ws + 4);
-  gram_tf32x3_kernel<<<num_sms, GRAM_THREADS, GRAM_SMEM, stream>>>(P);
-  return cudaGetLastError();
-}
-
-size_t gram_workspace_bytes(int C) { return (size_t)(C + 1 + 4) * sizeof(int); }
-
-cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K, int N, int mode, uint32_t lbo,
-                              uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
-                              uint32_t kstep_bytes, cudaStream_t stream) {
-  const int smem = (mode >= 2 ? 8192 * 4 + 8 * 256 * 4 : (128 + N) * K * 4) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  umma_probe_kernel<<<1, 128, smem, stream>>>(A, B, Dout, K, N, mode, lbo, sbo, layout_type, a_major, b_major,
-                                              kstep_bytes);
+  gram_plan_kernel<<<1, 1024, 0, stream>>>(offsets, C, TT, P.KS, reinterpret_cast<int4*>(ws));
+  int grid = (num_sms / 2) * 2;
+  if (grid > 2 * P.njobs) grid = 2 * P.njobs;
+  gram_tf32x3_kernel<<<grid, GRAM2_THREADS, GRAM2_SMEM, stream>>>(P);
   return cudaGetLastError();
 }
 

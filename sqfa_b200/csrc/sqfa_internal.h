@@ -24,12 +24,14 @@ cudaError_t launch_stats_epilogue(const float* gram, const float* means, const f
                                   int D, int C, int estimator, int ddof, float* cov, float* sm, void* ws,
                                   cudaStream_t stream);
 
-// ---- gram.cu (K2) ----
-int gram_tiles_per_class(int D, int* TM_out, int* TN_out);
-size_t gram_workspace_bytes(int C);
+// ---- gram.cu (K2: tcgen05 cta_group::2 Gram on CTA pairs) ----
+int gram_tiles_per_class(int D, int* TT_out);
+int gram_ksplit(int64_t n, int C, int D, int num_sms);
+size_t gram_workspace_bytes(int C, int D, int ksplit_max);
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                              const float* shift, int D, int C, float* gram, int accumulate, int chain_rows,
-                              int* ws, int num_sms, cudaStream_t stream);
+                              const float* shift, int64_t n, int D, int C, float* gram, int accumulate,
+                              int chain_rows, void* ws, int num_sms, cudaStream_t stream);
+// ---- umma_probe.cu (test hook) ----
 cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K, int N, int mode, uint32_t lbo,
                               uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
                               uint32_t kstep_bytes, cudaStream_t stream);
@@ -70,12 +72,3 @@ cudaError_t launch_fused_loss(const float* S, const float* M, const float* F, in
                               cudaStream_t st);
 }  // namespace sqfa
 
-namespace sqfa {
-// ---- gram2.cu (K2 on CTA pairs, cta_group::2) ----
-int gram2_tiles_per_class(int D, int* TT_out);
-int gram2_ksplit(int64_t n, int C, int D, int num_sms);
-size_t gram2_workspace_bytes(int C, int D, int ksplit_max);
-cudaError_t launch_class_gram2(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate,
-                               int chain_rows, void* ws, int num_sms, cudaStream_t stream);
-}  // namespace sqfa

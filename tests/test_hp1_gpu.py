@@ -131,22 +131,14 @@ def test_sample_covariance_and_pca():
         S.pca(X.cuda(), 97)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
-@pytest.mark.parametrize("n,d,c,kw", [(3000, 104, 19, {}), (6000, 784, 10, {}), (4000, 512, 40, {"skew": True}),
-                                      (1500, 1027, 4, {}), (5000, 3072, 2, {})])
-def test_gram_schedules_agree_with_oracle(variant, n, d, c, kw):
-    """Both tensor-core schedules (one CTA per tile / CTA pairs with cta_group::2) vs the oracle."""
-    from sqfa_b200 import _lib
+@pytest.mark.parametrize("n,d,c,kw", [(20000, 256, 3, {}), (9000, 520, 7, {"skew": True}), (700, 2048, 2, {})])
+def test_gram_long_chains_and_k_split(n, d, c, kw):
+    """Classes much longer than one accumulation chain (512 samples) and few tiles (K split with
+    red.add): the per-chain drains keep the tensor-core truncation bias out of the result."""
     from sqfa_b200.statistics import class_statistics
 
-    lib = _lib.load()
-    X, y = make_class_data(n, d, c, seed=d, **kw)
+    X, y = make_class_data(n, d, c, seed=n, **kw)
     ref64 = O.class_statistics(X.double(), y)
-    assert lib.sqfa_debug_set_gram_variant(variant) == 0
-    try:
-        got = class_statistics(X.cuda(), y.cuda())
-        torch.cuda.synchronize()
-    finally:
-        lib.sqfa_debug_set_gram_variant(1)
+    got = class_statistics(X.cuda(), y.cuda())
     for key in ("means", "covariances", "second_moments"):
-        assert rel_err(got[key], ref64[key]) < TOL, key
+        assert rel_err(got[key], ref64[key]) < TOL / 3, key

@@ -8,7 +8,6 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import make_class_data
 
 lib = _lib.load()
-if len(sys.argv) > 1: lib.sqfa_debug_set_gram_variant(int(sys.argv[1]))
 dev = torch.device("cuda")
 
 def gram_with(X, perm, offsets, means, C, ks):
