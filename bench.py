@@ -53,7 +53,8 @@ def synth(n, d, c, device, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, every ~2 ms; falls back
+    to polling nvidia-smi if the NVML bindings are missing)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -62,28 +63,58 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.max_mhz, self.nvml, self.handle = None, None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = {
+            "hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        self.samples.append((mhz, [k for k, v in flags.items() if bits & v]))
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
+                if self.nvml is not None:
+                    self._sample_nvml()
+                    self._stop_evt.wait(0.002)
+                    continue
                 out = subprocess.run(
                     ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                     capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                    f = [x.strip() for x in out.split(",")]
+                    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                    self.max_mhz = int(float(f[1]))
+                    self.samples.append((int(float(f[0])), [n for n, v in zip(names, f[3:7]) if v.lower() == "active"]))
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.strip().lower() == "active"})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted({r for s in self.samples for r in s[1]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def load_peaks():
