@@ -13,14 +13,19 @@
 // bytes read from shared memory and the transform work (gather + centre + hi/lo split + store) by
 // 1/3 -- shared-memory bandwidth and instruction issue are what bound 3xTF32.
 //
-// Warp roles per CTA (21 warps, 80 registers each):
-//   0-15  producers : a thread owns one operand column and half of a stage's 16 samples; it gathers
-//                     them through the bucket permutation straight into registers (4 stages of
-//                     loads in flight), centres, splits hi/lo, stores K-major UMMA operands and
-//                     its warp arrives on the LEADER's full[s]
-//   16    MMA       : leader CTA only; per K=8 step 3 tcgen05.mma.cta_group::2 (cross terms into
+// Warp roles per CTA (13 warps):
+//   0-7   producers : a thread owns a block of 4 samples x 4 adjacent columns of a stage: four
+//                     LDG.128 (512 B per warp and sample row, gathered through the bucket
+//                     permutation) straight into registers, 4 stages of loads in flight; it
+//                     centres, splits hi/lo and stores four K-major 16-byte chunks per half. The four
+//                     columns of a thread go to operand SLOTS l, 32+l, 64+l, 96+l (slot s holds
+//                     column 4 (s % 32) + s / 32 of the tile), which keeps every STS.128
+//                     conflict-free; the epilogue undoes the permutation. Load instructions and
+//                     address arithmetic per element drop 4x against one column per thread (the
+//                     LSU issue rate of 32-bit loads was the limiter).
+//   8     MMA       : leader CTA only; per K=8 step 3 tcgen05.mma.cta_group::2 (cross terms into
 //                     their own TMEM accumulator, hi*hi into the main one), multicast commits
-//   17-20 epilogue  : the tensor core truncates when it adds into its fp32 accumulator (bias
+//   9-12  epilogue  : the tensor core truncates when it adds into its fp32 accumulator (bias
 //                     ~ -2^-25 per MMA, measured), so the main accumulator only ever holds a CHAIN
 //                     of <= chain_rows samples: at every chain end these warps add it (fp32,
 //                     round-to-nearest) to a 128 x 256 running sum in shared memory and hand the
@@ -44,8 +49,7 @@ constexpr int TM2 = 256;  // tile rows    (UMMA M over the CTA pair)
 constexpr int TN2 = 256;  // tile columns (UMMA N)
 constexpr int BK = 16;    // samples per stage
 constexpr int STAGES2 = 3;
-constexpr int PROD_WARPS2 = 16;  // per 32-column group two warps: samples 0-7 and 8-15 of a stage
-constexpr int HR = BK / 2;       // samples per producer thread and stage
+constexpr int PROD_WARPS2 = 8;   // warp = (operand A/B, quad of 4 samples); a thread owns a 4 x 4 block
 constexpr int PREFETCH = 4;      // stages of loads in flight per producer thread (registers)
 constexpr int EPI_WARPS2 = 4;   // one per TMEM lane quarter
 constexpr int MMA_WARP2 = PROD_WARPS2;
@@ -77,7 +81,7 @@ struct GramParams {
   int chain_kb;      // stages per accumulation chain
   int atomic_out;    // KS > 1 or accumulate: red.add into gram, else plain store
   int vec_ok;
-  int idx32;         // every element index row * ldx + col fits 32 bits
+  int vecx;          // rows of X are 16-byte aligned: LDG.128
   int flags;         // tuning switches (env SQFA_GRAM_FLAGS): bit 0 = no A-as-B reuse on diagonal tiles
 };
 
@@ -113,11 +117,9 @@ __device__ __forceinline__ JobGeom decode_job(const GramParams& P, int j) {
   g.c = jb.x;
   g.m0 = jb.y * TM2;
   g.n0 = jb.z * TN2;
-  int n_eff = P.D - g.n0;
-  n_eff = n_eff > TN2 ? TN2 : ((n_eff + 31) & ~31);  // multiple of 32: each CTA holds n_eff / 2 columns of B
-  g.n_eff = n_eff;
-  g.nh = n_eff >> 1;
-  g.diag = (jb.y == jb.z) && n_eff == TN2 && !(P.flags & 1);
+  g.n_eff = TN2;  // full N: the slot permutation spreads a tile's columns over all 128 slots of a CTA
+  g.nh = TN2 / 2;
+  g.diag = (jb.y == jb.z) && !(P.flags & 1);
   g.row_begin = P.offsets[g.c];
   g.n_c = P.offsets[g.c + 1] - g.row_begin;
   const int nkb_total = (int)((g.n_c + BK - 1) / BK);
@@ -164,32 +166,17 @@ gram_tf32x3_kernel(const GramParams P) {
   if (warp < PROD_WARPS2) {
     // =========================== producers (both CTAs) ===========================
     uint32_t stage = 0, phase = 0;
-    const int grp = warp & 7, half = warp >> 3;  // 32-column group (0-3: A, 4-7: B) and sample half
-    const bool isA = grp < 4;
-    const int cw = (grp & 3) * 32 + lane;  // column inside this CTA's 128-wide operand
-    // K-major chunk (4 samples x 16 B) of this column; this thread's samples are chunks 2*half, 2*half+1
-    const uint32_t hi_base =
-        smem_u32(smem) + (isA ? 0 : 2 * OP_BYTES) + ((cw >> 3) * 128 + (cw & 7) * 16) + 2 * half * OP_LBO;
+    const bool isA = (warp & 1) == 0;
+    const int quad = warp >> 1;  // samples 4 quad .. 4 quad + 3 of a stage = K-major chunk `quad`
+    // chunk of slot 32 j + lane in k-chunk `quad`:  quad * 2048 + j * 512 + (lane / 8) * 128 + (lane % 8) * 16
+    const uint32_t hi_base = smem_u32(smem) + (isA ? 0 : 2 * OP_BYTES) + quad * OP_LBO + (lane >> 3) * 128 + (lane & 7) * 16;
     const uint32_t lo_base = hi_base + OP_BYTES;  // 32-bit shared addresses: no 64-bit math in the loop
-    const int lane8 = lane & (HR - 1);
     const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's barriers, cluster window
+    const bool vecx = P.vecx != 0;
     for (int j = pair; j < P.njobs; j += npairs) {
       const JobGeom g = decode_job(P, j);
       const int kb0 = g.kb0, kb1 = g.kb1;
       const int64_t n_c = g.n_c;
-      const int col = isA ? (g.m0 + 128 * (int)rank + cw) : (g.n0 + g.nh * (int)rank + cw);
-      const bool col_ok = col < D && (isA || cw < g.nh);
-      // Instruction issue is a bottleneck of these loops, so everything per-thread is folded into a
-      // column base pointer, a row stride in bytes and the centring shift. Columns outside the
-      // matrix read a device zero with stride 0 and shift 0 -> exact zeros without selects.
-      const char* xcol = col_ok ? reinterpret_cast<const char*>(P.X + col) : reinterpret_cast<const char*>(g_zero);
-      const uint32_t ldb = col_ok ? (uint32_t)(P.ldx * 4) : 0u;
-      const bool idx32 = P.idx32 != 0;
-      // idx32 path: columns outside the matrix read X[0][0] with stride 0 and use it as their
-      // shift -> exact zeros again, and the base pointer stays the (uniform) kernel argument
-      const float sh = col_ok ? (P.shift != nullptr ? __ldg(P.shift + (int64_t)g.c * D + col) : 0.f)
-                              : (idx32 ? __ldg(P.X) : 0.f);
-      const int32_t* const permc = P.perm + g.row_begin;
       if (g.diag && !isA) {
         // diagonal tile: the MMA reads this CTA's A buffers as its B half; the B warps only keep
         // the barrier protocol going (arrival counts are fixed)
@@ -201,67 +188,76 @@ gram_tf32x3_kernel(const GramParams P) {
         }
         continue;
       }
+      const int col = (isA ? g.m0 : g.n0) + 128 * (int)rank + 4 * lane;  // first of this thread's 4 columns
+      const int ncol = col >= D ? 0 : (D - col >= 4 ? 4 : D - col);      // how many of them exist
+      const bool fast = vecx && ncol == 4;
+      float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (P.shift != nullptr && ncol > 0) {
+        const float* sp = P.shift + (int64_t)g.c * D + col;
+        sh.x = __ldg(sp);
+        if (ncol > 1) sh.y = __ldg(sp + 1);
+        if (ncol > 2) sh.z = __ldg(sp + 2);
+        if (ncol > 3) sh.w = __ldg(sp + 3);
+      }
+      const int32_t* const permc = P.perm + g.row_begin;
+      const float* const xcol = P.X + (ncol > 0 ? col : 0);
+      const uint32_t ldx32 = (uint32_t)P.ldx;
 
-      float buf[PREFETCH][HR];
-      // lane r < 8 holds sample (8 * half + r) of a stage: its row id times the row stride, so the
-      // per-element address is one shuffle, one add and one widening multiply-add away.
-      // idx32: element indices fit 32 bits (always, unless a shard holds more than 2^32 floats).
-      const uint32_t ldx32 = (uint32_t)P.ldx;       // applied by the lane that HOLDS the row id
-      const uint32_t rmul = col_ok ? 1u : 0u;       // applied by the lane that READS it
-      const uint32_t col32 = col_ok ? (uint32_t)col : 0u;
-      const float* const xb = P.X;
+      float4 buf[PREFETCH][4];
+      // lane r < 4 holds the row id of sample (4 quad + r) of a stage; row ids travel two issue()
+      // calls ahead of their use, so their load latency is never waited on
       auto load_row = [&](int kb) -> uint32_t {
-        const int64_t k = (int64_t)kb * BK + HR * half + lane8;
-        const uint32_t row = (kb < kb1 && k < n_c) ? (uint32_t)__ldg(permc + k) : 0u;
-        return idx32 ? row * ldx32 : row;
+        const int64_t k = (int64_t)kb * BK + 4 * quad + (lane & 3);
+        return (kb < kb1 && k < n_c) ? (uint32_t)__ldg(permc + k) : 0u;
       };
-      // row ids travel two issue() calls ahead of their use, so their load latency is never waited on
       uint32_t nextrow = load_row(kb0), nextrow2 = load_row(kb0 + 1);
-      auto issue = [&](int kb, float(&b)[HR]) {
+      auto issue = [&](int kb, float4(&b)[4]) {
         const uint32_t myrow = nextrow;
-        if (P.flags & 2) { nextrow = load_row(kb + 1); }
-        else { nextrow = nextrow2; nextrow2 = load_row(kb + 2); }
-        if (idx32) {
+        nextrow = nextrow2;
+        nextrow2 = load_row(kb + 2);
 #pragma unroll
-          for (int r = 0; r < HR; ++r) {  // SHFL + IADD + IMAD.WIDE.U32 (uniform base) + LDG per element
-            const uint32_t e = __shfl_sync(0xffffffffu, myrow, r) * rmul + col32;
-            uint64_t addr;
-            asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(e), "l"(xb));
-            b[r] = __ldg(reinterpret_cast<const float*>(addr));
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < HR; ++r) {
-            const uint32_t row = __shfl_sync(0xffffffffu, myrow, r);
-            uint64_t addr;
-            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(ldb), "l"(xcol));
-            b[r] = __ldg(reinterpret_cast<const float*>(addr));
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t row = __shfl_sync(0xffffffffu, myrow, r);
+          uint64_t addr;  // xcol + row * ldx floats
+          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(ldx32 * 4u), "l"(xcol));
+          const float* ptr = reinterpret_cast<const float*>(addr);
+          if (fast) {
+            b[r] = __ldg(reinterpret_cast<const float4*>(ptr));
+          } else {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ncol > 0) v.x = __ldg(ptr);
+            if (ncol > 1) v.y = __ldg(ptr + 1);
+            if (ncol > 2) v.z = __ldg(ptr + 2);
+            if (ncol > 3) v.w = __ldg(ptr + 3);
+            b[r] = v;
           }
         }
       };
-      auto consume = [&](int kb, float(&b)[HR]) {
+      auto put = [&](uint32_t hp, uint32_t lp, float x0, float x1, float x2, float x3) {
+        float4 h, l;
+        h.x = to_tf32(x0); l.x = x0 - h.x;
+        h.y = to_tf32(x1); l.y = x1 - h.y;
+        h.z = to_tf32(x2); l.z = x2 - h.z;
+        h.w = to_tf32(x3); l.w = x3 - h.w;
+        st_shared_v4(hp, h);
+        st_shared_v4(lp, l);
+      };
+      auto consume = [&](int kb, float4(&b)[4]) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int64_t nv = n_c - (int64_t)kb * BK - HR * half;  // valid samples among this thread's
-        float x[HR];
-        if (nv >= HR) {  // full: FADD, CVT, FADD per element
+        const int64_t nv = n_c - (int64_t)kb * BK - 4 * quad;  // valid samples among this thread's four
+        if (nv < 4) {  // ragged last stage of the class: padded samples must be exact zeros
+          const float4 z = make_float4(sh.x, sh.y, sh.z, sh.w);
 #pragma unroll
-          for (int r = 0; r < HR; ++r) x[r] = b[r] - sh;
-        } else {         // ragged last stage of the class: padded samples are exact zeros
-#pragma unroll
-          for (int r = 0; r < HR; ++r) x[r] = (r < (int)nv) ? b[r] - sh : 0.f;
+          for (int r = 0; r < 4; ++r)
+            if (r >= (int)nv) b[r] = z;
         }
         const uint32_t hp = hi_base + stage * STAGE2_BYTES;
         const uint32_t lp = lo_base + stage * STAGE2_BYTES;
-#pragma unroll
-        for (int kc = 0; kc < HR / 4; ++kc) {
-          float4 h, l;
-          h.x = to_tf32(x[4 * kc + 0]); l.x = x[4 * kc + 0] - h.x;
-          h.y = to_tf32(x[4 * kc + 1]); l.y = x[4 * kc + 1] - h.y;
-          h.z = to_tf32(x[4 * kc + 2]); l.z = x[4 * kc + 2] - h.z;
-          h.w = to_tf32(x[4 * kc + 3]); l.w = x[4 * kc + 3] - h.w;
-          st_shared_v4(hp + kc * OP_LBO, h);
-          st_shared_v4(lp + kc * OP_LBO, l);
-        }
+        // column j of the thread -> slot 32 j + lane -> + j * 512 bytes; the 4 samples are one chunk
+        put(hp, lp, b[0].x - sh.x, b[1].x - sh.x, b[2].x - sh.x, b[3].x - sh.x);
+        put(hp + 512, lp + 512, b[0].y - sh.y, b[1].y - sh.y, b[2].y - sh.y, b[3].y - sh.y);
+        put(hp + 1024, lp + 1024, b[0].z - sh.z, b[1].z - sh.z, b[2].z - sh.z, b[3].z - sh.z);
+        put(hp + 1536, lp + 1536, b[0].w - sh.w, b[1].w - sh.w, b[2].w - sh.w, b[3].w - sh.w);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
@@ -331,11 +327,12 @@ gram_tf32x3_kernel(const GramParams P) {
     uint32_t acc_phase = 0;
     for (int j = pair; j < P.njobs; j += npairs) {
       const JobGeom g = decode_job(P, j);
-      const int row = g.m0 + 128 * (int)rank + lrow;
+      // TMEM lane i = 32 q + lane is operand slot i of this CTA -> tile row 4 (i % 32) + i / 32
+      const int row = g.m0 + 128 * (int)rank + 4 * lane + q;
       float* grow = P.gram + ((int64_t)g.c * D + row) * D;
       if (g.kb1 <= g.kb0) {  // empty class / empty K part: the tile contribution is exactly zero
         if (!P.atomic_out && row < D)
-          for (int cc = 0; cc < g.n_eff; ++cc)
+          for (int cc = 0; cc < TN2; ++cc)
             if (g.n0 + cc < D) grow[g.n0 + cc] = 0.f;
         continue;
       }
@@ -380,26 +377,16 @@ gram_tf32x3_kernel(const GramParams P) {
               v[jj] = __float_as_uint(a + __uint_as_float(w[jj]));
             }
             if (row < D) {
-              const int gc = g.n0 + col0;
-              if (P.vec_ok && gc + 16 <= D) {
-                if (P.atomic_out) {
+              // accumulator column n = 128 (n / 128) + slot  ->  tile column 128 (n / 128) + 4 (slot % 32) + slot / 32:
+              // the 16 columns of this chunk are 16 bytes apart in the output row
+              const int gc = g.n0 + (col0 & 128) + 4 * (col0 & 31) + ((col0 & 127) >> 5);
 #pragma unroll
-                  for (int jj = 0; jj < 16; jj += 4)
-                    atomicAdd(reinterpret_cast<float4*>(grow + gc + jj),
-                              make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]),
-                                          __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3])));
-                } else {
-#pragma unroll
-                  for (int jj = 0; jj < 16; jj += 4)
-                    *reinterpret_cast<uint4*>(grow + gc + jj) = make_uint4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+              for (int jj = 0; jj < 16; ++jj) {
+                const int cidx = gc + 4 * jj;
+                if (cidx < D) {
+                  if (P.atomic_out) atomicAdd(grow + cidx, __uint_as_float(v[jj]));
+                  else grow[cidx] = __uint_as_float(v[jj]);
                 }
-              } else {
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj)
-                  if (gc + jj < D) {
-                    if (P.atomic_out) atomicAdd(grow + gc + jj, __uint_as_float(v[jj]));
-                    else grow[gc + jj] = __uint_as_float(v[jj]);
-                  }
               }
             }
           }
@@ -464,7 +451,8 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
   P.vec_ok = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(gram) & 15) == 0);
   static const int env_flags = [] { const char* e = getenv("SQFA_GRAM_FLAGS"); return e ? atoi(e) : 0; }();
   P.flags = env_flags;
-  P.idx32 = ((double)n * (double)ldx + (double)D < 4.0e9 && !(env_flags & 4)) ? 1 : 0;
+  P.vecx = ((ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && !(env_flags & 4)) ? 1 : 0;
+  if ((uint64_t)ldx * 4ull >= (1ull << 32)) return cudaErrorInvalidValue;
   if (P.atomic_out && !accumulate) {  // K parts are summed with red.add -> start from zero
     cudaError_t e = cudaMemsetAsync(gram, 0, (size_t)C * D * D * sizeof(float), stream);
     if (e != cudaSuccess) return e;
