@@ -204,17 +204,19 @@ gram_tf32x3_kernel(const GramParams P) {
       const uint32_t ldx32 = (uint32_t)P.ldx;
 
       float4 buf[PREFETCH][4];
-      // lane r < 4 holds the row id of sample (4 quad + r) of a stage; row ids travel two issue()
-      // calls ahead of their use, so their load latency is never waited on
+      // lane r < 4 holds the row id of sample (4 quad + r) of a stage. Each prefetch slot keeps its
+      // own row-id register, refilled for the slot's NEXT use (PREFETCH stages later) while the
+      // current one is consumed: no register rotation, so the id load is never waited on
       auto load_row = [&](int kb) -> uint32_t {
         const int64_t k = (int64_t)kb * BK + 4 * quad + (lane & 3);
         return (kb < kb1 && k < n_c) ? (uint32_t)__ldg(permc + k) : 0u;
       };
-      uint32_t nextrow = load_row(kb0), nextrow2 = load_row(kb0 + 1);
-      auto issue = [&](int kb, float4(&b)[4]) {
-        const uint32_t myrow = nextrow;
-        nextrow = nextrow2;
-        nextrow2 = load_row(kb + 2);
+      uint32_t rowreg[PREFETCH];
+#pragma unroll
+      for (int u = 0; u < PREFETCH; ++u) rowreg[u] = load_row(kb0 + u);
+      auto issue = [&](int kb, float4(&b)[4], uint32_t& rr) {
+        const uint32_t myrow = rr;
+        rr = load_row(kb + PREFETCH);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const uint32_t row = __shfl_sync(0xffffffffu, myrow, r);
@@ -265,13 +267,13 @@ gram_tf32x3_kernel(const GramParams P) {
       };
 #pragma unroll
       for (int u = 0; u < PREFETCH; ++u)
-        if (kb0 + u < kb1) issue(kb0 + u, buf[u]);
+        if (kb0 + u < kb1) issue(kb0 + u, buf[u], rowreg[u]);
       for (int kb = kb0; kb < kb1; kb += PREFETCH) {
 #pragma unroll
         for (int u = 0; u < PREFETCH; ++u) {
           if (kb + u < kb1) {
             consume(kb + u, buf[u]);
-            if (kb + u + PREFETCH < kb1) issue(kb + u + PREFETCH, buf[u]);
+            if (kb + u + PREFETCH < kb1) issue(kb + u + PREFETCH, buf[u], rowreg[u]);
           }
         }
       }
