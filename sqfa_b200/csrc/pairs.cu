@@ -362,6 +362,204 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
 }
 
 // ------------------------------------------------------------------------------------------------
+// pair kernel, affine-invariant family, REGISTER-RESIDENT variant for m <= 32 (MP = m rounded up to
+// a multiple of 4): lane q keeps column q of A = (L_j^-1 L_i)^T in MP registers; a Jacobi round is
+// MP warp shuffles (the partner's column) + 3 MP FMAs; column norms are carried along incrementally
+// (alpha' = alpha - t gamma, beta' = beta + t gamma) and recomputed exactly once per sweep.
+// Shared memory only stages the triangular factors (broadcast reads) and the final
+// sum_q c_q y_q y_q^T. ~3x fewer issue slots per pair than the shared-memory variant above,
+// which stays in use for 32 < m <= 64.
+// ------------------------------------------------------------------------------------------------
+template <int MP>
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int nA, int nB, int m, int dist,
+                   int tri, int64_t pair_begin, int64_t pair_end, float weight, const float* __restrict__ gD,
+                   float* __restrict__ dist_out, float* __restrict__ loss, float* gEa, float* gEb,
+                   float* __restrict__ eig_out) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float s_d[PAIR_WARPS];
+  __shared__ float s_bad[PAIR_WARPS];
+  constexpr int LDT = 33;
+  constexpr int PER_WARP = MP * LDT + 2 * MP * MP + 3;  // sT | sL | sZ (+ pad to keep 16-byte alignment)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t p = pair_begin + (int64_t)blockIdx.x * nwarps + warp;
+  float* sT = smem + (size_t)warp * ((PER_WARP + 3) & ~3) + 2 * MP * MP;  // [MP][33]: Linv_j^T, later Y
+  float* sL = smem + (size_t)warp * ((PER_WARP + 3) & ~3);               // [MP][MP]: L_i, Linv_i, later Zj
+  float* sZ = sL + MP * MP;                                              // [MP][MP]: Zi
+  float dval = 0.f, bad = 0.f;
+  if (p < pair_end) {
+    int i, j;
+    if (tri) decode_pair(p, i, j);
+    else { i = (int)(p / nB); j = (int)(p % nB); }
+    const float* Wi = Wa + (int64_t)i * 2 * m * m;
+    const float* Wj = Wb + (int64_t)j * 2 * m * m;
+    const int mp = (m + 1) & ~1;
+    // ---- stage L_i (row-major, zero padded to MP) and Linv_j transposed
+    for (int idx = lane; idx < MP * MP; idx += 32) sL[idx] = 0.f;
+    __syncwarp();
+    for (int idx = lane; idx < m * m; idx += 32) {
+      const int r = idx / m, c = idx % m;
+      sL[r * MP + c] = Wi[idx];
+      sT[c * LDT + r] = Wj[m * m + idx];  // sT[r'][q] = Linv_j[q][r']
+    }
+    __syncwarp();
+    // ---- column `lane` of A: a[s] = sum_r Linv_j[lane][r] L_i[r][s]   (both factors lower triangular)
+    float a[MP], y[MP];
+#pragma unroll
+    for (int s = 0; s < MP; ++s) a[s] = 0.f;
+    if (lane < m) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) {
+        if (r < m) {
+          const float l = sT[r * LDT + lane];
+#pragma unroll
+          for (int s4 = 0; s4 < MP / 4; ++s4) {
+            const float4 w = *reinterpret_cast<const float4*>(sL + r * MP + 4 * s4);
+            a[4 * s4 + 0] += l * w.x; a[4 * s4 + 1] += l * w.y; a[4 * s4 + 2] += l * w.z; a[4 * s4 + 3] += l * w.w;
+          }
+        }
+      }
+    }
+    // ---- one-sided Jacobi, columns in registers
+    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+      float nrm = 0.f;
+#pragma unroll
+      for (int s = 0; s < MP; ++s) nrm += a[s] * a[s];
+      bool rotated = false;
+      for (int r = 0; r < mp - 1; ++r) {
+        const int q = lane < mp ? rr_partner(lane, r, mp) : lane;
+        const float nq = __shfl_sync(0xffffffffu, nrm, q);
+        float ab = 0.f;
+#pragma unroll
+        for (int s = 0; s < MP; ++s) {
+          y[s] = __shfl_sync(0xffffffffu, a[s], q);
+          ab += a[s] * y[s];
+        }
+        const bool is_lo = lane < q;
+        const float alpha = is_lo ? nrm : nq, beta = is_lo ? nq : nrm;
+        float cs = 1.f, sn = 0.f;
+        if (lane < mp && fabsf(ab) > JACOBI_TOL * sqrtf(alpha * beta) && alpha > 0.f && beta > 0.f) {
+          const float zeta = (beta - alpha) / (2.f * ab);
+          const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+          cs = rsqrtf(1.f + tt * tt);
+          sn = cs * tt;
+          nrm = is_lo ? alpha - tt * ab : beta + tt * ab;
+          rotated = true;
+        }
+        const float other = is_lo ? -sn : sn;
+#pragma unroll
+        for (int s = 0; s < MP; ++s) a[s] = cs * a[s] + other * y[s];
+      }
+      if (!__any_sync(0xffffffffu, rotated)) break;
+    }
+    // ---- eigenvalues, distance
+    float n2 = 0.f;
+#pragma unroll
+    for (int s = 0; s < MP; ++s) n2 += a[s] * a[s];
+    const float ll = lane < m ? logf(n2) : 0.f;
+    const float d2 = warp_sum(ll * ll);
+    if (eig_out != nullptr) {  // descending order (linalg.py:69-70)
+      int rank = 0;
+      for (int u = 0; u < m; ++u) {
+        const float v = __shfl_sync(0xffffffffu, n2, u);
+        rank += (v > n2 || (v == n2 && u < lane)) ? 1 : 0;
+      }
+      if (lane < m) eig_out[((int64_t)i * nB + j) * m + rank] = n2;
+    }
+    float dd_dd2;
+    dval = finish_distance(d2, dist, &dd_dd2);
+    if (!isfinite(dval)) bad = 1.f;
+    if (dist_out != nullptr && lane == 0) {
+      dist_out[(int64_t)i * nB + j] = dval;
+      if (tri) dist_out[(int64_t)j * nB + i] = dval;
+    }
+    if (gEa != nullptr) {
+      float w = weight * dd_dd2;
+      if (gD != nullptr) w *= tri ? (gD[(int64_t)i * nB + j] + gD[(int64_t)j * nB + i]) : gD[(int64_t)i * nB + j];
+      const float ci = lane < m ? w * 2.f * ll / n2 : 0.f, cj = lane < m ? -w * 2.f * ll : 0.f;
+      // ---- Y = L_i^-T A_f : y[r] = sum_{s >= r} Linv_i[s][r] a[s]
+      __syncwarp();
+      for (int idx = lane; idx < m * m; idx += 32) sL[(idx / m) * MP + idx % m] = Wi[m * m + idx];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < MP; ++r) y[r] = 0.f;
+#pragma unroll
+      for (int s = 0; s < MP; ++s) {
+        if (s < m) {
+#pragma unroll
+          for (int r4 = 0; r4 < MP / 4; ++r4) {
+            const float4 wv = *reinterpret_cast<const float4*>(sL + s * MP + 4 * r4);
+            y[4 * r4 + 0] += wv.x * a[s]; y[4 * r4 + 1] += wv.y * a[s]; y[4 * r4 + 2] += wv.z * a[s]; y[4 * r4 + 3] += wv.w * a[s];
+          }
+        }
+      }
+      __syncwarp();
+      // ---- Y -> sT[r][q], Zi = Y diag(ci) -> sZ[r][q], Zj = Y diag(cj) -> sL[r][q]   (q = lane)
+#pragma unroll
+      for (int r = 0; r < MP; ++r) {
+        const float yr = lane < m ? y[r] : 0.f;
+        sT[r * LDT + lane] = yr;
+        if (lane < MP) {
+          sZ[r * MP + lane] = ci * yr;
+          sL[r * MP + lane] = cj * yr;
+        }
+      }
+      __syncwarp();
+      // ---- G_i[r][s'] = sum_q Zi[r][q] Y[s'][q], G_j likewise; lane = s', its row of Y in registers
+      if (lane < m) {
+#pragma unroll
+        for (int q = 0; q < MP; ++q) y[q] = sT[lane * LDT + q];
+        float* gi = gEa + (int64_t)i * m * m;
+        float* gj = gEb + (int64_t)j * m * m;
+        for (int r = 0; r < m; ++r) {
+          float ga = 0.f, gb = 0.f;
+#pragma unroll
+          for (int q4 = 0; q4 < MP / 4; ++q4) {
+            const float4 zi = *reinterpret_cast<const float4*>(sZ + r * MP + 4 * q4);
+            const float4 zj = *reinterpret_cast<const float4*>(sL + r * MP + 4 * q4);
+            ga += zi.x * y[4 * q4] + zi.y * y[4 * q4 + 1] + zi.z * y[4 * q4 + 2] + zi.w * y[4 * q4 + 3];
+            gb += zj.x * y[4 * q4] + zj.y * y[4 * q4 + 1] + zj.z * y[4 * q4 + 2] + zj.w * y[4 * q4 + 3];
+          }
+          atomicAdd(gi + r * m + lane, ga);
+          atomicAdd(gj + r * m + lane, gb);
+        }
+      }
+    }
+  }
+  if (loss != nullptr) {
+    if (lane == 0) { s_d[warp] = dval; s_bad[warp] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float sa = 0.f, sb = 0.f;
+      for (int w = 0; w < nwarps; ++w) { sa += s_d[w]; sb += s_bad[w]; }
+      atomicAdd(loss, sa);
+      if (sb != 0.f) atomicAdd(loss + 1, sb);
+    }
+  }
+}
+
+template <int MP>
+static cudaError_t launch_pair_reg(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
+                                   int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
+                                   float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
+                                   cudaStream_t st) {
+  constexpr int per_warp_floats = ((MP * 33 + 2 * MP * MP + 3) + 3) & ~3;
+  const int smem = PAIR_WARPS * per_warp_floats * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pair_ai_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int64_t npairs = pair_end - pair_begin;
+  const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
+  pair_ai_reg_kernel<MP><<<blocks, PAIR_WARPS * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end,
+                                                                weight, gD, dist_out, loss, gEa, gEb, eig_out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // pair kernel, log-Euclidean: d^2 = |logE_i - logE_j|_F^2; gradient w.r.t. the matrix logarithms
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
@@ -525,6 +723,22 @@ cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int 
     pair_le_kernel<<<blocks, PAIR_WARPS * 32, 0, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
                                                        dist_out, loss, gEa, gEb);
     return cudaGetLastError();
+  }
+  if (m <= 32) {  // register-resident Jacobi
+#define SQFA_PAIR_REG(MPV)                                                                                      \
+  return launch_pair_reg<MPV>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD, dist_out, loss, gEa, \
+                              gEb, eig_out, st)
+    switch ((m + 3) / 4) {
+      case 1: SQFA_PAIR_REG(4);
+      case 2: SQFA_PAIR_REG(8);
+      case 3: SQFA_PAIR_REG(12);
+      case 4: SQFA_PAIR_REG(16);
+      case 5: SQFA_PAIR_REG(20);
+      case 6: SQFA_PAIR_REG(24);
+      case 7: SQFA_PAIR_REG(28);
+      default: SQFA_PAIR_REG(32);
+    }
+#undef SQFA_PAIR_REG
   }
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
