@@ -37,6 +37,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include "ptx.cuh"
 #include "sqfa_internal.h"
@@ -71,6 +72,7 @@ __device__ float g_zero[4] = {0.f, 0.f, 0.f, 0.f};
 struct GramParams {
   const float* X;
   int64_t ldx;
+  int64_t n;         // rows of X (= entries of perm)
   const int32_t* perm;
   const int64_t* offsets;
   const float* shift;
@@ -190,7 +192,6 @@ gram_tf32x3_kernel(const GramParams P) {
       }
       const int col = (isA ? g.m0 : g.n0) + 128 * (int)rank + 4 * lane;  // first of this thread's 4 columns
       const int ncol = col >= D ? 0 : (D - col >= 4 ? 4 : D - col);      // how many of them exist
-      const bool fast = vecx && ncol == 4;
       float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
       if (P.shift != nullptr && ncol > 0) {
         const float* sp = P.shift + (int64_t)g.c * D + col;
@@ -199,84 +200,98 @@ gram_tf32x3_kernel(const GramParams P) {
         if (ncol > 2) sh.z = __ldg(sp + 2);
         if (ncol > 3) sh.w = __ldg(sp + 3);
       }
-      const int32_t* const permc = P.perm + g.row_begin;
-      const float* const xcol = P.X + (ncol > 0 ? col : 0);
-      const uint32_t ldx32 = (uint32_t)P.ldx;
+      // a thread without columns (past D) reads a fixed zero vector with row stride 0
+      const float* const xcol = ncol > 0 ? P.X + col : g_zero;
+      const uint32_t stride = ncol > 0 ? (uint32_t)P.ldx * 4u : 0u;
+      // warp-uniform choice of the load path: LDG.128 when rows are 16-byte aligned and every
+      // thread of the warp owns all four of its columns or none (straight-line code, no
+      // per-load branches); scalar loads only in the last column tile of a D not divisible by 4
+      const bool fastw = __all_sync(0xffffffffu, vecx && (ncol == 4 || ncol == 0));
 
-      float4 buf[PREFETCH][4];
-      // lane r < 4 holds the row id of sample (4 quad + r) of a stage. Each prefetch slot keeps its
-      // own row-id register, refilled for the slot's NEXT use (PREFETCH stages later) while the
-      // current one is consumed: no register rotation, so the id load is never waited on
-      auto load_row = [&](int kb) -> uint32_t {
-        const int64_t k = (int64_t)kb * BK + 4 * quad + (lane & 3);
-        return (kb < kb1 && k < n_c) ? (uint32_t)__ldg(permc + k) : 0u;
-      };
-      uint32_t rowreg[PREFETCH];
+      auto produce = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        float4 buf[PREFETCH][4];
+        // lane r < 4 holds the row id of sample (4 quad + r) of a stage. Each prefetch slot keeps
+        // its own row-id register, refilled for the slot's NEXT use (PREFETCH stages later) while
+        // the current one is consumed, so the id load is never waited on
+        // (unconditional and clamped, never predicated: a predicated load needs a select on its
+        // result, and that select waits for the load right where it was issued)
+        auto load_row = [&](int kb) -> uint32_t {
+          const int64_t k = (int64_t)kb * BK + 4 * quad + (lane & 3);
+          const int64_t idx = g.row_begin + min(k, n_c - 1);  // an empty class may sit at either end
+          return (uint32_t)__ldg(P.perm + max(min(idx, P.n - 1), (int64_t)0));
+        };
+        uint32_t rowreg[PREFETCH];
 #pragma unroll
-      for (int u = 0; u < PREFETCH; ++u) rowreg[u] = load_row(kb0 + u);
-      auto issue = [&](int kb, float4(&b)[4], uint32_t& rr) {
-        const uint32_t myrow = rr;
-        rr = load_row(kb + PREFETCH);
+        for (int u = 0; u < PREFETCH; ++u) rowreg[u] = load_row(kb0 + u);
+        auto issue = [&](int kb, float4(&b)[4], uint32_t& rr) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const uint32_t row = __shfl_sync(0xffffffffu, myrow, r);
-          uint64_t addr;  // xcol + row * ldx floats
-          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(ldx32 * 4u), "l"(xcol));
-          const float* ptr = reinterpret_cast<const float*>(addr);
-          if (fast) {
-            b[r] = __ldg(reinterpret_cast<const float4*>(ptr));
-          } else {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ncol > 0) v.x = __ldg(ptr);
-            if (ncol > 1) v.y = __ldg(ptr + 1);
-            if (ncol > 2) v.z = __ldg(ptr + 2);
-            if (ncol > 3) v.w = __ldg(ptr + 3);
-            b[r] = v;
+          for (int r = 0; r < 4; ++r) {
+            const uint32_t row = __shfl_sync(0xffffffffu, rr, r);
+            uint64_t addr;  // xcol + row * ldx floats
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(stride), "l"(xcol));
+            const float* ptr = reinterpret_cast<const float*>(addr);
+            if constexpr (FAST) {
+              b[r] = __ldg(reinterpret_cast<const float4*>(ptr));
+            } else {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ncol > 0) v.x = __ldg(ptr);
+              if (ncol > 1) v.y = __ldg(ptr + 1);
+              if (ncol > 2) v.z = __ldg(ptr + 2);
+              if (ncol > 3) v.w = __ldg(ptr + 3);
+              b[r] = v;
+            }
+          }
+          // refill AFTER the last use so the load can target the same register (otherwise a MOV
+          // right behind the load waits for it)
+          rr = load_row(kb + PREFETCH);
+        };
+        auto put = [&](uint32_t hp, uint32_t lp, float x0, float x1, float x2, float x3) {
+          float4 h, l;
+          h.x = to_tf32(x0); l.x = x0 - h.x;
+          h.y = to_tf32(x1); l.y = x1 - h.y;
+          h.z = to_tf32(x2); l.z = x2 - h.z;
+          h.w = to_tf32(x3); l.w = x3 - h.w;
+          st_shared_v4(hp, h);
+          st_shared_v4(lp, l);
+        };
+        auto consume = [&](int kb, float4(&b)[4]) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int64_t nv = n_c - (int64_t)kb * BK - 4 * quad;  // valid samples among this thread's four
+          if (nv < 4) {  // ragged last stage of the class: padded samples must be exact zeros
+            const float4 z = make_float4(sh.x, sh.y, sh.z, sh.w);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (r >= (int)nv) b[r] = z;
+          }
+          const uint32_t hp = hi_base + stage * STAGE2_BYTES;
+          const uint32_t lp = lo_base + stage * STAGE2_BYTES;
+          // column j of the thread -> slot 32 j + lane -> + j * 512 bytes; the 4 samples are one chunk
+          put(hp, lp, b[0].x - sh.x, b[1].x - sh.x, b[2].x - sh.x, b[3].x - sh.x);
+          put(hp + 512, lp + 512, b[0].y - sh.y, b[1].y - sh.y, b[2].y - sh.y, b[3].y - sh.y);
+          put(hp + 1024, lp + 1024, b[0].z - sh.z, b[1].z - sh.z, b[2].z - sh.z, b[3].z - sh.z);
+          put(hp + 1536, lp + 1536, b[0].w - sh.w, b[1].w - sh.w, b[2].w - sh.w, b[3].w - sh.w);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        };
+        // Loads are issued unconditionally (stages past the end re-read row 0 and are never
+        // consumed): a conditional refill makes the compiler merge the row-id registers with a MOV
+        // that waits for the id load just issued -- one full memory latency per stage (ncu).
+#pragma unroll
+        for (int u = 0; u < PREFETCH; ++u) issue(kb0 + u, buf[u], rowreg[u]);
+        for (int kb = kb0; kb < kb1; kb += PREFETCH) {
+#pragma unroll
+          for (int u = 0; u < PREFETCH; ++u) {
+            if (kb + u < kb1) {
+              consume(kb + u, buf[u]);
+              issue(kb + u + PREFETCH, buf[u], rowreg[u]);
+            }
           }
         }
       };
-      auto put = [&](uint32_t hp, uint32_t lp, float x0, float x1, float x2, float x3) {
-        float4 h, l;
-        h.x = to_tf32(x0); l.x = x0 - h.x;
-        h.y = to_tf32(x1); l.y = x1 - h.y;
-        h.z = to_tf32(x2); l.z = x2 - h.z;
-        h.w = to_tf32(x3); l.w = x3 - h.w;
-        st_shared_v4(hp, h);
-        st_shared_v4(lp, l);
-      };
-      auto consume = [&](int kb, float4(&b)[4]) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int64_t nv = n_c - (int64_t)kb * BK - 4 * quad;  // valid samples among this thread's four
-        if (nv < 4) {  // ragged last stage of the class: padded samples must be exact zeros
-          const float4 z = make_float4(sh.x, sh.y, sh.z, sh.w);
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            if (r >= (int)nv) b[r] = z;
-        }
-        const uint32_t hp = hi_base + stage * STAGE2_BYTES;
-        const uint32_t lp = lo_base + stage * STAGE2_BYTES;
-        // column j of the thread -> slot 32 j + lane -> + j * 512 bytes; the 4 samples are one chunk
-        put(hp, lp, b[0].x - sh.x, b[1].x - sh.x, b[2].x - sh.x, b[3].x - sh.x);
-        put(hp + 512, lp + 512, b[0].y - sh.y, b[1].y - sh.y, b[2].y - sh.y, b[3].y - sh.y);
-        put(hp + 1024, lp + 1024, b[0].z - sh.z, b[1].z - sh.z, b[2].z - sh.z, b[3].z - sh.z);
-        put(hp + 1536, lp + 1536, b[0].w - sh.w, b[1].w - sh.w, b[2].w - sh.w, b[3].w - sh.w);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
-        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
-      };
-#pragma unroll
-      for (int u = 0; u < PREFETCH; ++u)
-        if (kb0 + u < kb1) issue(kb0 + u, buf[u], rowreg[u]);
-      for (int kb = kb0; kb < kb1; kb += PREFETCH) {
-#pragma unroll
-        for (int u = 0; u < PREFETCH; ++u) {
-          if (kb + u < kb1) {
-            consume(kb + u, buf[u]);
-            if (kb + u + PREFETCH < kb1) issue(kb + u + PREFETCH, buf[u], rowreg[u]);
-          }
-        }
-      }
+      if (fastw) produce(std::true_type{}); else produce(std::false_type{});
     }
   } else if (warp == MMA_WARP2) {
     // =========================== MMA issuer (leader CTA only) ===========================
@@ -285,32 +300,57 @@ gram_tf32x3_kernel(const GramParams P) {
       for (int j = pair; j < P.njobs; j += npairs) {
         const JobGeom g = decode_job(P, j);
         const uint32_t idesc = make_idesc_tf32(TM2, (uint32_t)g.n_eff, 0, 0);
+        // cross terms (small accumulator) / hi*hi (main accumulator) of one stage
+        auto issue_stage = [&](uint32_t stg, bool cross, bool mainp, int kb, int cb) {
+          const uint32_t st = smem_u32(smem + stg * STAGE2_BYTES);
+          const uint32_t a_hi = st, a_lo = st + OP_BYTES;
+          const uint32_t b_hi = g.diag ? a_hi : st + 2 * OP_BYTES, b_lo = g.diag ? a_lo : st + 3 * OP_BYTES;
+#pragma unroll
+          for (int k8 = 0; k8 < BK / 8; ++k8) {
+            const uint32_t ko = k8 * 2 * OP_LBO;
+            const uint64_t dA_hi = make_smem_desc(a_hi + ko, OP_LBO, OP_SBO2, 0);
+            const uint64_t dA_lo = make_smem_desc(a_lo + ko, OP_LBO, OP_SBO2, 0);
+            const uint64_t dB_hi = make_smem_desc(b_hi + ko, OP_LBO, OP_SBO2, 0);
+            const uint64_t dB_lo = make_smem_desc(b_lo + ko, OP_LBO, OP_SBO2, 0);
+            if (cross) {
+              const uint32_t acc_small = (kb > g.kb0 || k8 > 0) ? 1u : 0u;  // zeroed once per job
+              umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_lo, dB_hi, idesc, acc_small);
+              umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_hi, dB_lo, idesc, 1u);
+            }
+            if (mainp) {
+              const uint32_t acc_main = (kb > cb || k8 > 0) ? 1u : 0u;  // zeroed at every chain start
+              umma_tf32_ss_2cta(tmem_base, dA_hi, dB_hi, idesc, acc_main);
+            }
+          }
+        };
         for (int cb = g.kb0; cb < g.kb1; cb += P.chain_kb) {
           const int ce = min(g.kb1, cb + P.chain_kb);
+          // While the epilogue warps drain the previous chain's main accumulator, the cross terms
+          // of the first stages of this chain (they go to the OTHER accumulator, which is only read
+          // at the end of the job) keep the tensor pipe busy.
+          const int early = (cb > g.kb0 && !(P.flags & 8)) ? min(STAGES2, ce - cb) : 0;
+          {
+            uint32_t st = stage, ph = phase;
+            for (int e = 0; e < early; ++e) {
+              mbar_wait_cluster(&full_bar[st], ph);
+              tc_fence_after_sync();
+              if (elect_one()) issue_stage(st, true, false, cb + e, cb);
+              __syncwarp();
+              if (++st == STAGES2) { st = 0; ph ^= 1; }
+            }
+          }
           // the epilogue warps of both CTAs must have drained the previous chain
           mbar_wait_cluster(&acc_empty_bar, chain_phase ^ 1);
           chain_phase ^= 1;
           tc_fence_after_sync();
           for (int kb = cb; kb < ce; ++kb) {
-            mbar_wait_cluster(&full_bar[stage], phase);
-            tc_fence_after_sync();
+            const bool crossed = kb - cb < early;
+            if (!crossed) {
+              mbar_wait_cluster(&full_bar[stage], phase);
+              tc_fence_after_sync();
+            }
             if (elect_one()) {
-              const uint32_t st = smem_u32(smem + stage * STAGE2_BYTES);
-              const uint32_t a_hi = st, a_lo = st + OP_BYTES;
-              const uint32_t b_hi = g.diag ? a_hi : st + 2 * OP_BYTES, b_lo = g.diag ? a_lo : st + 3 * OP_BYTES;
-#pragma unroll
-              for (int k8 = 0; k8 < BK / 8; ++k8) {
-                const uint32_t ko = k8 * 2 * OP_LBO;
-                const uint64_t dA_hi = make_smem_desc(a_hi + ko, OP_LBO, OP_SBO2, 0);
-                const uint64_t dA_lo = make_smem_desc(a_lo + ko, OP_LBO, OP_SBO2, 0);
-                const uint64_t dB_hi = make_smem_desc(b_hi + ko, OP_LBO, OP_SBO2, 0);
-                const uint64_t dB_lo = make_smem_desc(b_lo + ko, OP_LBO, OP_SBO2, 0);
-                const uint32_t acc_small = (kb > g.kb0 || k8 > 0) ? 1u : 0u;  // zeroed once per job
-                const uint32_t acc_main = (kb > cb || k8 > 0) ? 1u : 0u;      // zeroed at every chain start
-                umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_lo, dB_hi, idesc, acc_small);
-                umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_hi, dB_lo, idesc, 1u);
-                umma_tf32_ss_2cta(tmem_base, dA_hi, dB_hi, idesc, acc_main);
-              }
+              issue_stage(stage, !crossed, true, kb, cb);
               umma_commit_2cta(&empty_bar[stage], 3);
               if (kb == ce - 1) umma_commit_2cta(&acc_full_bar, 3);
             }
@@ -344,39 +384,63 @@ gram_tf32x3_kernel(const GramParams P) {
         mbar_wait(&acc_full_bar, acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
-#pragma unroll 1
-        for (int col0 = 0; col0 < g.n_eff; col0 += 16) {  // 16 columns at a time: the role fits 80 registers
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tq + (uint32_t)col0, v);
-          float* rp = run + col0 * 128 + lrow;
-          if (!last) {
+        // running sum layout: float4 (columns 4 t .. 4 t + 3 of TMEM lane r) at run4[t * 128 + r]:
+        // every warp access is 512 contiguous bytes (LDS.128 / STS.128, conflict-free)
+        float4* const run4 = reinterpret_cast<float4*>(run) + lrow;
+        if (!last) {
+          // Drain the chain's main accumulator in 32-column chunks, the TMEM load of chunk c + 1 in
+          // flight while chunk c is added to the running sum; the accumulator goes back to the MMA
+          // warp as soon as the last load has landed.
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(tq, va);
+          auto add_chunk = [&](int c, const uint32_t(&v)[32]) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              float4* rp = run4 + (8 * c + t) * 128;
+              float4 a = make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]),
+                                     __uint_as_float(v[4 * t + 2]), __uint_as_float(v[4 * t + 3]));
+              if (!first) {
+                const float4 o = *rp;
+                a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+              }
+              *rp = a;
+            }
+          };
+#pragma unroll
+          for (int c = 0; c < TN2 / 32; c += 2) {
             tmem_ld_wait();
-            if (col0 + 16 >= g.n_eff) {  // main accumulator fully read: hand it back to the MMA warp
+            tmem_ld_32x32b_x32(tq + (uint32_t)(32 * (c + 1)), vb);
+            add_chunk(c, va);
+            tmem_ld_wait();
+            if (c + 2 < TN2 / 32) {
+              tmem_ld_32x32b_x32(tq + (uint32_t)(32 * (c + 2)), va);
+            } else {  // main accumulator fully read: hand it back to the MMA warp
               tc_fence_before_sync();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster(acc_empty0);
             }
-            if (first) {
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) rp[jj * 128] = __uint_as_float(v[jj]);
-            } else {
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) rp[jj * 128] += __uint_as_float(v[jj]);
-            }
-          } else {
-            uint32_t w[16];
+            add_chunk(c + 1, vb);
+          }
+        } else {
+#pragma unroll 1
+          for (int col0 = 0; col0 < TN2; col0 += 16) {
+            uint32_t v[16], w[16];
+            tmem_ld_32x32b_x16(tq + (uint32_t)col0, v);
             tmem_ld_32x32b_x16(tq + TMEM_SMALL2 + (uint32_t)col0, w);
             tmem_ld_wait();
-            if (col0 + 16 >= g.n_eff) {  // both accumulators read: the next job may start
+            if (col0 + 16 >= TN2) {  // both accumulators read: the next job may start
               tc_fence_before_sync();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster(acc_empty0);
             }
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              float a = __uint_as_float(v[jj]);
-              if (!first) a += rp[jj * 128];
-              v[jj] = __float_as_uint(a + __uint_as_float(w[jj]));
+            for (int t = 0; t < 4; ++t) {
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!first) o = run4[(col0 / 4 + t) * 128];
+              v[4 * t] = __float_as_uint(__uint_as_float(v[4 * t]) + o.x + __uint_as_float(w[4 * t]));
+              v[4 * t + 1] = __float_as_uint(__uint_as_float(v[4 * t + 1]) + o.y + __uint_as_float(w[4 * t + 1]));
+              v[4 * t + 2] = __float_as_uint(__uint_as_float(v[4 * t + 2]) + o.z + __uint_as_float(w[4 * t + 2]));
+              v[4 * t + 3] = __float_as_uint(__uint_as_float(v[4 * t + 3]) + o.w + __uint_as_float(w[4 * t + 3]));
             }
             if (row < D) {
               // accumulator column n = 128 (n / 128) + slot  ->  tile column 128 (n / 128) + 4 (slot % 32) + slot / 32:
@@ -442,7 +506,7 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
   GramParams P;
   int TT = 0;
   const int T = gram_tiles_per_class(D, &TT);
-  P.X = X; P.ldx = ldx; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram;
+  P.X = X; P.ldx = ldx; P.n = n; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram;
   P.jobs = reinterpret_cast<const int4*>(ws);
   P.D = D; P.C = C;
   P.KS = gram_ksplit(n, C, D, num_sms);
