@@ -51,8 +51,10 @@ constexpr int TN2 = 256;  // tile columns (UMMA N)
 constexpr int BK = 16;    // samples per stage
 constexpr int STAGES2 = 3;
 constexpr int PROD_WARPS2 = 8;   // warp = (operand A/B, quad of 4 samples); a thread owns a 4 x 4 block
-constexpr int PREFETCH = 4;      // stages of loads in flight per producer thread (registers)
+constexpr int PROD_REGS = 144, OTHER_REGS = 96;
+constexpr int GB = 3;            // stages per producer register batch (two batches of registers)
 constexpr int EPI_WARPS2 = 4;   // one per TMEM lane quarter
+static_assert(PROD_WARPS2 * PROD_REGS + (1 + EPI_WARPS2) * OTHER_REGS <= (PROD_WARPS2 + 1 + EPI_WARPS2) * 128, "register pool");
 constexpr int MMA_WARP2 = PROD_WARPS2;
 constexpr int GRAM2_THREADS = (PROD_WARPS2 + 1 + EPI_WARPS2) * 32;
 constexpr int OP_BYTES = 128 * BK * 4;                    // 8 KB: 128 columns x 16 samples
@@ -165,6 +167,12 @@ gram_tf32x3_kernel(const GramParams P) {
   const int D = P.D;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
+  // Registers: 13 warps put 4 warps on one SM sub-partition, so the launch gets 128 per thread.
+  // The MMA and epilogue warps (warpgroups 2, 3) give some back and the producers (warpgroups 0, 1)
+  // take them for their load pipeline. The pool is per CTA: 8 x 144 + 5 x 96 <= 13 x 128 (a
+  // request beyond the pool never completes), and per sub-partition 2 x 144 + 2 x 96 <= 512.
+  if (warp < PROD_WARPS2) setmaxnreg_inc<PROD_REGS>(); else setmaxnreg_dec<OTHER_REGS>();
+
   if (warp < PROD_WARPS2) {
     // =========================== producers (both CTAs) ===========================
     uint32_t stage = 0, phase = 0;
@@ -210,41 +218,45 @@ gram_tf32x3_kernel(const GramParams P) {
 
       auto produce = [&](auto fast_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
-        float4 buf[PREFETCH][4];
-        // lane r < 4 holds the row id of sample (4 quad + r) of a stage. Each prefetch slot keeps
-        // its own row-id register, refilled for the slot's NEXT use (PREFETCH stages later) while
-        // the current one is consumed, so the id load is never waited on
-        // (unconditional and clamped, never predicated: a predicated load needs a select on its
-        // result, and that select waits for the load right where it was issued)
+        // Register pipeline. ptxas tracks every global load of this loop on ONE scoreboard, so the
+        // first use of any loaded value waits for ALL loads in flight (ncu: the per-slot prefetch
+        // of the previous version waited for the refill issued one stage earlier). The loop is
+        // therefore organised in batches of GB stages and two register sets: the loads of batch
+        // j + 1 are issued right after the single wait of batch j and have the whole time batch j
+        // is being written to shared memory (GB stage periods) to land. All loads are volatile
+        // asm so they stay where they are written relative to the barrier waits and stores.
+        b128_t bufA[GB][4], bufB[GB][4];
+        // lane r < 4 holds the row id of sample (4 quad + r) of a stage; refilled one batch ahead,
+        // unconditional and clamped (a predicated load needs a select that waits on it)
         auto load_row = [&](int kb) -> uint32_t {
           const int64_t k = (int64_t)kb * BK + 4 * quad + (lane & 3);
           const int64_t idx = g.row_begin + min(k, n_c - 1);  // an empty class may sit at either end
-          return (uint32_t)__ldg(P.perm + max(min(idx, P.n - 1), (int64_t)0));
+          return ldg_nc_u32(P.perm + max(min(idx, P.n - 1), (int64_t)0));
         };
-        uint32_t rowreg[PREFETCH];
+        uint32_t rowreg[GB];
+        auto issue = [&](int kb, b128_t(&b)[GB][4]) {  // loads of stages kb .. kb + GB - 1
 #pragma unroll
-        for (int u = 0; u < PREFETCH; ++u) rowreg[u] = load_row(kb0 + u);
-        auto issue = [&](int kb, float4(&b)[4], uint32_t& rr) {
+          for (int u = 0; u < GB; ++u) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const uint32_t row = __shfl_sync(0xffffffffu, rr, r);
-            uint64_t addr;  // xcol + row * ldx floats
-            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(stride), "l"(xcol));
-            const float* ptr = reinterpret_cast<const float*>(addr);
-            if constexpr (FAST) {
-              b[r] = __ldg(reinterpret_cast<const float4*>(ptr));
-            } else {
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ncol > 0) v.x = __ldg(ptr);
-              if (ncol > 1) v.y = __ldg(ptr + 1);
-              if (ncol > 2) v.z = __ldg(ptr + 2);
-              if (ncol > 3) v.w = __ldg(ptr + 3);
-              b[r] = v;
+            for (int r = 0; r < 4; ++r) {
+              const uint32_t row = __shfl_sync(0xffffffffu, rowreg[u], r);
+              uint64_t addr;  // xcol + row * ldx floats
+              asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(row), "r"(stride), "l"(xcol));
+              const float* ptr = reinterpret_cast<const float*>(addr);
+              if constexpr (FAST) {
+                b[u][r] = ldg_nc_b128(ptr);
+              } else {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ncol > 0) v.x = ldg_nc_f32(ptr);
+                if (ncol > 1) v.y = ldg_nc_f32(ptr + 1);
+                if (ncol > 2) v.z = ldg_nc_f32(ptr + 2);
+                if (ncol > 3) v.w = ldg_nc_f32(ptr + 3);
+                b[u][r] = pack_b128(v);
+              }
             }
           }
-          // refill AFTER the last use so the load can target the same register (otherwise a MOV
-          // right behind the load waits for it)
-          rr = load_row(kb + PREFETCH);
+#pragma unroll
+          for (int u = 0; u < GB; ++u) rowreg[u] = load_row(kb + GB + u);  // ids of the NEXT batch
         };
         auto put = [&](uint32_t hp, uint32_t lp, float x0, float x1, float x2, float x3) {
           float4 h, l;
@@ -255,8 +267,11 @@ gram_tf32x3_kernel(const GramParams P) {
           st_shared_v4(hp, h);
           st_shared_v4(lp, l);
         };
-        auto consume = [&](int kb, float4(&b)[4]) {
+        auto consume = [&](int kb, const b128_t(&bq)[4]) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          float4 b[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) b[r] = unpack_b128(bq[r]);
           const int64_t nv = n_c - (int64_t)kb * BK - 4 * quad;  // valid samples among this thread's four
           if (nv < 4) {  // ragged last stage of the class: padded samples must be exact zeros
             const float4 z = make_float4(sh.x, sh.y, sh.z, sh.w);
@@ -276,19 +291,21 @@ gram_tf32x3_kernel(const GramParams P) {
           if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         };
-        // Loads are issued unconditionally (stages past the end re-read row 0 and are never
-        // consumed): a conditional refill makes the compiler merge the row-id registers with a MOV
-        // that waits for the id load just issued -- one full memory latency per stage (ncu).
+        // one batch: the first stage's write (which contains the one wait for the batch's loads),
+        // then the loads of the next batch into the other register set, then the remaining stages
+        auto batch = [&](int kb, b128_t(&cur)[GB][4], b128_t(&nxt)[GB][4]) {
+          if (kb < kb1) consume(kb, cur[0]);
+          issue(kb + GB, nxt);  // unconditional: stages past the end re-read valid rows, never consumed
 #pragma unroll
-        for (int u = 0; u < PREFETCH; ++u) issue(kb0 + u, buf[u], rowreg[u]);
-        for (int kb = kb0; kb < kb1; kb += PREFETCH) {
+          for (int u = 1; u < GB; ++u)
+            if (kb + u < kb1) consume(kb + u, cur[u]);
+        };
 #pragma unroll
-          for (int u = 0; u < PREFETCH; ++u) {
-            if (kb + u < kb1) {
-              consume(kb + u, buf[u]);
-              issue(kb + u + PREFETCH, buf[u], rowreg[u]);
-            }
-          }
+        for (int u = 0; u < GB; ++u) rowreg[u] = load_row(kb0 + u);
+        issue(kb0, bufA);
+        for (int kb = kb0; kb < kb1; kb += 2 * GB) {
+          batch(kb, bufA, bufB);
+          batch(kb + GB, bufB, bufA);
         }
       };
       if (fastw) produce(std::true_type{}); else produce(std::false_type{});

@@ -191,6 +191,45 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// Register reallocation between warp roles (warpgroup-aligned: all warps of a group of 4 execute it)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+// Read-only global loads as volatile asm: they keep their place relative to other volatile asm
+// (barrier waits, shared stores), which a register software pipeline relies on.
+// 16-byte load into ONE 128-bit register: the four words stay an aligned unit until unpack_b128,
+// so the register allocator can never put a (load-waiting) MOV behind the load itself.
+typedef unsigned __int128 b128_t;
+__device__ __forceinline__ b128_t ldg_nc_b128(const float* p) {
+  b128_t v;
+  asm volatile("ld.global.nc.b128 %0, [%1];" : "=q"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 unpack_b128(b128_t q) {
+  float4 v;
+  asm volatile("mov.b128 {%0, %1, %2, %3}, %4;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "q"(q));
+  return v;
+}
+__device__ __forceinline__ b128_t pack_b128(float4 v) {
+  b128_t q;
+  asm volatile("mov.b128 %0, {%1, %2, %3, %4};" : "=q"(q) : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+  return q;
+}
+__device__ __forceinline__ float ldg_nc_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_nc_u32(const int32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
