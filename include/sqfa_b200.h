@@ -13,6 +13,7 @@
  *   HP1  statistics.py:8-54   class_statistics      -> sqfa_label_max, sqfa_bucket_labels,
  *        statistics.py:97-124 sample_covariance        sqfa_class_sums, sqfa_class_means,
  *        statistics.py:57-94  oas_covariance           sqfa_class_gram, sqfa_stats_epilogue
+ *                                                  (all of them in one call: sqfa_class_statistics)
  *   HP2  linalg.py:19-45      conjugate_matrix      -> sqfa_project_fwd / sqfa_project_bwd
  *        model.py:172-237     transform_scatters / transform -> sqfa_project_fwd / sqfa_transform
  *        linalg.py:48-70      generalized_eigenvalues  \
@@ -110,6 +111,22 @@ size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes);
 int sqfa_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
                         int32_t n_dim, int32_t n_classes, int estimator, int ddof, float* cov, float* sm, void* ws,
                         size_t ws_bytes, sqfa_stream_t stream);
+
+/* class_statistics in ONE call (statistics.py:8-54) for n rows resident on one device: bucket the
+ * labels, per-class sums and means, Gram of the rows centred by their class mean, epilogue. It is
+ * exactly the sequence sqfa_bucket_labels -> sqfa_class_sums -> sqfa_class_means ->
+ * sqfa_class_gram (shift = means) -> sqfa_stats_epilogue enqueued on `stream` from one host call
+ * (no host round trips between the steps); multi-device callers use the separate entry points and
+ * all-reduce the partial sums between them.
+ *   means   (n_classes, n_dim)          out
+ *   cov     (n_classes, n_dim, n_dim)   out (the Gram is accumulated here, then finalised in place)
+ *   sm      (n_classes, n_dim, n_dim)   out, may be NULL
+ *   counts [n_classes + 1], offsets [n_classes + 2], perm [n]   out, as in sqfa_bucket_labels */
+size_t sqfa_class_statistics_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes);
+int sqfa_class_statistics(const float* X, int64_t ldx, const int64_t* labels, int64_t n, int32_t n_dim,
+                          int32_t n_classes, int estimator, int ddof, float* means, float* cov, float* sm,
+                          int64_t* counts, int64_t* offsets, int32_t* perm, void* ws, size_t ws_bytes,
+                          sqfa_stream_t stream);
 
 /* Test hook: D[128 x N] = A^T B through one tcgen05.mma chain with a caller-chosen operand
  * layout / descriptor (pins the UMMA layout assumptions of sqfa_class_gram on hardware). */

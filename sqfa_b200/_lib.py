@@ -47,6 +47,12 @@ SIGNATURES = {
         c_int,
         [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_int, c_int, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
     ),
+    "sqfa_class_statistics_workspace_bytes": (c_size, [c_i64, c_i32, c_i32]),
+    "sqfa_class_statistics": (
+        c_int,
+        [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_i32, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+         c_size, c_ptr],
+    ),
     "sqfa_debug_umma_probe": (
         c_int,
         [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, c_ptr],

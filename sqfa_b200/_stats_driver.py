@@ -110,6 +110,29 @@ class CudaStatsOps:
         return gram, sm
 
 
+    def fused(self, X, y, C, estimator_id, ddof, want_sm):
+        """All local steps from ONE C call (sqfa_class_statistics): no host work between kernels."""
+        lib, dev = self.lib, X.device
+        n, D = X.shape
+        means = torch.empty(C, D, dtype=torch.float32, device=dev)
+        cov = torch.empty(C, D, D, dtype=torch.float32, device=dev)
+        sm = torch.empty(C, D, D, dtype=torch.float32, device=dev) if want_sm else None
+        meta = torch.empty(2 * C + 4, dtype=torch.int64, device=dev)  # counts [C+1] | offsets [C+2]
+        counts, offsets = meta[: C + 1], meta[C + 1 : 2 * C + 3]
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        ws_bytes = lib.sqfa_class_statistics_workspace_bytes(n, D, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.sqfa_class_statistics(
+                _lib.ptr(X), X.stride(0), _lib.ptr(y), n, D, C, estimator_id, ddof, _lib.ptr(means), _lib.ptr(cov),
+                _lib.ptr(sm), _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(perm), _lib.ptr(ws), ws_bytes,
+                _lib.stream_ptr(dev),
+            ),
+            "sqfa_class_statistics",
+        )
+        return means, cov, sm, (perm, offsets, counts)
+
+
 def _all_reduce(t, group, op=None):
     import torch.distributed as dist
 
@@ -131,6 +154,11 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
             _all_reduce(mx, group, dist.ReduceOp.MAX)
         n_classes = int(mx.item()) + 1  # the one host read the reference also does (statistics.py:29)
     C = n_classes
+    if (
+        group is None and centre is None and C > 0 and y.numel() > 0
+        and getattr(ops, "fused", None) is not None and getattr(ops, "gram_events", None) is None
+    ):
+        return ops.fused(X, y, C, estimator_id, ddof, want_sm)
     perm, offsets, counts = ops.bucket(y, C)
     sums = ops.class_sums(X, perm, offsets, C)
     class_counts = counts[:C].clone()

@@ -269,3 +269,54 @@ int sqfa_fused_loss(const float* S_, const float* M, const float* F, int32_t n_c
 }
 
 }  // extern "C"
+
+extern "C" {
+
+// ---- the whole of class_statistics for rows resident on one device, in one call ----
+namespace {
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+struct StatsWs { size_t bucket, sums_ws, sums, gram, epi, total; };
+inline StatsWs stats_ws(int64_t n, int32_t D, int32_t C) {
+  StatsWs w;
+  w.bucket = align256(sqfa_bucket_workspace_bytes(n, C));
+  w.sums_ws = align256(sqfa_class_sums_workspace_bytes(n, D, C));
+  w.sums = align256((size_t)(C > 0 ? C : 1) * (size_t)(D > 0 ? D : 1) * sizeof(float));
+  w.gram = align256(sqfa_class_gram_workspace_bytes(n, D, C));
+  w.epi = align256(sqfa_stats_epilogue_workspace_bytes(C));
+  w.total = w.bucket + w.sums_ws + w.sums + w.gram + w.epi;
+  return w;
+}
+}  // namespace
+
+size_t sqfa_class_statistics_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes) {
+  return stats_ws(n < 0 ? 0 : n, n_dim, n_classes).total;
+}
+
+int sqfa_class_statistics(const float* X, int64_t ldx, const int64_t* labels, int64_t n, int32_t n_dim,
+                          int32_t n_classes, int estimator, int ddof, float* means, float* cov, float* sm,
+                          int64_t* counts, int64_t* offsets, int32_t* perm, void* ws, size_t ws_bytes,
+                          sqfa_stream_t stream) {
+  if (X == nullptr || labels == nullptr || means == nullptr || cov == nullptr || counts == nullptr ||
+      offsets == nullptr || perm == nullptr || ws == nullptr || n <= 0 || n_dim <= 0 || n_classes <= 0)
+    return fail_arg(__func__, "bad argument");
+  const StatsWs w = stats_ws(n, n_dim, n_classes);
+  if (ws_bytes < w.total) return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  void* ws_bucket = p;
+  void* ws_sums = p + w.bucket;
+  float* sums = reinterpret_cast<float*>(p + w.bucket + w.sums_ws);
+  void* ws_gram = p + w.bucket + w.sums_ws + w.sums;
+  void* ws_epi = p + w.bucket + w.sums_ws + w.sums + w.gram;
+  int rc = sqfa_bucket_labels(labels, n, n_classes, counts, offsets, perm, ws_bucket, w.bucket, stream);
+  if (rc) return rc;
+  rc = sqfa_class_sums(X, ldx, perm, offsets, nullptr, n, n_dim, n_classes, sums, 0, ws_sums, w.sums_ws, stream);
+  if (rc) return rc;
+  rc = sqfa_class_means(sums, counts, nullptr, n_dim, n_classes, means, stream);
+  if (rc) return rc;
+  rc = sqfa_class_gram(X, ldx, perm, offsets, means, n, n_dim, n_classes, cov, 0, 0, ws_gram, w.gram, stream);
+  if (rc) return rc;
+  return sqfa_stats_epilogue(cov, means, nullptr, counts, n_dim, n_classes, estimator, ddof, cov, sm, ws_epi, w.epi,
+                             stream);
+}
+
+}  // extern "C"
