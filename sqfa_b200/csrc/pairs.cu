@@ -31,6 +31,7 @@ namespace {
 constexpr int PAIR_WARPS = 4;
 constexpr float JACOBI_TOL = 1e-6f;  // |a_p . a_q| <= tol |a_p||a_q| counts as orthogonal
 constexpr int JACOBI_MAX_SWEEPS = 24;
+constexpr float JACOBI_LAST = 3e-4f;  // a sweep of rotations all below this is the last (they leave ~1e-7)
 constexpr float DIST_EPS = 1e-6f;    // distances.py:29 EPSILON
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -405,54 +406,70 @@ pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, i
     }
     __syncwarp();
     // ---- column `lane` of A: a[s] = sum_r Linv_j[lane][r] L_i[r][s]   (both factors lower triangular)
-    float a[MP], y[MP];
+    // The column lives in MP / 2 packed register pairs: dot products and rotations are packed-fp32
+    // instructions (fma.rn.f32x2 / mul.rn.f32x2), half the FMA issue slots of scalar code.
+    float2 a2[MP / 2];
+    float y[MP];
 #pragma unroll
-    for (int s = 0; s < MP; ++s) a[s] = 0.f;
+    for (int s = 0; s < MP / 2; ++s) a2[s] = make_float2(0.f, 0.f);
     if (lane < m) {
 #pragma unroll
       for (int r = 0; r < MP; ++r) {
         if (r < m) {
           const float l = sT[r * LDT + lane];
+          const float2 l2 = make_float2(l, l);
 #pragma unroll
           for (int s4 = 0; s4 < MP / 4; ++s4) {
             const float4 w = *reinterpret_cast<const float4*>(sL + r * MP + 4 * s4);
-            a[4 * s4 + 0] += l * w.x; a[4 * s4 + 1] += l * w.y; a[4 * s4 + 2] += l * w.z; a[4 * s4 + 3] += l * w.w;
+            a2[2 * s4] = __ffma2_rn(l2, make_float2(w.x, w.y), a2[2 * s4]);
+            a2[2 * s4 + 1] = __ffma2_rn(l2, make_float2(w.z, w.w), a2[2 * s4 + 1]);
           }
         }
       }
     }
     // ---- one-sided Jacobi, columns in registers
     for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
-      float nrm = 0.f;
+      float2 n2p = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int s = 0; s < MP; ++s) nrm += a[s] * a[s];
+      for (int s = 0; s < MP / 2; ++s) n2p = __ffma2_rn(a2[s], a2[s], n2p);
+      float nrm = n2p.x + n2p.y;
+      // a sweep whose largest rotation was below JACOBI_LAST leaves off-diagonals of that size
+      // squared (quadratic convergence): no verification sweep needed after it
       bool rotated = false;
       for (int r = 0; r < mp - 1; ++r) {
         const int q = lane < mp ? rr_partner(lane, r, mp) : lane;
         const float nq = __shfl_sync(0xffffffffu, nrm, q);
-        float ab = 0.f;
+        float2 y2[MP / 2];
+        float2 ab2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int s = 0; s < MP; ++s) {
-          y[s] = __shfl_sync(0xffffffffu, a[s], q);
-          ab += a[s] * y[s];
+        for (int s = 0; s < MP / 2; ++s) {
+          y2[s].x = __shfl_sync(0xffffffffu, a2[s].x, q);
+          y2[s].y = __shfl_sync(0xffffffffu, a2[s].y, q);
+          ab2 = __ffma2_rn(a2[s], y2[s], ab2);
         }
+        const float ab = ab2.x + ab2.y;
         const bool is_lo = lane < q;
         const float alpha = is_lo ? nrm : nq, beta = is_lo ? nq : nrm;
         float cs = 1.f, sn = 0.f;
-        if (lane < mp && fabsf(ab) > JACOBI_TOL * sqrtf(alpha * beta) && alpha > 0.f && beta > 0.f) {
+        const float ab_sq = ab * ab, scale = alpha * beta;
+        if (lane < mp && ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale && alpha > 0.f && beta > 0.f) {
           const float zeta = (beta - alpha) / (2.f * ab);
           const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
           cs = rsqrtf(1.f + tt * tt);
           sn = cs * tt;
           nrm = is_lo ? alpha - tt * ab : beta + tt * ab;
-          rotated = true;
+          rotated = rotated || ab_sq > (JACOBI_LAST * JACOBI_LAST) * scale;
         }
         const float other = is_lo ? -sn : sn;
+        const float2 cs2 = make_float2(cs, cs), ot2 = make_float2(other, other);
 #pragma unroll
-        for (int s = 0; s < MP; ++s) a[s] = cs * a[s] + other * y[s];
+        for (int s = 0; s < MP / 2; ++s) a2[s] = __ffma2_rn(cs2, a2[s], __fmul2_rn(ot2, y2[s]));
       }
       if (!__any_sync(0xffffffffu, rotated)) break;
     }
+    float a[MP];
+#pragma unroll
+    for (int s = 0; s < MP / 2; ++s) { a[2 * s] = a2[s].x; a[2 * s + 1] = a2[s].y; }
     // ---- eigenvalues, distance
     float n2 = 0.f;
 #pragma unroll

@@ -20,160 +20,178 @@ namespace sqfa {
 
 namespace {
 
-constexpr int PJ_THREADS = 256;
-constexpr int PJ_WARPS = PJ_THREADS / 32;
-constexpr int PJ_COLS = 128;  // columns per block (one float4 per lane)
-constexpr int PJ_ROWS = 256;  // rows of S per block
+constexpr int PS_WARPS = 4;
+constexpr int PS_THREADS = PS_WARPS * 32;
+constexpr int PS_COLS = PS_WARPS * 128;  // columns per block: one 128-column strip (float4 per lane) per warp
+constexpr int PS_MAXROWS = 256;          // rows of S per block (F^T tile in shared memory)
 
 // partial[split][c][f][j] = sum_{i in rows of split} F[f][i] * S[c][i][j]
+// Every warp streams its own 128-column strip down the rows of the split (512 contiguous bytes per
+// row and warp, R rows in flight per thread), so there is no cross-warp reduction: a thread's
+// accumulators are final for its 4 columns. HBM-bound for k <= 8.
 template <int KT>
-__global__ void __launch_bounds__(PJ_THREADS)
-project_partial_kernel(const float* __restrict__ S, const float* __restrict__ F, int C, int D, int k, int f0,
-                       int nsplit, float* __restrict__ partial, float* __restrict__ psi_partial) {
-  __shared__ __align__(16) float Fs[PJ_ROWS][KT];      // F^T tile: [row i][filter]
-  __shared__ __align__(16) float red[KT][PJ_COLS];     // cross-warp reduction buffer
+__global__ void __launch_bounds__(PS_THREADS)
+project_stream_kernel(const float* __restrict__ S, const float* __restrict__ F, int C, int D, int k, int rows,
+                      float* __restrict__ partial) {
+  __shared__ __align__(16) float Fs[PS_MAXROWS][KT];  // F^T tile: [row i][filter]
   const int c = blockIdx.z, split = blockIdx.y;
-  const int j0 = blockIdx.x * PJ_COLS;
-  const int i0 = split * PJ_ROWS;
-  const int i1 = min(D, i0 + PJ_ROWS);
+  const int i0 = split * rows;
+  const int i1 = min(D, i0 + rows);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  for (int idx = tid; idx < PJ_ROWS * KT; idx += PJ_THREADS) {
-    const int ii = idx / KT, f = idx % KT;
-    Fs[ii][f] = (i0 + ii < i1 && f0 + f < k) ? F[(int64_t)(f0 + f) * D + i0 + ii] : 0.f;
+  for (int idx = tid; idx < rows * KT; idx += PS_THREADS) {
+    const int f = idx / rows, ii = idx % rows;  // consecutive threads read consecutive i: coalesced
+    Fs[ii][f] = (i0 + ii < i1 && f < k) ? F[(int64_t)f * D + i0 + ii] : 0.f;
   }
-  for (int idx = tid; idx < KT * PJ_COLS; idx += PJ_THREADS) (&red[0][0])[idx] = 0.f;
   __syncthreads();
-
-  const int col = j0 + 4 * lane;
-  const bool vec = (D % 4 == 0) && (col + 4 <= D);
-  // accumulators packed over filter pairs: acc2[f/2][col] = (acc of filter f, acc of filter f+1)
-  // so every update is ONE Blackwell packed-fp32 FMA (fma.rn.f32x2 / FFMA2): this kernel is
-  // FMA-issue-bound, not HBM-bound, once k >= 8.
+  const int col = blockIdx.x * PS_COLS + warp * 128 + 4 * lane;
+  if (col >= D) return;
+  const bool vec = (D % 4 == 0);  // then col + 4 <= D and every row start is 16-byte aligned
+  // accumulators packed over filter pairs: acc2[f/2][q] = (filter f, filter f+1) of column col+q,
+  // so every update is ONE packed-fp32 FMA (fma.rn.f32x2): FMA issue binds this kernel for k >= 16
   float2 acc2[KT / 2][4];
 #pragma unroll
   for (int f = 0; f < KT / 2; ++f)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc2[f][q] = make_float2(0.f, 0.f);
-
-  const float* Sc = S + (int64_t)c * D * D;
-  if (col < D) {
-    // R independent 16-byte loads in flight per thread before the FMAs that consume them
-    constexpr int R = (KT >= 32) ? 4 : 8;
-    for (int ib = i0 + warp * R; ib < i1; ib += PJ_WARPS * R) {
-      float4 v[R];
+  const float* Sc = S + (int64_t)c * D * D + col;
+  constexpr int R = (KT >= 32) ? 4 : 8;  // independent 16-byte loads in flight per thread
+  for (int ib = i0; ib < i1; ib += R) {
+    float4 v[R];
 #pragma unroll
-      for (int u = 0; u < R; ++u) {
-        const int i = ib + u;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < i1) {
-          const float* p = Sc + (int64_t)i * D + col;
-          if (vec) {
-            v[u] = __ldg(reinterpret_cast<const float4*>(p));
-          } else {
-            v[u].x = __ldg(p);
-            v[u].y = col + 1 < D ? __ldg(p + 1) : 0.f;
-            v[u].z = col + 2 < D ? __ldg(p + 2) : 0.f;
-            v[u].w = col + 3 < D ? __ldg(p + 3) : 0.f;
+    for (int u = 0; u < R; ++u) {
+      const int i = ib + u;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < i1) {
+        const float* p = Sc + (int64_t)i * D;
+        if (vec) {
+          v[u] = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          v[u].x = __ldg(p);
+          v[u].y = col + 1 < D ? __ldg(p + 1) : 0.f;
+          v[u].z = col + 2 < D ? __ldg(p + 2) : 0.f;
+          v[u].w = col + 3 < D ? __ldg(p + 3) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const float* fr = Fs[min(ib + u, i1 - 1) - i0];  // rows past the end carry v = 0
+      const float2 vx = make_float2(v[u].x, v[u].x), vy = make_float2(v[u].y, v[u].y);
+      const float2 vz = make_float2(v[u].z, v[u].z), vw = make_float2(v[u].w, v[u].w);
+#pragma unroll
+      for (int f = 0; f < KT; f += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(fr + f);
+        const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+        acc2[f / 2][0] = __ffma2_rn(w01, vx, acc2[f / 2][0]);
+        acc2[f / 2][1] = __ffma2_rn(w01, vy, acc2[f / 2][1]);
+        acc2[f / 2][2] = __ffma2_rn(w01, vz, acc2[f / 2][2]);
+        acc2[f / 2][3] = __ffma2_rn(w01, vw, acc2[f / 2][3]);
+        acc2[f / 2 + 1][0] = __ffma2_rn(w23, vx, acc2[f / 2 + 1][0]);
+        acc2[f / 2 + 1][1] = __ffma2_rn(w23, vy, acc2[f / 2 + 1][1]);
+        acc2[f / 2 + 1][2] = __ffma2_rn(w23, vz, acc2[f / 2 + 1][2]);
+        acc2[f / 2 + 1][3] = __ffma2_rn(w23, vw, acc2[f / 2 + 1][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < KT; ++f) {
+    if (f < k) {
+      const float2* a = acc2[f / 2];
+      const float4 t = (f & 1) ? make_float4(a[0].y, a[1].y, a[2].y, a[3].y)
+                               : make_float4(a[0].x, a[1].x, a[2].x, a[3].x);
+      float* o = partial + (((int64_t)split * C + c) * k + f) * D + col;
+      if (vec) {
+        *reinterpret_cast<float4*>(o) = t;
+      } else {
+        o[0] = t.x;
+        if (col + 1 < D) o[1] = t.y;
+        if (col + 2 < D) o[2] = t.z;
+        if (col + 3 < D) o[3] = t.w;
+      }
+    }
+  }
+}
+
+// Row r = (c, f) of T, `tpr` threads per row (a multiple of 32, 256 / tpr rows per block):
+// T[c][f][:] = sum over the row splits of the partial products; Psi[c][f][:] = T[c][f][:] F^T and
+// mu'[c][f] = F[f][:] . m[c] from the same pass. Fixed reduction tree: deterministic.
+template <int KT, int VW>
+__global__ void __launch_bounds__(256)
+project_finish_kernel(const float* __restrict__ partial, const float* __restrict__ F, const float* __restrict__ M,
+                      int C, int D, int k, int nsplit, int tpr, float* __restrict__ T, float* __restrict__ Psi,
+                      float* __restrict__ Mu) {
+  __shared__ float red[8][KT + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (256 / tpr) + threadIdx.x / tpr, lt = threadIdx.x % tpr;
+  const bool valid = r < C * k;
+  const int c = valid ? r / k : 0, f = valid ? r % k : 0;
+  float psi[KT];
+#pragma unroll
+  for (int g = 0; g < KT; ++g) psi[g] = 0.f;
+  float mu = 0.f;
+  const int64_t row = (int64_t)r * D, sstride = (int64_t)C * k * D;
+  if (valid) {
+    for (int j = VW * lt; j < D; j += VW * tpr) {
+      if constexpr (VW == 4) {
+        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0, t3 = t0;
+        const float* pj = partial + row + j;
+        int s = 0;
+        for (; s + 4 <= nsplit; s += 4) {  // four independent loads in flight
+          const float4 a0 = *reinterpret_cast<const float4*>(pj + (int64_t)s * sstride);
+          const float4 a1 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 1) * sstride);
+          const float4 a2 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 2) * sstride);
+          const float4 a3 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 3) * sstride);
+          t0.x += a0.x; t0.y += a0.y; t0.z += a0.z; t0.w += a0.w;
+          t1.x += a1.x; t1.y += a1.y; t1.z += a1.z; t1.w += a1.w;
+          t2.x += a2.x; t2.y += a2.y; t2.z += a2.z; t2.w += a2.w;
+          t3.x += a3.x; t3.y += a3.y; t3.z += a3.z; t3.w += a3.w;
+        }
+        for (; s < nsplit; ++s) {
+          const float4 a0 = *reinterpret_cast<const float4*>(pj + (int64_t)s * sstride);
+          t0.x += a0.x; t0.y += a0.y; t0.z += a0.z; t0.w += a0.w;
+        }
+        const float4 t = make_float4((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y),
+                                     (t0.z + t1.z) + (t2.z + t3.z), (t0.w + t1.w) + (t2.w + t3.w));
+        *reinterpret_cast<float4*>(T + row + j) = t;
+#pragma unroll
+        for (int g = 0; g < KT; ++g) {
+          if (g < k) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(F + (int64_t)g * D + j));
+            psi[g] += (t.x * w.x + t.y * w.y) + (t.z * w.z + t.w * w.w);
           }
         }
-      }
-#pragma unroll
-      for (int u = 0; u < R; ++u) {
-        const int i = ib + u < i1 ? ib + u : i0;  // rows past the end carry v = 0
-        const float* fr = Fs[i - i0];
-#pragma unroll
-        const float2 vx = make_float2(v[u].x, v[u].x), vy = make_float2(v[u].y, v[u].y);
-        const float2 vz = make_float2(v[u].z, v[u].z), vw = make_float2(v[u].w, v[u].w);
-#pragma unroll
-        for (int f = 0; f < KT; f += 4) {
-          const float4 w = *reinterpret_cast<const float4*>(fr + f);
-          const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
-          acc2[f / 2][0] = __ffma2_rn(w01, vx, acc2[f / 2][0]);
-          acc2[f / 2][1] = __ffma2_rn(w01, vy, acc2[f / 2][1]);
-          acc2[f / 2][2] = __ffma2_rn(w01, vz, acc2[f / 2][2]);
-          acc2[f / 2][3] = __ffma2_rn(w01, vw, acc2[f / 2][3]);
-          acc2[f / 2 + 1][0] = __ffma2_rn(w23, vx, acc2[f / 2 + 1][0]);
-          acc2[f / 2 + 1][1] = __ffma2_rn(w23, vy, acc2[f / 2 + 1][1]);
-          acc2[f / 2 + 1][2] = __ffma2_rn(w23, vz, acc2[f / 2 + 1][2]);
-          acc2[f / 2 + 1][3] = __ffma2_rn(w23, vw, acc2[f / 2 + 1][3]);
+        if (M != nullptr) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(F + (int64_t)f * D + j));
+          const float4 m = __ldg(reinterpret_cast<const float4*>(M + (int64_t)c * D + j));
+          mu += (w.x * m.x + w.y * m.y) + (w.z * m.z + w.w * m.w);
         }
-      }
-    }
-  }
-  // deterministic cross-warp reduction: warps add in turn
-  for (int w = 0; w < PJ_WARPS; ++w) {
-    if (warp == w) {
+      } else {
+        float t = 0.f;
+        for (int s = 0; s < nsplit; ++s) t += partial[(int64_t)s * sstride + row + j];
+        T[row + j] = t;
 #pragma unroll
-      for (int f = 0; f < KT; ++f) {
-        float4* r = reinterpret_cast<float4*>(&red[f][4 * lane]);
-        float4 t = *r;
-        const float2* a = acc2[f / 2];
-        if (f & 1) { t.x += a[0].y; t.y += a[1].y; t.z += a[2].y; t.w += a[3].y; }
-        else       { t.x += a[0].x; t.y += a[1].x; t.z += a[2].x; t.w += a[3].x; }
-        *r = t;
+        for (int g = 0; g < KT; ++g)
+          if (g < k) psi[g] += t * __ldg(F + (int64_t)g * D + j);
+        if (M != nullptr) mu += __ldg(F + (int64_t)f * D + j) * __ldg(M + (int64_t)c * D + j);
       }
     }
-    __syncthreads();
   }
-  for (int idx = tid; idx < KT * PJ_COLS; idx += PJ_THREADS) {
-    const int f = idx / PJ_COLS, jj = idx % PJ_COLS;
-    if (f0 + f < k && j0 + jj < D)
-      partial[(((int64_t)split * C + c) * k + f0 + f) * D + j0 + jj] = red[f][jj];
+#pragma unroll
+  for (int g = 0; g < KT; ++g) {
+    float a = psi[g];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) red[warp][g] = a;
   }
-  // Psi = T F^T is linear in T: this block adds  sum_{j in its 128 columns} Tpart[f][j] F[g][j].
-  // The F^T tile of the main loop is dead now; its memory holds F[:, j0:j0+128].
-  float* Fj = &Fs[0][0];  // [KT][128]
-  for (int idx = tid; idx < KT * PJ_COLS; idx += PJ_THREADS) {
-    const int g = idx / PJ_COLS, jj = idx % PJ_COLS;
-    Fj[idx] = (g < k && j0 + jj < D) ? F[(int64_t)g * D + j0 + jj] : 0.f;
-  }
+  for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
+  if (lane == 0) red[warp][KT] = mu;
   __syncthreads();
-  const int nblk = nsplit * gridDim.x;
-  const int blk = split * gridDim.x + blockIdx.x;
-  float* pp = psi_partial + (int64_t)c * k * k * nblk + blk;  // layout [c][o][blk]
-  for (int o = tid; o < k * k; o += PJ_THREADS) {
-    const int f = o / k, g = o % k;
-    float a = 0.f;
-#pragma unroll 8
-    for (int jj = 0; jj < PJ_COLS; ++jj) {
-      const int j = (jj + lane) & (PJ_COLS - 1);  // per-lane rotation: conflict-free without padding
-      a += red[f][j] * Fj[g * PJ_COLS + j];
-    }
-    pp[(int64_t)o * nblk] = a;
-  }
-}
-
-// T = sum over row splits of the partial products (elementwise, fully parallel)
-__global__ void project_reduce_T_kernel(const float* __restrict__ partial, int64_t total, int nsplit,
-                                        float* __restrict__ T) {
-  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  float a = 0.f;
-  for (int s = 0; s < nsplit; ++s) a += partial[(int64_t)s * total + idx];
-  T[idx] = a;
-}
-
-// Per class: Psi = sum of the per-block partial Psi, mu' = F m (one warp per filter).
-__global__ void __launch_bounds__(256)
-project_reduce_psi_kernel(const float* __restrict__ psi_partial, const float* __restrict__ F,
-                          const float* __restrict__ M, int D, int k, int nblk, float* __restrict__ Psi,
-                          float* __restrict__ Mu) {
-  const int c = blockIdx.x;
-  const float* pp = psi_partial + (int64_t)c * nblk * k * k;  // [o][blk]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < k * k; o += 8) {  // one warp per output, lanes stride the blocks
-    float a = 0.f;
-    for (int b = lane; b < nblk; b += 32) a += pp[(int64_t)o * nblk + b];
-    for (int sh = 16; sh > 0; sh >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);
-    if (lane == 0) Psi[(int64_t)c * k * k + o] = a;
-  }
-  if (M != nullptr) {
-    for (int f = warp; f < k; f += 8) {
+  if (valid) {  // the warps of a row are contiguous: sum them in order
+    const int w0 = (threadIdx.x / tpr) * (tpr / 32);
+    for (int e = lt; e <= KT; e += tpr) {
       float a = 0.f;
-      for (int j = lane; j < D; j += 32) a += F[(int64_t)f * D + j] * M[(int64_t)c * D + j];
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) Mu[(int64_t)c * k + f] = a;
+      for (int w = 0; w < tpr / 32; ++w) a += red[w0 + w][e];
+      if (e < k) Psi[(int64_t)r * k + e] = a;
+      if (e == KT && M != nullptr) Mu[r] = a;
     }
   }
 }
@@ -315,10 +333,20 @@ __global__ void embed_bwd_kernel(const float* __restrict__ gE, const float* __re
 }
 
 template <int KT>
-cudaError_t run_partial(const float* S, const float* F, int C, int D, int k, int nsplit, float* partial,
-                        float* psi_partial, cudaStream_t st) {
-  dim3 grid((D + PJ_COLS - 1) / PJ_COLS, nsplit, C);  // k <= KT: a single filter chunk
-  project_partial_kernel<KT><<<grid, PJ_THREADS, 0, st>>>(S, F, C, D, k, 0, nsplit, partial, psi_partial);
+cudaError_t run_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, int rows, int nsplit,
+                            float* partial, float* T, float* Psi, float* Mu, cudaStream_t st) {
+  dim3 grid((D + PS_COLS - 1) / PS_COLS, nsplit, C);
+  project_stream_kernel<KT><<<grid, PS_THREADS, 0, st>>>(S, F, C, D, k, rows, partial);
+  int tpr = 32;  // threads per (class, filter) row: about 4 float4 per thread, 32 .. 256
+  while (tpr < 256 && tpr * 16 < D) tpr *= 2;
+  const int rpb = 256 / tpr;
+  const unsigned nb = (unsigned)(((int64_t)C * k + rpb - 1) / rpb);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(T) |
+                      reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(M)) & 15) == 0;
+  if (D % 4 == 0 && al16)
+    project_finish_kernel<KT, 4><<<nb, 256, 0, st>>>(partial, F, M, C, D, k, nsplit, tpr, T, Psi, Mu);
+  else
+    project_finish_kernel<KT, 1><<<nb, 256, 0, st>>>(partial, F, M, C, D, k, nsplit, tpr, T, Psi, Mu);
   return cudaGetLastError();
 }
 
@@ -340,13 +368,26 @@ cudaError_t run_transform(const float* X, int64_t ldx, const float* F, int64_t n
 
 }  // namespace
 
-int project_nsplit(int D) { return (D + PJ_ROWS - 1) / PJ_ROWS; }
+// Rows of S per block: as many as fit the F^T tile, fewer when the grid would not fill the GPU
+// (about 8 blocks of 128 threads per SM), never fewer than 64.
+int project_rows_per_split(int C, int D) {
+  const int64_t colblocks = (D + PS_COLS - 1) / PS_COLS;
+  const int64_t want = (8 * 148 + colblocks * C - 1) / (colblocks * (C > 0 ? C : 1));  // splits wanted
+  int rows = (int)((D + want - 1) / (want > 0 ? want : 1));
+  rows = (rows + 7) & ~7;
+  if (rows < 64) rows = 64;
+  if (rows > PS_MAXROWS) rows = PS_MAXROWS;
+  return rows;
+}
+int project_nsplit(int C, int D) {
+  const int rows = project_rows_per_split(C, D);
+  return (D + rows - 1) / rows;
+}
 
-static size_t project_partial_floats(int C, int D, int k) { return (size_t)project_nsplit(D) * C * k * D; }
+static size_t project_partial_floats(int C, int D, int k) { return (size_t)project_nsplit(C, D) * C * k * D; }
 
 size_t project_workspace_bytes(int C, int D, int k) {
-  const size_t nblk = (size_t)project_nsplit(D) * ((D + PJ_COLS - 1) / PJ_COLS);
-  const size_t fwd = (project_partial_floats(C, D, k) + (size_t)C * nblk * k * k) * sizeof(float);
+  const size_t fwd = project_partial_floats(C, D, k) * sizeof(float);
   const size_t bwd = (size_t)64 * k * D * sizeof(float);
   return fwd > bwd ? fwd : bwd;
 }
@@ -354,19 +395,13 @@ size_t project_workspace_bytes(int C, int D, int k) {
 cudaError_t launch_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
                                float* Psi, float* Mu, float* ws, cudaStream_t st) {
   if (C <= 0) return cudaSuccess;
-  const int nsplit = project_nsplit(D);
-  float* psi_partial = ws + project_partial_floats(C, D, k);
-  const int nblk = nsplit * ((D + PJ_COLS - 1) / PJ_COLS);
+  const int rows = project_rows_per_split(C, D), nsplit = project_nsplit(C, D);
   cudaError_t e;
-  if (k <= 4) e = run_partial<4>(S, F, C, D, k, nsplit, ws, psi_partial, st);
-  else if (k <= 8) e = run_partial<8>(S, F, C, D, k, nsplit, ws, psi_partial, st);
-  else if (k <= 16) e = run_partial<16>(S, F, C, D, k, nsplit, ws, psi_partial, st);
-  else e = run_partial<32>(S, F, C, D, k, nsplit, ws, psi_partial, st);
-  if (e != cudaSuccess) return e;
-  const int64_t total = (int64_t)C * k * D;
-  project_reduce_T_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, total, nsplit, T);
-  project_reduce_psi_kernel<<<C, 256, 0, st>>>(psi_partial, F, M, D, k, nblk, Psi, Mu);
-  return cudaGetLastError();
+  if (k <= 4) e = run_project_fwd<4>(S, M, F, C, D, k, rows, nsplit, ws, T, Psi, Mu, st);
+  else if (k <= 8) e = run_project_fwd<8>(S, M, F, C, D, k, rows, nsplit, ws, T, Psi, Mu, st);
+  else if (k <= 16) e = run_project_fwd<16>(S, M, F, C, D, k, rows, nsplit, ws, T, Psi, Mu, st);
+  else e = run_project_fwd<32>(S, M, F, C, D, k, rows, nsplit, ws, T, Psi, Mu, st);
+  return e;
 }
 
 cudaError_t launch_project_bwd(const float* gPsi, const float* gMu, const float* T, const float* M, int C, int D,

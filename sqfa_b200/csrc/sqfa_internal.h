@@ -40,7 +40,7 @@ cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K
 
 namespace sqfa {
 // ---- project.cu (K4, K6, transform, embedding) ----
-int project_nsplit(int D);
+int project_nsplit(int C, int D);
 size_t project_workspace_bytes(int C, int D, int k);
 cudaError_t launch_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
                                float* Psi, float* Mu, float* ws, cudaStream_t st);
