@@ -371,7 +371,7 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
 // sum_q c_q y_q y_q^T. ~3x fewer issue slots per pair than the shared-memory variant above,
 // which stays in use for 32 < m <= 64.
 // ------------------------------------------------------------------------------------------------
-template <int MP>
+template <int MP, int MJ>  // MP: padded size (multiple of 4, shared-memory strides); MJ: even m, the Jacobi width
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int nA, int nB, int m, int dist,
                    int tri, int64_t pair_begin, int64_t pair_end, float weight, const float* __restrict__ gD,
@@ -427,11 +427,11 @@ pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, i
         }
       }
     }
-    // ---- one-sided Jacobi, columns in registers
+    // ---- one-sided Jacobi, columns in registers (entries >= MJ are padding zeros and stay zero)
     for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
       float2 n2p = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int s = 0; s < MP / 2; ++s) n2p = __ffma2_rn(a2[s], a2[s], n2p);
+      for (int s = 0; s < MJ / 2; ++s) n2p = __ffma2_rn(a2[s], a2[s], n2p);
       float nrm = n2p.x + n2p.y;
       // a sweep whose largest rotation was below JACOBI_LAST leaves off-diagonals of that size
       // squared (quadratic convergence): no verification sweep needed after it
@@ -439,10 +439,10 @@ pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, i
       for (int r = 0; r < mp - 1; ++r) {
         const int q = lane < mp ? rr_partner(lane, r, mp) : lane;
         const float nq = __shfl_sync(0xffffffffu, nrm, q);
-        float2 y2[MP / 2];
+        float2 y2[MJ / 2];
         float2 ab2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int s = 0; s < MP / 2; ++s) {
+        for (int s = 0; s < MJ / 2; ++s) {
           y2[s].x = __shfl_sync(0xffffffffu, a2[s].x, q);
           y2[s].y = __shfl_sync(0xffffffffu, a2[s].y, q);
           ab2 = __ffma2_rn(a2[s], y2[s], ab2);
@@ -463,7 +463,7 @@ pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, i
         const float other = is_lo ? -sn : sn;
         const float2 cs2 = make_float2(cs, cs), ot2 = make_float2(other, other);
 #pragma unroll
-        for (int s = 0; s < MP / 2; ++s) a2[s] = __ffma2_rn(cs2, a2[s], __fmul2_rn(ot2, y2[s]));
+        for (int s = 0; s < MJ / 2; ++s) a2[s] = __ffma2_rn(cs2, a2[s], __fmul2_rn(ot2, y2[s]));
       }
       if (!__any_sync(0xffffffffu, rotated)) break;
     }
@@ -556,7 +556,7 @@ pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, i
   }
 }
 
-template <int MP>
+template <int MP, int MJ>
 static cudaError_t launch_pair_reg(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
                                    int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
                                    float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
@@ -565,13 +565,13 @@ static cudaError_t launch_pair_reg(const float* Wa, const float* Wb, int nA, int
   const int smem = PAIR_WARPS * per_warp_floats * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(pair_ai_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(pair_ai_reg_kernel<MP, MJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int64_t npairs = pair_end - pair_begin;
   const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
-  pair_ai_reg_kernel<MP><<<blocks, PAIR_WARPS * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end,
+  pair_ai_reg_kernel<MP, MJ><<<blocks, PAIR_WARPS * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end,
                                                                 weight, gD, dist_out, loss, gEa, gEb, eig_out);
   return cudaGetLastError();
 }
@@ -742,9 +742,12 @@ cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int 
     return cudaGetLastError();
   }
   if (m <= 32) {  // register-resident Jacobi
-#define SQFA_PAIR_REG(MPV)                                                                                      \
-  return launch_pair_reg<MPV>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD, dist_out, loss, gEa, \
-                              gEb, eig_out, st)
+#define SQFA_PAIR_REG(MPV)                                                                                   \
+  if (((m + 1) & ~1) < MPV)                                                                                    \
+    return launch_pair_reg<MPV, MPV - 2>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD, dist_out, \
+                                         loss, gEa, gEb, eig_out, st);                                          \
+  return launch_pair_reg<MPV, MPV>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD, dist_out, loss, \
+                                   gEa, gEb, eig_out, st)
     switch ((m + 3) / 4) {
       case 1: SQFA_PAIR_REG(4);
       case 2: SQFA_PAIR_REG(8);
