@@ -53,7 +53,7 @@ def synth(n, d, c, device, seed):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons sampled DURING the timed region (NVML, every ~2 ms; falls back
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, every ~10 ms; falls back
     to polling nvidia-smi if the NVML bindings are missing)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -63,6 +63,8 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        # NVML queries take a driver lock that kernel launches also need: sample sparsely
+        self.period = float(os.environ.get("SQFA_BENCH_CLOCK_PERIOD", "0.01"))
         self.max_mhz, self.nvml, self.handle = None, None, None
         try:
             import pynvml
@@ -94,7 +96,7 @@ class ClockSampler(threading.Thread):
             try:
                 if self.nvml is not None:
                     self._sample_nvml()
-                    self._stop_evt.wait(0.002)
+                    self._stop_evt.wait(self.period)
                     continue
                 out = subprocess.run(
                     ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -205,12 +207,18 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step()
-    # ---- timed region: HBM-resident inputs
-    sync_all()
+        stats = step()  # held like in the timed loop: the caching allocator reaches its steady state here
+    # ---- timed region: HBM-resident inputs (no Python garbage collection pauses inside it)
+    import gc
+
+    gc.collect()
+    gc.disable()
+    # NVML is initialised and the sampler thread started BEFORE the barrier: done after it, rank 0
+    # enters the timed region tens of ms late and every other rank's clock counts the wait
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

@@ -42,6 +42,11 @@ typedef void* sqfa_stream_t; /* cudaStream_t */
 /* estimator argument of sqfa_stats_epilogue (reference: estimator="empirical" | "oas") */
 #define SQFA_EST_EMPIRICAL 0
 #define SQFA_EST_OAS 1
+#define SQFA_EST_PACKED_GRAM 16 /* OR-ed in: the gram argument is the packed upper-tile list (below) */
+
+/* `accumulate` argument of sqfa_class_gram: a bit set */
+#define SQFA_GRAM_ACCUMULATE 1 /* add to the existing content (streaming / chunked input) */
+#define SQFA_GRAM_PACKED 2     /* write the packed list of upper tiles instead of (C, D, D) */
 
 /* distance selector of the pair kernels */
 #define SQFA_DIST_AFFINE_INVARIANT 0 /* distances.py:70-89  sqrt(sum log^2 lambda + 1e-6)      */
@@ -88,8 +93,13 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
 /* Segmented Gram on the tensor cores (tcgen05, 3xTF32):
  *   gram[c] (+)= sum_{i in c} (x_i - shift_c)(x_i - shift_c)^T        (statistics.py:119-120)
  * Only the upper triangle of every gram[c] (D x D, row-major) is defined on return.
- *   accumulate 0: gram is overwritten (zeroed, then summed); 1: added to the existing content
- *              (streaming / chunked input).
+ *   accumulate 0: gram is overwritten (zeroed, then summed); SQFA_GRAM_ACCUMULATE: added to the
+ *              existing content (streaming / chunked input). SQFA_GRAM_PACKED: gram is not
+ *              (C, D, D) but the list of the 256 x 256 tiles that intersect the upper triangle,
+ *              [class][tile (tm <= tn, row-major over the upper triangle)][256][256] floats,
+ *              sqfa_gram_packed_floats(n_dim, n_classes) in total -- the buffer a multi-device
+ *              caller all-reduces (54 % of C D^2 at D = 3072); sqfa_stats_epilogue reads it with
+ *              SQFA_EST_PACKED_GRAM. Entries of edge tiles beyond D are never written or read.
  *   chain_rows samples per tensor-core accumulation chain (0 = default 512). Every chain starts
  *              from a zero accumulator and is added to gram with fp32 red.global.add, which bounds
  *              the accumulator truncation bias of the tensor core.
@@ -97,6 +107,7 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
  *              class offsets are read)
  *   ws         sqfa_class_gram_workspace_bytes(n, n_dim, n_classes) bytes (device-side job plan). */
 size_t sqfa_class_gram_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes);
+size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes);
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
                     void* ws, size_t ws_bytes, sqfa_stream_t stream);
@@ -106,7 +117,8 @@ int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int6
  *   ddof = 1: unbiased estimate; ddof = 0: `assume_centered` (statistics.py:116)
  *   estimator == SQFA_EST_OAS applies the OAS shrinkage to cov
  *   sm[c]  = cov[c] + means[c] means[c]^T       (sm may be NULL)
- * Reads the upper triangle of gram, writes full symmetric cov and sm; cov may alias gram. */
+ * Reads the upper triangle of gram, writes full symmetric cov and sm; cov may alias gram unless
+ * gram is packed (estimator | SQFA_EST_PACKED_GRAM). */
 size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes);
 int sqfa_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
                         int32_t n_dim, int32_t n_classes, int estimator, int ddof, float* cov, float* sm, void* ws,

@@ -42,6 +42,7 @@ SIGNATURES = {
         c_int,
         [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_size, c_ptr],
     ),
+    "sqfa_gram_packed_floats": (c_size, [c_i32, c_i32]),
     "sqfa_stats_epilogue_workspace_bytes": (c_size, [c_i32]),
     "sqfa_stats_epilogue": (
         c_int,

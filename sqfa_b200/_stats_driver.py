@@ -71,11 +71,22 @@ class CudaStatsOps:
         )
         return means
 
-    def class_gram(self, X, perm, offsets, centre, C):
-        """Upper triangle of sum_{i in c} (x_i - centre_c)(x_i - centre_c)^T per class (tcgen05)."""
+    supports_packed = True  # class_gram / finalize understand the packed upper-tile layout
+
+    def packed_is_smaller(self, D, C):
+        return self.lib.sqfa_gram_packed_floats(D, C) < C * D * D  # padding to 256 can outweigh the triangle
+
+    def class_gram(self, X, perm, offsets, centre, C, packed=False):
+        """Upper triangle of sum_{i in c} (x_i - centre_c)(x_i - centre_c)^T per class (tcgen05).
+
+        packed=True returns the flat list of 256 x 256 upper tiles (what ranks all-reduce: about
+        half the bytes of (C, D, D)); `finalize(..., packed=True)` consumes it."""
         lib, dev = self.lib, X.device
         n, D = X.shape
-        gram = torch.empty(C, D, D, dtype=torch.float32, device=dev)
+        if packed:
+            gram = torch.empty(lib.sqfa_gram_packed_floats(D, C), dtype=torch.float32, device=dev)
+        else:
+            gram = torch.empty(C, D, D, dtype=torch.float32, device=dev)
         ws_bytes = lib.sqfa_class_gram_workspace_bytes(n, D, C)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         if self.gram_events is not None:
@@ -84,7 +95,7 @@ class CudaStatsOps:
         _lib.check(
             lib.sqfa_class_gram(
                 _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), n, D, C,
-                _lib.ptr(gram), 0, 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+                _lib.ptr(gram), 2 if packed else 0, 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
             ),
             "sqfa_class_gram",
         )
@@ -93,21 +104,22 @@ class CudaStatsOps:
             self.gram_events.append(ev)
         return gram
 
-    def finalize(self, gram, means, counts, estimator_id, ddof, want_sm):
-        """cov (in place over gram, mirrored), optional OAS shrinkage, second moments."""
+    def finalize(self, gram, means, counts, estimator_id, ddof, want_sm, packed=False):
+        """cov (in place over gram unless it is packed; mirrored), optional OAS shrinkage, second moments."""
         lib, dev = self.lib, gram.device
-        C, D, _ = gram.shape
+        C, D = means.shape
+        cov = torch.empty(C, D, D, dtype=torch.float32, device=dev) if packed else gram
         sm = torch.empty(C, D, D, dtype=torch.float32, device=dev) if want_sm else None
         ws_bytes = lib.sqfa_stats_epilogue_workspace_bytes(C)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(
             lib.sqfa_stats_epilogue(
-                _lib.ptr(gram), _lib.ptr(means), None, _lib.ptr(counts), D, C, estimator_id, ddof, _lib.ptr(gram),
-                _lib.ptr(sm), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+                _lib.ptr(gram), _lib.ptr(means), None, _lib.ptr(counts), D, C, estimator_id | (16 if packed else 0),
+                ddof, _lib.ptr(cov), _lib.ptr(sm), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
             ),
             "sqfa_stats_epilogue",
         )
-        return gram, sm
+        return cov, sm
 
 
     def fused(self, X, y, C, estimator_id, ddof, want_sm):
@@ -166,10 +178,17 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
         _all_reduce(sums, group)
         _all_reduce(class_counts, group)
     means = ops.class_means(sums, class_counts)
-    gram = ops.class_gram(X, perm, offsets, means if centre is None else centre, C)
-    if group is not None:
-        _all_reduce(gram, group)  # the one large collective: C x D x D partial sums over NVLink
-    cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm)
+    shift = means if centre is None else centre
+    if group is not None and getattr(ops, "supports_packed", False) and ops.packed_is_smaller(X.shape[1], C):
+        # the one large collective: partial Gram sums over NVLink, upper 256 x 256 tiles only
+        gram = ops.class_gram(X, perm, offsets, shift, C, packed=True)
+        _all_reduce(gram, group)
+        cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm, packed=True)
+    else:
+        gram = ops.class_gram(X, perm, offsets, shift, C)
+        if group is not None:
+            _all_reduce(gram, group)
+        cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm)
     return means, cov, sm, (perm, offsets, counts)
 
 

@@ -98,11 +98,16 @@ size_t sqfa_class_gram_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_class
                                     sqfa::gram_ksplit(n < 0 ? 0 : n, n_classes, n_dim, sms > 0 ? sms : 148));
 }
 
+size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes) {
+  if (n_dim <= 0 || n_classes <= 0) return 0;
+  return sqfa::gram_packed_floats(n_dim, n_classes);
+}
+
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
                     void* ws, size_t ws_bytes, sqfa_stream_t stream) {
   if (n_dim <= 0 || n_classes < 0 || offsets == nullptr || gram == nullptr || ws == nullptr || ldx < n_dim ||
-      X == nullptr || perm == nullptr)
+      X == nullptr || perm == nullptr || (accumulate & ~(SQFA_GRAM_ACCUMULATE | SQFA_GRAM_PACKED)))
     return fail_arg(__func__, "bad argument");
   if (n < 0) return fail_arg(__func__, "bad argument");
   if (ws_bytes < sqfa_class_gram_workspace_bytes(n, n_dim, n_classes))
@@ -111,7 +116,8 @@ int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int6
     return fail_arg(__func__, "too many (class, tile) jobs", SQFA_E_UNSUPPORTED);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail_arg(__func__, "no CUDA device");
-  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram, accumulate,
+  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram,
+                                                accumulate & SQFA_GRAM_ACCUMULATE, accumulate & SQFA_GRAM_PACKED,
                                                 chain_rows, ws, sms, S(stream)));
 }
 
@@ -122,13 +128,16 @@ size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes) {
 int sqfa_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
                         int32_t n_dim, int32_t n_classes, int estimator, int ddof, float* cov, float* sm, void* ws,
                         size_t ws_bytes, sqfa_stream_t stream) {
+  const int packed = estimator & SQFA_EST_PACKED_GRAM;
+  estimator &= ~SQFA_EST_PACKED_GRAM;
   if (gram == nullptr || means == nullptr || counts == nullptr || cov == nullptr || n_dim <= 0 || n_classes < 0 ||
-      (estimator != SQFA_EST_EMPIRICAL && estimator != SQFA_EST_OAS) || (ddof != 0 && ddof != 1))
+      (estimator != SQFA_EST_EMPIRICAL && estimator != SQFA_EST_OAS) || (ddof != 0 && ddof != 1) ||
+      (packed && cov == gram))
     return fail_arg(__func__, "bad argument");
   if (estimator == SQFA_EST_OAS && (ws == nullptr || ws_bytes < sqfa::stats_epilogue_workspace_bytes(n_classes)))
     return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
-  return wrap(__func__, sqfa::launch_stats_epilogue(gram, means, shift, counts, n_dim, n_classes, estimator, ddof, cov,
-                                                    sm, ws, S(stream)));
+  return wrap(__func__, sqfa::launch_stats_epilogue(gram, packed, means, shift, counts, n_dim, n_classes, estimator,
+                                                    ddof, cov, sm, ws, S(stream)));
 }
 
 int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K, int32_t N, int32_t mode,

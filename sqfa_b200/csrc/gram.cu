@@ -84,6 +84,8 @@ struct GramParams {
   int D, C, KS;
   int chain_kb;      // stages per accumulation chain
   int atomic_out;    // KS > 1 or accumulate: red.add into gram, else plain store
+  int packed;        // gram = packed list of upper tiles [class][tile][256][256] instead of (C, D, D)
+  int T, TT;         // tiles per class, tiles per side
   int vec_ok;
   int vecx;          // rows of X are 16-byte aligned: LDG.128
   int flags;         // tuning switches (env SQFA_GRAM_FLAGS): bit 0 = no A-as-B reuse on diagonal tiles
@@ -388,7 +390,16 @@ gram_tf32x3_kernel(const GramParams P) {
       const JobGeom g = decode_job(P, j);
       // TMEM lane i = 32 q + lane is operand slot i of this CTA -> tile row 4 (i % 32) + i / 32
       const int row = g.m0 + 128 * (int)rank + 4 * lane + q;
-      float* grow = P.gram + ((int64_t)g.c * D + row) * D;
+      // output row pointer, indexed by the GLOBAL column: full (C, D, D) layout, or the packed
+      // tile list (what a multi-device caller all-reduces: upper tiles only)
+      float* grow;
+      if (P.packed) {
+        const int tm = g.m0 / TM2, tn = g.n0 / TN2;
+        const int64_t t = (int64_t)tm * P.TT - (int64_t)tm * (tm - 1) / 2 + (tn - tm);
+        grow = P.gram + (((int64_t)g.c * P.T + t) * TM2 + (row - g.m0)) * TN2 - g.n0;
+      } else {
+        grow = P.gram + ((int64_t)g.c * D + row) * D;
+      }
       if (g.kb1 <= g.kb0) {  // empty class / empty K part: the tile contribution is exactly zero
         if (!P.atomic_out && row < D)
           for (int cc = 0; cc < TN2; ++cc)
@@ -486,6 +497,10 @@ gram_tf32x3_kernel(const GramParams P) {
 
 }  // namespace
 
+size_t gram_packed_floats(int D, int C) {
+  return (size_t)(C > 0 ? C : 0) * gram_tiles_per_class(D, nullptr) * TM2 * TN2;
+}
+
 int gram_tiles_per_class(int D, int* TT_out) {
   const int TT = (D + TM2 - 1) / TM2;
   if (TT_out) *TT_out = TT;
@@ -510,7 +525,7 @@ size_t gram_workspace_bytes(int C, int D, int ksplit_max) {
 }
 
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate,
+                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate, int packed,
                                int chain_rows, void* ws, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -531,13 +546,15 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
   const int cr = chain_rows > 0 ? chain_rows : 512;
   P.chain_kb = (cr + BK - 1) / BK;
   P.atomic_out = (accumulate || P.KS > 1) ? 1 : 0;
+  P.packed = packed ? 1 : 0; P.T = T; P.TT = TT;
   P.vec_ok = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(gram) & 15) == 0);
   static const int env_flags = [] { const char* e = getenv("SQFA_GRAM_FLAGS"); return e ? atoi(e) : 0; }();
   P.flags = env_flags;
   P.vecx = ((ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && !(env_flags & 4)) ? 1 : 0;
   if ((uint64_t)ldx * 4ull >= (1ull << 32)) return cudaErrorInvalidValue;
   if (P.atomic_out && !accumulate) {  // K parts are summed with red.add -> start from zero
-    cudaError_t e = cudaMemsetAsync(gram, 0, (size_t)C * D * D * sizeof(float), stream);
+    const size_t floats = packed ? (size_t)C * T * TM2 * TN2 : (size_t)C * D * D;
+    cudaError_t e = cudaMemsetAsync(gram, 0, floats * sizeof(float), stream);
     if (e != cudaSuccess) return e;
   }
   gram_plan_kernel<<<1, 1024, 0, stream>>>(offsets, C, TT, P.KS, reinterpret_cast<int4*>(ws));

@@ -20,17 +20,18 @@ cudaError_t launch_class_sums(const float* X, int64_t ldx, const int32_t* perm, 
 cudaError_t launch_class_means(const float* sums, const int64_t* counts, const float* shift, int D, int C,
                                float* means, cudaStream_t stream);
 size_t stats_epilogue_workspace_bytes(int C);
-cudaError_t launch_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
-                                  int D, int C, int estimator, int ddof, float* cov, float* sm, void* ws,
-                                  cudaStream_t stream);
+cudaError_t launch_stats_epilogue(const float* gram, int packed, const float* means, const float* shift,
+                                  const int64_t* counts, int D, int C, int estimator, int ddof, float* cov, float* sm,
+                                  void* ws, cudaStream_t stream);
 
 // ---- gram.cu (K2: tcgen05 cta_group::2 Gram on CTA pairs) ----
 int gram_tiles_per_class(int D, int* TT_out);
 int gram_ksplit(int64_t n, int C, int D, int num_sms);
 size_t gram_workspace_bytes(int C, int D, int ksplit_max);
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                              const float* shift, int64_t n, int D, int C, float* gram, int accumulate,
+                              const float* shift, int64_t n, int D, int C, float* gram, int accumulate, int packed,
                               int chain_rows, void* ws, int num_sms, cudaStream_t stream);
+size_t gram_packed_floats(int D, int C);  // floats of the packed upper-tile list (256 x 256 tiles)
 // ---- umma_probe.cu (test hook) ----
 cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K, int N, int mode, uint32_t lbo,
                               uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,

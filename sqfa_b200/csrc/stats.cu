@@ -117,8 +117,18 @@ __global__ void class_means_kernel(const float* __restrict__ sums, const int64_t
 // `cov` may alias `gram` (a block reads only its own upper tile before it writes that tile and its
 // mirror, and no other block touches either). `sm` may be NULL. ddof = 1 (unbiased) or 0.
 // ------------------------------------------------------------------------------------------------
+// Address of Gram element (r, q), r <= q tile-wise, in the full (C, D, D) layout or in the packed
+// list of 256 x 256 upper tiles written by the Gram kernel for multi-device callers.
+__device__ __forceinline__ const float* gram_elem(const float* gram, int packed, int c, int D, int r, int q) {
+  if (!packed) return gram + ((int64_t)c * D + r) * D + q;
+  const int TT = (D + 255) / 256, T = TT * (TT + 1) / 2;
+  const int tm = r >> 8, tn = q >> 8;
+  const int64_t t = (int64_t)tm * TT - (int64_t)tm * (tm - 1) / 2 + (tn - tm);
+  return gram + (((int64_t)c * T + t) * 256 + (r & 255)) * 256 + (q & 255);
+}
+
 __global__ void __launch_bounds__(256)
-stats_epilogue_kernel(const float* gram, const float* __restrict__ means,
+stats_epilogue_kernel(const float* gram, int packed, const float* __restrict__ means,
                       const float* __restrict__ shift, const int64_t* __restrict__ counts, int D, int NT, int ddof,
                       float* cov, float* sm) {
   __shared__ float s_cov[32][33];
@@ -144,12 +154,11 @@ stats_epilogue_kernel(const float* gram, const float* __restrict__ means,
   __syncthreads();
   const float n = (float)counts[c];
   const float nm1 = n - (float)ddof;
-  const float* G = gram + (int64_t)c * D * D;
   for (int rr = ty; rr < 32; rr += 8) {
     const int r = ti * 32 + rr, q = tj * 32 + tx;
     float v = 0.f;
     if (r < D && q < D) {
-      float g = G[(int64_t)r * D + q];
+      float g = *gram_elem(gram, packed, c, D, r, q);
       if (shift != nullptr) g -= n * s_d_i[rr] * s_d_j[tx];
       v = g / nm1;
     }
@@ -184,8 +193,9 @@ stats_epilogue_kernel(const float* gram, const float* __restrict__ means,
 // float4 of a 256-byte row segment (the 32 x 32 scalar version moves 128-byte segments and reaches
 // about half of the HBM bandwidth). Reads 1/2 C D^2 floats, writes 2 C D^2: HBM-bound.
 __global__ void __launch_bounds__(256)
-stats_epilogue_v4_kernel(const float* gram, const float* __restrict__ means, const float* __restrict__ shift,
-                         const int64_t* __restrict__ counts, int D, int NT, int ddof, float* cov, float* sm) {
+stats_epilogue_v4_kernel(const float* gram, int packed, const float* __restrict__ means,
+                         const float* __restrict__ shift, const int64_t* __restrict__ counts, int D, int NT, int ddof,
+                         float* cov, float* sm) {
   __shared__ float s_cov[64][65];
   __shared__ float s_mu_i[64], s_mu_j[64], s_d_i[64], s_d_j[64];
   const int c = blockIdx.y;
@@ -208,14 +218,13 @@ stats_epilogue_v4_kernel(const float* gram, const float* __restrict__ means, con
   __syncthreads();
   const float n = (float)counts[c];
   const float nm1 = n - (float)ddof;
-  const float* G = gram + (int64_t)c * D * D;
   const int q0 = tj * 64 + 4 * tx;  // D % 4 == 0: a float4 is entirely inside or outside the matrix
 #pragma unroll
   for (int rr = ty; rr < 64; rr += 16) {
     const int r = ti * 64 + rr;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < D && q0 < D) {
-      g = *reinterpret_cast<const float4*>(G + (int64_t)r * D + q0);
+      g = *reinterpret_cast<const float4*>(gram_elem(gram, packed, c, D, r, q0));
       if (shift != nullptr) {
         const float a = n * s_d_i[rr];
         g.x -= a * s_d_j[4 * tx]; g.y -= a * s_d_j[4 * tx + 1];
@@ -375,20 +384,20 @@ cudaError_t launch_class_means(const float* sums, const int64_t* counts, const f
 
 size_t stats_epilogue_workspace_bytes(int C) { return (size_t)(C > 0 ? C : 1) * OAS_BLOCKS * 2 * sizeof(double); }
 
-cudaError_t launch_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
-                                  int D, int C, int estimator, int ddof, float* cov, float* sm, void* ws,
-                                  cudaStream_t stream) {
+cudaError_t launch_stats_epilogue(const float* gram, int packed, const float* means, const float* shift,
+                                  const int64_t* counts, int D, int C, int estimator, int ddof, float* cov, float* sm,
+                                  void* ws, cudaStream_t stream) {
   if (C <= 0 || D <= 0) return cudaSuccess;
   const bool al16 = ((reinterpret_cast<uintptr_t>(gram) | reinterpret_cast<uintptr_t>(cov) |
                       reinterpret_cast<uintptr_t>(sm)) & 15) == 0;
   if (D % 4 == 0 && al16) {
     const int NT = (D + 63) / 64;
-    stats_epilogue_v4_kernel<<<dim3(NT * (NT + 1) / 2, C), 256, 0, stream>>>(gram, means, shift, counts, D, NT, ddof,
-                                                                             cov, sm);
+    stats_epilogue_v4_kernel<<<dim3(NT * (NT + 1) / 2, C), 256, 0, stream>>>(gram, packed, means, shift, counts, D, NT,
+                                                                             ddof, cov, sm);
   } else {
     const int NT = (D + 31) / 32;
-    stats_epilogue_kernel<<<dim3(NT * (NT + 1) / 2, C), 256, 0, stream>>>(gram, means, shift, counts, D, NT, ddof, cov,
-                                                                          sm);
+    stats_epilogue_kernel<<<dim3(NT * (NT + 1) / 2, C), 256, 0, stream>>>(gram, packed, means, shift, counts, D, NT, ddof,
+                                                                          cov, sm);
   }
   if (estimator == 1) {
     double* partial = static_cast<double*>(ws);

@@ -142,3 +142,26 @@ def test_gram_long_chains_and_k_split(n, d, c, kw):
     got = class_statistics(X.cuda(), y.cuda())
     for key in ("means", "covariances", "second_moments"):
         assert rel_err(got[key], ref64[key]) < TOL / 3, key
+
+
+@pytest.mark.parametrize("n,d,c", [(6000, 784, 4), (3000, 1027, 3), (9000, 520, 7), (4000, 200, 5)])
+def test_packed_gram_exchange_layout(n, d, c):
+    """The packed upper-tile Gram (the buffer ranks all-reduce) gives bit-identical statistics to the
+    full (C, D, D) layout, also for D that is not a multiple of the tile or of 4 and with a K split."""
+    from sqfa_b200 import _lib
+    from sqfa_b200._stats_driver import CudaStatsOps
+
+    X, y = make_class_data(n, d, c, seed=d)
+    X, y = X.cuda(), y.cuda()
+    ops = CudaStatsOps()
+    perm, offsets, counts = ops.bucket(y, c)
+    means = ops.class_means(ops.class_sums(X, perm, offsets, c), counts[:c].clone())
+    full = ops.class_gram(X, perm, offsets, means, c)
+    packed = ops.class_gram(X, perm, offsets, means, c, packed=True)
+    assert packed.numel() == _lib.load().sqfa_gram_packed_floats(d, c)
+    cov_f, sm_f = ops.finalize(full, means, counts[:c].clone(), 0, 1, True)
+    cov_p, sm_p = ops.finalize(packed, means, counts[:c].clone(), 0, 1, True, packed=True)
+    assert torch.equal(cov_f, cov_p) and torch.equal(sm_f, sm_p)
+    cov_o, sm_o = ops.finalize(packed, means, counts[:c].clone(), 1, 1, True, packed=True)  # OAS from packed
+    ref = O.class_statistics(X.double().cpu(), y.cpu(), estimator="oas")
+    assert rel_err(cov_o, ref["covariances"]) < TOL and rel_err(sm_o, ref["second_moments"]) < TOL
