@@ -64,8 +64,11 @@ int sqfa_device_sm_count(void);
  * HP1: class_statistics (statistics.py:8-54)
  * ------------------------------------------------------------------------------------------- */
 
-/* max(labels) -> *out_max (device int64; -1 when n == 0 or all labels negative).
- * Reference: `n_classes = int(torch.max(labels) + 1)` statistics.py:29. */
+/* max(labels) -> *out_max (int64; -1 when n == 0 or all labels negative).
+ * Reference: `n_classes = int(torch.max(labels) + 1)` statistics.py:29.
+ * out_max may be device memory or MAPPED PINNED HOST memory: the kernel stores the result there
+ * itself, so the host can wait on an event recorded behind the call and read the value without a
+ * device-to-host copy (which would queue behind bulk transfers of other streams on the copy engine). */
 int sqfa_label_max(const int64_t* labels, int64_t n, int64_t* out_max, sqfa_stream_t stream);
 
 /* Stable bucketing of rows by label (statistics.py:37, `(labels == i).nonzero()` for every i).

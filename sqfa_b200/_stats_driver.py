@@ -29,6 +29,27 @@ class CudaStatsOps:
         )
         return mx
 
+    _HOST_SLOTS = 32
+
+    def label_max_host(self, y):
+        """max(labels) as a Python int: the kernel stores it in mapped pinned host memory and the
+        host waits on an event. No device-to-host copy, so the read does not queue behind bulk
+        transfers other streams have on the copy engine (`.item()` would)."""
+        if getattr(self, "_host_mx", None) is None:
+            self._host_mx = torch.empty(self._HOST_SLOTS, dtype=torch.int64).pin_memory()
+            self._host_next = 0
+        k = self._host_next
+        self._host_next = (k + 1) % self._HOST_SLOTS
+        slot = self._host_mx[k : k + 1]
+        _lib.check(
+            self.lib.sqfa_label_max(_lib.ptr(y), y.numel(), _lib.ptr(slot), _lib.stream_ptr(y.device)),
+            "sqfa_label_max",
+        )
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(y.device))
+        ev.synchronize()
+        return int(slot[0])
+
     def bucket(self, y, C):
         lib, dev, n = self.lib, y.device, y.numel()
         counts = torch.empty(C + 1, dtype=torch.int64, device=dev)
@@ -159,12 +180,19 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
     rows, statistics.py:118-120). `centre` (C, D) overrides the centring vectors.
     """
     if n_classes is None:
-        mx = ops.label_max(y)
-        if group is not None:
-            import torch.distributed as dist
+        # the one host read the reference also does (statistics.py:29)
+        if group is None and getattr(ops, "label_max_host", None) is not None:
+            n_classes = ops.label_max_host(y) + 1
+        else:
+            mx = ops.label_max(y)
+            if group is not None:
+                import torch.distributed as dist
 
-            _all_reduce(mx, group, dist.ReduceOp.MAX)
-        n_classes = int(mx.item()) + 1  # the one host read the reference also does (statistics.py:29)
+                _all_reduce(mx, group, dist.ReduceOp.MAX)
+            if getattr(ops, "label_max_host", None) is not None:
+                n_classes = ops.label_max_host(mx) + 1  # max of one element: publishes it to the host
+            else:
+                n_classes = int(mx.item()) + 1
     C = n_classes
     if (
         group is None and centre is None and C > 0 and y.numel() > 0

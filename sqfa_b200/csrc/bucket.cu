@@ -7,6 +7,7 @@
 // rows whose label is outside [0, C) belong to no class in the reference and are parked in a
 // trailing "dropped" bucket with key C.
 #include <cstdint>
+#include <atomic>
 #include <cuda_runtime.h>
 
 #include "sqfa_internal.h"
@@ -23,7 +24,17 @@ constexpr int TILE = 32 * STEPS_PER_TILE;  // elements per warp tile
 
 __device__ __forceinline__ int32_t clip_label(int64_t y, int32_t C) { return (y < 0 || y >= C) ? C : (int32_t)y; }
 
-__global__ void label_max_kernel(const int64_t* __restrict__ labels, int64_t n, long long* out) {
+// max(labels) without touching a copy engine: block maxima meet in a scratch slot (device globals,
+// one of LM_SLOTS per call so that calls on different streams do not share one), the last block
+// publishes the result to `out` -- device memory or MAPPED PINNED HOST memory (then the caller
+// waits on an event instead of issuing a device-to-host copy that would queue behind bulk
+// transfers of other streams) -- and resets the slot for its next use.
+constexpr int LM_SLOTS = 64;
+__device__ long long g_lm_max[LM_SLOTS] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+__device__ unsigned int g_lm_count[LM_SLOTS];  // zero-initialised
+
+__global__ void label_max_kernel(const int64_t* __restrict__ labels, int64_t n, int slot, long long* out) {
+  __shared__ long long s_m[8];
   long long m = -1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const long long v = labels[i];
@@ -33,7 +44,20 @@ __global__ void label_max_kernel(const int64_t* __restrict__ labels, int64_t n, 
     const long long other = __shfl_xor_sync(0xffffffffu, m, o);
     m = other > m ? other : m;
   }
-  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = s_m[w] > m ? s_m[w] : m;
+    atomicMax(&g_lm_max[slot], m);
+    __threadfence();
+    if (atomicAdd(&g_lm_count[slot], 1u) == gridDim.x - 1) {  // last block: publish and reset the slot
+      __threadfence();
+      const long long r = (long long)atomicExch(reinterpret_cast<unsigned long long*>(&g_lm_max[slot]), ~0ull);
+      g_lm_count[slot] = 0u;
+      *reinterpret_cast<volatile long long*>(out) = r;
+      __threadfence_system();
+    }
+  }
 }
 
 template <bool FIRST>
@@ -148,15 +172,13 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace
 
 cudaError_t launch_label_max(const int64_t* labels, int64_t n, int64_t* out_max, cudaStream_t stream) {
-  const long long init = -1;
-  cudaError_t e = cudaMemcpyAsync(out_max, &init, sizeof(init), cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess) return e;
-  if (n > 0) {
-    const int threads = 256;
-    int64_t blocks = (n + threads * 8 - 1) / (threads * 8);
-    if (blocks > 1184) blocks = 1184;
-    label_max_kernel<<<(int)blocks, threads, 0, stream>>>(labels, n, reinterpret_cast<long long*>(out_max));
-  }
+  static std::atomic<unsigned> next_slot{0};
+  const int slot = (int)(next_slot.fetch_add(1u) % LM_SLOTS);
+  const int threads = 256;
+  int64_t blocks = (n + threads * 8 - 1) / (threads * 8);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;  // n == 0: one block publishes -1
+  label_max_kernel<<<(int)blocks, threads, 0, stream>>>(labels, n, slot, reinterpret_cast<long long*>(out_max));
   return cudaGetLastError();
 }
 

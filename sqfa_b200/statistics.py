@@ -64,7 +64,7 @@ def bucket_labels(labels, n_classes=None):
     ops = _cuda_ops()
     with torch.cuda.device(dev):
         if n_classes is None:
-            n_classes = int(ops.label_max(y).item()) + 1
+            n_classes = ops.label_max_host(y) + 1
         return ops.bucket(y, int(n_classes))
 
 
