@@ -165,3 +165,40 @@ def test_packed_gram_exchange_layout(n, d, c):
     cov_o, sm_o = ops.finalize(packed, means, counts[:c].clone(), 1, 1, True, packed=True)  # OAS from packed
     ref = O.class_statistics(X.double().cpu(), y.cpu(), estimator="oas")
     assert rel_err(cov_o, ref["covariances"]) < TOL and rel_err(sm_o, ref["second_moments"]) < TOL
+
+
+@pytest.mark.parametrize("n,d,c,est", [(5000, 512, 6, "empirical"), (3000, 203, 4, "oas"), (2000, 1027, 3, "empirical")])
+def test_single_call_entry_matches_stepwise(n, d, c, est):
+    """sqfa_class_statistics (one host call) enqueues exactly the step-by-step sequence: identical bits."""
+    from sqfa_b200._stats_driver import CudaStatsOps, run_class_statistics
+
+    X, y = make_class_data(n, d, c, seed=7 * d)
+    X, y = X.cuda(), y.cuda()
+    ops = CudaStatsOps()
+    est_id = 1 if est == "oas" else 0
+    m1, cov1, sm1, (perm1, off1, cnt1) = run_class_statistics(ops, X, y, est_id)  # fused path
+    ops.gram_events = []  # instrumented -> step by step
+    m2, cov2, sm2, (perm2, off2, cnt2) = run_class_statistics(ops, X, y, est_id)
+    ops.gram_events = None
+    assert torch.equal(m1, m2) and torch.equal(cov1, cov2) and torch.equal(sm1, sm2)
+    assert torch.equal(perm1, perm2) and torch.equal(off1, off2) and torch.equal(cnt1, cnt2)
+    ref = O.class_statistics(X.double().cpu(), y.cpu(), estimator=est)
+    assert rel_err(cov1, ref["covariances"]) < TOL
+
+
+def test_label_max_published_to_mapped_host_memory():
+    """The label maximum lands in pinned host memory without a device-to-host copy, also when calls
+    from several streams are in flight and for empty / all-negative labels."""
+    from sqfa_b200._stats_driver import CudaStatsOps
+
+    ops = CudaStatsOps()
+    g = torch.Generator().manual_seed(3)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    for rep in range(40):  # more calls than scratch slots
+        hi = int(torch.randint(1, 5000, (1,), generator=g))
+        y = torch.randint(0, hi, (int(torch.randint(1, 200000, (1,), generator=g)),), generator=g)
+        with torch.cuda.stream(streams[rep % 4]):
+            yd = y.cuda(non_blocking=False)
+            assert ops.label_max_host(yd) == int(y.max())
+    assert ops.label_max_host(torch.empty(0, dtype=torch.int64, device="cuda")) == -1
+    assert ops.label_max_host(torch.full((1000,), -7, dtype=torch.int64, device="cuda")) == -1

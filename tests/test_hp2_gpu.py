@@ -235,3 +235,20 @@ def test_error_types_match_reference():
         )
     with pytest.raises(TypeError):
         SQFA(n_dim=8, n_filters=2).get_class_distances(stats["second_moments"])
+
+
+@pytest.mark.parametrize("C,D,k", [(3, 1027, 5), (7, 40, 3), (2, 3072, 8), (130, 96, 16), (5, 520, 32)])
+def test_project_forward_shapes(C, D, k):
+    """T = F S, Psi = T F^T, mu' = F m for row splits, partial column strips, D % 4 != 0, every KT."""
+    from sqfa_b200 import _ops
+
+    g = torch.Generator().manual_seed(C * D + k)
+    A = torch.randn(C, D, D, generator=g)
+    S = (A + A.transpose(1, 2)) / 2
+    M = torch.randn(C, D, generator=g)
+    F = torch.randn(k, D, generator=g) / D**0.5
+    T, Psi, Mu = _ops.project_fwd_raw(S.cuda(), M.cuda(), F.cuda())
+    T64 = torch.einsum("fi,cij->cfj", F.double(), S.double())
+    assert rel_err(T, T64) < 1e-5
+    assert rel_err(Psi, torch.einsum("cfj,gj->cfg", T64, F.double())) < 1e-5
+    assert rel_err(Mu, M.double() @ F.double().T) < 1e-5
