@@ -81,6 +81,22 @@ class CudaStatsOps:
         )
         return sums
 
+    def class_sums_shifted(self, X, perm, offsets, shift, C):
+        """sum over each class of (x - shift_c) (streaming accumulator)."""
+        lib, dev = self.lib, X.device
+        n, D = X.shape
+        sums = torch.empty(C, D, dtype=torch.float32, device=dev)
+        ws_bytes = lib.sqfa_class_sums_workspace_bytes(n, D, C)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.sqfa_class_sums(
+                _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(shift), n, D, C, _lib.ptr(sums),
+                0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+            ),
+            "sqfa_class_sums",
+        )
+        return sums
+
     def class_means(self, sums, counts):
         C, D = sums.shape
         means = torch.empty_like(sums)

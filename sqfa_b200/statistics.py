@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._stats_driver import CudaStatsOps, run_class_statistics
 
-__all__ = ["class_statistics", "oas_covariance", "pca", "pca_from_scatter"]
+__all__ = ["class_statistics", "oas_covariance", "pca", "pca_from_scatter"]  # the reference's; extensions below
 
 _ESTIMATORS = {"empirical": 0, "oas": 1}
 _ops_singleton = None
@@ -110,6 +110,142 @@ def class_statistics(points, labels, estimator="empirical", keep_on_device=False
     if out_dev != dev and not keep_on_device:
         stats = {k: v.to(out_dev) for k, v in stats.items()}
     return stats
+
+
+class StreamingClassStatistics:
+    """Out-of-core `class_statistics`: chunks of labeled rows are folded into the additive per-class
+    state (count, sum (x - s), sum (x - s)(x - s)^T) with a fixed shift s, and `finalize` returns the
+    reference's statistics dict (statistics.py:8-54) for all rows seen so far.
+
+    This is BASELINE config 5 (N = 100 M rows do not exist as one tensor) and SURVEY section 8(f)
+    row 2; it uses the same kernels as `class_statistics` with their `accumulate` / `shift`
+    arguments. The shift only has to be near the class means (it keeps the accumulated Gram
+    well-conditioned; the epilogue removes it exactly): by default it is the class means of the
+    first chunk. With `group`, every rank streams its own rows, the shift of rank 0 is broadcast at
+    the first update and `finalize` all-reduces the state.
+
+    >>> acc = StreamingClassStatistics(n_dim=1024, n_classes=100)
+    >>> for X_chunk, y_chunk in loader: acc.update(X_chunk, y_chunk)
+    >>> stats = acc.finalize()            # {"means", "covariances", "second_moments"}
+    """
+
+    def __init__(self, n_dim, n_classes, shift=None, device=None, group=None):
+        self.D, self.C = int(n_dim), int(n_classes)
+        if self.D <= 0 or self.C <= 0:
+            raise ValueError("n_dim and n_classes must be positive")
+        self.dev = _lib.compute_device() if device is None else torch.device(device)
+        self.group = group
+        self.lib = _lib.load()
+        self.shift = None if shift is None else torch.as_tensor(shift, dtype=torch.float32).to(self.dev).contiguous()
+        if self.shift is not None and tuple(self.shift.shape) != (self.C, self.D):
+            raise ValueError("shift must have shape (n_classes, n_dim)")
+        with torch.cuda.device(self.dev):
+            self.counts = torch.zeros(self.C, dtype=torch.int64, device=self.dev)
+            self.sums = torch.zeros(self.C, self.D, dtype=torch.float32, device=self.dev)
+            self.gram = torch.zeros(self.C, self.D, self.D, dtype=torch.float32, device=self.dev)
+        self.n_rows = 0
+        self._auto_shift = shift is None and group is None  # ranks must keep identical shifts
+        self._rows_at_shift = 0
+
+    def _first_shift(self, X, perm, offsets, counts):
+        ops = _cuda_ops()
+        m = ops.class_means(ops.class_sums(X, perm, offsets, self.C), counts[: self.C].clone())
+        fallback = X.mean(dim=0, keepdim=True).expand_as(m)  # classes absent from the first chunk
+        shift = torch.where(torch.isfinite(m), m, fallback).contiguous()
+        if self.group is not None:
+            import torch.distributed as dist
+
+            dist.broadcast(shift, src=dist.get_global_rank(self.group, 0), group=self.group)
+        return shift
+
+    def update(self, points, labels):
+        """Fold a chunk of rows (n, n_dim) float32 with labels (n,) into the state. Rows whose label is
+        outside [0, n_classes) are ignored, like rows no `labels == i` selects in the reference."""
+        lib, dev, C, D = self.lib, self.dev, self.C, self.D
+        X = _as_device_points(points, dev)
+        y = _as_device_labels(labels, dev)
+        if X.shape[1] != D or y.numel() != X.shape[0]:
+            raise ValueError("chunk must have shape (n, n_dim) and one label per row")
+        n = X.shape[0]
+        if n == 0:
+            return self
+        with torch.cuda.device(dev):
+            ops = _cuda_ops()
+            perm, offsets, counts = ops.bucket(y, C)
+            if self.shift is None:
+                self.shift = self._first_shift(X, perm, offsets, counts)
+                self._rows_at_shift = n
+            elif self._auto_shift and self.n_rows + n >= 4 * self._rows_at_shift:
+                self._recentre(X, perm, offsets, counts)
+            st = _lib.stream_ptr(dev)
+            nb = lib.sqfa_class_sums_workspace_bytes(n, D, C)
+            ws = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
+            _lib.check(
+                lib.sqfa_class_sums(_lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(self.shift),
+                                    n, D, C, _lib.ptr(self.sums), 1, _lib.ptr(ws), nb, st),
+                "sqfa_class_sums",
+            )
+            nb = lib.sqfa_class_gram_workspace_bytes(n, D, C)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.check(
+                lib.sqfa_class_gram(_lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(self.shift),
+                                    n, D, C, _lib.ptr(self.gram), 1, 0, _lib.ptr(ws), nb, st),
+                "sqfa_class_gram",
+            )
+            self.counts += counts[:C]
+            self.n_rows += n
+        return self
+
+    def _recentre(self, X, perm, offsets, counts):
+        """Move the shift to the class means of (rows so far + the incoming chunk) BEFORE the chunk is
+        accumulated. Exact algebra: with m = s' - s the old state becomes G - m u^T - u m^T + n m m^T,
+        u - n m. Done every time the number of rows grows 4x, so the shift stays within a few
+        standard errors of the means whatever the first chunk looked like -- a shift far from the
+        mean inflates the accumulated Gram by n d d^T and with it the fp32 rounding error."""
+        ops = _cuda_ops()
+        u_c = ops.class_sums_shifted(X, perm, offsets, self.shift, self.C)
+        n_old = self.counts.to(torch.float32)[:, None]
+        n_all = n_old + counts[: self.C].to(torch.float32)[:, None]
+        m = torch.where(n_all > 0, (self.sums + u_c) / n_all.clamp_min(1.0), torch.zeros_like(self.sums))
+        u = self.sums
+        self.gram.addcmul_(m.unsqueeze(2), u.unsqueeze(1), value=-1.0)  # elementwise fp32, no temporaries
+        self.gram.addcmul_(u.unsqueeze(2), m.unsqueeze(1), value=-1.0)
+        self.gram.addcmul_((m * n_old).unsqueeze(2), m.unsqueeze(1), value=1.0)
+        self.sums = (u - n_old * m).contiguous()
+        self.shift = (self.shift + m).contiguous()
+        self._rows_at_shift = self.n_rows + X.shape[0]
+
+    def finalize(self, estimator="empirical"):
+        """Statistics of all rows folded in so far (the state is left untouched: more chunks may follow)."""
+        if estimator not in _ESTIMATORS:
+            raise ValueError(f"estimator must be 'empirical' or 'oas', got {estimator!r}")
+        if self.shift is None:
+            raise RuntimeError("StreamingClassStatistics.finalize: no rows were folded in")
+        lib, dev, C, D = self.lib, self.dev, self.C, self.D
+        with torch.cuda.device(dev):
+            counts, sums, gram = self.counts, self.sums, self.gram
+            if self.group is not None:
+                import torch.distributed as dist
+
+                counts, sums, gram = counts.clone(), sums.clone(), gram.clone()
+                for t in (counts, sums, gram):
+                    dist.all_reduce(t, group=self.group)
+            st = _lib.stream_ptr(dev)
+            means = torch.empty(C, D, dtype=torch.float32, device=dev)
+            _lib.check(
+                lib.sqfa_class_means(_lib.ptr(sums), _lib.ptr(counts), _lib.ptr(self.shift), D, C, _lib.ptr(means), st),
+                "sqfa_class_means",
+            )
+            cov = torch.empty(C, D, D, dtype=torch.float32, device=dev)
+            sm = torch.empty(C, D, D, dtype=torch.float32, device=dev)
+            nb = lib.sqfa_stats_epilogue_workspace_bytes(C)
+            ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.check(
+                lib.sqfa_stats_epilogue(_lib.ptr(gram), _lib.ptr(means), _lib.ptr(self.shift), _lib.ptr(counts), D, C,
+                                        _ESTIMATORS[estimator], 1, _lib.ptr(cov), _lib.ptr(sm), _lib.ptr(ws), nb, st),
+                "sqfa_stats_epilogue",
+            )
+        return {"means": means, "covariances": cov, "second_moments": sm}
 
 
 def _single_class(points, estimator_id, assume_centered):

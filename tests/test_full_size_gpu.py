@@ -97,3 +97,44 @@ def test_closure_and_fit_full_size_properties(cfg):
     loss, _ = model.fit(data_statistics=stats, max_epochs=epochs, show_progress=False, return_loss=True)
     assert torch.isfinite(loss).all()
     assert float(loss[-1]) <= float(loss[0]) + 1e-7  # the objective (minus mean distance) goes down
+
+
+def test_c5_shard_full_size_and_streaming():
+    """BASELINE config 5, the shard one of 8 GPUs holds: 12.5 M rows x 1024 dims (51 GB), 100 classes.
+    One-shot class_statistics on the resident shard against (a) the streaming accumulator fed in four
+    chunks (different code path: fixed shift + accumulate) and (b) an fp64 computation of two classes."""
+    from sqfa_b200.statistics import StreamingClassStatistics, class_statistics
+
+    n, d, c = 12_500_000, 1024, 100
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80e9:
+        pytest.skip("needs 80 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    y = torch.randint(0, c, (n,), generator=g, device="cuda")
+    means = 0.3 * torch.randn(c, d, generator=g, device="cuda")
+    scale = 0.5 + torch.rand(c, 1, generator=g, device="cuda")
+    X = torch.empty(n, d, device="cuda")
+    step = 500_000
+    for lo in range(0, n, step):  # chunked generation: no second 51 GB temporary
+        yy = y[lo:lo + step]
+        blk = torch.randn(yy.numel(), d, generator=g, device="cuda")
+        X[lo:lo + step] = blk * scale[yy] + means[yy]
+    del blk
+    s = class_statistics(X, y)
+    acc = StreamingClassStatistics(d, c)
+    cuts = [0, 1_000_003, 5_000_000, 9_999_999, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        acc.update(X[a:b], y[a:b])
+    t = acc.finalize()
+    for key in ("means", "covariances", "second_moments"):
+        err = float((s[key].double() - t[key].double()).norm() / t[key].double().norm())
+        assert err < 1e-5, (key, err)
+    for cls in (0, 57):
+        rows = X[y == cls].double()
+        mu = rows.mean(0)
+        xc = rows - mu
+        cov = xc.T @ xc / (rows.shape[0] - 1)
+        assert float((s["means"][cls].double() - mu).norm() / mu.norm()) < 1e-5
+        assert float((s["covariances"][cls].double() - cov).norm() / cov.norm()) < 1e-5
+        sm = cov + torch.outer(mu, mu)
+        assert float((s["second_moments"][cls].double() - sm).norm() / sm.norm()) < 1e-5

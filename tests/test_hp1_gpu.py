@@ -202,3 +202,29 @@ def test_label_max_published_to_mapped_host_memory():
             assert ops.label_max_host(yd) == int(y.max())
     assert ops.label_max_host(torch.empty(0, dtype=torch.int64, device="cuda")) == -1
     assert ops.label_max_host(torch.full((1000,), -7, dtype=torch.int64, device="cuda")) == -1
+
+
+@pytest.mark.parametrize("est", ["empirical", "oas"])
+def test_streaming_statistics_match_one_shot(est):
+    """Chunked accumulation (ragged chunks, a class absent from the first chunk, rows with labels out
+    of range) equals class_statistics on the concatenation and the oracle."""
+    from sqfa_b200.statistics import StreamingClassStatistics, class_statistics
+
+    n, d, c = 20000, 300, 7
+    X, y = make_class_data(n, d, c, seed=11)
+    X = X + 3.0  # means far from zero: the shift matters
+    order = torch.argsort((y == 6).float(), stable=True)  # class 6 only shows up late
+    X, y = X[order].contiguous(), y[order].contiguous()
+    ref = O.class_statistics(X.double(), y, estimator=est)
+    one = class_statistics(X.cuda(), y.cuda(), estimator=est)
+    acc = StreamingClassStatistics(d, c)
+    cuts = [0, 1, 5000, 5000, 12001, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        acc.update(X[a:b], y[a:b])  # CPU chunks: uploaded by update
+    junk = torch.randn(50, d)
+    acc.update(junk, torch.full((50,), c + 3))  # out-of-range labels are dropped
+    got = acc.finalize(estimator=est)
+    assert acc.n_rows == n + 50
+    for key in ("means", "covariances", "second_moments"):
+        assert rel_err(got[key], ref[key]) < TOL, key
+        assert rel_err(got[key], one[key].double().cpu()) < TOL, key
