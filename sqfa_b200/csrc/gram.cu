@@ -15,22 +15,24 @@
 //
 // Warp roles per CTA (13 warps):
 //   0-7   producers : a thread owns a block of 4 samples x 4 adjacent columns of a stage: four
-//                     LDG.128 (512 B per warp and sample row, gathered through the bucket
-//                     permutation) straight into registers, 4 stages of loads in flight; it
-//                     centres, splits hi/lo and stores four K-major 16-byte chunks per half. The four
-//                     columns of a thread go to operand SLOTS l, 32+l, 64+l, 96+l (slot s holds
-//                     column 4 (s % 32) + s / 32 of the tile), which keeps every STS.128
-//                     conflict-free; the epilogue undoes the permutation. Load instructions and
-//                     address arithmetic per element drop 4x against one column per thread (the
-//                     LSU issue rate of 32-bit loads was the limiter).
+//                     16-byte loads (512 B per warp and sample row, gathered through the bucket
+//                     permutation) straight into registers; it centres, splits hi/lo and stores four
+//                     K-major 16-byte chunks per half. The four columns of a thread go to operand
+//                     SLOTS l, 32+l, 64+l, 96+l (slot s holds column 4 (s % 32) + s / 32 of the
+//                     tile), which keeps every STS.128 conflict-free; the epilogue undoes the
+//                     permutation. The loads run as a register pipeline in batches of GB stages
+//                     with ONE wait per batch (ptxas tracks all of them on one scoreboard), the
+//                     next batch's loads issued right behind that wait; registers for it come from
+//                     setmaxnreg (producers 144, the other warps 96).
 //   8     MMA       : leader CTA only; per K=8 step 3 tcgen05.mma.cta_group::2 (cross terms into
 //                     their own TMEM accumulator, hi*hi into the main one), multicast commits
 //   9-12  epilogue  : the tensor core truncates when it adds into its fp32 accumulator (bias
 //                     ~ -2^-25 per MMA, measured), so the main accumulator only ever holds a CHAIN
 //                     of <= chain_rows samples: at every chain end these warps add it (fp32,
-//                     round-to-nearest) to a 128 x 256 running sum in shared memory and hand the
-//                     accumulator back; at the end of the tile they add the cross-term accumulator
-//                     and store the tile (red.global.add only when a tile is split along K).
+//                     round-to-nearest, pipelined tcgen05.ld + LDS.128/STS.128) to a 128 x 256
+//                     running sum in shared memory and hand the accumulator back; at the end of
+//                     the tile they add the cross-term accumulator and store the tile
+//                     (red.global.add only when a tile is split along K or the caller accumulates).
 // Jobs (class, tile, K part) are listed by a device-side plan (largest classes first) and dealt
 // round-robin to the CTA pairs: no atomics, no host sync, no cluster barrier per job.
 #include <cstdint>
@@ -88,7 +90,8 @@ struct GramParams {
   int T, TT;         // tiles per class, tiles per side
   int vec_ok;
   int vecx;          // rows of X are 16-byte aligned: LDG.128
-  int flags;         // tuning switches (env SQFA_GRAM_FLAGS): bit 0 = no A-as-B reuse on diagonal tiles
+  int flags;         // tuning switches (env SQFA_GRAM_FLAGS): 1 = no A-as-B reuse on diagonal tiles,
+                     // 4 = scalar loads, 8 = no early cross-term MMAs during a chain drain
 };
 
 // Job list: classes in descending size, tiles of a class adjacent (they share the gathered rows
