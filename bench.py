@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = {"name": "configs[1] CIFAR-10-shaped synthetic", "N": 50000, "D": 3072, "C": 10, "k": 8}
 METRIC = "class_statistics samples/sec"
-KERNELS_PER_STEP = 13  # label_max, hist, scan, scatter, offsets, counts, sums, sums_finalize, means,
+KERNELS_PER_STEP = 15  # label_max, radix hist + 3 scan + scatter, offsets, counts, sums + finalize, means, plan, gram, epilogue
 #                        gram_plan, gram_tf32x3, stats_epilogue (+ transposed write) -- ours, per step
 
 

@@ -89,29 +89,105 @@ radix_hist_kernel(const int64_t* __restrict__ labels, const int32_t* __restrict_
   for (int b = lane; b < RADIX; b += 32) hist[(int64_t)b * ntiles + tile] = h[b];
 }
 
-// exclusive scan, one block; n is small (256 * ntiles)
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int32_t* a, int64_t n) {
-  __shared__ int64_t s_sum[1024];
-  const int tid = threadIdx.x;
-  const int64_t chunk = (n + 1023) / 1024;
-  const int64_t lo = tid * chunk;
-  const int64_t hi = lo + chunk < n ? lo + chunk : n;
-  int64_t sum = 0;
-  for (int64_t i = lo; i < hi; ++i) sum += a[i];
-  s_sum[tid] = sum;
+// Exclusive scan of the (digit-major) histogram in three coalesced kernels: per-chunk sums, scan of
+// the chunk sums (one block), per-chunk scan with the chunk offset. A chunk is 8192 entries: every
+// thread of a 1024-thread block owns 8 consecutive ones (two int4 loads).
+constexpr int SCAN_THREADS = 1024, SCAN_PER_THREAD = 8, SCAN_CHUNK = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ void scan_load8(const int32_t* a, int64_t n, int64_t i0, int32_t (&v)[8]) {
+  if (i0 + 8 <= n) {
+    const int4 x = *reinterpret_cast<const int4*>(a + i0), y = *reinterpret_cast<const int4*>(a + i0 + 4);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = i0 + j < n ? a[i0 + j] : 0;
+  }
+}
+
+// block-wide exclusive scan of one value per thread (1024 threads); returns the block total in *total
+__device__ __forceinline__ int32_t block_exclusive_scan(int32_t x, int32_t* s_warp, int32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t inc = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-    int64_t v = tid >= o ? s_sum[tid - o] : 0;
-    __syncthreads();
-    s_sum[tid] += v;
-    __syncthreads();
+  if (warp == 0) {
+    int32_t w = s_warp[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w;           // exclusive offset of warp `lane`
+    if (lane == 31) s_warp[32] = wi;  // block total
   }
-  int64_t run = s_sum[tid] - sum;
-  for (int64_t i = lo; i < hi; ++i) {
-    const int32_t t = a[i];
-    a[i] = (int32_t)run;
-    run += t;
+  __syncthreads();
+  const int32_t r = s_warp[warp] + inc - x;
+  *total = s_warp[32];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_chunk_sums_kernel(const int32_t* __restrict__ a, int64_t n,
+                                                                       int32_t* __restrict__ sums) {
+  __shared__ int32_t s_warp[33];
+  int32_t v[8];
+  scan_load8(a, n, (int64_t)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD, v);
+  int32_t t = 0, total;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t += v[j];
+  block_exclusive_scan(t, s_warp, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int32_t* sums, int nchunks) {
+  __shared__ int32_t s_warp[33];
+  int32_t carry = 0;
+  for (int base = 0; base < nchunks; base += SCAN_THREADS) {
+    const int i = base + threadIdx.x;
+    const int32_t x = i < nchunks ? sums[i] : 0;
+    int32_t total;
+    const int32_t e = block_exclusive_scan(x, s_warp, &total);
+    if (i < nchunks) sums[i] = carry + e;
+    carry += total;
   }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int32_t* a, int64_t n,
+                                                                  const int32_t* __restrict__ sums) {
+  __shared__ int32_t s_warp[33];
+  const int64_t i0 = (int64_t)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD;
+  int32_t v[8];
+  scan_load8(a, n, i0, v);
+  int32_t t = 0, total;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t += v[j];
+  int32_t run = sums[blockIdx.x] + block_exclusive_scan(t, s_warp, &total);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int32_t x = v[j];
+    v[j] = run;
+    run += x;
+  }
+  if (i0 + 8 <= n) {
+    *reinterpret_cast<int4*>(a + i0) = make_int4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<int4*>(a + i0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (i0 + j < n) a[i0 + j] = v[j];
+  }
+}
+
+static void launch_exclusive_scan(int32_t* a, int64_t n, int32_t* chunk_sums, cudaStream_t stream) {
+  const int nchunks = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  scan_chunk_sums_kernel<<<nchunks, SCAN_THREADS, 0, stream>>>(a, n, chunk_sums);
+  scan_sums_kernel<<<1, SCAN_THREADS, 0, stream>>>(chunk_sums, nchunks);
+  scan_apply_kernel<<<nchunks, SCAN_THREADS, 0, stream>>>(a, n, chunk_sums);
 }
 
 template <bool FIRST>
@@ -187,7 +263,9 @@ size_t bucket_workspace_bytes(int64_t n, int32_t C) {
   const int64_t ntiles = (n + TILE - 1) / TILE;
   size_t b = 0;
   b += 4 * align_up((size_t)(n > 0 ? n : 1) * sizeof(int32_t), 256);  // keys x2, vals x2
-  b += align_up((size_t)(ntiles > 0 ? ntiles : 1) * RADIX * sizeof(int32_t), 256);
+  const size_t hist_entries = (size_t)(ntiles > 0 ? ntiles : 1) * RADIX;
+  b += align_up(hist_entries * sizeof(int32_t), 256);
+  b += align_up(((hist_entries + SCAN_CHUNK - 1) / SCAN_CHUNK) * sizeof(int32_t), 256);  // scan chunk sums
   return b;
 }
 
@@ -201,6 +279,8 @@ cudaError_t launch_bucket_labels(const int64_t* labels, int64_t n, int32_t C, in
   int32_t* keys[2] = {reinterpret_cast<int32_t*>(p), reinterpret_cast<int32_t*>(p + nb)};
   int32_t* vals[2] = {reinterpret_cast<int32_t*>(p + 2 * nb), reinterpret_cast<int32_t*>(p + 3 * nb)};
   int32_t* hist = reinterpret_cast<int32_t*>(p + 4 * nb);
+  int32_t* chunk_sums = reinterpret_cast<int32_t*>(
+      p + 4 * nb + align_up((size_t)(ntiles > 0 ? ntiles : 1) * RADIX * sizeof(int32_t), 256));
 
   int bits = 0;
   while ((1ll << bits) < (int64_t)C + 1) ++bits;  // keys take values 0..C
@@ -218,12 +298,12 @@ cudaError_t launch_bucket_labels(const int64_t* labels, int64_t n, int32_t C, in
       int32_t* vout = (pass == passes - 1) ? perm : vals[cur ^ 1];
       if (pass == 0) {
         radix_hist_kernel<true><<<blocks, threads, 0, stream>>>(labels, nullptr, n, C, shift, hist, ntiles);
-        exclusive_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int64_t)ntiles * RADIX);
+        launch_exclusive_scan(hist, (int64_t)ntiles * RADIX, chunk_sums, stream);
         radix_scatter_kernel<true><<<blocks, threads, 0, stream>>>(labels, nullptr, nullptr, n, C, shift, hist,
                                                                    ntiles, keys[cur ^ 1], vout);
       } else {
         radix_hist_kernel<false><<<blocks, threads, 0, stream>>>(nullptr, keys[cur], n, C, shift, hist, ntiles);
-        exclusive_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int64_t)ntiles * RADIX);
+        launch_exclusive_scan(hist, (int64_t)ntiles * RADIX, chunk_sums, stream);
         radix_scatter_kernel<false><<<blocks, threads, 0, stream>>>(nullptr, keys[cur], vals[cur], n, C, shift,
                                                                     hist, ntiles, keys[cur ^ 1], vout);
       }
