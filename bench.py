@@ -30,8 +30,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = {"name": "configs[1] CIFAR-10-shaped synthetic", "N": 50000, "D": 3072, "C": 10, "k": 8}
 METRIC = "class_statistics samples/sec"
-KERNELS_PER_STEP = 15  # label_max, radix hist + 3 scan + scatter, offsets, counts, sums + finalize, means, plan, gram, epilogue
-#                        gram_plan, gram_tf32x3, stats_epilogue (+ transposed write) -- ours, per step
+# ours, per step: label_max, radix hist + 3 scan kernels + scatter, class offsets, counts, class sums +
+# finalize, means, gram_plan, gram_tf32x3, stats_epilogue
+KERNELS_PER_STEP = 15
 
 
 def synth(n, d, c, device, seed):
