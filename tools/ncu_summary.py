@@ -44,7 +44,11 @@ def main():
                 out[key + "_unit"] = units[i]
             except ValueError:
                 pass
-    out = {k: v for k, v in out.items() if not (k.endswith("_unit") and v in ("", "%", "ms", "Mbyte", "register/thread"))}
+    # durations are reported by ncu in a unit of its choosing: normalise to ms
+    u = out.get("duration_ms_unit", "ms")
+    if "duration_ms" in out:
+        out["duration_ms"] = round(out["duration_ms"] * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1.0), 5)
+    out = {k: v for k, v in out.items() if not (k.endswith("_unit") and v in ("", "%", "ms", "us", "ns", "Mbyte", "register/thread"))}
     src = list(csv.reader(io.StringIO(run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + regex]))))
     h = src[1]
     stalls = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
