@@ -39,14 +39,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // round-robin (circle method) partner of player p in round r, mp players (mp even)
 __device__ __forceinline__ int rr_partner(int p, int r, int mp) {
   const int n1 = mp - 1;
   // players i, j < n1 meet in the round with i + j == 2 r (mod n1); the one left over (2 i == 2 r,
   // i.e. i == r because n1 is odd) meets the fixed player n1
   if (p == n1) return r;
-  int q = (2 * r - p) % n1;
+  int q = 2 * r - p;  // in (-n1, 2 n1): one conditional correction replaces the modulo
   if (q < 0) q += n1;
+  else if (q >= n1) q -= n1;
   return q == p ? n1 : q;
 }
 
@@ -453,9 +465,12 @@ pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, i
         float cs = 1.f, sn = 0.f;
         const float ab_sq = ab * ab, scale = alpha * beta;
         if (lane < mp && ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale && alpha > 0.f && beta > 0.f) {
-          const float zeta = (beta - alpha) / (2.f * ab);
-          const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-          cs = rsqrtf(1.f + tt * tt);
+          // approximate reciprocal / square root (1 MUFU each): a Jacobi rotation only has to be
+          // orthogonal to fp32 precision (cs^2 + sn^2 = 1 from the same rsqrt as before); an angle
+          // off by 1e-7 relative leaves an off-diagonal of that size, far below the tolerance
+          const float zeta = (beta - alpha) * rcp_approx(2.f * ab);
+          const float tt = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
+          cs = rsqrtf(fmaf(tt, tt, 1.f));
           sn = cs * tt;
           nrm = is_lo ? alpha - tt * ab : beta + tt * ab;
           rotated = rotated || ab_sq > (JACOBI_LAST * JACOBI_LAST) * scale;
