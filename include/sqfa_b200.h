@@ -229,6 +229,29 @@ int sqfa_fused_loss(const float* S, const float* M, const float* F, int32_t n_cl
                     int32_t n_filters, float noise, int32_t dist, int64_t pair_begin, int64_t pair_end, float* out,
                     float* dF, void* ws, size_t ws_bytes, sqfa_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser support (reference: torch.optim.LBFGS driven by fitting_loop, _optim.py:78-96)
+ * ------------------------------------------------------------------------------------------- */
+
+/* One L-BFGS iteration's "update memory + two-loop recursion" (torch/optim/lbfgs.py, no line search)
+ * in one launch, same arithmetic in the same order:
+ *   unless first:  y = g - prev_g,  s = t_prev * d,  ys = y.s;
+ *                  if ys > 1e-10: append (y, s, 1/ys) to the history (dropping the oldest pair when
+ *                  `history` pairs are held) and set H = ys / y.y
+ *   q = -g; newest..oldest: al_i = ro_i s_i.q, q -= al_i y_i;  r = H q;
+ *   oldest..newest: r += (al_i - ro_i y_i.r) s_i;   d = r;  prev_g = g      (first: d = -g, H = 1)
+ * State owned by the caller, all device memory: prev_g, d [n]; S, Y [(history + 1) * n] (ring with
+ * one spare row); ro [history + 1]; hdiag [1]; meta int32 [2] = {ring head, pairs held}.
+ * out_scalars [5] = {ys, g.d, max|d|, sum|g|, pairs held} may be device or MAPPED PINNED HOST
+ * memory (the host then needs only an event wait to apply the optimiser's stopping rules).
+ * n <= sqfa_lbfgs_max_n() (the vector lives in the registers of one 8-CTA cluster),
+ * history <= sqfa_lbfgs_max_history(); otherwise SQFA_E_UNSUPPORTED. */
+int64_t sqfa_lbfgs_max_n(void);
+int32_t sqfa_lbfgs_max_history(void);
+int sqfa_lbfgs_direction(const float* g, float* prev_g, float* d, float* S, float* Y, float* ro, float* hdiag,
+                         int32_t* meta, int64_t n, int32_t history, float t_prev, int first, float* out_scalars,
+                         sqfa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,12 @@ SIGNATURES = {
         [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_i32, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
          c_size, c_ptr],
     ),
+    "sqfa_lbfgs_max_n": (c_i64, []),
+    "sqfa_lbfgs_max_history": (c_i32, []),
+    "sqfa_lbfgs_direction": (
+        c_int,
+        [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i32, ctypes.c_float, c_int, c_ptr, c_ptr],
+    ),
     "sqfa_debug_umma_probe": (
         c_int,
         [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, c_ptr],

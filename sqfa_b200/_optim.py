@@ -10,8 +10,10 @@ backward` sequence is ONE fused native evaluation (`_ops.FusedLoss`), for any ot
 import time
 
 import torch
-from torch import optim
+from torch import optim  # noqa: F401  (kept: the reference module exposes it)
 from tqdm import tqdm
+
+from ._lbfgs import LBFGS
 
 __all__ = ["fitting_loop"]
 
@@ -56,7 +58,7 @@ def fitting_loop(
     stops after 3 consecutive epochs whose loss change is below `atol`. Returns
     `(loss per epoch, elapsed time per epoch)` tensors when `return_loss` is True, else None.
     """
-    optimizer = optim.LBFGS(model.parameters(), lr=lr, **kwargs)
+    optimizer = LBFGS(model.parameters(), lr=lr, **kwargs)  # torch.optim.LBFGS, direction update on the device
 
     if isinstance(data_statistics, dict):
         n_classes = data_statistics["means"].shape[0]

@@ -329,3 +329,22 @@ int sqfa_class_statistics(const float* X, int64_t ldx, const int64_t* labels, in
 }
 
 }  // extern "C"
+
+extern "C" {
+
+int64_t sqfa_lbfgs_max_n(void) { return sqfa::lbfgs_max_n(); }
+int32_t sqfa_lbfgs_max_history(void) { return sqfa::lbfgs_max_history(); }
+
+int sqfa_lbfgs_direction(const float* g, float* prev_g, float* d, float* S_, float* Y, float* ro, float* hdiag,
+                         int32_t* meta, int64_t n, int32_t history, float t_prev, int first, float* out_scalars,
+                         sqfa_stream_t stream) {
+  if (g == nullptr || prev_g == nullptr || d == nullptr || S_ == nullptr || Y == nullptr || ro == nullptr ||
+      hdiag == nullptr || meta == nullptr || out_scalars == nullptr || n <= 0 || history < 1)
+    return fail_arg(__func__, "bad argument");
+  if (n > sqfa::lbfgs_max_n() || history > sqfa::lbfgs_max_history())
+    return fail_arg(__func__, "vector or history too large for the single-cluster kernel", SQFA_E_UNSUPPORTED);
+  return wrap(__func__, sqfa::launch_lbfgs_direction(g, prev_g, d, S_, Y, ro, hdiag, meta, n, history, t_prev,
+                                                     first ? 1 : 0, out_scalars, S(stream)));
+}
+
+}  // extern "C"

@@ -73,3 +73,12 @@ cudaError_t launch_fused_loss(const float* S, const float* M, const float* F, in
                               cudaStream_t st);
 }  // namespace sqfa
 
+
+namespace sqfa {
+// ---- lbfgs.cu (device-side L-BFGS direction update) ----
+int lbfgs_max_n();
+int lbfgs_max_history();
+cudaError_t launch_lbfgs_direction(const float* g, float* prev_g, float* d, float* S, float* Y, float* ro, float* hdiag,
+                                   int32_t* meta, int64_t n, int history, float t_prev, int first, float* out,
+                                   cudaStream_t stream);
+}  // namespace sqfa

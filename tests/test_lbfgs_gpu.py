@@ -1,0 +1,84 @@
+"""GPU: the device-side L-BFGS direction update against torch.optim.LBFGS (the reference's optimiser,
+_optim.py:78-79) -- same iterates up to the summation order inside the dot products."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _quadratic(n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    diag = torch.exp(torch.empty(n, device="cuda").uniform_(-4.0, 4.0, generator=g))  # condition number ~3000
+    U = torch.randn(n, 8, generator=g, device="cuda") / n**0.5
+    b = torch.randn(n, generator=g, device="cuda")
+
+    def f(x):  # 0.5 x^T (diag + U U^T) x - b^T x
+        return 0.5 * (x * diag * x).sum() + 0.5 * ((x @ U) ** 2).sum() - (b * x).sum()
+
+    return f
+
+
+def _run(opt_cls, f, n, steps, **kw):
+    x = torch.nn.Parameter(torch.zeros(n, device="cuda"))
+    opt = opt_cls([x], **kw)
+    losses = []
+
+    def closure():
+        opt.zero_grad()
+        loss = f(x)
+        loss.backward()
+        return loss
+
+    for _ in range(steps):
+        losses.append(float(opt.step(closure)))
+    return x.detach().clone(), losses, opt
+
+
+@pytest.mark.parametrize("n,hist", [(3000, 5), (20000, 100), (100000, 7), (8192 * 16, 3)])
+def test_direction_update_matches_torch_lbfgs(n, hist):
+    from sqfa_b200._lbfgs import LBFGS
+
+    f = _quadratic(n, n)
+    kw = dict(lr=0.3, history_size=hist, max_iter=12)
+    x_ref, l_ref, opt_ref = _run(torch.optim.LBFGS, f, n, 3, **kw)
+    x_got, l_got, opt = _run(LBFGS, f, n, 3, **kw)
+    st, st_ref = opt.state[opt._params[0]], opt_ref.state[opt_ref._params[0]]
+    assert "sqfa_native" in st, "the native path was not taken"
+    assert st["n_iter"] == st_ref["n_iter"] == 36 and st["func_evals"] == st_ref["func_evals"]
+    assert float((x_got - x_ref).norm() / x_ref.norm()) < 1e-4
+    for a, b in zip(l_got, l_ref):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(b))
+    assert int(st["sqfa_native"]["meta"][1]) == len(st_ref["old_dirs"]) == min(hist, 35)  # the ring wrapped
+
+
+def test_unsupported_configurations_fall_back_to_torch():
+    from sqfa_b200._lbfgs import LBFGS
+
+    f = _quadratic(500, 1)
+    x_ref, l_ref, _ = _run(torch.optim.LBFGS, f, 500, 2, lr=1.0, line_search_fn="strong_wolfe")
+    x_got, l_got, opt = _run(LBFGS, f, 500, 2, lr=1.0, line_search_fn="strong_wolfe")
+    assert "sqfa_native" not in opt.state[opt._params[0]]
+    assert torch.equal(x_ref, x_got) and l_ref == l_got
+
+
+def test_fit_with_device_lbfgs_matches_torch_lbfgs(monkeypatch):
+    """SQFA.fit loss per epoch: device-side direction update vs plain torch.optim.LBFGS."""
+    import sqfa_b200._optim as optim_mod
+    from conftest import make_class_data
+    from sqfa_b200.model import SQFA
+    from sqfa_b200.statistics import class_statistics
+
+    X, y = make_class_data(4000, 60, 5, seed=2)
+    stats = class_statistics(X.cuda(), y.cuda())
+    F0 = torch.randn(3, 60, generator=torch.Generator().manual_seed(0))
+    out = {}
+    for name, cls in (("native", optim_mod.LBFGS), ("torch", torch.optim.LBFGS)):
+        monkeypatch.setattr(optim_mod, "LBFGS", cls)
+        model = SQFA(n_dim=60, feature_noise=0.01, n_filters=3, filters=F0.clone())
+        loss, _ = model.fit(data_statistics=stats, max_epochs=3, atol=0.0, show_progress=False, return_loss=True,
+                            max_iter=8)
+        out[name] = (loss, model.filters.detach().cpu())
+    assert torch.allclose(out["native"][0], out["torch"][0], rtol=2e-4, atol=1e-6)
+    Fa, Fb = out["native"][1], out["torch"][1]
+    assert float((Fa - Fb).norm() / Fb.norm()) < 5e-3
