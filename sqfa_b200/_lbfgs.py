@@ -63,6 +63,16 @@ class LBFGS(torch.optim.LBFGS):
         ev.synchronize()  # the kernel stored the scalars in pinned host memory itself: no copy
         return nat["out"][:5].tolist()
 
+    def _grad_and_absmax(self, p):
+        """Flat gradient (a view when possible: the kernel copies what it keeps) and max|grad|; a
+        closure that already read that scalar with its loss leaves it in `_last_grad_absmax`."""
+        g = p.grad
+        flat = g.view(-1) if (g is not None and g.is_contiguous() and not g.is_sparse) else self._gather_flat_grad()
+        absmax = self.__dict__.pop("_last_grad_absmax", None)
+        if absmax is None:
+            absmax = float(flat.abs().max())
+        return flat, absmax
+
     @torch.no_grad()
     def step(self, closure):  # noqa: C901  (mirrors the control flow of torch.optim.LBFGS.step)
         nat = self._native_state()
@@ -85,8 +95,8 @@ class LBFGS(torch.optim.LBFGS):
         current_evals = 1
         state["func_evals"] += 1
         with torch.cuda.device(p.device):
-            flat_grad = self._gather_flat_grad()
-            if float(flat_grad.abs().max()) <= tolerance_grad:
+            flat_grad, grad_absmax = self._grad_and_absmax(p)
+            if grad_absmax <= tolerance_grad:
                 return orig_loss
 
             prev_loss = state.get("prev_loss")
@@ -107,8 +117,8 @@ class LBFGS(torch.optim.LBFGS):
                 opt_cond = False
                 if n_iter != max_iter:
                     loss = float(closure())
-                    flat_grad = self._gather_flat_grad()
-                    opt_cond = float(flat_grad.abs().max()) <= tolerance_grad
+                    flat_grad, grad_absmax = self._grad_and_absmax(p)
+                    opt_cond = grad_absmax <= tolerance_grad
                     ls_func_evals = 1
                 current_evals += ls_func_evals
                 state["func_evals"] += ls_func_evals

@@ -250,6 +250,41 @@ class PairDistance(torch.autograd.Function):
         return ga, gb, None, None
 
 
+def fused_loss_raw(F, S, M, noise, dist, group=None, ws=None):
+    """One native evaluation of the closure body at the (constrained) filters F: returns the packed
+    device vector [loss, #non-finite pair distances, dLoss/dF (k*D)]. With a process group the pair
+    list is split across ranks and the vector is all-reduced."""
+    lib = _lib.load()
+    dev = S.device
+    Fc = f32c(F, dev)
+    C, D, _ = S.shape
+    k = Fc.shape[0]
+    P = C * (C - 1) // 2
+    rank, world = 0, 1
+    if group is not None:
+        import torch.distributed as dist_mod
+
+        rank, world = dist_mod.get_rank(group), dist_mod.get_world_size(group)
+    p0, p1 = (P * rank) // world, (P * (rank + 1)) // world
+    nbytes = lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist)
+    if ws is None or ws.numel() < nbytes or ws.device != dev:
+        ws = _ws(nbytes, dev)
+    # [loss, #non-finite, dF...] in one buffer: one all-reduce when the pair list is sharded
+    packed = torch.empty(2 + k * D, dtype=torch.float32, device=dev)
+    _lib.check(
+        lib.sqfa_fused_loss(
+            _lib.ptr(S), _lib.ptr(M), _lib.ptr(Fc), C, D, k, float(noise), dist, p0, p1, _lib.ptr(packed),
+            ctypes.c_void_p(packed.data_ptr() + 8), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
+        ),
+        "sqfa_fused_loss",
+    )
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.all_reduce(packed, group=group)
+    return packed
+
+
 class FusedLoss(torch.autograd.Function):
     """The whole closure body of the reference's fitting loop (_optim.py:90-96) at fixed filters:
 
@@ -264,34 +299,8 @@ class FusedLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, F, S, M, noise, dist, group, ws=None):
-        lib = _lib.load()
-        dev = S.device
-        Fc = f32c(F, dev)
-        C, D, _ = S.shape
-        k = Fc.shape[0]
-        P = C * (C - 1) // 2
-        rank, world = 0, 1
-        if group is not None:
-            import torch.distributed as dist_mod
-
-            rank, world = dist_mod.get_rank(group), dist_mod.get_world_size(group)
-        p0, p1 = (P * rank) // world, (P * (rank + 1)) // world
-        nbytes = lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist)
-        if ws is None or ws.numel() < nbytes or ws.device != dev:
-            ws = _ws(nbytes, dev)
-        # [loss, #non-finite, dF...] in one buffer: one all-reduce when the pair list is sharded
-        packed = torch.empty(2 + k * D, dtype=torch.float32, device=dev)
-        _lib.check(
-            lib.sqfa_fused_loss(
-                _lib.ptr(S), _lib.ptr(M), _lib.ptr(Fc), C, D, k, float(noise), dist, p0, p1, _lib.ptr(packed),
-                ctypes.c_void_p(packed.data_ptr() + 8), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
-            ),
-            "sqfa_fused_loss",
-        )
-        if world > 1:
-            import torch.distributed as dist_mod
-
-            dist_mod.all_reduce(packed, group=group)
+        packed = fused_loss_raw(F, S, M, noise, dist, group, ws)
+        k, D = F.shape[0], S.shape[1]
         ctx.save_for_backward(packed[2:].view(k, D))
         return packed[:2]
 

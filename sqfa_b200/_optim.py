@@ -66,10 +66,19 @@ def fitting_loop(
         n_classes = data_statistics.shape[0]
 
     fused = model._fused_loss_plan(data_statistics) if hasattr(model, "_fused_loss_plan") else None
+    direct = model._fused_direct_plan(data_statistics) if hasattr(model, "_fused_direct_plan") else None
     tril_ind = None
 
     def closure():
         nonlocal tril_ind
+        if direct is not None:
+            # native loss + gradient, gradient written to .grad without an autograd graph; ONE host
+            # read per evaluation, which also carries max|grad| for the optimiser's first stopping test
+            loss_value, bad, grad_absmax = direct().tolist()
+            if bad != 0 or loss_value != loss_value:
+                raise ValueError(_NAN_MSG if loss_value != loss_value else _INF_MSG)
+            optimizer._last_grad_absmax = grad_absmax
+            return torch.tensor(loss_value)
         optimizer.zero_grad()
         if fused is not None:
             out = fused()  # [loss, #non-finite pair distances] -- one native evaluation
