@@ -295,6 +295,112 @@ transform_kernel(const float* __restrict__ X, int64_t ldx, const float* __restri
   }
 }
 
+// Z = X F^T for 16-byte aligned rows: a persistent mini-GEMM. A block walks row tiles of 64 rows;
+// per 128-column chunk the X tile (64 x 128, padded rows: conflict-free LDS.128) and the F^T tile
+// ([column][filter], so four filters of one column are one LDS.128 broadcast) arrive with cp.async
+// while the previous chunk is being multiplied (two buffers). Thread (row, g) owns KF = KT/4
+// filters of one row, accumulated as packed pairs: one fma.rn.f32x2 per two filters and column.
+// HBM-bound for k <= 16 (one read of X), about FMA-bound at k = 32.
+constexpr int TT_ROWS = 64, TT_COLS = 128, TT_LDX = TT_COLS + 4, TT_THREADS = 256;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int KF>
+__global__ void __launch_bounds__(TT_THREADS)
+transform_tile_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ F, int64_t n, int D, int k,
+                      float* __restrict__ Z) {
+  constexpr int KT = 4 * KF;
+  extern __shared__ __align__(16) float tsm[];
+  float* Xs = tsm;                              // [2][TT_ROWS][TT_LDX]
+  float* Fs = tsm + 2 * TT_ROWS * TT_LDX;       // [2][TT_COLS][KT]
+  const int tid = threadIdx.x;
+  const int row = tid & (TT_ROWS - 1), fg = tid >> 6;  // a warp: 32 consecutive rows, one filter group
+  const int nchunks = (D + TT_COLS - 1) / TT_COLS;
+  const int64_t ntiles = (n + TT_ROWS - 1) / TT_ROWS;
+  const uint32_t xs_u = (uint32_t)__cvta_generic_to_shared(Xs), fs_u = (uint32_t)__cvta_generic_to_shared(Fs);
+
+  auto load_chunk = [&](int64_t r0, int c0, int buf) {
+    // X tile: 64 rows x 32 float4; rows past n and columns past D are zero-filled (src_bytes = 0)
+    for (int idx = tid; idx < TT_ROWS * (TT_COLS / 4); idx += TT_THREADS) {
+      const int r = idx >> 5, c4 = idx & 31;
+      const int64_t gr = r0 + r;
+      const int gc = c0 + 4 * c4;
+      const bool ok = gr < n && gc < D;  // D % 4 == 0 on this path: a float4 is all inside or all outside
+      const float* src = ok ? X + gr * ldx + gc : X;
+      cp_async_16(xs_u + (uint32_t)(((buf * TT_ROWS + r) * TT_LDX + 4 * c4) * 4), src, ok ? 16 : 0);
+    }
+    // F^T tile: Fs[c][f] = F[f][c0 + c]
+    for (int idx = tid; idx < TT_COLS * KT; idx += TT_THREADS) {
+      const int f = idx / TT_COLS, c = idx % TT_COLS;  // consecutive threads read consecutive columns
+      const bool ok = f < k && c0 + c < D;
+      const float* src = ok ? F + (int64_t)f * D + c0 + c : F;
+      cp_async_4(fs_u + (uint32_t)(((buf * TT_COLS + c) * KT + f) * 4), src, ok ? 4 : 0);
+    }
+    cp_async_commit();
+  };
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = tile * TT_ROWS;
+    float2 acc[KF / 2];
+#pragma unroll
+    for (int i = 0; i < KF / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+    load_chunk(r0, 0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int buf = ch & 1;
+      if (ch + 1 < nchunks) {
+        load_chunk(r0, (ch + 1) * TT_COLS, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const float* xr = Xs + (buf * TT_ROWS + row) * TT_LDX;
+      const float* fb = Fs + buf * TT_COLS * KT + fg * KF;
+#pragma unroll 4
+      for (int c4 = 0; c4 < TT_COLS / 4; ++c4) {
+        const float4 x = *reinterpret_cast<const float4*>(xr + 4 * c4);
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 xx = make_float2(xv[u], xv[u]);
+          const float* fr = fb + (4 * c4 + u) * KT;
+          if constexpr (KF >= 4) {
+#pragma unroll
+            for (int g = 0; g < KF / 4; ++g) {
+              const float4 w = *reinterpret_cast<const float4*>(fr + 4 * g);
+              acc[2 * g] = __ffma2_rn(xx, make_float2(w.x, w.y), acc[2 * g]);
+              acc[2 * g + 1] = __ffma2_rn(xx, make_float2(w.z, w.w), acc[2 * g + 1]);
+            }
+          } else {
+            const float2 w = *reinterpret_cast<const float2*>(fr);
+            acc[0] = __ffma2_rn(xx, w, acc[0]);
+          }
+        }
+      }
+      __syncthreads();  // the buffer is refilled two chunks later
+    }
+    const int64_t gr = r0 + row;
+    if (gr < n) {
+#pragma unroll
+      for (int i = 0; i < KF / 2; ++i) {
+        const int f = fg * KF + 2 * i;
+        if (f < k) Z[gr * k + f] = acc[i].x;
+        if (f + 1 < k) Z[gr * k + f + 1] = acc[i].y;
+      }
+    }
+  }
+}
+
 __global__ void embed_fwd_kernel(const float* __restrict__ Psi, const float* __restrict__ Mu, float noise, int C,
                                  int k, int fr, float* __restrict__ E) {
   const int m = fr ? k + 1 : k;
@@ -417,9 +523,32 @@ cudaError_t launch_project_bwd(const float* gPsi, const float* gMu, const float*
   return cudaGetLastError();
 }
 
+template <int KF>
+static cudaError_t run_transform_tile(const float* X, int64_t ldx, const float* F, int64_t n, int D, int k, float* Z,
+                                      cudaStream_t st) {
+  const int smem = (2 * TT_ROWS * TT_LDX + 2 * TT_COLS * 4 * KF) * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(transform_tile_kernel<KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ntiles = (n + TT_ROWS - 1) / TT_ROWS;
+  const int64_t grid = ntiles < 2 * (int64_t)sms ? ntiles : 2 * (int64_t)sms;
+  transform_tile_kernel<KF><<<(unsigned)grid, TT_THREADS, smem, st>>>(X, ldx, F, n, D, k, Z);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_transform(const float* X, int64_t ldx, const float* F, int64_t n, int D, int k, float* Z,
                              cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
+  if (D % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && k <= 32) {
+    if (k <= 8) return run_transform_tile<2>(X, ldx, F, n, D, k, Z, st);
+    if (k <= 16) return run_transform_tile<4>(X, ldx, F, n, D, k, Z, st);
+    return run_transform_tile<8>(X, ldx, F, n, D, k, Z, st);
+  }
   if (k <= 4) return run_transform<4>(X, ldx, F, n, D, k, Z, st);
   if (k <= 8) return run_transform<8>(X, ldx, F, n, D, k, Z, st);
   return run_transform<16>(X, ldx, F, n, D, k, Z, st);
