@@ -115,6 +115,20 @@ int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int6
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
                     void* ws, size_t ws_bytes, sqfa_stream_t stream);
 
+/* The Gram fused with its all-reduce over NVSwitch: every finished 256 x 256 tile is added with
+ * multimem.red (16 bytes per instruction) through `gram_multicast` -- the multicast alias of a
+ * buffer that exists at the same offset on every device of the group (e.g. torch symmetric
+ * memory) -- so each device's copy receives the partial sums of all devices while the tensor cores
+ * are still working on the next tiles; no separate collective. Packed tile layout
+ * (sqfa_gram_packed_floats). `gram_local` is this device's own mapping of the same buffer (only
+ * used for address arithmetic). The CALLER zero-fills every device's buffer and makes sure (a
+ * barrier or any collective) that all devices have done so before any of them calls this, and
+ * synchronises the devices again before anyone reads the sums. */
+int sqfa_class_gram_multicast(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                              const float* shift, int64_t n, int32_t n_dim, int32_t n_classes, float* gram_local,
+                              float* gram_multicast, int chain_rows, void* ws, size_t ws_bytes,
+                              sqfa_stream_t stream);
+
 /* Statistics epilogue (statistics.py:43-47, 84-93, 116, 120-122):
  *   cov[c] = (gram[c] - n_c d d^T) / (n_c - ddof),  d = means[c] - shift[c]  (shift NULL -> d = 0)
  *   ddof = 1: unbiased estimate; ddof = 0: `assume_centered` (statistics.py:116)

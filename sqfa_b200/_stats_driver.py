@@ -141,6 +141,56 @@ class CudaStatsOps:
             self.gram_events.append(ev)
         return gram
 
+    def multicast_buffer(self, group, C, D, dev):
+        """(buffer, symmetric-memory handle) for the fused Gram + all-reduce: a packed-Gram buffer that
+        sits at the same offset on every rank, with an NVSwitch multicast alias; None unless enabled
+        (SQFA_GRAM_MULTICAST=1) and supported by the platform. Collective: every rank of the group calls it
+        with the same arguments. The buffers are cached per (group, size)."""
+        import os
+
+        import torch.distributed as dist
+
+        # Opt-in (SQFA_GRAM_MULTICAST=1). Measured on 2 B200s at c2: 4.39 ms per step against 2.85 ms
+        # with the packed NCCL all-reduce -- the 16-byte multimem.red instructions issued by the four
+        # epilogue warps per CTA are latency-limited and hold up the accumulator hand-over; a bulk
+        # (TMA-sized) push is what this path needs before it can be the default (DESIGN.md section 8).
+        if os.environ.get("SQFA_GRAM_MULTICAST") != "1" or dist.get_world_size(group) < 2:
+            return None
+        numel = self.lib.sqfa_gram_packed_floats(D, C)
+        cache = self.__dict__.setdefault("_mc_cache", {})
+        key = (id(group), numel)
+        if key not in cache:
+            entry = None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                buf = symm_mem.empty(numel, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, group.group_name)
+                ok = int(hdl.multicast_ptr) != 0
+                entry = (buf, hdl)
+            except Exception:  # no symmetric memory on this platform / backend
+                ok = False
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # all ranks take the same path
+            cache[key] = entry if int(flag.item()) == 1 else None
+        return cache[key]
+
+    def class_gram_multicast(self, X, perm, offsets, centre, C, buf, multicast_ptr):
+        """This rank's Gram partials, added tile by tile into every rank's `buf` through NVSwitch."""
+        import ctypes
+
+        lib, dev = self.lib, X.device
+        n, D = X.shape
+        ws_bytes = lib.sqfa_class_gram_workspace_bytes(n, D, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.sqfa_class_gram_multicast(
+                _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), n, D, C, _lib.ptr(buf),
+                ctypes.c_void_p(int(multicast_ptr)), 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+            ),
+            "sqfa_class_gram_multicast",
+        )
+
     def finalize(self, gram, means, counts, estimator_id, ddof, want_sm, packed=False):
         """cov (in place over gram unless it is packed; mirrored), optional OAS shrinkage, second moments."""
         lib, dev = self.lib, gram.device
@@ -216,6 +266,13 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
     ):
         return ops.fused(X, y, C, estimator_id, ddof, want_sm)
     perm, offsets, counts = ops.bucket(y, C)
+    mc = None
+    if group is not None and centre is None and getattr(ops, "multicast_buffer", None) is not None:
+        mc = ops.multicast_buffer(group, C, X.shape[1], X.device)
+        if mc is not None:
+            # zero-filled BEFORE the all-reduce below: that collective cannot complete anywhere until
+            # every rank has contributed, i.e. has passed this point in its stream
+            mc[0].zero_()
     sums = ops.class_sums(X, perm, offsets, C)
     class_counts = counts[:C].clone()
     if group is not None:
@@ -223,7 +280,14 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
         _all_reduce(class_counts, group)
     means = ops.class_means(sums, class_counts)
     shift = means if centre is None else centre
-    if group is not None and getattr(ops, "supports_packed", False) and ops.packed_is_smaller(X.shape[1], C):
+    if mc is not None:
+        # Gram fused with its all-reduce: every finished tile is multimem.red-added into the copy of
+        # every rank while the tensor cores work on the next one; one barrier, no collective
+        buf, hdl = mc
+        ops.class_gram_multicast(X, perm, offsets, shift, C, buf, hdl.multicast_ptr)
+        hdl.barrier()
+        cov, sm = ops.finalize(buf, means, class_counts, estimator_id, ddof, want_sm, packed=True)
+    elif group is not None and getattr(ops, "supports_packed", False) and ops.packed_is_smaller(X.shape[1], C):
         # the one large collective: partial Gram sums over NVLink, upper 256 x 256 tiles only
         gram = ops.class_gram(X, perm, offsets, shift, C, packed=True)
         _all_reduce(gram, group)

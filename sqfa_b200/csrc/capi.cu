@@ -116,9 +116,26 @@ int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int6
     return fail_arg(__func__, "too many (class, tile) jobs", SQFA_E_UNSUPPORTED);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail_arg(__func__, "no CUDA device");
-  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram,
+  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram, nullptr,
                                                 accumulate & SQFA_GRAM_ACCUMULATE, accumulate & SQFA_GRAM_PACKED,
                                                 chain_rows, ws, sms, S(stream)));
+}
+
+int sqfa_class_gram_multicast(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                              const float* shift, int64_t n, int32_t n_dim, int32_t n_classes, float* gram_local,
+                              float* gram_multicast, int chain_rows, void* ws, size_t ws_bytes,
+                              sqfa_stream_t stream) {
+  if (n_dim <= 0 || n_classes < 0 || n < 0 || offsets == nullptr || gram_local == nullptr ||
+      gram_multicast == nullptr || ws == nullptr || ldx < n_dim || X == nullptr || perm == nullptr)
+    return fail_arg(__func__, "bad argument");
+  if (ws_bytes < sqfa_class_gram_workspace_bytes(n, n_dim, n_classes))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  if ((int64_t)n_classes * sqfa::gram_tiles_per_class(n_dim, nullptr) > (1ll << 30) / 4096)
+    return fail_arg(__func__, "too many (class, tile) jobs", SQFA_E_UNSUPPORTED);
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail_arg(__func__, "no CUDA device");
+  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram_local,
+                                                gram_multicast, 1, 1, chain_rows, ws, sms, S(stream)));
 }
 
 size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes) {

@@ -81,6 +81,7 @@ struct GramParams {
   const int64_t* offsets;
   const float* shift;
   float* gram;
+  float* mc_gram;    // NVSwitch multicast alias of gram (packed layout): tiles are multimem.red-added into every device's copy
   const int4* jobs;  // (class, tile row, tile col, K part)
   int njobs;
   int D, C, KS;
@@ -452,6 +453,50 @@ gram_tf32x3_kernel(const GramParams P) {
             }
             add_chunk(c + 1, vb);
           }
+        } else if (P.vec_ok) {
+          // Last chain of the tile: main + running sum + cross terms -> output, 16 bytes at a time.
+          // Tile columns 4 s .. 4 s + 3 are accumulator columns s, 32 + s, 64 + s, 96 + s of a
+          // 128-column half (the slot permutation), so one chunk reads 4 slots from each quarter.
+          float* const mcrow = P.mc_gram != nullptr ? P.mc_gram + (grow - P.gram) : nullptr;
+#pragma unroll 1
+          for (int ch = 0; ch < 16; ++ch) {  // 4 slots from each quarter per chunk (register budget of this role)
+            const int half = ch >> 3, s0 = 4 * (ch & 7);
+            uint32_t m[4][4], w[4][4];
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const uint32_t col = (uint32_t)(128 * half + 32 * qd + s0);
+              tmem_ld_32x32b_x4(tq + col, m[qd]);
+              tmem_ld_32x32b_x4(tq + TMEM_SMALL2 + col, w[qd]);
+            }
+            tmem_ld_wait();
+            if (ch == 15) {  // both accumulators read: the next job may start
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(acc_empty0);
+            }
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!first) o = run4[((128 * half + 32 * qd + s0) / 4) * 128];
+              m[qd][0] = __float_as_uint(__uint_as_float(m[qd][0]) + o.x + __uint_as_float(w[qd][0]));
+              m[qd][1] = __float_as_uint(__uint_as_float(m[qd][1]) + o.y + __uint_as_float(w[qd][1]));
+              m[qd][2] = __float_as_uint(__uint_as_float(m[qd][2]) + o.z + __uint_as_float(w[qd][2]));
+              m[qd][3] = __float_as_uint(__uint_as_float(m[qd][3]) + o.w + __uint_as_float(w[qd][3]));
+            }
+            if (row < D) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int cidx = g.n0 + 128 * half + 4 * (s0 + jj);
+                if (cidx < D) {  // D % 4 == 0: the four columns are all inside
+                  const float4 v = make_float4(__uint_as_float(m[0][jj]), __uint_as_float(m[1][jj]),
+                                               __uint_as_float(m[2][jj]), __uint_as_float(m[3][jj]));
+                  if (mcrow != nullptr) multimem_red_add_v4(mcrow + cidx, v);
+                  else if (P.atomic_out) red_add_v4(grow + cidx, v);
+                  else *reinterpret_cast<float4*>(grow + cidx) = v;
+                }
+              }
+            }
+          }
         } else {
 #pragma unroll 1
           for (int col0 = 0; col0 < TN2; col0 += 16) {
@@ -477,11 +522,13 @@ gram_tf32x3_kernel(const GramParams P) {
               // accumulator column n = 128 (n / 128) + slot  ->  tile column 128 (n / 128) + 4 (slot % 32) + slot / 32:
               // the 16 columns of this chunk are 16 bytes apart in the output row
               const int gc = g.n0 + (col0 & 128) + 4 * (col0 & 31) + ((col0 & 127) >> 5);
+              float* const mcrow = P.mc_gram != nullptr ? P.mc_gram + (grow - P.gram) : nullptr;
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) {
                 const int cidx = gc + 4 * jj;
                 if (cidx < D) {
-                  if (P.atomic_out) atomicAdd(grow + cidx, __uint_as_float(v[jj]));
+                  if (mcrow != nullptr) multimem_red_add_f32(mcrow + cidx, __uint_as_float(v[jj]));
+                  else if (P.atomic_out) atomicAdd(grow + cidx, __uint_as_float(v[jj]));
                   else grow[cidx] = __uint_as_float(v[jj]);
                 }
               }
@@ -528,8 +575,8 @@ size_t gram_workspace_bytes(int C, int D, int ksplit_max) {
 }
 
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate, int packed,
-                               int chain_rows, void* ws, int num_sms, cudaStream_t stream) {
+                               const float* shift, int64_t n, int D, int C, float* gram, float* mc_gram, int accumulate,
+                               int packed, int chain_rows, void* ws, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -541,21 +588,22 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
   GramParams P;
   int TT = 0;
   const int T = gram_tiles_per_class(D, &TT);
-  P.X = X; P.ldx = ldx; P.n = n; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram;
+  P.X = X; P.ldx = ldx; P.n = n; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram; P.mc_gram = mc_gram;
   P.jobs = reinterpret_cast<const int4*>(ws);
   P.D = D; P.C = C;
   P.KS = gram_ksplit(n, C, D, num_sms);
   P.njobs = C * T * P.KS;
   const int cr = chain_rows > 0 ? chain_rows : 512;
   P.chain_kb = (cr + BK - 1) / BK;
-  P.atomic_out = (accumulate || P.KS > 1) ? 1 : 0;
+  P.atomic_out = (accumulate || P.KS > 1 || mc_gram != nullptr) ? 1 : 0;
   P.packed = packed ? 1 : 0; P.T = T; P.TT = TT;
   P.vec_ok = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(gram) & 15) == 0);
   static const int env_flags = [] { const char* e = getenv("SQFA_GRAM_FLAGS"); return e ? atoi(e) : 0; }();
   P.flags = env_flags;
   P.vecx = ((ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && !(env_flags & 4)) ? 1 : 0;
   if ((uint64_t)ldx * 4ull >= (1ull << 32)) return cudaErrorInvalidValue;
-  if (P.atomic_out && !accumulate) {  // K parts are summed with red.add -> start from zero
+  if (P.atomic_out && !accumulate && mc_gram == nullptr) {  // K parts are summed with red.add -> start from zero
+    // (multicast mode: the caller zero-fills every device's buffer before any device starts)
     const size_t floats = packed ? (size_t)C * T * TM2 * TN2 : (size_t)C * D * D;
     cudaError_t e = cudaMemsetAsync(gram, 0, floats * sizeof(float), stream);
     if (e != cudaSuccess) return e;
