@@ -71,7 +71,7 @@ constexpr int GRAM2_SMEM = STAGES2 * STAGE2_BYTES + RUN_BYTES + 1024;
 constexpr uint32_t OP_LBO = 128 * 16, OP_SBO2 = 128;
 constexpr uint32_t TMEM_COLS2 = 512, TMEM_SMALL2 = 256;
 
-__device__ float g_zero[4] = {0.f, 0.f, 0.f, 0.f};
+__device__ __align__(16) float g_zero[4] = {0.f, 0.f, 0.f, 0.f};  // read with 16-byte loads
 
 struct GramParams {
   const float* X;

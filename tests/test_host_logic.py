@@ -82,3 +82,40 @@ def test_pair_ranges_tile_the_pair_list(n_pairs, world):
         assert a1 == b0 and a0 <= a1
     sizes = [b - a for a, b in ranges]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_lbfgs_on_cpu_parameters_is_torch_lbfgs():
+    """sqfa_b200._lbfgs.LBFGS only takes the native path for one float32 CUDA parameter without line
+    search; anything else must behave exactly like torch.optim.LBFGS (same iterates, same state)."""
+    from sqfa_b200._lbfgs import LBFGS
+
+    def run(cls, **kw):
+        torch.manual_seed(0)
+        x = torch.nn.Parameter(torch.randn(50))
+        A = torch.diag(torch.linspace(0.5, 5.0, 50))
+        opt = cls([x], lr=0.5, history_size=6, **kw)
+
+        def closure():
+            opt.zero_grad()
+            loss = 0.5 * x @ A @ x - x.sum()
+            loss.backward()
+            return loss
+
+        losses = [float(opt.step(closure)) for _ in range(3)]
+        return x.detach().clone(), losses, opt.state[opt._params[0]]
+
+    for kw in ({}, {"line_search_fn": "strong_wolfe"}):
+        x_ref, l_ref, _ = run(torch.optim.LBFGS, **kw)
+        x_got, l_got, state = run(LBFGS, **kw)
+        assert torch.equal(x_ref, x_got) and l_ref == l_got
+        assert "sqfa_native" not in state
+
+
+def test_streaming_statistics_need_the_gpu_and_validate_arguments():
+    from sqfa_b200.statistics import StreamingClassStatistics
+
+    with pytest.raises(ValueError):
+        StreamingClassStatistics(0, 3)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SqfaNativeError):
+            StreamingClassStatistics(8, 3)
