@@ -169,7 +169,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "N": w["N"], "D": w["D"], "classes": w["C"]},
+        "config": {"workload": w["name"], "N_per_gpu": w["N"], "D": w["D"], "classes": w["C"], "n_filters": w["k"],
+                   "l2": "host arm: not applicable",
+                   "parallelism": f"reference CPU path, {torch.get_num_threads()} host threads (rank 0 only)"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"full workload, {args.steps} repetitions of N={w['N']} (warm-up on 5000 rows)"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
