@@ -295,13 +295,14 @@ transform_kernel(const float* __restrict__ X, int64_t ldx, const float* __restri
   }
 }
 
-// Z = X F^T for 16-byte aligned rows: a persistent mini-GEMM. A block walks row tiles of 64 rows;
-// per 128-column chunk the X tile (64 x 128, padded rows: conflict-free LDS.128) and the F^T tile
+// Z = X F^T for 16-byte aligned rows: a persistent mini-GEMM. A block walks row tiles of 128 rows;
+// per 64-column chunk the X tile (128 x 64, padded rows: conflict-free LDS.128) and the F^T tile
 // ([column][filter], so four filters of one column are one LDS.128 broadcast) arrive with cp.async
-// while the previous chunk is being multiplied (two buffers). Thread (row, g) owns KF = KT/4
-// filters of one row, accumulated as packed pairs: one fma.rn.f32x2 per two filters and column.
+// while the previous chunk is being multiplied (two buffers). Thread (row pair, g) owns KF = KT/4
+// filters of TWO rows (every F value loaded from shared memory feeds two FMAs), accumulated as
+// packed pairs: one fma.rn.f32x2 per two filters, row and column.
 // HBM-bound for k <= 16 (one read of X), about FMA-bound at k = 32.
-constexpr int TT_ROWS = 64, TT_COLS = 128, TT_LDX = TT_COLS + 4, TT_THREADS = 256;
+constexpr int TT_ROWS = 128, TT_COLS = 64, TT_LDX = TT_COLS + 4, TT_THREADS = 256;
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -324,15 +325,15 @@ transform_tile_kernel(const float* __restrict__ X, int64_t ldx, const float* __r
   float* Xs = tsm;                              // [2][TT_ROWS][TT_LDX]
   float* Fs = tsm + 2 * TT_ROWS * TT_LDX;       // [2][TT_COLS][KT]
   const int tid = threadIdx.x;
-  const int row = tid & (TT_ROWS - 1), fg = tid >> 6;  // a warp: 32 consecutive rows, one filter group
+  const int rp = tid & 63, fg = tid >> 6;  // rows rp and rp + 64; a warp: 32 consecutive rows, one filter group
   const int nchunks = (D + TT_COLS - 1) / TT_COLS;
   const int64_t ntiles = (n + TT_ROWS - 1) / TT_ROWS;
   const uint32_t xs_u = (uint32_t)__cvta_generic_to_shared(Xs), fs_u = (uint32_t)__cvta_generic_to_shared(Fs);
 
   auto load_chunk = [&](int64_t r0, int c0, int buf) {
-    // X tile: 64 rows x 32 float4; rows past n and columns past D are zero-filled (src_bytes = 0)
+    // X tile: 128 rows x 16 float4; rows past n and columns past D are zero-filled (src_bytes = 0)
     for (int idx = tid; idx < TT_ROWS * (TT_COLS / 4); idx += TT_THREADS) {
-      const int r = idx >> 5, c4 = idx & 31;
+      const int r = idx >> 4, c4 = idx & 15;
       const int64_t gr = r0 + r;
       const int gc = c0 + 4 * c4;
       const bool ok = gr < n && gc < D;  // D % 4 == 0 on this path: a float4 is all inside or all outside
@@ -351,9 +352,9 @@ transform_tile_kernel(const float* __restrict__ X, int64_t ldx, const float* __r
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t r0 = tile * TT_ROWS;
-    float2 acc[KF / 2];
+    float2 acc0[KF / 2], acc1[KF / 2];
 #pragma unroll
-    for (int i = 0; i < KF / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < KF / 2; ++i) acc0[i] = acc1[i] = make_float2(0.f, 0.f);
     load_chunk(r0, 0, 0);
     for (int ch = 0; ch < nchunks; ++ch) {
       const int buf = ch & 1;
@@ -364,38 +365,48 @@ transform_tile_kernel(const float* __restrict__ X, int64_t ldx, const float* __r
         cp_async_wait<0>();
       }
       __syncthreads();
-      const float* xr = Xs + (buf * TT_ROWS + row) * TT_LDX;
+      const float* xr0 = Xs + (buf * TT_ROWS + rp) * TT_LDX;
+      const float* xr1 = xr0 + 64 * TT_LDX;
       const float* fb = Fs + buf * TT_COLS * KT + fg * KF;
 #pragma unroll 4
       for (int c4 = 0; c4 < TT_COLS / 4; ++c4) {
-        const float4 x = *reinterpret_cast<const float4*>(xr + 4 * c4);
-        const float xv[4] = {x.x, x.y, x.z, x.w};
+        const float4 xa = *reinterpret_cast<const float4*>(xr0 + 4 * c4);
+        const float4 xb = *reinterpret_cast<const float4*>(xr1 + 4 * c4);
+        const float va[4] = {xa.x, xa.y, xa.z, xa.w}, vb[4] = {xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float2 xx = make_float2(xv[u], xv[u]);
+          const float2 a2 = make_float2(va[u], va[u]), b2 = make_float2(vb[u], vb[u]);
           const float* fr = fb + (4 * c4 + u) * KT;
           if constexpr (KF >= 4) {
 #pragma unroll
             for (int g = 0; g < KF / 4; ++g) {
               const float4 w = *reinterpret_cast<const float4*>(fr + 4 * g);
-              acc[2 * g] = __ffma2_rn(xx, make_float2(w.x, w.y), acc[2 * g]);
-              acc[2 * g + 1] = __ffma2_rn(xx, make_float2(w.z, w.w), acc[2 * g + 1]);
+              const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+              acc0[2 * g] = __ffma2_rn(a2, w01, acc0[2 * g]);
+              acc0[2 * g + 1] = __ffma2_rn(a2, w23, acc0[2 * g + 1]);
+              acc1[2 * g] = __ffma2_rn(b2, w01, acc1[2 * g]);
+              acc1[2 * g + 1] = __ffma2_rn(b2, w23, acc1[2 * g + 1]);
             }
           } else {
             const float2 w = *reinterpret_cast<const float2*>(fr);
-            acc[0] = __ffma2_rn(xx, w, acc[0]);
+            acc0[0] = __ffma2_rn(a2, w, acc0[0]);
+            acc1[0] = __ffma2_rn(b2, w, acc1[0]);
           }
         }
       }
       __syncthreads();  // the buffer is refilled two chunks later
     }
-    const int64_t gr = r0 + row;
-    if (gr < n) {
 #pragma unroll
-      for (int i = 0; i < KF / 2; ++i) {
-        const int f = fg * KF + 2 * i;
-        if (f < k) Z[gr * k + f] = acc[i].x;
-        if (f + 1 < k) Z[gr * k + f + 1] = acc[i].y;
+    for (int h = 0; h < 2; ++h) {
+      const int64_t gr = r0 + rp + 64 * h;
+      if (gr < n) {
+#pragma unroll
+        for (int i = 0; i < KF / 2; ++i) {
+          const int f = fg * KF + 2 * i;
+          const float2 a = h ? acc1[i] : acc0[i];
+          if (f < k) Z[gr * k + f] = a.x;
+          if (f + 1 < k) Z[gr * k + f + 1] = a.y;
+        }
       }
     }
   }
