@@ -282,15 +282,21 @@ def run_ours(args):
         torch.cuda.synchronize()  # all steps' results are in host memory
         return last
 
+    # PCIe and host memory are shared with whatever else runs on the host: the K-step run is
+    # repeated and the median repetition reported (all repetitions are listed in the JSON)
     e2e_steps = max(4, args.steps)
-    e2e_run(2)
-    sync_all()
-    e0.record()
-    last = e2e_run(e2e_steps)
-    e1.record()
-    sync_all()
+    e2e_run(4)  # both buffer sets twice: the per-stream allocator pools reach their steady state
+    e2e_ms = []
+    for _ in range(3):
+        sync_all()
+        e0.record()
+        last = e2e_run(e2e_steps)
+        e1.record()
+        sync_all()
+        e2e_ms.append(e0.elapsed_time(e1))
+    e2e_med = sorted(e2e_ms)[1]
     stats = {key: v.to(dev) for key, v in out_h[(e2e_steps - 1) % 2].items()}
-    ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ems = torch.tensor([e2e_med], device=dev)
     if world > 1:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_value = n * world * e2e_steps / (float(ems) * 1e-3)
@@ -383,7 +389,8 @@ def run_ours(args):
                    "l2": "inputs (614 MB per GPU) exceed the 126 MB L2; no flush needed",
                    "parallelism": f"samples sharded over {world} GPU(s), 3 all-reduces" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "overlap": "2 CUDA streams / buffer sets, inputs of step i+1 uploaded while step i computes and downloads"},
+                "steps": e2e_steps, "repetitions_ms": [round(x, 2) for x in e2e_ms], "reported": "median repetition",
+                "overlap": "2 CUDA streams / buffer sets, inputs of step i+1 uploaded while step i computes and downloads"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "fit": fit,
     }
