@@ -1,3 +1,5 @@
+"""Does torch symmetric memory work on this box and is there an NVSwitch multicast address?
+(run under torchrun with >= 2 ranks; the opt-in multicast Gram path needs both)"""
 import os, torch, torch.distributed as dist
 rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
