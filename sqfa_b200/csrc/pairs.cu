@@ -118,12 +118,15 @@ __device__ float* warp_jacobi(float* cur, float* nxt, int m, int mp, int ld, int
           const bool is_lo = p < q;
           const float alpha = is_lo ? aa : bb, beta = is_lo ? bb : aa;
           float cs = 1.f, sn = 0.f;
-          if (fabsf(ab) > JACOBI_TOL * sqrtf(alpha * beta) && alpha > 0.f && beta > 0.f) {
-            const float zeta = (beta - alpha) / (2.f * ab);
-            const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-            cs = rsqrtf(1.f + tt * tt);
+          const float ab_sq = ab * ab, scale = alpha * beta;
+          if (ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale && alpha > 0.f && beta > 0.f) {
+            // same rules as the register kernel: approximate reciprocal / square root for the angle,
+            // and a sweep whose rotations were all below JACOBI_LAST is the last one
+            const float zeta = (beta - alpha) * rcp_approx(2.f * ab);
+            const float tt = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
+            cs = rsqrtf(fmaf(tt, tt, 1.f));
             sn = cs * tt;
-            rotated = true;
+            rotated = rotated || ab_sq > (JACOBI_LAST * JACOBI_LAST) * scale;
           }
           const float mine = cs, other = is_lo ? -sn : sn;
           for (int s = 0; s < m; ++s) nxt[s * ld + p] = mine * cur[s * ld + p] + other * cur[s * ld + q];
