@@ -577,12 +577,10 @@ size_t gram_workspace_bytes(int C, int D, int ksplit_max) {
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
                                const float* shift, int64_t n, int D, int C, float* gram, float* mc_gram, int accumulate,
                                int packed, int chain_rows, void* ws, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gram_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM2_SMEM);
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(gram_tf32x3_kernel, GRAM2_SMEM, smem_set);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (C <= 0) return cudaSuccess;
   GramParams P;

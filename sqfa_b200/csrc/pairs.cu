@@ -581,11 +581,10 @@ static cudaError_t launch_pair_reg(const float* Wa, const float* Wb, int nA, int
                                    cudaStream_t st) {
   constexpr int per_warp_floats = ((MP * 33 + 2 * MP * MP + 3) + 3) & ~3;
   const int smem = PAIR_WARPS * per_warp_floats * (int)sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(pair_ai_reg_kernel<MP, MJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(pair_ai_reg_kernel<MP, MJ>, smem, smem_set);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int64_t npairs = pair_end - pair_begin;
   const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
@@ -731,11 +730,10 @@ cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W
   const int per_warp = (4 * m * ld + 2 * m) * (int)sizeof(float);
   const int nw = warps_for(per_warp);
   const int smem = nw * per_warp;
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(class_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(class_factor_kernel, smem, smem_set);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
   if (e != cudaSuccess) return e;
@@ -784,11 +782,10 @@ cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int 
   const int nw = warps_for(per_warp);
   const int smem = nw * per_warp;
   const unsigned blocks = (unsigned)((npairs + nw - 1) / nw);
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(pair_ai_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(pair_ai_kernel, smem, smem_set);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   pair_ai_kernel<<<blocks, nw * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
                                                 dist_out, loss, gEa, gEb, eig_out);
@@ -801,11 +798,10 @@ cudaError_t launch_class_factor_bwd(const float* W, const float* gLog, int C, in
   const int per_warp = 3 * m * m * (int)sizeof(float);
   const int nw = warps_for(per_warp);
   const int smem = nw * per_warp;
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(le_factor_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(le_factor_bwd_kernel, smem, smem_set);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   le_factor_bwd_kernel<<<(C + nw - 1) / nw, nw * 32, smem, st>>>(W, gLog, C, m, gE);
   return cudaGetLastError();

@@ -471,11 +471,10 @@ template <int KT>
 cudaError_t run_transform(const float* X, int64_t ldx, const float* F, int64_t n, int D, int k, float* Z,
                           cudaStream_t st) {
   const int smem = KT * 512 * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(transform_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(transform_kernel<KT>, smem, smem_set);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   const int64_t blocks = (n + 63) / 64;
   for (int f0 = 0; f0 < k; f0 += KT)
@@ -538,11 +537,10 @@ template <int KF>
 static cudaError_t run_transform_tile(const float* X, int64_t ldx, const float* F, int64_t n, int D, int k, float* Z,
                                       cudaStream_t st) {
   const int smem = (2 * TT_ROWS * TT_LDX + 2 * TT_COLS * 4 * KF) * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(transform_tile_kernel<KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(transform_tile_kernel<KF>, smem, smem_set);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

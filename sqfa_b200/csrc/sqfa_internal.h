@@ -6,6 +6,21 @@
 
 namespace sqfa {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember what was set on
+// which device (a process may drive several), raise it when a launch needs more.
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, int (&set_bytes)[kMaxDevices]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  if (set_bytes[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) set_bytes[dev] = bytes;
+  return e;
+}
+
 // ---- bucket.cu (K1) ----
 cudaError_t launch_label_max(const int64_t* labels, int64_t n, int64_t* out_max, cudaStream_t stream);
 size_t bucket_workspace_bytes(int64_t n, int32_t C);
