@@ -243,6 +243,70 @@ __global__ void class_counts_kernel(const int64_t* __restrict__ offsets, int32_t
   if (c <= C) counts[c] = offsets[c + 1] - offsets[c];
 }
 
+// Small problems (n <= 65536 rows, at most 255 classes: one 8-bit pass) in ONE block: per-tile
+// histograms, their scan, offsets / counts and the stable scatter all stay in shared memory -- the
+// eight launches of the general path cost more in launch latency than in work at this size.
+constexpr int SMALL_MAX_TILES = 64;
+
+__global__ void __launch_bounds__(1024) bucket_small_kernel(const int64_t* __restrict__ labels, int n, int32_t C,
+                                                            int ntiles, int64_t* __restrict__ counts,
+                                                            int64_t* __restrict__ offsets, int32_t* __restrict__ perm) {
+  extern __shared__ int32_t s_hist[];  // [RADIX][ntiles], digit-major like the general path
+  __shared__ int32_t s_warp[33];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total = RADIX * ntiles;
+  for (int i = tid; i < total; i += 1024) s_hist[i] = 0;
+  __syncthreads();
+  for (int tile = warp; tile < ntiles; tile += 32) {  // a tile's column is private to its warp
+    const int base = tile * TILE;
+    for (int s = 0; s < STEPS_PER_TILE; ++s) {
+      const int i = base + s * 32 + lane;
+      const bool valid = i < n;
+      const uint32_t d = valid ? (uint32_t)clip_label(labels[i], C) : RADIX;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (__ffs(peers) - 1) == lane) s_hist[d * ntiles + tile] += __popc(peers);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // exclusive scan over the digit-major histogram: a contiguous run of entries per thread
+  const int per = (total + 1023) / 1024;
+  const int lo = tid * per, hi = min(total, lo + per);
+  int32_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += s_hist[i];
+  int32_t tot;
+  int32_t run = block_exclusive_scan(sum, s_warp, &tot);
+  for (int i = lo; i < hi; ++i) {
+    const int32_t t = s_hist[i];
+    s_hist[i] = run;
+    run += t;
+  }
+  __syncthreads();
+  // class c is digit c: its first row sits at the scanned entry of (digit c, tile 0)
+  for (int c = tid; c <= C + 1; c += 1024) offsets[c] = (c <= C) ? (int64_t)s_hist[c * ntiles] : (int64_t)n;
+  for (int c = tid; c <= C; c += 1024) {
+    const int64_t nxt = (c + 1 <= C) ? (int64_t)s_hist[(c + 1) * ntiles] : (int64_t)n;
+    counts[c] = nxt - (int64_t)s_hist[c * ntiles];
+  }
+  __syncthreads();
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int tile = warp; tile < ntiles; tile += 32) {
+    const int base = tile * TILE;
+    for (int s = 0; s < STEPS_PER_TILE; ++s) {
+      const int i = base + s * 32 + lane;
+      const bool valid = i < n;
+      const uint32_t d = valid ? (uint32_t)clip_label(labels[i], C) : RADIX;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      int32_t pos = 0;
+      if (valid) pos = s_hist[d * ntiles + tile] + __popc(peers & lt);  // stable: earlier lanes first
+      __syncwarp();
+      if (valid && (__ffs(peers) - 1) == lane) s_hist[d * ntiles + tile] += __popc(peers);
+      __syncwarp();
+      if (valid) perm[pos] = i;
+    }
+  }
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
@@ -274,6 +338,14 @@ cudaError_t launch_bucket_labels(const int64_t* labels, int64_t n, int32_t C, in
   if (ws_bytes < bucket_workspace_bytes(n, C)) return cudaErrorInvalidValue;
   if (n >= (int64_t)1 << 31) return cudaErrorInvalidValue;
   const int ntiles = (int)((n + TILE - 1) / TILE);
+  if (n > 0 && ntiles <= SMALL_MAX_TILES && C + 1 <= RADIX) {
+    const int smem = RADIX * ntiles * (int)sizeof(int32_t);
+    static int smem_set[kMaxDevices] = {0};
+    cudaError_t e = ensure_dynamic_smem(bucket_small_kernel, smem, smem_set);
+    if (e != cudaSuccess) return e;
+    bucket_small_kernel<<<1, 1024, smem, stream>>>(labels, (int)n, C, ntiles, counts, offsets, perm);
+    return cudaGetLastError();
+  }
   uint8_t* p = static_cast<uint8_t*>(ws);
   const size_t nb = align_up((size_t)(n > 0 ? n : 1) * sizeof(int32_t), 256);
   int32_t* keys[2] = {reinterpret_cast<int32_t*>(p), reinterpret_cast<int32_t*>(p + nb)};
