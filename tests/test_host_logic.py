@@ -119,3 +119,15 @@ def test_streaming_statistics_need_the_gpu_and_validate_arguments():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.SqfaNativeError):
             StreamingClassStatistics(8, 3)
+
+
+def test_direct_closure_plan_only_for_closed_form_constraints():
+    """The graph-free closure needs a CUDA float32 parameter and constraints with a closed-form adjoint;
+    on the CPU (this suite) and for torch's orthogonal parametrisation it must decline, so fitting_loop
+    falls back to the autograd path instead of silently computing something else."""
+    stats = {"means": torch.zeros(3, 6), "covariances": torch.eye(6).repeat(3, 1, 1)}
+    for constraint in ("sphere", "none", "orthogonal"):
+        model = SQFA(n_dim=6, n_filters=2, feature_noise=0.01, constraint=constraint)
+        assert model._fused_direct_plan(stats) is None  # CPU parameter
+    model = SecondMomentsSQFA(n_dim=6, n_filters=2, feature_noise=0.01)
+    assert model._fused_direct_plan(stats["covariances"]) is None
