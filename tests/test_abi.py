@@ -70,3 +70,20 @@ def test_sass_has_blackwell_tensor_core_instructions():
     assert "UTCHMMA" in sass or "UTCMMA" in sass  # tcgen05.mma
     assert "LDTM" in sass                          # tcgen05.ld
     assert "HMMA.16" not in sass                   # no legacy mma.sync path
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (and as C++) on its own."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    src = tmp_path / "t.c"
+    src.write_text('#include "sqfa_b200.h"\nint main(void) { return 0; }\n')
+    for args in (["-std=c99", "-pedantic"], ["-x", "c++", "-std=c++17"]):
+        res = subprocess.run([gcc, *args, "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
