@@ -111,6 +111,9 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
  *   ws         sqfa_class_gram_workspace_bytes(n, n_dim, n_classes) bytes (device-side job plan). */
 size_t sqfa_class_gram_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes);
 size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes);
+/* rows x columns of tensor-core accumulator the kernel executes per sample and class for this n_dim
+ * (every upper tile is a full MMA tile): executed TF32 flop of a launch = 3 * 2 * n * this. */
+int64_t sqfa_gram_executed_tile_area(int32_t n_dim);
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
                     void* ws, size_t ws_bytes, sqfa_stream_t stream);

@@ -43,6 +43,7 @@ SIGNATURES = {
         [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_size, c_ptr],
     ),
     "sqfa_gram_packed_floats": (c_size, [c_i32, c_i32]),
+    "sqfa_gram_executed_tile_area": (c_i64, [c_i32]),
     "sqfa_class_gram_multicast": (
         c_int,
         [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_int, c_ptr, c_size, c_ptr],

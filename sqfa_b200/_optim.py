@@ -40,6 +40,40 @@ def check_distances_valid(distances):
         raise ValueError(_INF_MSG)
 
 
+class _PlateauStop:
+    """The reference's stopping rule (_optim.py:111-133) as one object: the loss of an epoch is compared
+    with the loss of the epoch before (0.0 before the first), and training stops once the change
+    has stayed below `atol` for `patience` epochs in a row."""
+
+    def __init__(self, atol, patience=3):
+        self.atol, self.patience = atol, patience
+        self.last, self.run = 0.0, 0
+
+    def observe(self, loss_value):
+        self.run = self.run + 1 if abs(self.last - loss_value) < self.atol else 0
+        self.last = loss_value
+
+    @property
+    def met(self):
+        return self.run >= self.patience
+
+
+class _EpochHistory:
+    """Loss and wall-clock time since the start of the fit, one entry per epoch."""
+
+    def __init__(self):
+        self.t0 = time.time()
+        self.losses, self.seconds = [], []
+
+    def add(self, loss_value):
+        self.seconds.append(time.time() - self.t0)
+        self.losses.append(loss_value)
+
+    @property
+    def epochs(self):
+        return len(self.losses)
+
+
 def fitting_loop(
     model,
     data_statistics,
@@ -68,9 +102,11 @@ def fitting_loop(
     fused = model._fused_loss_plan(data_statistics) if hasattr(model, "_fused_loss_plan") else None
     direct = model._fused_direct_plan(data_statistics) if hasattr(model, "_fused_direct_plan") else None
     tril_ind = None
+    evaluations = 0
 
     def closure():
-        nonlocal tril_ind
+        nonlocal tril_ind, evaluations
+        evaluations += 1
         if direct is not None:
             # native loss + gradient, gradient written to .grad without an autograd graph; ONE host
             # read per evaluation, which also carries max|grad| for the optimiser's first stopping test
@@ -97,38 +133,27 @@ def fitting_loop(
         epoch_loss.backward()
         return epoch_loss
 
-    loss_list = []
-    training_time = []
-    total_start_time = time.time()
-
-    prev_loss = 0.0
-    consecutive_stopping_criteria_met = 0
-
-    for e in tqdm(range(max_epochs), desc="Epochs", unit="epoch", disable=not show_progress):
-        epoch_loss = float(optimizer.step(closure))
-        epoch_time = time.time() - total_start_time
-
-        loss_change = abs(prev_loss - epoch_loss)
-        if loss_change < atol:
-            consecutive_stopping_criteria_met += 1
-        else:
-            consecutive_stopping_criteria_met = 0
-
-        prev_loss = epoch_loss
-        training_time.append(epoch_time)
-        loss_list.append(epoch_loss)
-
-        if consecutive_stopping_criteria_met >= 3:
-            tqdm.write(
-                f"Loss change below {atol} for 3 consecutive epochs. Stopping training at epoch {e + 1}/{max_epochs}."
-            )
-            break
+    stop_rule = _PlateauStop(atol)
+    history = _EpochHistory()
+    with tqdm(total=max_epochs, desc="Epochs", unit="epoch", disable=not show_progress) as bar:
+        while history.epochs < max_epochs and not stop_rule.met:
+            history.add(float(optimizer.step(closure)))
+            stop_rule.observe(history.losses[-1])
+            bar.update(1)
+    if stop_rule.met:
+        tqdm.write(
+            f"Loss change below {atol} for 3 consecutive epochs. "
+            f"Stopping training at epoch {history.epochs}/{max_epochs}."
+        )
     else:
         print(
             f"Reached max_epochs ({max_epochs}) without meeting stopping criteria."
             + "Consider increasing max_epochs, changing initialization or using dtype=torch.float64."
         )
 
+    # closure evaluations of this fit (benchmarks extrapolate the CPU fit time from it); summed over
+    # the stages of a pairwise curriculum
+    model._last_fit_evaluations = getattr(model, "_last_fit_evaluations", 0) + evaluations
     if return_loss:
-        return torch.tensor(loss_list), torch.tensor(training_time)
+        return torch.tensor(history.losses), torch.tensor(history.seconds)
     return None

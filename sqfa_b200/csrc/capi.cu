@@ -98,6 +98,10 @@ size_t sqfa_class_gram_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_class
                                     sqfa::gram_ksplit(n < 0 ? 0 : n, n_classes, n_dim, sms > 0 ? sms : 148));
 }
 
+int64_t sqfa_gram_executed_tile_area(int32_t n_dim) {
+  return n_dim > 0 ? sqfa::gram_executed_tile_area(n_dim) : 0;
+}
+
 size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes) {
   if (n_dim <= 0 || n_classes <= 0) return 0;
   return sqfa::gram_packed_floats(n_dim, n_classes);

@@ -557,6 +557,10 @@ int gram_tiles_per_class(int D, int* TT_out) {
   return TT * (TT + 1) / 2;
 }
 
+// Accumulator area (rows x columns) the tensor cores execute per sample for one class: every tile that
+// intersects the upper triangle is a full TM2 x TN2 MMA, whatever part of it lies beyond D.
+int64_t gram_executed_tile_area(int D) { return (int64_t)gram_tiles_per_class(D, nullptr) * TM2 * TN2; }
+
 // K parts per tile so that small problems still fill the CTA pairs
 int gram_ksplit(int64_t n, int C, int D, int num_sms) {
   const int64_t tiles = (int64_t)C * gram_tiles_per_class(D, nullptr);

@@ -32,7 +32,7 @@ constexpr int PS_MAXROWS = 256;          // rows of S per block (F^T tile in sha
 template <int KT>
 __global__ void __launch_bounds__(PS_THREADS)
 project_stream_kernel(const float* __restrict__ S, const float* __restrict__ F, int C, int D, int k, int rows,
-                      float* __restrict__ partial) {
+                      int vec16, float* __restrict__ partial) {
   __shared__ __align__(16) float Fs[PS_MAXROWS][KT];  // F^T tile: [row i][filter]
   const int c = blockIdx.z, split = blockIdx.y;
   const int i0 = split * rows;
@@ -45,7 +45,9 @@ project_stream_kernel(const float* __restrict__ S, const float* __restrict__ F, 
   __syncthreads();
   const int col = blockIdx.x * PS_COLS + warp * 128 + 4 * lane;
   if (col >= D) return;
-  const bool vec = (D % 4 == 0);  // then col + 4 <= D and every row start is 16-byte aligned
+  // D % 4 == 0 and 16-byte aligned S / partial (checked by the launcher): col + 4 <= D and every
+  // row start is 16-byte aligned; otherwise scalar accesses
+  const bool vec = vec16 != 0;
   // accumulators packed over filter pairs: acc2[f/2][q] = (filter f, filter f+1) of column col+q,
   // so every update is ONE packed-fp32 FMA (fma.rn.f32x2): FMA issue binds this kernel for k >= 16
   float2 acc2[KT / 2][4];
@@ -453,7 +455,9 @@ template <int KT>
 cudaError_t run_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, int rows, int nsplit,
                             float* partial, float* T, float* Psi, float* Mu, cudaStream_t st) {
   dim3 grid((D + PS_COLS - 1) / PS_COLS, nsplit, C);
-  project_stream_kernel<KT><<<grid, PS_THREADS, 0, st>>>(S, F, C, D, k, rows, partial);
+  const int vec16 =
+      (D % 4 == 0 && ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0) ? 1 : 0;
+  project_stream_kernel<KT><<<grid, PS_THREADS, 0, st>>>(S, F, C, D, k, rows, vec16, partial);
   int tpr = 32;  // threads per (class, filter) row: about 4 float4 per thread, 32 .. 256
   while (tpr < 256 && tpr * 16 < D) tpr *= 2;
   const int rpb = 256 / tpr;

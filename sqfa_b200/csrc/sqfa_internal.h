@@ -41,6 +41,7 @@ cudaError_t launch_stats_epilogue(const float* gram, int packed, const float* me
 
 // ---- gram.cu (K2: tcgen05 cta_group::2 Gram on CTA pairs) ----
 int gram_tiles_per_class(int D, int* TT_out);
+int64_t gram_executed_tile_area(int D);
 int gram_ksplit(int64_t n, int C, int D, int num_sms);
 size_t gram_workspace_bytes(int C, int D, int ksplit_max);
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,

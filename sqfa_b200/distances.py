@@ -39,6 +39,27 @@ def _batch3(A):
     return A.unsqueeze(0) if A.dim() == 2 else A
 
 
+def _unsq_mean(x):
+    return x.unsqueeze(0) if x.dim() == 1 else x
+
+
+def _pairwise_composed(a3, b3, dist):
+    """The reference's own composition (distances.py:46-138) with device-side library calls, in the
+    dtype of the inputs: for what the pair kernels do not take (float64, matrices above 64 x 64)."""
+    from . import linalg
+
+    if (dist & 15) == _ops.DIST_LE:
+        diff = linalg.spd_log(a3)[:, None] - linalg.spd_log(b3)[None]
+        d2 = (diff * diff).sum(dim=(-2, -1))
+    else:
+        W = linalg.spd_inv_sqrt(b3)
+        conj = W[None] @ a3[:, None] @ W.transpose(-2, -1)[None]
+        d2 = (torch.log(torch.linalg.eigvalsh(conj)) ** 2).sum(dim=-1)
+        if (dist & 15) == _ops.DIST_FR:
+            d2 = d2 / 2
+    return d2 if dist & _ops.SQUARED else torch.sqrt(d2 + EPSILON)
+
+
 def _pairwise(A, B, dist):
     """D[a, b] = d(A_a, B_b) through the native pair kernels; squeezes like the reference."""
     same = A is B
@@ -47,7 +68,10 @@ def _pairwise(A, B, dist):
         raise ValueError("expected SPD matrices of equal size, shapes (n, m, m)")
     dev = _lib.compute_device(A, B)
     with torch.cuda.device(dev):
-        D = _ops.PairDistance.apply(a3.to(dev), None if same else b3.to(dev), dist, same)
+        if a3.dtype == torch.float32 and b3.dtype == torch.float32 and a3.shape[-1] <= _ops.MAX_M:
+            D = _ops.PairDistance.apply(a3.to(dev), None if same else b3.to(dev), dist, same)
+        else:
+            D = _pairwise_composed(a3.to(dev), b3.to(dev), dist)
     return torch.squeeze(D).to(device=A.device, dtype=A.dtype)
 
 
@@ -85,10 +109,30 @@ def _embed_gaussian(statistics):
         return _ops.Embed.apply(covariances.to(dev), means.to(dev), 0.0, _ops.DIST_FR)
 
 
+def _embed_gaussian_composed(statistics):
+    """distances.py:141-174 with torch ops (any dtype / size)."""
+    means = _unsq_mean(statistics["means"])
+    covariances = _batch3(statistics["covariances"])
+    second = covariances + means.unsqueeze(-1) * means.unsqueeze(-2)
+    top = torch.cat([second, means.unsqueeze(-1)], dim=-1)
+    one = torch.ones(means.shape[0], 1, 1, dtype=means.dtype, device=means.device)
+    bottom = torch.cat([means.unsqueeze(-2), one], dim=-1)
+    return torch.cat([top, bottom], dim=-2)
+
+
 def _fisher_rao(statistics_A, statistics_B, dist):
+    ref = statistics_A["means"]
+    cov = statistics_A["covariances"]
+    if ref.dtype != torch.float32 or cov.dtype != torch.float32 or cov.shape[-1] + 1 > _ops.MAX_M:
+        dev = _lib.compute_device(ref, cov)
+        with torch.cuda.device(dev):
+            EA = _embed_gaussian_composed({k: v.to(dev) for k, v in statistics_A.items()})
+            EB = EA if statistics_B is statistics_A else _embed_gaussian_composed(
+                {k: v.to(dev) for k, v in statistics_B.items()})
+            D = _pairwise_composed(EA, EB, dist)
+        return torch.squeeze(D).to(device=ref.device, dtype=ref.dtype)
     EA = _embed_gaussian(statistics_A)
     EB = EA if statistics_B is statistics_A else _embed_gaussian(statistics_B)
-    ref = statistics_A["means"]
     with torch.cuda.device(EA.device):
         D = _ops.PairDistance.apply(EA, None if EB is EA else EB, dist, EB is EA)
     return torch.squeeze(D).to(device=ref.device, dtype=ref.dtype)
@@ -108,10 +152,6 @@ def fisher_rao_lower_bound(statistics_A, statistics_B):
 # ------------------------------------------------------------------------------------------------
 # Plug-in distances outside the hot path (reference distances.py:240-432): device-side torch.
 # ------------------------------------------------------------------------------------------------
-def _unsq_mean(x):
-    return x.unsqueeze(0) if x.dim() == 1 else x
-
-
 def bhattacharyya(statistics_A, statistics_B):
     """Bhattacharyya distance between Gaussians (reference distances.py:240-280)."""
     mu_a, mu_b = _unsq_mean(statistics_A["means"]), _unsq_mean(statistics_B["means"])

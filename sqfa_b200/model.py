@@ -8,6 +8,8 @@ moves the model to the CUDA device for the duration of the optimisation and back
 every method returns results on the device of its inputs.
 """
 
+import contextlib
+
 import torch
 import torch.nn as nn
 from torch.nn.utils.parametrizations import orthogonal
@@ -98,6 +100,40 @@ class _Transform(torch.autograd.Function):
         dF = gZ.t() @ X if ctx.needs_input_grad[0] else None
         dX = gZ @ Fc if ctx.needs_input_grad[1] else None
         return dF, dX
+
+
+class _PairwiseCurriculum:
+    """`fit(pairwise=True)` (reference model.py:348-409): the filters are learned two at a time.
+    Stage s optimises a model that holds the 2 s filters learned so far, frozen, followed by rows
+    [2 s, 2 s + 2) of the initial filters; the noise buffer is resized with it. One object owns the
+    swaps of parameter, constraint and buffer so that `fit` only sees a sequence of stages."""
+
+    def __init__(self, model):
+        n_filters = model.filters.shape[0]
+        if n_filters % 2 != 0:
+            raise ValueError("Number of filters must be even for pairwise training.")
+        self.model = model
+        self.n_stages = n_filters // 2
+        self.start = model.filters.detach().clone()
+        self.noise_level = model.noise_mat.detach()[0, 0].clone()
+        self.loss, self.seconds = torch.tensor([]), torch.tensor([])
+
+    @contextlib.contextmanager
+    def stage(self, s):
+        model, lo, hi = self.model, 2 * s, 2 * s + 2
+        learned = model.filters.detach()[:lo].clone()
+        model._install_filters(torch.cat((learned, self.start[lo:hi])).contiguous(), n_frozen=lo)
+        model.register_buffer("noise_mat", self.noise_level * torch.eye(hi, device=self.start.device))
+        try:
+            yield
+        finally:
+            model._install_filters(model.filters.detach().clone())  # drops the freeze, keeps the constraint
+
+    def log(self, stage_loss, stage_seconds):
+        """Append a stage's per-epoch losses; its clock continues where the previous stage stopped."""
+        offset = self.seconds[-1] if self.seconds.numel() > 0 else 0.0
+        self.loss = torch.cat((self.loss, stage_loss))
+        self.seconds = torch.cat((self.seconds, stage_seconds + offset))
 
 
 class SecondMomentsSQFA(nn.Module):
@@ -275,9 +311,7 @@ class SecondMomentsSQFA(nn.Module):
             pca_filters = pca_from_scatter(_stats_to_scatter(data_statistics), n_components)
 
         device = self.filters.device
-        remove_parametrizations(self, "filters")
-        self.filters = nn.Parameter(pca_filters.detach().to(device=device, dtype=torch.float32).contiguous())
-        self._add_constraint(constraint=self.constraint)
+        self._install_filters(pca_filters.detach().to(device=device, dtype=torch.float32).contiguous())
 
     def fit(
         self,
@@ -313,6 +347,7 @@ class SecondMomentsSQFA(nn.Module):
         )
         home = self.filters.device
         self._process_group = process_group
+        self._last_fit_evaluations = 0
         with torch.cuda.device(dev):
             stats_dev = _statistics_to(data_statistics, dev)
             self.to(dev)
@@ -329,62 +364,29 @@ class SecondMomentsSQFA(nn.Module):
         return None
 
     def _fit_on_device(self, data_statistics, max_epochs, lr, pairwise, show_progress, atol, **kwargs):
-        if not pairwise:
+        def run_optimiser():
             return fitting_loop(
-                model=self,
-                data_statistics=data_statistics,
-                max_epochs=max_epochs,
-                lr=lr,
-                show_progress=show_progress,
-                return_loss=True,
-                atol=atol,
-                **kwargs,
+                model=self, data_statistics=data_statistics, max_epochs=max_epochs, lr=lr,
+                show_progress=show_progress, return_loss=True, atol=atol, **kwargs,
             )
 
-        # pairwise curriculum (reference model.py:349-409): train filters two at a time, keeping
-        # the already trained ones fixed
-        n_pairs = self.filters.shape[0] // 2
-        filters_original = self.filters.detach().clone()
-        noise_original = self.noise_mat.detach().clone()[0, 0]
-        if self.filters.shape[0] % 2 != 0:
-            raise ValueError("Number of filters must be even for pairwise training.")
+        if not pairwise:
+            return run_optimiser()
+        curriculum = _PairwiseCurriculum(self)
+        for stage in range(curriculum.n_stages):
+            with curriculum.stage(stage):
+                curriculum.log(*run_optimiser())
+        return curriculum.loss, curriculum.seconds
 
-        device = filters_original.device
-        loss = torch.tensor([])
-        training_time = torch.tensor([])
-        for i in range(n_pairs):
-            filters_last_trained = self.filters.detach().clone()
-            if i == 0:
-                filters_new_init = filters_original[:2].contiguous()
-            else:
-                filters_new_init = torch.cat((filters_last_trained, filters_original[2 * i : 2 * (i + 1)]))
+    def _install_filters(self, value, n_frozen=0):
+        """Make `value` (k, n_dim) the raw filter parameter under the model's constraint; the first
+        `n_frozen` rows receive no gradient (FixedFilters stacked on top of the constraint)."""
+        if parametrize_is_parametrized(self, "filters"):
             remove_parametrizations(self, "filters")
-            self.filters = nn.Parameter(filters_new_init)
-            self._add_constraint(constraint=self.constraint)
-
-            self.register_buffer("noise_mat", noise_original * torch.eye(2 * (i + 1), device=device))
-
-            if i > 0:
-                register_parametrization(self, "filters", FixedFilters(n_row_fixed=i * 2))
-
-            loss_pair, training_time_pair = fitting_loop(
-                model=self,
-                data_statistics=data_statistics,
-                max_epochs=max_epochs,
-                lr=lr,
-                show_progress=show_progress,
-                return_loss=True,
-                atol=atol,
-                **kwargs,
-            )
-
-            remove_parametrizations(self, "filters")
-            self._add_constraint(constraint=self.constraint)
-            loss = torch.cat((loss, loss_pair))
-            if training_time.numel() > 0:
-                training_time_pair = training_time_pair + training_time[-1]
-            training_time = torch.cat((training_time, training_time_pair))
-        return loss, training_time
+        self.filters = nn.Parameter(value)
+        self._add_constraint(constraint=self.constraint)
+        if n_frozen > 0:
+            register_parametrization(self, "filters", FixedFilters(n_row_fixed=n_frozen))
 
     def _add_constraint(self, constraint="none"):
         """Register the filter parametrization: 'none', 'sphere' or 'orthogonal'

@@ -13,6 +13,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with `-m gpu`")
+    config.addinivalue_line("markers", "slow: about a minute of CPU oracle work (deselect with -m 'gpu and not slow')")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -76,4 +76,8 @@ def test_closure_and_fit_golden(tag, kind, dist):
         losses, _ = m.fit(data_statistics=stats, max_epochs=200, show_progress=False, return_loss=True)
         ref = g[kind + "_fit_losses"]
         assert abs(float(losses[-1]) - float(ref[-1])) < 1e-4 * abs(float(ref[-1]))
-        assert O.subspace_angle(m.filters.detach().cpu(), g[kind + "_fit_filters"]) < 5e-3
+        # north_star: learned filters within 1e-3 in subspace angle. (The reference's own float32 fit of
+        # this problem ends 3e-5 .. 7e-5 from its float64 fit, measured with oracle/ref_loader.)
+        angle = O.subspace_angle(m.filters.detach().cpu(), g[kind + "_fit_filters"])
+        print(f"{kind}: converged fit, subspace angle to the reference's float64 filters {angle:.2e}")
+        assert angle < 1e-3

@@ -252,3 +252,118 @@ def test_project_forward_shapes(C, D, k):
     assert rel_err(T, T64) < 1e-5
     assert rel_err(Psi, torch.einsum("cfj,gj->cfg", T64, F.double())) < 1e-5
     assert rel_err(Mu, M.double() @ F.double().T) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd through the public linalg functions (user distance_funs are built from them)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["spd_sqrt", "spd_log", "spd_inv_sqrt"])
+@pytest.mark.parametrize("n,m", [(3, 4), (5, 9)])
+def test_linalg_functions_are_differentiable(name, n, m):
+    """d/dM of a scalar function of spd_sqrt / spd_log / spd_inv_sqrt against fp64 autograd through
+    torch.linalg.eigh (what the reference differentiates through, linalg.py:121-183)."""
+    from sqfa_b200 import linalg as Ln
+
+    M = sample_spd(n, m, seed=7 * m + n)
+    Wt = torch.randn(n, m, m, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+
+    def scalar(fun_out):
+        if name == "spd_inv_sqrt":  # rows of the whitening matrix come in the solver's order: use W^T W = M^-1
+            fun_out = fun_out.transpose(-2, -1) @ fun_out
+        return (fun_out * Wt.to(fun_out)).sum()
+
+    M64 = M.clone().requires_grad_(True)
+    lam, V = torch.linalg.eigh(M64)
+    ref_out = {"spd_sqrt": (V * lam.sqrt().unsqueeze(-2)) @ V.transpose(-2, -1),
+               "spd_log": (V * lam.log().unsqueeze(-2)) @ V.transpose(-2, -1),
+               "spd_inv_sqrt": (V * lam.rsqrt().unsqueeze(-2)).transpose(-2, -1)}[name]
+    scalar(ref_out).backward()
+    g_ref = 0.5 * (M64.grad + M64.grad.transpose(-2, -1))
+
+    M32 = M.float().cuda().requires_grad_(True)
+    out = getattr(Ln, name)(M32)
+    assert out.requires_grad and out.grad_fn is not None
+    scalar(out).backward()
+    g_got = 0.5 * (M32.grad + M32.grad.transpose(-2, -1))
+    assert rel_err(g_got, g_ref) < 1e-3
+    # float64 input: computed in float64 (the reference follows the input dtype)
+    M64d = M.cuda().requires_grad_(True)
+    out64 = getattr(Ln, name)(M64d)
+    assert out64.dtype == torch.float64
+    scalar(out64).backward()
+    assert rel_err(0.5 * (M64d.grad + M64d.grad.transpose(-2, -1)), g_ref) < 1e-9
+
+
+def _bw_distance_sq(A, B, linalg):
+    """The Bures-Wasserstein distance_fun of the reference's tutorial (docs/source/tutorials/distances.md)."""
+    tr_A = torch.einsum("ijj->i", A)
+    tr_B = torch.einsum("ijj->i", B)
+    A_sqrt = linalg.spd_sqrt(A)
+    C = linalg.conjugate_matrix(B, A_sqrt)
+    tr_C = torch.sum(torch.sqrt(torch.linalg.eigvalsh(C)), dim=-1)
+    return tr_A[None, :] + tr_B[:, None] - 2 * tr_C
+
+
+def test_user_distance_fun_trains_with_correct_gradients():
+    """A fit with the tutorial's Bures-Wasserstein distance: the gradient of the first closure
+    evaluation (through spd_sqrt) and the losses of a short fit against the oracle in fp64."""
+    from sqfa_b200 import linalg as Ln
+    from sqfa_b200.model import SecondMomentsSQFA
+
+    class OracleLinalg:  # the reference's formulas for the two functions the tutorial uses
+        conjugate_matrix = staticmethod(O.conjugate_matrix)
+
+        @staticmethod
+        def spd_sqrt(M):
+            lam, V = torch.linalg.eigh(M)
+            return torch.einsum("...ij,...j,...kj->...ik", V, torch.sqrt(lam), V)
+
+    def bw(A, B):
+        return torch.sqrt(torch.abs(_bw_distance_sq(A, B, Ln)) + 1e-6)
+
+    def bw_oracle(A, B):
+        return torch.sqrt(torch.abs(_bw_distance_sq(A, B, OracleLinalg)) + 1e-6)
+
+    n, d, c, k = 3000, 20, 5, 3
+    stats = stats_for(n, d, c, seed=21)
+    F0 = torch.randn(k, d, generator=torch.Generator().manual_seed(2))
+    loss64, grad64, _ = O.loss_and_grad("second_moments", stats, F0.double(), noise=0.01, distance=bw_oracle)
+    model = SecondMomentsSQFA(n_dim=d, feature_noise=0.01, n_filters=k, filters=F0.clone(), distance_fun=bw).cuda()
+    sc = to_f32_cuda(stats)
+    dmat = model.get_class_distances(sc, regularized=True)
+    i, j = torch.tril_indices(c, c, -1)
+    loss = -dmat[i, j].mean()
+    loss.backward()
+    assert abs(float(loss) - float(loss64)) < DIST_TOL * abs(float(loss64))
+    assert rel_err(model.parametrizations.filters.original.grad, grad64) < GRAD_TOL
+    _, losses_o, _ = O.fit_lbfgs("second_moments", stats, F0.double(), noise=0.01, distance=bw_oracle, max_epochs=2,
+                                 max_iter=5)
+    model = SecondMomentsSQFA(n_dim=d, feature_noise=0.01, n_filters=k, filters=F0.clone(), distance_fun=bw)
+    losses, _ = model.fit(data_statistics={kk: v.float() for kk, v in stats.items()}, max_epochs=2,
+                          show_progress=False, return_loss=True, max_iter=5)
+    assert torch.allclose(losses.double(), losses_o.double(), rtol=1e-3)
+
+
+def test_large_and_double_inputs_take_the_composed_path():
+    """Matrices above 64 x 64 and float64 inputs: same semantics as the reference (any size, output dtype
+    follows the input), computed with device-side library calls instead of the pair kernels."""
+    from sqfa_b200 import distances as Dn
+    from sqfa_b200 import linalg as Ln
+
+    A = sample_spd(3, 80, seed=1)
+    B = sample_spd(2, 80, seed=2)
+    got = Dn.affine_invariant(A.float().cuda(), B.float().cuda())
+    assert got.dtype == torch.float32 and rel_err(got, O.affine_invariant(A, B)) < 1e-3
+    W = Ln.spd_inv_sqrt(A.float().cuda()).double().cpu()
+    assert torch.allclose(W @ A @ W.transpose(-2, -1), torch.eye(80, dtype=torch.float64).expand(3, 80, 80), atol=1e-3)
+    A6, B6 = sample_spd(4, 6, seed=3), sample_spd(3, 6, seed=4)
+    for name in ("affine_invariant_sq", "affine_invariant", "log_euclidean_sq", "log_euclidean"):
+        got = getattr(Dn, name)(A6.cuda(), B6.cuda())
+        assert got.dtype == torch.float64
+        assert rel_err(got, getattr(O, name)(A6, B6)) < 1e-10, name
+    mu = torch.randn(4, 6, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    sd = {"means": mu, "covariances": A6}
+    got = Dn.fisher_rao_lower_bound({k: v.cuda() for k, v in sd.items()}, {k: v.cuda() for k, v in sd.items()})
+    assert got.dtype == torch.float64 and rel_err(got, O.fisher_rao_lower_bound(sd, sd)) < 1e-8
+    lam = Ln.generalized_eigenvalues(A6.cuda(), B6.cuda())
+    assert lam.dtype == torch.float64 and rel_err(lam, O.generalized_eigenvalues(A6, B6)) < 1e-10
