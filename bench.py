@@ -570,7 +570,12 @@ def run_ours(args):
 
     gc.enable()
     peaks = load_peaks()
-    tf32_peak = measure_tf32_peak(dev)  # every rank measures (keeps the ranks in step); rank 0 reports
+    # Dense TF32 peak: measured in this run with cuBLAS (every rank measures, which keeps the ranks in
+    # step). The roofline denominator is the LARGER of that and half the measured bf16 peak of
+    # MEASURED_PEAKS.json (the hardware ratio): cuBLAS TF32 does not reach the pipe's peak on this part
+    # (the Gram kernel runs above it), and a fraction against the smaller figure would flatter the kernel.
+    tf32_cublas = measure_tf32_peak(dev)
+    tf32_peak = max(tf32_cublas, peaks["bf16_tflops"] / 2.0)
     # ---- second hot path on the headline config: SQFA fit on the statistics just computed
     fit = fit_leg(stats, d, c, k, dev, None, 1, peaks, n_eval=50, epochs=5, label="configs[1]") if rank == 0 else None
     del stats, out_h
@@ -600,9 +605,10 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
                 "kernel_ms": gram_ms, "executed_flop_per_launch": executed,
                 "algorithmic_flop_per_launch": 2.0 * n * d * d,
-                "peak_source": "measured in this run: cuBLAS TF32 matmul 8192^3, best of 10",
-                "peak_crosscheck_bf16_over_2": peaks["bf16_tflops"] / 2.0,
-                "frac_of_bf16_over_2": achieved / (peaks["bf16_tflops"] / 2.0)}
+                "peak_source": "max(cuBLAS TF32 matmul 8192^3 measured in this run (best of 10), "
+                               "MEASURED_PEAKS.json bf16_tflops / 2)",
+                "tf32_cublas_measured_in_run": tf32_cublas, "bf16_over_2": peaks["bf16_tflops"] / 2.0,
+                "frac_of_cublas_tf32": achieved / tf32_cublas}
     prof = os.path.join(ROOT, "profiles", "gram_traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
@@ -629,7 +635,7 @@ def run_ours(args):
                 "overlap": f"{nbuf} CUDA streams / buffer sets, inputs of step i+1 uploaded while step i computes and downloads"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "fit": fit, "fit_c4": fit_c4,
-        "hp1_table": table, "tf32_peak_measured_tflops": tf32_peak,
+        "hp1_table": table, "tf32_peak_measured_tflops": tf32_cublas,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -199,11 +199,12 @@ def test_c4_pair_subsets_match_oracle():
     g_got = gE.double().cpu()
     g_got = 0.5 * (g_got + g_got.transpose(1, 2))
     touched = g_ref.reshape(C, -1).norm(dim=1) > 0
-    assert int(touched.sum()) > 1500
+    assert int(touched.sum()) >= 900  # the slices' columns sweep almost every class
     err = float((g_got - g_ref).norm() / g_ref.norm())
     print(f"c4 pair slices: worst distance rel err {worst:.2e}, dLoss/dE rel err {err:.2e}")
     assert err < GRAD_TOL
-    assert float(g_got[~touched].abs().max()) == 0.0
+    if bool((~touched).any()):
+        assert float(g_got[~touched].abs().max()) == 0.0
     assert abs(float(loss[0]) - float(total)) < DIST_TOL * abs(float(total)) and float(loss[1]) == 0
 
 
