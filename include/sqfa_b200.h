@@ -223,11 +223,17 @@ int sqfa_class_factor(const float* E, int32_t n_classes, int32_t m, int32_t dist
  *              when triangular) : 1). For LE these are gradients w.r.t. the matrix logarithms
  *              (feed them to sqfa_class_factor_bwd). gEa == gEb is allowed.
  *   eig_out    [n_a][n_b][m] or NULL (AI / FR, triangular == 0 only): the generalized eigenvalues
- *              of (A_a, B_b) in descending order (generalized_eigenvalues, linalg.py:48-70) */
+ *              of (A_a, B_b) in descending order (generalized_eigenvalues, linalg.py:48-70)
+ *   ws         needed when loss or gEa is given: sqfa_pair_distances_workspace_bytes(...) bytes,
+ *              16-byte aligned. Sums are DETERMINISTIC: every warp stores the partial loss / gradient
+ *              of its tile of pairs there and a second kernel adds them per class in a fixed order
+ *              (no floating-point atomics), so results are bit-identical from run to run. */
+size_t sqfa_pair_distances_workspace_bytes(int32_t n_a, int32_t n_b, int32_t m, int32_t dist, int32_t triangular,
+                                           int64_t pair_begin, int64_t pair_end);
 int sqfa_pair_distances(const float* Wa, const float* Wb, int32_t n_a, int32_t n_b, int32_t m, int32_t dist,
                         int32_t triangular, int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
-                        float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
-                        sqfa_stream_t stream);
+                        float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out, void* ws,
+                        size_t ws_bytes, sqfa_stream_t stream);
 
 /* LE only: gE[c] += adjoint of logE = V log(Lambda) V^T applied to gLog[c] (Daleckii-Krein).
  * No-op for AI / FR, whose gradients sqfa_pair_distances accumulates directly on E. */
@@ -237,14 +243,29 @@ int sqfa_class_factor_bwd(const float* W, const float* gLog, int32_t n_classes, 
 /* The whole closure body of the fitting loop (_optim.py:90-96) in one call, at fixed filters F:
  *   out[0] = -mean_{i>j} d(E_i, E_j) over pairs [pair_begin, pair_end) (scaled by 1/P of ALL pairs,
  *            so partial results of a sharded pair list add up), out[1] = # non-finite distances,
+ *   out[2] = max |dF|,
  *   dF     = d out[0] / dF   (k x D),
  * with E_c = F S_c F^T + noise I (AI, LE) or its Calvo-Oller embedding with mu'_c = F m_c (FR).
- * Sequences sqfa_project_fwd, sqfa_embed_fwd, sqfa_class_factor, sqfa_pair_distances,
- * (sqfa_class_factor_bwd,) sqfa_embed_bwd and sqfa_project_bwd on `stream` inside `ws`. */
-size_t sqfa_fused_loss_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters, int32_t dist);
+ * Eight kernels on `stream` inside `ws` (16-byte aligned, sqfa_fused_loss_workspace_bytes for the same
+ * pair range): projection (stream + finish), per-class embedding + factorisation, pair kernel,
+ * per-class gradient reduction + embedding adjoint, projection adjoint. Deterministic. */
+size_t sqfa_fused_loss_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters, int32_t dist,
+                                       int64_t pair_begin, int64_t pair_end);
 int sqfa_fused_loss(const float* S, const float* M, const float* F, int32_t n_classes, int32_t n_dim,
                     int32_t n_filters, float noise, int32_t dist, int64_t pair_begin, int64_t pair_end, float* out,
                     float* dF, void* ws, size_t ws_bytes, sqfa_stream_t stream);
+
+/* The same evaluation at the RAW filter parameter W of a constrained model, constraint included
+ * (constraints.py:17-141): F = W / |W| row-wise (SQFA_CONSTRAINT_SPHERE) or F = W
+ * (SQFA_CONSTRAINT_NONE); grad = d out[0] / dW through the constraint's adjoint, with zero rows for
+ * the first n_fixed filters (FixedFilters of the pairwise curriculum); out[2] = max |grad|, the
+ * quantity L-BFGS tests first. One call per closure evaluation of the fitting loop. */
+#define SQFA_CONSTRAINT_NONE 0
+#define SQFA_CONSTRAINT_SPHERE 1
+int sqfa_closure_eval(const float* S, const float* M, const float* raw_filters, int32_t n_classes, int32_t n_dim,
+                      int32_t n_filters, float noise, int32_t dist, int32_t constraint, int32_t n_fixed,
+                      int64_t pair_begin, int64_t pair_end, float* out, float* grad, void* ws, size_t ws_bytes,
+                      sqfa_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimiser support (reference: torch.optim.LBFGS driven by fitting_loop, _optim.py:78-96)

@@ -83,16 +83,22 @@ SIGNATURES = {
     "sqfa_embed_bwd": (c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "sqfa_class_factor_floats": (c_size, [c_i32, c_i32]),
     "sqfa_class_factor": (c_int, [c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    "sqfa_pair_distances_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64]),
     "sqfa_pair_distances": (
         c_int,
         [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-         c_ptr, c_ptr],
+         c_ptr, c_ptr, c_size, c_ptr],
     ),
     "sqfa_class_factor_bwd": (c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
-    "sqfa_fused_loss_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32]),
+    "sqfa_fused_loss_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32, c_i64, c_i64]),
     "sqfa_fused_loss": (
         c_int,
         [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, c_i32, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
+    ),
+    "sqfa_closure_eval": (
+        c_int,
+        [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, c_i32, c_i32, c_i32, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
+         c_size, c_ptr],
     ),
 }
 

@@ -130,10 +130,14 @@ def pair_raw(Wa, Wb, n_a, n_b, m, dist, tri, weight=1.0, gD=None, dist_out=None,
     lib = _lib.load()
     total = n_a * (n_a - 1) // 2 if tri else n_a * n_b
     p0, p1 = (0, total) if pair_range is None else pair_range
+    ws, nbytes = None, 0
+    if loss is not None or gEa is not None:  # per-tile partial sums, reduced in a fixed order
+        nbytes = lib.sqfa_pair_distances_workspace_bytes(n_a, n_b, m, dist, 1 if tri else 0, p0, p1)
+        ws = _ws(nbytes, Wa.device)
     _lib.check(
         lib.sqfa_pair_distances(
             _lib.ptr(Wa), _lib.ptr(Wb), n_a, n_b, m, dist, 1 if tri else 0, p0, p1, float(weight), _lib.ptr(gD),
-            _lib.ptr(dist_out), _lib.ptr(loss), _lib.ptr(gEa), _lib.ptr(gEb), _lib.ptr(eig_out),
+            _lib.ptr(dist_out), _lib.ptr(loss), _lib.ptr(gEa), _lib.ptr(gEb), _lib.ptr(eig_out), _lib.ptr(ws), nbytes,
             _lib.stream_ptr(Wa.device),
         ),
         "sqfa_pair_distances",
@@ -250,10 +254,40 @@ class PairDistance(torch.autograd.Function):
         return ga, gb, None, None
 
 
+N_OUT = 3  # [loss, number of non-finite pair distances, max |gradient|]
+
+
+def shard_pairs(n_pairs, n_classes, rank, world):
+    """Slice [begin, end) of the linearised lower-triangle pair list (p = i (i - 1) / 2 + j) owned by
+    `rank`: whole rows i, cut where the pair count is balanced and at multiples of 4 rows (the pair
+    kernel works on 4 x 4 tiles, so tiles are never split between ranks)."""
+    if world <= 1:
+        return 0, n_pairs
+
+    def cut(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return n_pairs
+        target = n_pairs * r / world
+        i = int((1 + (1 + 8 * target) ** 0.5) / 2)  # row whose first pair is nearest to the target
+        i = min(max(4 * round(i / 4), 0), n_classes)
+        return i * (i - 1) // 2
+
+    return cut(rank), cut(rank + 1)
+
+
+def _closure_workspace(lib, C, D, k, dist, p0, p1, dev, ws):
+    nbytes = lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist, p0, p1)
+    if ws is None or ws.numel() < nbytes or ws.device != dev:
+        ws = _ws(nbytes, dev)
+    return ws
+
+
 def fused_loss_raw(F, S, M, noise, dist, group=None, ws=None):
     """One native evaluation of the closure body at the (constrained) filters F: returns the packed
-    device vector [loss, #non-finite pair distances, dLoss/dF (k*D)]. With a process group the pair
-    list is split across ranks and the vector is all-reduced."""
+    device vector [loss, #non-finite pair distances, max|dF|, dLoss/dF (k*D)]. With a process group the
+    pair list is split across ranks and the vector is all-reduced (entry 2 is then meaningless)."""
     lib = _lib.load()
     dev = S.device
     Fc = f32c(F, dev)
@@ -265,16 +299,14 @@ def fused_loss_raw(F, S, M, noise, dist, group=None, ws=None):
         import torch.distributed as dist_mod
 
         rank, world = dist_mod.get_rank(group), dist_mod.get_world_size(group)
-    p0, p1 = (P * rank) // world, (P * (rank + 1)) // world
-    nbytes = lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist)
-    if ws is None or ws.numel() < nbytes or ws.device != dev:
-        ws = _ws(nbytes, dev)
-    # [loss, #non-finite, dF...] in one buffer: one all-reduce when the pair list is sharded
-    packed = torch.empty(2 + k * D, dtype=torch.float32, device=dev)
+    p0, p1 = shard_pairs(P, C, rank, world)
+    ws = _closure_workspace(lib, C, D, k, dist, p0, p1, dev, ws)
+    # [loss, #non-finite, max|dF|, pad, dF...] in one buffer: one all-reduce when the pair list is sharded
+    packed = torch.empty(4 + k * D, dtype=torch.float32, device=dev)
     _lib.check(
         lib.sqfa_fused_loss(
             _lib.ptr(S), _lib.ptr(M), _lib.ptr(Fc), C, D, k, float(noise), dist, p0, p1, _lib.ptr(packed),
-            ctypes.c_void_p(packed.data_ptr() + 8), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
+            ctypes.c_void_p(packed.data_ptr() + 16), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
         ),
         "sqfa_fused_loss",
     )
@@ -283,6 +315,23 @@ def fused_loss_raw(F, S, M, noise, dist, group=None, ws=None):
 
         dist_mod.all_reduce(packed, group=group)
     return packed
+
+
+def closure_eval_raw(W, S, M, noise, dist, sphere, n_fixed, out, grad, ws):
+    """One closure evaluation of the fitting loop at the RAW filter parameter W, constraint included:
+    out <- [loss, #non-finite pair distances, max|grad|], grad <- dLoss/dW. Everything preallocated by
+    the caller (the call is capturable in a CUDA graph)."""
+    lib = _lib.load()
+    C, D, _ = S.shape
+    k = W.shape[0]
+    P = C * (C - 1) // 2
+    _lib.check(
+        lib.sqfa_closure_eval(
+            _lib.ptr(S), _lib.ptr(M), _lib.ptr(W), C, D, k, float(noise), dist, 1 if sphere else 0, int(n_fixed), 0, P,
+            _lib.ptr(out), _lib.ptr(grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(S.device),
+        ),
+        "sqfa_closure_eval",
+    )
 
 
 class FusedLoss(torch.autograd.Function):
@@ -301,7 +350,7 @@ class FusedLoss(torch.autograd.Function):
     def forward(ctx, F, S, M, noise, dist, group, ws=None):
         packed = fused_loss_raw(F, S, M, noise, dist, group, ws)
         k, D = F.shape[0], S.shape[1]
-        ctx.save_for_backward(packed[2:].view(k, D))
+        ctx.save_for_backward(packed[4:].view(k, D))
         return packed[:2]
 
     @staticmethod

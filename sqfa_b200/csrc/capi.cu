@@ -248,10 +248,17 @@ int sqfa_class_factor(const float* E, int32_t n_classes, int32_t m, int32_t dist
   return wrap(__func__, sqfa::launch_class_factor(E, n_classes, m, dist, W, flag, S(stream)));
 }
 
+size_t sqfa_pair_distances_workspace_bytes(int32_t n_a, int32_t n_b, int32_t m, int32_t dist, int32_t triangular,
+                                           int64_t pair_begin, int64_t pair_end) {
+  if (n_a <= 0 || n_b <= 0 || m <= 0 || !dist_ok(dist)) return 256;
+  return sqfa::pair_workspace(n_a, n_b, m, dist, triangular ? 1 : 0, pair_begin, pair_end).total_floats *
+             sizeof(float) + 256;
+}
+
 int sqfa_pair_distances(const float* Wa, const float* Wb, int32_t n_a, int32_t n_b, int32_t m, int32_t dist,
                         int32_t triangular, int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
-                        float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
-                        sqfa_stream_t stream) {
+                        float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out, void* ws,
+                        size_t ws_bytes, sqfa_stream_t stream) {
   if (!dist_ok(dist) || Wa == nullptr || Wb == nullptr || n_a < 0 || n_b < 0 || m <= 0 ||
       (triangular && (n_a != n_b || Wa != Wb)) || ((gEa == nullptr) != (gEb == nullptr)) ||
       (eig_out != nullptr && (triangular || (dist & 15) == SQFA_DIST_LOG_EUCLIDEAN)))
@@ -259,9 +266,13 @@ int sqfa_pair_distances(const float* Wa, const float* Wb, int32_t n_a, int32_t n
   const int64_t P = triangular ? (int64_t)n_a * (n_a - 1) / 2 : (int64_t)n_a * n_b;
   if (pair_begin < 0 || pair_end > P || pair_begin > pair_end) return fail_arg(__func__, "bad pair range");
   if (m > SQFA_MAX_M) return fail_arg(__func__, "m exceeds SQFA_MAX_M", SQFA_E_UNSUPPORTED);
+  const bool needs_ws = (loss != nullptr || gEa != nullptr) && pair_end > pair_begin;
+  if (needs_ws && (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 15) != 0 ||
+                   ws_bytes < sqfa_pair_distances_workspace_bytes(n_a, n_b, m, dist, triangular, pair_begin, pair_end)))
+    return fail_arg(__func__, "workspace missing, misaligned or too small", SQFA_E_WORKSPACE);
   return wrap(__func__, sqfa::launch_pair_distances(Wa, Wb, n_a, n_b, m, dist, triangular ? 1 : 0, pair_begin,
                                                     pair_end, weight, gD, dist_out, loss, gEa, gEb, eig_out,
-                                                    S(stream)));
+                                                    static_cast<float*>(ws), S(stream)));
 }
 
 int sqfa_class_factor_bwd(const float* W, const float* gLog, int32_t n_classes, int32_t m, int32_t dist,
@@ -276,26 +287,47 @@ int sqfa_class_factor_bwd(const float* W, const float* gLog, int32_t n_classes, 
 
 extern "C" {
 
-size_t sqfa_fused_loss_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters, int32_t dist) {
+size_t sqfa_fused_loss_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t n_filters, int32_t dist,
+                                       int64_t pair_begin, int64_t pair_end) {
   if (n_classes <= 0 || n_dim <= 0 || n_filters <= 0 || !dist_ok(dist)) return 256;
-  return sqfa::fused_loss_workspace_bytes(n_classes, n_dim, n_filters, dist);
+  return sqfa::fused_loss_workspace_bytes(n_classes, n_dim, n_filters, dist, pair_begin, pair_end);
+}
+
+static int closure_common(const char* fn, const float* S_, const float* M, const float* filters, int32_t n_classes,
+                          int32_t n_dim, int32_t n_filters, float noise, int32_t dist, int constraint, int n_fixed,
+                          int64_t pair_begin, int64_t pair_end, float* out, float* grad, void* ws, size_t ws_bytes,
+                          sqfa_stream_t stream) {
+  const int base = dist & 15;
+  if (!dist_ok(dist) || S_ == nullptr || filters == nullptr || out == nullptr || grad == nullptr || ws == nullptr ||
+      n_classes <= 0 || n_dim <= 0 || n_filters <= 0 || (base == SQFA_DIST_FISHER_RAO_LB && M == nullptr) ||
+      n_fixed < 0 || n_fixed > n_filters || (reinterpret_cast<uintptr_t>(ws) & 15) != 0)
+    return fail_arg(fn, "bad argument");
+  const int m = base == SQFA_DIST_FISHER_RAO_LB ? n_filters + 1 : n_filters;
+  if (n_filters > 32 || m > SQFA_MAX_M) return fail_arg(fn, "n_filters must be <= 32", SQFA_E_UNSUPPORTED);
+  const int64_t P = (int64_t)n_classes * (n_classes - 1) / 2;
+  if (pair_begin < 0 || pair_end > P || pair_begin > pair_end) return fail_arg(fn, "bad pair range");
+  if (ws_bytes < sqfa_fused_loss_workspace_bytes(n_classes, n_dim, n_filters, dist, pair_begin, pair_end))
+    return fail_arg(fn, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(fn, sqfa::launch_fused_loss(S_, M, filters, n_classes, n_dim, n_filters, noise, dist, constraint,
+                                          n_fixed, pair_begin, pair_end, out, grad, static_cast<float*>(ws),
+                                          S(stream)));
 }
 
 int sqfa_fused_loss(const float* S_, const float* M, const float* F, int32_t n_classes, int32_t n_dim,
                     int32_t n_filters, float noise, int32_t dist, int64_t pair_begin, int64_t pair_end, float* out,
                     float* dF, void* ws, size_t ws_bytes, sqfa_stream_t stream) {
-  const int base = dist & 15;
-  if (!dist_ok(dist) || S_ == nullptr || F == nullptr || out == nullptr || dF == nullptr || ws == nullptr ||
-      n_classes <= 0 || n_dim <= 0 || n_filters <= 0 || (base == SQFA_DIST_FISHER_RAO_LB && M == nullptr))
-    return fail_arg(__func__, "bad argument");
-  const int m = base == SQFA_DIST_FISHER_RAO_LB ? n_filters + 1 : n_filters;
-  if (n_filters > 32 || m > SQFA_MAX_M) return fail_arg(__func__, "n_filters must be <= 32", SQFA_E_UNSUPPORTED);
-  const int64_t P = (int64_t)n_classes * (n_classes - 1) / 2;
-  if (pair_begin < 0 || pair_end > P || pair_begin > pair_end) return fail_arg(__func__, "bad pair range");
-  if (ws_bytes < sqfa_fused_loss_workspace_bytes(n_classes, n_dim, n_filters, dist))
-    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
-  return wrap(__func__, sqfa::launch_fused_loss(S_, M, F, n_classes, n_dim, n_filters, noise, dist, pair_begin,
-                                                pair_end, out, dF, static_cast<float*>(ws), S(stream)));
+  return closure_common(__func__, S_, M, F, n_classes, n_dim, n_filters, noise, dist, -1, 0, pair_begin, pair_end,
+                        out, dF, ws, ws_bytes, stream);
+}
+
+int sqfa_closure_eval(const float* S_, const float* M, const float* raw_filters, int32_t n_classes, int32_t n_dim,
+                      int32_t n_filters, float noise, int32_t dist, int32_t constraint, int32_t n_fixed,
+                      int64_t pair_begin, int64_t pair_end, float* out, float* grad, void* ws, size_t ws_bytes,
+                      sqfa_stream_t stream) {
+  if (constraint != SQFA_CONSTRAINT_NONE && constraint != SQFA_CONSTRAINT_SPHERE)
+    return fail_arg(__func__, "constraint must be SQFA_CONSTRAINT_NONE or SQFA_CONSTRAINT_SPHERE");
+  return closure_common(__func__, S_, M, raw_filters, n_classes, n_dim, n_filters, noise, dist, constraint, n_fixed,
+                        pair_begin, pair_end, out, grad, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

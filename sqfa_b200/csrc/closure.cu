@@ -1,9 +1,19 @@
 // The whole closure body of the SQFA fitting loop as ONE native call:
-//   loss = -mean_{i>j} d(E_i, E_j),  E_c = embed(F S_c F^T + noise I [, F m_c]),  dF = dloss/dF
+//   loss = -mean_{i>j} d(E_i, E_j),  E_c = embed(F S_c F^T + noise I [, F m_c]),  grad = dloss/d(filters)
 // (reference: /root/reference/src/sqfa/_optim.py:90-96 -> model.py:190-220 / 508-546 ->
-//  distances.py -> linalg.py and the autograd backward of all of it).
-// It only sequences the kernels of project.cu and pairs.cu on the caller's stream with a
-// caller-provided workspace, so one evaluation costs one host call instead of ~12.
+//  distances.py -> linalg.py and the autograd backward of all of it, including the filter
+//  constraint constraints.py:37).
+// It sequences the kernels of project.cu and pairs.cu on the caller's stream inside a caller-provided
+// workspace -- 8 launches, no memsets, no atomics on floating-point sums:
+//   constraint_fwd          F = W / |W|                                  (sphere constraint only)
+//   project_stream          row-split partials of T_c = F S_c            (the one pass over C D^2 floats)
+//   project_finish          T_c, per-chunk partials of Psi_c = T_c F^T and mu'_c = F m_c
+//   class_prepare           Psi_c, mu'_c, E_c, factorisation W_c         (one warp per class)
+//   pair kernel             distances + per-tile partial dLoss/dE        (one warp per tile of pairs)
+//   pair_reduce             dLoss/dE_c in fixed order -> embedding adjoint (gPsi, gMu); loss
+//   project_bwd             class-split partials of dLoss/dF
+//   closure_finish          dLoss/dF, constraint adjoint -> grad, max |grad|
+// Log-Euclidean adds le_grad + le_factor_bwd + embed_bwd between the pair kernel and project_bwd.
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -14,50 +24,56 @@ namespace sqfa {
 
 namespace {
 
-__global__ void scale_loss_kernel(float* out, float w) { out[0] *= w; }
-
 inline size_t al(size_t n) { return (n + 63) & ~size_t(63); }  // floats, 256-byte granules
 
 struct ClosureLayout {
-  size_t T, Psi, Mu, E, W, gE, gLog, gPsi, gMu, flag, proj, total;
+  size_t F, inv_norm, T, Mu, E, W, gE, gLog, gPsi, gMu, flag, proj, psipart, mupart, pair, total;
 };
 
-ClosureLayout closure_layout(int C, int D, int k, int dist) {
+ClosureLayout closure_layout(int C, int D, int k, int dist, int64_t pair_begin, int64_t pair_end) {
   const int base = dist & 15;
   const int m = (base == SQFA_DIST_FISHER_RAO_LB) ? k + 1 : k;
+  const bool le = base == SQFA_DIST_LOG_EUCLIDEAN;
   ClosureLayout L;
   size_t o = 0;
-  L.T = o;    o += al((size_t)C * k * D);
-  L.Psi = o;  o += al((size_t)C * k * k);
-  L.Mu = o;   o += al((size_t)C * k);
-  L.E = o;    o += al((size_t)C * m * m);
-  L.W = o;    o += al((size_t)C * class_factor_floats(m, dist));
-  L.gE = o;   o += al((size_t)C * m * m);
-  L.gLog = o; o += al((size_t)C * m * m);
-  L.gPsi = o; o += al((size_t)C * k * k);
-  L.gMu = o;  o += al((size_t)C * k);
-  L.flag = o; o += al(16);
-  L.proj = o; o += al(project_workspace_bytes(C, D, k) / sizeof(float) + 1);
+  L.F = o;        o += al((size_t)k * D);
+  L.inv_norm = o; o += al(k);
+  L.T = o;        o += al((size_t)C * k * D);
+  L.Mu = o;       o += al((size_t)C * k);
+  L.E = o;        o += al((size_t)C * m * m);
+  L.W = o;        o += al((size_t)C * class_factor_floats(m, dist));
+  L.gE = o;       o += le ? al((size_t)C * m * m) : 0;
+  L.gLog = o;     o += le ? al((size_t)C * m * m) : 0;
+  L.gPsi = o;     o += al((size_t)C * k * k);
+  L.gMu = o;      o += al((size_t)C * k);
+  L.flag = o;     o += al(16);
+  L.proj = o;     o += al(project_workspace_bytes(C, D, k) / sizeof(float) + 1);
+  L.psipart = o;  o += project_psipart_floats(C, D, k);
+  L.mupart = o;   o += project_mupart_floats(C, D, k);
+  L.pair = o;     o += al(pair_workspace(C, C, m, dist, 1, pair_begin, pair_end).total_floats);
   L.total = o;
   return L;
 }
 
 }  // namespace
 
-size_t fused_loss_workspace_bytes(int C, int D, int k, int dist) {
-  return closure_layout(C, D, k, dist).total * sizeof(float);
+size_t fused_loss_workspace_bytes(int C, int D, int k, int dist, int64_t pair_begin, int64_t pair_end) {
+  return closure_layout(C, D, k, dist, pair_begin, pair_end).total * sizeof(float);
 }
 
-cudaError_t launch_fused_loss(const float* S, const float* M, const float* F, int C, int D, int k, float noise,
-                              int dist, int64_t pair_begin, int64_t pair_end, float* out, float* dF, float* ws,
-                              cudaStream_t st) {
+// filters: the constrained filters F (constraint < 0), or the raw parameter (constraint 0 = none,
+// 1 = sphere). grad: d out[0] / d filters.  out: {loss, #non-finite distances, max |grad|}.
+cudaError_t launch_fused_loss(const float* S, const float* M, const float* filters, int C, int D, int k, float noise,
+                              int dist, int constraint, int n_fixed, int64_t pair_begin, int64_t pair_end, float* out,
+                              float* grad, float* ws, cudaStream_t st) {
   const int base = dist & 15;
   const bool fr = base == SQFA_DIST_FISHER_RAO_LB;
   const bool le = base == SQFA_DIST_LOG_EUCLIDEAN;
   const int m = fr ? k + 1 : k;
-  const ClosureLayout L = closure_layout(C, D, k, dist);
+  const ClosureLayout L = closure_layout(C, D, k, dist, pair_begin, pair_end);
+  float* Fbuf = ws + L.F;
+  float* inv_norm = ws + L.inv_norm;
   float* T = ws + L.T;
-  float* Psi = ws + L.Psi;
   float* Mu = ws + L.Mu;
   float* E = ws + L.E;
   float* W = ws + L.W;
@@ -67,26 +83,35 @@ cudaError_t launch_fused_loss(const float* S, const float* M, const float* F, in
   float* gMu = ws + L.gMu;
   int32_t* flag = reinterpret_cast<int32_t*>(ws + L.flag);
   float* proj = ws + L.proj;
+  float* PsiPart = ws + L.psipart;
+  float* MuPart = ws + L.mupart;
+  float* pairws = ws + L.pair;
   const float* Mfr = fr ? M : nullptr;
   const int64_t P = (int64_t)C * (C - 1) / 2;
   const float weight = -1.0f / (float)(P > 0 ? P : 1);
+  const int sphere = constraint == 1 ? 1 : 0;
 
   cudaError_t e;
-  if ((e = launch_project_fwd(S, Mfr, F, C, D, k, T, Psi, fr ? Mu : nullptr, proj, st)) != cudaSuccess) return e;
-  if ((e = launch_embed_fwd(Psi, Mu, noise, C, k, fr ? 1 : 0, E, st)) != cudaSuccess) return e;
-  if ((e = launch_class_factor(E, C, m, dist, W, flag, st)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(out, 0, 2 * sizeof(float), st)) != cudaSuccess) return e;
-  // gE and gLog are adjacent in the workspace: one memset clears both
-  if ((e = cudaMemsetAsync(gE, 0, (L.gPsi - L.gE) * sizeof(float), st)) != cudaSuccess) return e;
-  float* acc = le ? gLog : gE;
-  if ((e = launch_pair_distances(W, W, C, C, m, dist, 1, pair_begin, pair_end, weight, nullptr, nullptr, out, acc,
-                                 acc, nullptr, st)) != cudaSuccess)
+  const float* F = filters;
+  if (sphere) {
+    if ((e = launch_constraint_fwd(filters, D, k, Fbuf, inv_norm, st)) != cudaSuccess) return e;
+    F = Fbuf;
+  }
+  if ((e = launch_project_partials(S, Mfr, F, C, D, k, T, proj, PsiPart, fr ? MuPart : nullptr, st)) != cudaSuccess)
     return e;
-  if (le && (e = launch_class_factor_bwd(W, gLog, C, m, dist, gE, st)) != cudaSuccess) return e;
-  if ((e = launch_embed_bwd(gE, Mu, C, k, fr ? 1 : 0, gPsi, gMu, st)) != cudaSuccess) return e;
-  if ((e = launch_project_bwd(gPsi, fr ? gMu : nullptr, T, Mfr, C, D, k, dF, proj, st)) != cudaSuccess) return e;
-  scale_loss_kernel<<<1, 1, 0, st>>>(out, weight);
-  return cudaGetLastError();
+  if ((e = launch_class_prepare(PsiPart, fr ? MuPart : nullptr, project_nchunk(D), noise, C, k, dist, Mu, E, W, flag,
+                                st)) != cudaSuccess)
+    return e;
+  if ((e = launch_pair_closure(W, C, m, dist, pair_begin, pair_end, weight, Mu, k, out, gPsi, gMu, gLog, pairws, st)) !=
+      cudaSuccess)
+    return e;
+  if (le) {
+    if ((e = cudaMemsetAsync(gE, 0, (size_t)C * m * m * sizeof(float), st)) != cudaSuccess) return e;
+    if ((e = launch_class_factor_bwd(W, gLog, C, m, dist, gE, st)) != cudaSuccess) return e;
+    if ((e = launch_embed_bwd(gE, Mu, C, k, 0, gPsi, gMu, st)) != cudaSuccess) return e;
+  }
+  return launch_project_bwd_constrained(gPsi, fr ? gMu : nullptr, T, Mfr, C, D, k, F, inv_norm, sphere, n_fixed, grad,
+                                        out, proj, st);
 }
 
 }  // namespace sqfa

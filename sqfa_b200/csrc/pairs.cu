@@ -18,6 +18,7 @@
 // -- no 1/(lambda_a - lambda_b) terms (the eigh backward of the reference has them and NaNs on
 // repeated eigenvalues). Only the strict lower triangle (i > j) is evaluated: the reference
 // computes all C*C pairs and then reads the lower triangle (_optim.py:94).
+#include <cmath>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -25,6 +26,45 @@
 #include "sqfa_internal.h"
 
 namespace sqfa {
+
+// Deterministic accumulation. A warp owns a TILE of R x R pairs, (rows i = bi R + ii, columns
+// j = bj R + jj); it walks the tile row by row and keeps dLoss/dE_i of the current row in registers
+// and dLoss/dE_j of its R columns in shared memory, then stores both as per-tile PARTIALS (plain
+// stores, every slot written). A second kernel sums, for every class, the partials of the tiles in
+// its block row and block column in a fixed order. No floating-point atomics anywhere: loss and
+// gradient are bit-reproducible from run to run (L-BFGS amplifies gradient noise).
+PairTiles make_pair_tiles(int nA, int nB, int tri, int64_t pair_begin, int64_t pair_end, int R) {
+  PairTiles T;
+  T.R = R < 1 ? 1 : R;
+  T.tri = tri;
+  T.nbj = (nB + T.R - 1) / T.R;
+  T.bi0 = 0; T.bi1 = -1; T.tile0 = 0; T.ntiles = 0;
+  if (pair_end <= pair_begin) return T;
+  int64_t i_first, i_last;
+  if (tri) {
+    auto row_of = [](int64_t p) {
+      int64_t ii = (int64_t)((1.0 + std::sqrt(1.0 + 8.0 * (double)p)) * 0.5);
+      while (ii * (ii - 1) / 2 > p) --ii;
+      while ((ii + 1) * ii / 2 <= p) ++ii;
+      return ii;
+    };
+    i_first = row_of(pair_begin);
+    i_last = row_of(pair_end - 1);
+  } else {
+    i_first = pair_begin / (nB > 0 ? nB : 1);
+    i_last = (pair_end - 1) / (nB > 0 ? nB : 1);
+  }
+  T.bi0 = (int)(i_first / T.R);
+  T.bi1 = (int)(i_last / T.R);
+  if (tri) {
+    T.tile0 = (int64_t)T.bi0 * (T.bi0 + 1) / 2;
+    T.ntiles = (int64_t)(T.bi1 + 1) * (T.bi1 + 2) / 2 - T.tile0;
+  } else {
+    T.tile0 = (int64_t)T.bi0 * T.nbj;
+    T.ntiles = (int64_t)(T.bi1 - T.bi0 + 1) * T.nbj;
+  }
+  return T;
+}
 
 namespace {
 
@@ -140,12 +180,27 @@ __device__ float* warp_jacobi(float* cur, float* nxt, int m, int mp, int ld, int
   return cur;
 }
 
-__device__ __forceinline__ void decode_pair(int64_t p, int& i, int& j) {
-  long long ii = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
-  while (ii * (ii - 1) / 2 > p) --ii;
-  while ((ii + 1) * ii / 2 <= p) ++ii;
-  i = (int)ii;
-  j = (int)(p - ii * (ii - 1) / 2);
+// local tile t of the launch -> block row / block column
+__device__ __forceinline__ void decode_tile(const PairTiles& T, int64_t t, int& bi, int& bj) {
+  const int64_t gt = T.tile0 + t;
+  if (T.tri) {
+    long long b = (long long)((sqrt(8.0 * (double)gt + 1.0) - 1.0) * 0.5);
+    while (b * (b + 1) / 2 > gt) --b;
+    while ((b + 1) * (b + 2) / 2 <= gt) ++b;
+    bi = (int)b;
+    bj = (int)(gt - b * (b + 1) / 2);
+  } else {
+    bi = (int)(gt / T.nbj);
+    bj = (int)(gt % T.nbj);
+  }
+}
+
+// pair (i, j) of a tile: is it part of this launch, and which linear pair index does it have
+__device__ __forceinline__ bool pair_in_launch(int i, int j, int nA, int nB, int tri, int64_t pair_begin,
+                                               int64_t pair_end) {
+  if (i >= nA || j >= nB || (tri && j >= i)) return false;
+  const int64_t p = tri ? (int64_t)i * (i - 1) / 2 + j : (int64_t)i * nB + j;
+  return p >= pair_begin && p < pair_end;
 }
 
 __device__ __forceinline__ float finish_distance(float d2, int dist, float* dd_dd2) {
@@ -165,27 +220,28 @@ __device__ __forceinline__ float finish_distance(float d2, int dist, float* dd_d
 //   AI / FR: W[c] = [L (m*m) | L^-1 (m*m)]
 //   LE     : W[c] = [V (m*m) | lambda (m) | log lambda (m) | logE (m*m)]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PAIR_WARPS * 32)
-class_factor_kernel(const float* __restrict__ E, int C, int m, int dist, float* __restrict__ W,
-                    int32_t* __restrict__ flag) {
-  extern __shared__ float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (c >= C) return;
+// floats of per-warp scratch of the factorisation
+__host__ __device__ inline int factor_scratch_floats(int m) {
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
-  const int per_warp = 4 * m * ld + 2 * m;
-  float* La = smem + (size_t)warp * per_warp;
+  return 4 * m * ld + 2 * m;
+}
+
+// One warp factorises one SPD matrix Esrc (m x m, global or shared memory) into W (layout above).
+__device__ void warp_factor_class(const float* Esrc, int m, int dist, float* __restrict__ Wc, int32_t* __restrict__ flag,
+                                  float* scratch, int lane) {
+  const int mp = (m + 1) & ~1;
+  const int ld = (mp > 32 ? 64 : 32) + 1;
+  float* La = scratch;
   float* Li = La + m * ld;
   float* bufA = Li + m * ld;
   float* bufB = bufA + m * ld;
   float* lam = bufB + m * ld;
   float* loglam = lam + m;
-  const bool ok = warp_cholesky_inverse(E + (int64_t)c * m * m, La, Li, m, ld, lane);
+  const bool ok = warp_cholesky_inverse(Esrc, La, Li, m, ld, lane);
   if (!ok && lane == 0) atomicOr(flag, 1);
   const bool le = (dist & 15) == SQFA_DIST_LOG_EUCLIDEAN;
   if (!le) {
-    float* Wc = W + (int64_t)c * 2 * m * m;
     for (int idx = lane; idx < m * m; idx += 32) {
       const int r = idx / m, q = idx % m;
       Wc[idx] = (q <= r) ? La[r * ld + q] : 0.f;
@@ -212,7 +268,6 @@ class_factor_kernel(const float* __restrict__ E, int C, int m, int dist, float* 
     }
   }
   __syncwarp();
-  float* Wc = W + (int64_t)c * (2 * m * m + 2 * m);
   for (int idx = lane; idx < m * m; idx += 32) {
     const int r = idx / m, s = idx % m;
     Wc[idx] = Vb[r * ld + s];
@@ -226,20 +281,83 @@ class_factor_kernel(const float* __restrict__ E, int C, int m, int dist, float* 
   }
 }
 
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+class_factor_kernel(const float* __restrict__ E, int C, int m, int dist, float* __restrict__ W,
+                    int32_t* __restrict__ flag) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= C) return;
+  const int64_t wfl = ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) ? 2 * m * m + 2 * m : 2 * m * m;
+  warp_factor_class(E + (int64_t)c * m * m, m, dist, W + c * wfl, flag, smem + (size_t)warp * factor_scratch_floats(m),
+                    lane);
+}
+
+// Closure: everything between the projection and the pair kernel for one class, one warp:
+//   Psi_c = sum over column chunks of the partial T_c F^T (fixed order), mu'_c likewise,
+//   E_c = Psi_c + noise I (+ Calvo-Oller embedding with mu'_c for Fisher-Rao)
+//         (reference model.py:216-217 / 537-538, distances.py:162-174),
+//   W_c = factorisation of E_c (above).  E is also written out (m x m per class).
+__global__ void __launch_bounds__(PAIR_WARPS * 32)
+class_prepare_kernel(const float* __restrict__ PsiPart, const float* __restrict__ MuPart, int nchunk, float noise,
+                     int C, int k, int dist, float* __restrict__ Mu, float* __restrict__ E, float* __restrict__ W,
+                     int32_t* __restrict__ flag) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= C) return;
+  const bool fr = (dist & 15) == SQFA_DIST_FISHER_RAO_LB;
+  const int m = fr ? k + 1 : k;
+  const int per_warp = factor_scratch_floats(m) + m * m + k;
+  float* scratch = smem + (size_t)warp * per_warp;
+  float* Es = scratch + factor_scratch_floats(m);
+  float* mus = Es + m * m;
+  if (fr) {
+    for (int r = lane; r < k; r += 32) {
+      float a = 0.f;
+      for (int ch = 0; ch < nchunk; ++ch) a += MuPart[((int64_t)c * nchunk + ch) * k + r];
+      mus[r] = a;
+      Mu[(int64_t)c * k + r] = a;
+    }
+    __syncwarp();
+  }
+  for (int idx = lane; idx < m * m; idx += 32) {
+    const int r = idx / m, s = idx % m;
+    float v;
+    if (r < k && s < k) {
+      v = 0.f;
+      const float* pp = PsiPart + (int64_t)c * nchunk * k * k + r * k + s;
+      for (int ch = 0; ch < nchunk; ++ch) v += pp[(int64_t)ch * k * k];
+      if (r == s) v += noise;
+      if (fr) v += mus[r] * mus[s];
+    } else if (r == k && s == k) {
+      v = 1.f;
+    } else {
+      v = mus[r < k ? r : s];
+    }
+    Es[idx] = v;
+    E[(int64_t)c * m * m + idx] = v;
+  }
+  __syncwarp();
+  const int64_t wfl = ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) ? 2 * m * m + 2 * m : 2 * m * m;
+  warp_factor_class(Es, m, dist, W + c * wfl, flag, scratch, lane);
+}
+
 // ------------------------------------------------------------------------------------------------
 // pair kernel, affine-invariant family (AI, FR lower bound): one warp per pair
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
-pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int nA, int nB, int m, int dist, int tri,
-               int64_t pair_begin, int64_t pair_end, float weight, const float* __restrict__ gD,
-               float* __restrict__ dist_out, float* __restrict__ loss, float* gEa, float* gEb,
-               float* __restrict__ eig_out) {
+pair_ai_kernel(const PairArgs A) {
+  // shared-memory variant (32 < m <= 64): tiles are single pairs (R = 1), tile (bi, bj) = pair (i, j)
   extern __shared__ float smem[];
-  __shared__ float s_d[PAIR_WARPS];
-  __shared__ float s_bad[PAIR_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t p = pair_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  const bool active = p < pair_end;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= A.T.ntiles) return;
+  const int m = A.m, nB = A.nB, tri = A.tri, dist = A.dist;
+  int i, j;
+  decode_tile(A.T, t, i, j);
+  const bool active = pair_in_launch(i, j, A.nA, nB, tri, A.pair_begin, A.pair_end);
+  const bool want_grad = A.rowpart != nullptr;
   const int mp = (m + 1) & ~1;
   const int ld = (mp > 32 ? 64 : 32) + 1;
   const int nslot = (mp + 31) >> 5;
@@ -251,12 +369,14 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
   float* cj = ci + m;
   float* lamv = cj + m;
   float dval = 0.f, bad = 0.f;
+  float* gi = want_grad ? A.rowpart + t * m * m : nullptr;
+  float* gj = want_grad ? A.colpart + t * m * m : nullptr;
+  if (!active && want_grad) {  // every partial slot is written: the reduction reads all of them
+    for (int idx = lane; idx < m * m; idx += 32) { gi[idx] = 0.f; gj[idx] = 0.f; }
+  }
   if (active) {
-    int i, j;
-    if (tri) decode_pair(p, i, j);
-    else { i = (int)(p / nB); j = (int)(p % nB); }
-    const float* Wi = Wa + (int64_t)i * 2 * m * m;
-    const float* Wj = Wb + (int64_t)j * 2 * m * m;
+    const float* Wi = A.Wa + (int64_t)i * 2 * m * m;
+    const float* Wj = A.Wb + (int64_t)j * 2 * m * m;
     // stage L_i (row-major) and L_j^-1 transposed: bufB[r][q] = Linv_j[q][r]
     for (int idx = lane; idx < m * m; idx += 32) {
       Ls[idx] = Wi[idx];
@@ -265,8 +385,8 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
     }
     __syncwarp();
     // A[s][q] = B[q][s] = sum_{r >= s} Linv_j[q][r] L_i[r][s];  columns >= m are zero (dummy players)
-    for (int t = 0; t < nslot; ++t) {
-      const int q = lane + 32 * t;
+    for (int tt = 0; tt < nslot; ++tt) {
+      const int q = lane + 32 * tt;
       if (q < ld - 1) {
         for (int s = 0; s < m; ++s) {
           float a = 0.f;
@@ -281,8 +401,8 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
     float* Yb = (Af == bufA) ? bufB : bufA;
     // eigenvalues and the distance
     float d2 = 0.f;
-    for (int t = 0; t < nslot; ++t) {
-      const int q = lane + 32 * t;
+    for (int tt = 0; tt < nslot; ++tt) {
+      const int q = lane + 32 * tt;
       if (q < m) {
         float n2 = 0.f;
         for (int s = 0; s < m; ++s) n2 += Af[s * ld + q] * Af[s * ld + q];
@@ -294,11 +414,11 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
       }
     }
     d2 = warp_sum(d2);
-    if (eig_out != nullptr) {  // generalized eigenvalues, descending (linalg.py:69-70)
+    if (A.eig_out != nullptr) {  // generalized eigenvalues, descending (linalg.py:69-70)
       __syncwarp();
-      float* eo = eig_out + ((int64_t)i * nB + j) * m;
-      for (int t = 0; t < nslot; ++t) {
-        const int q = lane + 32 * t;
+      float* eo = A.eig_out + ((int64_t)i * nB + j) * m;
+      for (int tt = 0; tt < nslot; ++tt) {
+        const int q = lane + 32 * tt;
         if (q < m) {
           const float v = lamv[q];
           int rank = 0;
@@ -310,19 +430,20 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
     float dd_dd2;
     dval = finish_distance(d2, dist, &dd_dd2);
     if (!isfinite(dval)) bad = 1.f;
-    if (dist_out != nullptr && lane == 0) {
-      dist_out[(int64_t)i * nB + j] = dval;
-      if (tri) dist_out[(int64_t)j * nB + i] = dval;
+    if (A.dist_out != nullptr && lane == 0) {
+      A.dist_out[(int64_t)i * nB + j] = dval;
+      if (tri) A.dist_out[(int64_t)j * nB + i] = dval;
     }
-    if (gEa != nullptr) {
-      float w = weight * dd_dd2;
-      if (gD != nullptr) w *= tri ? (gD[(int64_t)i * nB + j] + gD[(int64_t)j * nB + i]) : gD[(int64_t)i * nB + j];
+    if (want_grad) {
+      float w = A.weight * dd_dd2;
+      if (A.gD != nullptr)
+        w *= tri ? (A.gD[(int64_t)i * nB + j] + A.gD[(int64_t)j * nB + i]) : A.gD[(int64_t)i * nB + j];
       __syncwarp();
       // Y = L_i^-T A_f : Y[r][q] = sum_{s >= r} Linv_i[s][r] A_f[s][q]
       for (int idx = lane; idx < m * m; idx += 32) Ls[idx] = Wi[m * m + idx];
       __syncwarp();
-      for (int t = 0; t < nslot; ++t) {
-        const int q = lane + 32 * t;
+      for (int tt = 0; tt < nslot; ++tt) {
+        const int q = lane + 32 * tt;
         if (q < m) {
           for (int r = 0; r < m; ++r) {
             float v = 0.f;
@@ -333,8 +454,8 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
       }
       __syncwarp();
       // Zi = Y diag(w ci) -> over A_f's buffer, Zj = Y diag(w cj) -> Ls (row stride m)
-      for (int t = 0; t < nslot; ++t) {
-        const int q = lane + 32 * t;
+      for (int tt = 0; tt < nslot; ++tt) {
+        const int q = lane + 32 * tt;
         if (q < m) {
           const float a = w * ci[q], b = w * cj[q];
           for (int r = 0; r < m; ++r) {
@@ -345,11 +466,10 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
         }
       }
       __syncwarp();
-      // G_i[r][s] = sum_q Zi[r][q] Y[s][q],  G_j[r][s] = sum_q Zj[r][q] Y[s][q];  lane <-> column s
-      float* gi = gEa + (int64_t)i * m * m;
-      float* gj = gEb + (int64_t)j * m * m;
-      for (int t = 0; t < nslot; ++t) {
-        const int s = lane + 32 * t;
+      // G_i[r][s] = sum_q Zi[r][q] Y[s][q],  G_j[r][s] = sum_q Zj[r][q] Y[s][q];  lane <-> column s;
+      // stored as this pair's partials (plain stores)
+      for (int tt = 0; tt < nslot; ++tt) {
+        const int s = lane + 32 * tt;
         if (s < m) {
           for (int r = 0; r < m; ++r) {
             float a = 0.f, b = 0.f;
@@ -358,22 +478,16 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
               a += Af[r * ld + q] * y;
               b += Ls[r * m + q] * y;
             }
-            atomicAdd(gi + r * m + s, a);
-            atomicAdd(gj + r * m + s, b);
+            gi[r * m + s] = a;
+            gj[r * m + s] = b;
           }
         }
       }
     }
   }
-  if (loss != nullptr) {
-    if (lane == 0) { s_d[warp] = dval; s_bad[warp] = bad; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float a = 0.f, b = 0.f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_d[w]; b += s_bad[w]; }
-      atomicAdd(loss, a);
-      if (b != 0.f) atomicAdd(loss + 1, b);
-    }
+  if (A.losspart != nullptr && lane == 0) {
+    A.losspart[2 * t] = dval;
+    A.losspart[2 * t + 1] = bad;
   }
 }
 
@@ -388,261 +502,418 @@ pair_ai_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int n
 // ------------------------------------------------------------------------------------------------
 template <int MP, int MJ>  // MP: padded size (multiple of 4, shared-memory strides); MJ: even m, the Jacobi width
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
-pair_ai_reg_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int nA, int nB, int m, int dist,
-                   int tri, int64_t pair_begin, int64_t pair_end, float weight, const float* __restrict__ gD,
-                   float* __restrict__ dist_out, float* __restrict__ loss, float* gEa, float* gEb,
-                   float* __restrict__ eig_out) {
+pair_ai_reg_kernel(const PairArgs A) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ float s_d[PAIR_WARPS];
-  __shared__ float s_bad[PAIR_WARPS];
-  constexpr int LDT = 33;
-  constexpr int PER_WARP = MP * LDT + 2 * MP * MP + 3;  // sT | sL | sZ (+ pad to keep 16-byte alignment)
+  constexpr int LDT = MP + 1;                                  // odd stride: conflict-free transposed access
+  constexpr int PER_PAIR = MP * MP + ((MP * LDT + 3) & ~3);    // sL | sT, both 16-byte aligned
+  const int R = A.T.R;
+  const int m = A.m, nB = A.nB, tri = A.tri, dist = A.dist;
+  const int m2 = m * m;
+  const int per_warp = PER_PAIR + (((R + 1) * m2 + 3) & ~3);   // + row accumulator + R column accumulators
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
-  const int64_t p = pair_begin + (int64_t)blockIdx.x * nwarps + warp;
-  float* sT = smem + (size_t)warp * ((PER_WARP + 3) & ~3) + 2 * MP * MP;  // [MP][33]: Linv_j^T, later Y
-  float* sL = smem + (size_t)warp * ((PER_WARP + 3) & ~3);               // [MP][MP]: L_i, Linv_i, later Zj
-  float* sZ = sL + MP * MP;                                              // [MP][MP]: Zi
-  float dval = 0.f, bad = 0.f;
-  if (p < pair_end) {
-    int i, j;
-    if (tri) decode_pair(p, i, j);
-    else { i = (int)(p / nB); j = (int)(p % nB); }
-    const float* Wi = Wa + (int64_t)i * 2 * m * m;
-    const float* Wj = Wb + (int64_t)j * 2 * m * m;
-    const int mp = (m + 1) & ~1;
-    // ---- stage L_i (row-major, zero padded to MP) and Linv_j transposed
-    for (int idx = lane; idx < MP * MP; idx += 32) sL[idx] = 0.f;
-    __syncwarp();
-    for (int idx = lane; idx < m * m; idx += 32) {
-      const int r = idx / m, c = idx % m;
-      sL[r * MP + c] = Wi[idx];
-      sT[c * LDT + r] = Wj[m * m + idx];  // sT[r'][q] = Linv_j[q][r']
-    }
-    __syncwarp();
-    // ---- column `lane` of A: a[s] = sum_r Linv_j[lane][r] L_i[r][s]   (both factors lower triangular)
-    // The column lives in MP / 2 packed register pairs: dot products and rotations are packed-fp32
-    // instructions (fma.rn.f32x2 / mul.rn.f32x2), half the FMA issue slots of scalar code.
-    float2 a2[MP / 2];
-    float y[MP];
-#pragma unroll
-    for (int s = 0; s < MP / 2; ++s) a2[s] = make_float2(0.f, 0.f);
-    if (lane < m) {
-#pragma unroll
-      for (int r = 0; r < MP; ++r) {
-        if (r < m) {
-          const float l = sT[r * LDT + lane];
-          const float2 l2 = make_float2(l, l);
-#pragma unroll
-          for (int s4 = 0; s4 < MP / 4; ++s4) {
-            const float4 w = *reinterpret_cast<const float4*>(sL + r * MP + 4 * s4);
-            a2[2 * s4] = __ffma2_rn(l2, make_float2(w.x, w.y), a2[2 * s4]);
-            a2[2 * s4 + 1] = __ffma2_rn(l2, make_float2(w.z, w.w), a2[2 * s4 + 1]);
-          }
-        }
-      }
-    }
-    // ---- one-sided Jacobi, columns in registers (entries >= MJ are padding zeros and stay zero)
-    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
-      float2 n2p = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int s = 0; s < MJ / 2; ++s) n2p = __ffma2_rn(a2[s], a2[s], n2p);
-      float nrm = n2p.x + n2p.y;
-      // a sweep whose largest rotation was below JACOBI_LAST leaves off-diagonals of that size
-      // squared (quadratic convergence): no verification sweep needed after it
-      bool rotated = false;
-      for (int r = 0; r < mp - 1; ++r) {
-        const int q = lane < mp ? rr_partner(lane, r, mp) : lane;
-        const float nq = __shfl_sync(0xffffffffu, nrm, q);
-        float2 y2[MJ / 2];
-        float2 ab2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int s = 0; s < MJ / 2; ++s) {
-          y2[s].x = __shfl_sync(0xffffffffu, a2[s].x, q);
-          y2[s].y = __shfl_sync(0xffffffffu, a2[s].y, q);
-          ab2 = __ffma2_rn(a2[s], y2[s], ab2);
-        }
-        const float ab = ab2.x + ab2.y;
-        const bool is_lo = lane < q;
-        const float alpha = is_lo ? nrm : nq, beta = is_lo ? nq : nrm;
-        float cs = 1.f, sn = 0.f;
-        const float ab_sq = ab * ab, scale = alpha * beta;
-        if (lane < mp && ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale && alpha > 0.f && beta > 0.f) {
-          // approximate reciprocal / square root (1 MUFU each): a Jacobi rotation only has to be
-          // orthogonal to fp32 precision (cs^2 + sn^2 = 1 from the same rsqrt as before); an angle
-          // off by 1e-7 relative leaves an off-diagonal of that size, far below the tolerance
-          const float zeta = (beta - alpha) * rcp_approx(2.f * ab);
-          const float tt = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
-          cs = rsqrtf(fmaf(tt, tt, 1.f));
-          sn = cs * tt;
-          nrm = is_lo ? alpha - tt * ab : beta + tt * ab;
-          rotated = rotated || ab_sq > (JACOBI_LAST * JACOBI_LAST) * scale;
-        }
-        const float other = is_lo ? -sn : sn;
-        const float2 cs2 = make_float2(cs, cs), ot2 = make_float2(other, other);
-#pragma unroll
-        for (int s = 0; s < MJ / 2; ++s) a2[s] = __ffma2_rn(cs2, a2[s], __fmul2_rn(ot2, y2[s]));
-      }
-      if (!__any_sync(0xffffffffu, rotated)) break;
-    }
-    float a[MP];
-#pragma unroll
-    for (int s = 0; s < MP / 2; ++s) { a[2 * s] = a2[s].x; a[2 * s + 1] = a2[s].y; }
-    // ---- eigenvalues, distance
-    float n2 = 0.f;
-#pragma unroll
-    for (int s = 0; s < MP; ++s) n2 += a[s] * a[s];
-    const float ll = lane < m ? logf(n2) : 0.f;
-    const float d2 = warp_sum(ll * ll);
-    if (eig_out != nullptr) {  // descending order (linalg.py:69-70)
-      int rank = 0;
-      for (int u = 0; u < m; ++u) {
-        const float v = __shfl_sync(0xffffffffu, n2, u);
-        rank += (v > n2 || (v == n2 && u < lane)) ? 1 : 0;
-      }
-      if (lane < m) eig_out[((int64_t)i * nB + j) * m + rank] = n2;
-    }
-    float dd_dd2;
-    dval = finish_distance(d2, dist, &dd_dd2);
-    if (!isfinite(dval)) bad = 1.f;
-    if (dist_out != nullptr && lane == 0) {
-      dist_out[(int64_t)i * nB + j] = dval;
-      if (tri) dist_out[(int64_t)j * nB + i] = dval;
-    }
-    if (gEa != nullptr) {
-      float w = weight * dd_dd2;
-      if (gD != nullptr) w *= tri ? (gD[(int64_t)i * nB + j] + gD[(int64_t)j * nB + i]) : gD[(int64_t)i * nB + j];
-      const float ci = lane < m ? w * 2.f * ll / n2 : 0.f, cj = lane < m ? -w * 2.f * ll : 0.f;
-      // ---- Y = L_i^-T A_f : y[r] = sum_{s >= r} Linv_i[s][r] a[s]
+  const int64_t t = (int64_t)blockIdx.x * nwarps + warp;
+  if (t >= A.T.ntiles) return;  // no block-wide synchronisation below
+  float* sL = smem + (size_t)warp * per_warp;  // [MP][MP]: L_i, then Linv_i, then Y
+  float* sT = sL + MP * MP;                    // [MP][MP+1]: Linv_j^T; later the coefficient vectors ci | cj
+  float* sRow = sL + PER_PAIR;                 // [m][m]: dLoss/dE_i of the current row of the tile
+  float* sC = sRow + m2;                       // [R][m][m]: dLoss/dE_j of the tile's columns
+  const int mp = (m + 1) & ~1;
+  const bool want_grad = A.rowpart != nullptr;
+  int bi, bj;
+  decode_tile(A.T, t, bi, bj);
+  if (want_grad) {
+    for (int idx = lane; idx < R * m2; idx += 32) sC[idx] = 0.f;
+  }
+  float dsum = 0.f, badsum = 0.f;
+  for (int ii = 0; ii < R; ++ii) {
+    const int i = bi * R + ii;
+    if (want_grad) {
       __syncwarp();
-      for (int idx = lane; idx < m * m; idx += 32) sL[(idx / m) * MP + idx % m] = Wi[m * m + idx];
+      for (int idx = lane; idx < m2; idx += 32) sRow[idx] = 0.f;
+    }
+    for (int jj = 0; jj < R; ++jj) {
+      const int j = bj * R + jj;
+      if (!pair_in_launch(i, j, A.nA, nB, tri, A.pair_begin, A.pair_end)) continue;  // warp-uniform
+      const float* Wi = A.Wa + (int64_t)i * 2 * m * m;
+      const float* Wj = A.Wb + (int64_t)j * 2 * m * m;
+      // ---- stage L_i (row-major, zero padded to MP) and Linv_j transposed
       __syncwarp();
-#pragma unroll
-      for (int r = 0; r < MP; ++r) y[r] = 0.f;
-#pragma unroll
-      for (int s = 0; s < MP; ++s) {
-        if (s < m) {
-#pragma unroll
-          for (int r4 = 0; r4 < MP / 4; ++r4) {
-            const float4 wv = *reinterpret_cast<const float4*>(sL + s * MP + 4 * r4);
-            y[4 * r4 + 0] += wv.x * a[s]; y[4 * r4 + 1] += wv.y * a[s]; y[4 * r4 + 2] += wv.z * a[s]; y[4 * r4 + 3] += wv.w * a[s];
-          }
-        }
+      for (int idx = lane; idx < MP * MP; idx += 32) sL[idx] = 0.f;
+      __syncwarp();
+      for (int idx = lane; idx < m * m; idx += 32) {
+        const int r = idx / m, c = idx % m;
+        sL[r * MP + c] = Wi[idx];
+        sT[c * LDT + r] = Wj[m * m + idx];  // sT[r'][q] = Linv_j[q][r'], q < m <= MP
       }
       __syncwarp();
-      // ---- Y -> sT[r][q], Zi = Y diag(ci) -> sZ[r][q], Zj = Y diag(cj) -> sL[r][q]   (q = lane)
+      // ---- column `lane` of A: a[s] = sum_r Linv_j[lane][r] L_i[r][s]   (both factors lower triangular)
+      // The column lives in MP / 2 packed register pairs: dot products and rotations are packed-fp32
+      // instructions (fma.rn.f32x2 / mul.rn.f32x2), half the FMA issue slots of scalar code.
+      float2 a2[MP / 2];
+      float y[MP];
 #pragma unroll
-      for (int r = 0; r < MP; ++r) {
-        const float yr = lane < m ? y[r] : 0.f;
-        sT[r * LDT + lane] = yr;
-        if (lane < MP) {
-          sZ[r * MP + lane] = ci * yr;
-          sL[r * MP + lane] = cj * yr;
-        }
-      }
-      __syncwarp();
-      // ---- G_i[r][s'] = sum_q Zi[r][q] Y[s'][q], G_j likewise; lane = s', its row of Y in registers
+      for (int s = 0; s < MP / 2; ++s) a2[s] = make_float2(0.f, 0.f);
       if (lane < m) {
 #pragma unroll
-        for (int q = 0; q < MP; ++q) y[q] = sT[lane * LDT + q];
-        float* gi = gEa + (int64_t)i * m * m;
-        float* gj = gEb + (int64_t)j * m * m;
-        for (int r = 0; r < m; ++r) {
-          float ga = 0.f, gb = 0.f;
+        for (int r = 0; r < MP; ++r) {
+          if (r < m) {
+            const float l = sT[r * LDT + lane];
+            const float2 l2 = make_float2(l, l);
+#pragma unroll
+            for (int s4 = 0; s4 < MP / 4; ++s4) {
+              const float4 w = *reinterpret_cast<const float4*>(sL + r * MP + 4 * s4);
+              a2[2 * s4] = __ffma2_rn(l2, make_float2(w.x, w.y), a2[2 * s4]);
+              a2[2 * s4 + 1] = __ffma2_rn(l2, make_float2(w.z, w.w), a2[2 * s4 + 1]);
+            }
+          }
+        }
+      }
+      // ---- one-sided Jacobi, columns in registers (entries >= MJ are padding zeros and stay zero)
+      for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+        float2 n2p = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < MJ / 2; ++s) n2p = __ffma2_rn(a2[s], a2[s], n2p);
+        float nrm = n2p.x + n2p.y;
+        // a sweep whose largest rotation was below JACOBI_LAST leaves off-diagonals of that size
+        // squared (quadratic convergence): no verification sweep needed after it
+        bool rotated = false;
+        for (int r = 0; r < mp - 1; ++r) {
+          const int q = lane < mp ? rr_partner(lane, r, mp) : lane;
+          const float nq = __shfl_sync(0xffffffffu, nrm, q);
+          float2 y2[MJ / 2];
+          float2 ab2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int s = 0; s < MJ / 2; ++s) {
+            y2[s].x = __shfl_sync(0xffffffffu, a2[s].x, q);
+            y2[s].y = __shfl_sync(0xffffffffu, a2[s].y, q);
+            ab2 = __ffma2_rn(a2[s], y2[s], ab2);
+          }
+          const float ab = ab2.x + ab2.y;
+          const bool is_lo = lane < q;
+          const float alpha = is_lo ? nrm : nq, beta = is_lo ? nq : nrm;
+          float cs = 1.f, sn = 0.f;
+          const float ab_sq = ab * ab, scale = alpha * beta;
+          if (lane < mp && ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale && alpha > 0.f && beta > 0.f) {
+            // approximate reciprocal / square root (1 MUFU each): a Jacobi rotation only has to be
+            // orthogonal to fp32 precision (cs^2 + sn^2 = 1 from the same rsqrt as before); an angle
+            // off by 1e-7 relative leaves an off-diagonal of that size, far below the tolerance
+            const float zeta = (beta - alpha) * rcp_approx(2.f * ab);
+            const float tt = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
+            cs = rsqrtf(fmaf(tt, tt, 1.f));
+            sn = cs * tt;
+            nrm = is_lo ? alpha - tt * ab : beta + tt * ab;
+            rotated = rotated || ab_sq > (JACOBI_LAST * JACOBI_LAST) * scale;
+          }
+          const float other = is_lo ? -sn : sn;
+          const float2 cs2 = make_float2(cs, cs), ot2 = make_float2(other, other);
+#pragma unroll
+          for (int s = 0; s < MJ / 2; ++s) a2[s] = __ffma2_rn(cs2, a2[s], __fmul2_rn(ot2, y2[s]));
+        }
+        if (!__any_sync(0xffffffffu, rotated)) break;
+      }
+      float a[MP];
+#pragma unroll
+      for (int s = 0; s < MP / 2; ++s) { a[2 * s] = a2[s].x; a[2 * s + 1] = a2[s].y; }
+      // ---- eigenvalues, distance
+      float n2 = 0.f;
+#pragma unroll
+      for (int s = 0; s < MP; ++s) n2 += a[s] * a[s];
+      const float ll = lane < m ? logf(n2) : 0.f;
+      const float d2 = warp_sum(ll * ll);
+      if (A.eig_out != nullptr) {  // descending order (linalg.py:69-70)
+        int rank = 0;
+        for (int u = 0; u < m; ++u) {
+          const float v = __shfl_sync(0xffffffffu, n2, u);
+          rank += (v > n2 || (v == n2 && u < lane)) ? 1 : 0;
+        }
+        if (lane < m) A.eig_out[((int64_t)i * nB + j) * m + rank] = n2;
+      }
+      float dd_dd2;
+      const float dval = finish_distance(d2, dist, &dd_dd2);
+      dsum += dval;
+      if (!isfinite(dval)) badsum += 1.f;
+      if (A.dist_out != nullptr && lane == 0) {
+        A.dist_out[(int64_t)i * nB + j] = dval;
+        if (tri) A.dist_out[(int64_t)j * nB + i] = dval;
+      }
+      if (want_grad) {
+        float w = A.weight * dd_dd2;
+        if (A.gD != nullptr)
+          w *= tri ? (A.gD[(int64_t)i * nB + j] + A.gD[(int64_t)j * nB + i]) : A.gD[(int64_t)i * nB + j];
+        const float ci = lane < m ? w * 2.f * ll / n2 : 0.f, cj = lane < m ? -w * 2.f * ll : 0.f;
+        // ---- Y = L_i^-T A_f : y[r] = sum_{s >= r} Linv_i[s][r] a[s]
+        __syncwarp();
+        for (int idx = lane; idx < m * m; idx += 32) sL[(idx / m) * MP + idx % m] = Wi[m * m + idx];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < MP; ++r) y[r] = 0.f;
+#pragma unroll
+        for (int s = 0; s < MP; ++s) {
+          if (s < m) {
+#pragma unroll
+            for (int r4 = 0; r4 < MP / 4; ++r4) {
+              const float4 wv = *reinterpret_cast<const float4*>(sL + s * MP + 4 * r4);
+              y[4 * r4 + 0] += wv.x * a[s]; y[4 * r4 + 1] += wv.y * a[s]; y[4 * r4 + 2] += wv.z * a[s]; y[4 * r4 + 3] += wv.w * a[s];
+            }
+          }
+        }
+        __syncwarp();
+        // ---- Y -> sL[r][q] (q = lane), coefficient vectors ci | cj -> sT (Linv_j^T is dead)
+        float* sCi = sT;
+        float* sCj = sT + MP;
+        if (lane < MP) {
+#pragma unroll
+          for (int r = 0; r < MP; ++r) sL[r * MP + lane] = lane < m ? y[r] : 0.f;
+          sCi[lane] = ci;
+          sCj[lane] = cj;
+        }
+        __syncwarp();
+        // ---- G_i[r][s'] = sum_q ci_q Y[r][q] Y[s'][q], G_j likewise with cj; lane = s': its row of Y,
+        // scaled by the coefficients, stays in registers; rows Y[r][:] are broadcast 16-byte loads.
+        // G_i is added to the row accumulator, G_j to this column's accumulator (shared memory;
+        // element (r, lane) is only ever touched by this lane).
+        if (lane < m) {
+          float yi[MP], yj[MP];
 #pragma unroll
           for (int q4 = 0; q4 < MP / 4; ++q4) {
-            const float4 zi = *reinterpret_cast<const float4*>(sZ + r * MP + 4 * q4);
-            const float4 zj = *reinterpret_cast<const float4*>(sL + r * MP + 4 * q4);
-            ga += zi.x * y[4 * q4] + zi.y * y[4 * q4 + 1] + zi.z * y[4 * q4 + 2] + zi.w * y[4 * q4 + 3];
-            gb += zj.x * y[4 * q4] + zj.y * y[4 * q4 + 1] + zj.z * y[4 * q4 + 2] + zj.w * y[4 * q4 + 3];
+            const float4 yy = *reinterpret_cast<const float4*>(sL + lane * MP + 4 * q4);
+            const float4 c1 = *reinterpret_cast<const float4*>(sCi + 4 * q4);
+            const float4 c2 = *reinterpret_cast<const float4*>(sCj + 4 * q4);
+            yi[4 * q4] = yy.x * c1.x; yi[4 * q4 + 1] = yy.y * c1.y; yi[4 * q4 + 2] = yy.z * c1.z; yi[4 * q4 + 3] = yy.w * c1.w;
+            yj[4 * q4] = yy.x * c2.x; yj[4 * q4 + 1] = yy.y * c2.y; yj[4 * q4 + 2] = yy.z * c2.z; yj[4 * q4 + 3] = yy.w * c2.w;
           }
-          atomicAdd(gi + r * m + lane, ga);
-          atomicAdd(gj + r * m + lane, gb);
+          float* racc = sRow + lane;
+          float* cacc = sC + jj * m2 + lane;
+          for (int r = 0; r < m; ++r) {
+            float ga = 0.f, gb = 0.f;
+#pragma unroll
+            for (int q4 = 0; q4 < MP / 4; ++q4) {
+              const float4 yr = *reinterpret_cast<const float4*>(sL + r * MP + 4 * q4);
+              ga += yr.x * yi[4 * q4] + yr.y * yi[4 * q4 + 1] + yr.z * yi[4 * q4 + 2] + yr.w * yi[4 * q4 + 3];
+              gb += yr.x * yj[4 * q4] + yr.y * yj[4 * q4 + 1] + yr.z * yj[4 * q4 + 2] + yr.w * yj[4 * q4 + 3];
+            }
+            racc[r * m] += ga;
+            cacc[r * m] += gb;
+          }
         }
       }
     }
-  }
-  if (loss != nullptr) {
-    if (lane == 0) { s_d[warp] = dval; s_bad[warp] = bad; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float sa = 0.f, sb = 0.f;
-      for (int w = 0; w < nwarps; ++w) { sa += s_d[w]; sb += s_bad[w]; }
-      atomicAdd(loss, sa);
-      if (sb != 0.f) atomicAdd(loss + 1, sb);
+    if (want_grad) {  // row partial of (tile, ii): every slot is written (zeros if the row had no pair)
+      __syncwarp();
+      float* rp = A.rowpart + ((int64_t)t * R + ii) * m2;
+      for (int idx = lane; idx < m2; idx += 32) rp[idx] = sRow[idx];
     }
+  }
+  if (want_grad) {
+    __syncwarp();
+    float* cp = A.colpart + (int64_t)t * R * m2;
+    for (int idx = lane; idx < R * m2; idx += 32) cp[idx] = sC[idx];
+  }
+  if (A.losspart != nullptr && lane == 0) {
+    A.losspart[2 * t] = dsum;
+    A.losspart[2 * t + 1] = badsum;
   }
 }
 
 template <int MP, int MJ>
-static cudaError_t launch_pair_reg(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
-                                   int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
-                                   float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
-                                   cudaStream_t st) {
-  constexpr int per_warp_floats = ((MP * 33 + 2 * MP * MP + 3) + 3) & ~3;
-  const int smem = PAIR_WARPS * per_warp_floats * (int)sizeof(float);
+static cudaError_t launch_pair_reg(const PairArgs& A, cudaStream_t st) {
+  constexpr int per_pair_floats = MP * MP + ((MP * (MP + 1) + 3) & ~3);
+  const int smem = PAIR_WARPS * (per_pair_floats + (((A.T.R + 1) * A.m * A.m + 3) & ~3)) * (int)sizeof(float);
   static int smem_set[kMaxDevices] = {0};
   {
     cudaError_t e = ensure_dynamic_smem(pair_ai_reg_kernel<MP, MJ>, smem, smem_set);
     if (e != cudaSuccess) return e;
   }
-  const int64_t npairs = pair_end - pair_begin;
-  const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
-  pair_ai_reg_kernel<MP, MJ><<<blocks, PAIR_WARPS * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end,
-                                                                weight, gD, dist_out, loss, gEa, gEb, eig_out);
+  const unsigned blocks = (unsigned)((A.T.ntiles + PAIR_WARPS - 1) / PAIR_WARPS);
+  pair_ai_reg_kernel<MP, MJ><<<blocks, PAIR_WARPS * 32, smem, st>>>(A);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
-// pair kernel, log-Euclidean: d^2 = |logE_i - logE_j|_F^2; gradient w.r.t. the matrix logarithms
+// pair kernel, log-Euclidean: d^2 = |logE_i - logE_j|_F^2. Tiles are single pairs. The gradient
+// w.r.t. the matrix logarithms is sum_o pw(c, o) (logE_c - logE_o): this kernel stores the per-pair
+// factor pw = 2 w dd/d(d^2) and le_grad_kernel forms the sums class by class in a fixed order.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
-pair_le_kernel(const float* __restrict__ Wa, const float* __restrict__ Wb, int nA, int nB, int m, int dist, int tri,
-               int64_t pair_begin, int64_t pair_end, float weight, const float* __restrict__ gD,
-               float* __restrict__ dist_out, float* __restrict__ loss, float* gLa, float* gLb) {
-  __shared__ float s_d[PAIR_WARPS];
-  __shared__ float s_bad[PAIR_WARPS];
+pair_le_kernel(const PairArgs A) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t p = pair_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= A.T.ntiles) return;
+  const int m = A.m, nB = A.nB, tri = A.tri;
+  int i, j;
+  decode_tile(A.T, t, i, j);
   const int stride = 2 * m * m + 2 * m;
-  float dval = 0.f, bad = 0.f;
-  if (p < pair_end) {
-    int i, j;
-    if (tri) decode_pair(p, i, j);
-    else { i = (int)(p / nB); j = (int)(p % nB); }
-    const float* Li = Wa + (int64_t)i * stride + m * m + 2 * m;
-    const float* Lj = Wb + (int64_t)j * stride + m * m + 2 * m;
+  float dval = 0.f, bad = 0.f, pw = 0.f;
+  if (pair_in_launch(i, j, A.nA, nB, tri, A.pair_begin, A.pair_end)) {
+    const float* Li = A.Wa + (int64_t)i * stride + m * m + 2 * m;
+    const float* Lj = A.Wb + (int64_t)j * stride + m * m + 2 * m;
     float d2 = 0.f;
     for (int idx = lane; idx < m * m; idx += 32) {
-      const float t = Li[idx] - Lj[idx];
-      d2 += t * t;
+      const float df = Li[idx] - Lj[idx];
+      d2 += df * df;
     }
     d2 = warp_sum(d2);
     float dd_dd2;
-    dval = finish_distance(d2, dist, &dd_dd2);
+    dval = finish_distance(d2, A.dist, &dd_dd2);
     if (!isfinite(dval)) bad = 1.f;
-    if (dist_out != nullptr && lane == 0) {
-      dist_out[(int64_t)i * nB + j] = dval;
-      if (tri) dist_out[(int64_t)j * nB + i] = dval;
+    if (A.dist_out != nullptr && lane == 0) {
+      A.dist_out[(int64_t)i * nB + j] = dval;
+      if (tri) A.dist_out[(int64_t)j * nB + i] = dval;
     }
-    if (gLa != nullptr) {
-      float w = 2.f * weight * dd_dd2;
-      if (gD != nullptr) w *= tri ? (gD[(int64_t)i * nB + j] + gD[(int64_t)j * nB + i]) : gD[(int64_t)i * nB + j];
-      for (int idx = lane; idx < m * m; idx += 32) {
-        const float t = w * (Li[idx] - Lj[idx]);
-        atomicAdd(gLa + (int64_t)i * m * m + idx, t);
-        atomicAdd(gLb + (int64_t)j * m * m + idx, -t);
-      }
+    pw = 2.f * A.weight * dd_dd2;
+    if (A.gD != nullptr)
+      pw *= tri ? (A.gD[(int64_t)i * nB + j] + A.gD[(int64_t)j * nB + i]) : A.gD[(int64_t)i * nB + j];
+  }
+  if (lane == 0) {
+    if (A.rowpart != nullptr) A.rowpart[t] = pw;  // LE: rowpart holds one factor per pair
+    if (A.losspart != nullptr) {
+      A.losspart[2 * t] = dval;
+      A.losspart[2 * t + 1] = bad;
     }
   }
-  if (loss != nullptr) {
-    if (lane == 0) { s_d[warp] = dval; s_bad[warp] = bad; }
+}
+
+// gLa[c] += sum_b pw(c, b) (logA_c - logB_b)   and   gLb[c] -= sum_a pw(a, c) (logA_a - logB_c),
+// pairs in launch order; block = class, thread = matrix element. Self distances (tri): one sum over
+// all other classes.
+__global__ void __launch_bounds__(256)
+le_grad_kernel(const PairTiles T, const float* __restrict__ Wa, const float* __restrict__ Wb, int nA, int nB, int m,
+               const float* __restrict__ pw, float* gLa, float* gLb) {
+  const int c = blockIdx.x;
+  const int m2 = m * m, stride = 2 * m2 + 2 * m, off = m2 + 2 * m;
+  for (int e = threadIdx.x; e < m2; e += blockDim.x) {
+    float ga = 0.f, gb = 0.f;
+    if (c < nA && c >= T.bi0 && c <= T.bi1) {  // row side: pairs (c, j)
+      const float lc = Wa[(int64_t)c * stride + off + e];
+      const int nj = T.tri ? c : nB;  // (c, c) itself holds pw = 0
+      const int64_t base = (T.tri ? (int64_t)c * (c + 1) / 2 : (int64_t)c * T.nbj) - T.tile0;
+      for (int j = 0; j < nj; ++j) ga += pw[base + j] * (lc - Wb[(int64_t)j * stride + off + e]);
+    }
+    if (c < nB) {  // column side: pairs (i, c)
+      const float lc = Wb[(int64_t)c * stride + off + e];
+      const int i0 = T.tri ? max(T.bi0, c + 1) : T.bi0;
+      for (int i = i0; i <= T.bi1; ++i) {
+        const int64_t tt = (T.tri ? (int64_t)i * (i + 1) / 2 : (int64_t)i * T.nbj) + c - T.tile0;
+        gb -= pw[tt] * (Wa[(int64_t)i * stride + off + e] - lc);
+      }
+    }
+    if (gLa == gLb) {
+      if (c < nA) gLa[(int64_t)c * m2 + e] += ga + gb;
+    } else {
+      if (c < nA) gLa[(int64_t)c * m2 + e] += ga;
+      if (c < nB) gLb[(int64_t)c * m2 + e] += gb;
+    }
+  }
+}
+
+// fixed-order sum of the per-tile {sum of distances, non-finite count}: every thread sums a strided
+// subset in ascending tile order, then a fixed tree over the block
+__device__ void reduce_loss_partials(const float* __restrict__ losspart, int64_t ntiles, float& sum, float& bad) {
+  __shared__ float red[2][256];
+  float a = 0.f, b = 0.f;
+  for (int64_t t = threadIdx.x; t < ntiles; t += 256) {
+    a += losspart[2 * t];
+    b += losspart[2 * t + 1];
+  }
+  red[0][threadIdx.x] = a;
+  red[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    }
     __syncthreads();
+  }
+  sum = red[0][0];
+  bad = red[1][0];
+}
+
+// dLoss/dE of class c = its row partials (tiles of block row c / R, ascending block column) + its
+// column partials (tiles of block column c / R, ascending block row): blocks 0 .. max(nA, nB) - 1.
+// The last block reduces the loss partials. 256 threads.
+//   CLOSURE = false: gEa[c] += rows, gEb[c] += columns (gEa == gEb: one sum); loss[0..1] += {sum d, #bad}
+//   CLOSURE = true : the closure's tail fused in: (gPsi, gMu) = adjoint of the embedding applied to the
+//                    reduced dLoss/dE (reference model.py:216-217 / 537-538, distances.py:162-174) and
+//                    loss = {weight * sum d, #bad, 0}
+template <bool CLOSURE>
+__global__ void __launch_bounds__(256)
+pair_reduce_kernel(const PairTiles T, int nA, int nB, int m, const float* __restrict__ rowpart,
+                   const float* __restrict__ colpart, const float* __restrict__ losspart, float* gEa, float* gEb,
+                   float* loss, float weight, const float* __restrict__ Mu, int k, int fr, float* __restrict__ gPsi,
+                   float* __restrict__ gMu) {
+  extern __shared__ float sg[];  // CLOSURE: the reduced m x m gradient of this class
+  const int nC = max(nA, nB);
+  const int c = blockIdx.x;
+  if (c == nC) {
+    if (loss == nullptr || losspart == nullptr) return;
+    float sum, bad;
+    reduce_loss_partials(losspart, T.ntiles, sum, bad);
     if (threadIdx.x == 0) {
-      float a = 0.f, b = 0.f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_d[w]; b += s_bad[w]; }
-      atomicAdd(loss, a);
-      if (b != 0.f) atomicAdd(loss + 1, b);
+      if (CLOSURE) {
+        loss[0] = weight * sum;
+        loss[1] = bad;
+        loss[2] = 0.f;  // max |grad|, filled by closure_finish_kernel with atomicMax on the float bits
+      } else {
+        loss[0] += sum;
+        loss[1] += bad;
+      }
+    }
+    return;
+  }
+  if (rowpart == nullptr) return;
+  const int R = T.R, m2 = m * m;
+  const int slot = c % R, bc = c / R;
+  const int64_t pstride = (int64_t)R * m2;
+  for (int e = threadIdx.x; e < m2; e += 256) {
+    float a = 0.f, b = 0.f;
+    if (c < nA && bc >= T.bi0 && bc <= T.bi1) {
+      const int nb = T.tri ? bc + 1 : T.nbj;
+      const float* p = rowpart + ((T.tri ? (int64_t)bc * (bc + 1) / 2 : (int64_t)bc * T.nbj) - T.tile0) * pstride +
+                       (int64_t)slot * m2 + e;
+      int bj = 0;
+      for (; bj + 4 <= nb; bj += 4) {  // four loads in flight, added in order
+        const float v0 = p[0], v1 = p[pstride], v2 = p[2 * pstride], v3 = p[3 * pstride];
+        a += v0; a += v1; a += v2; a += v3;
+        p += 4 * pstride;
+      }
+      for (; bj < nb; ++bj, p += pstride) a += *p;
+    }
+    if (c < nB) {
+      const int i0 = T.tri ? max(T.bi0, bc) : T.bi0;
+      int bi = i0;
+      auto cp = [&](int bi_) {
+        const int64_t tt = (T.tri ? (int64_t)bi_ * (bi_ + 1) / 2 + bc : (int64_t)bi_ * T.nbj + bc) - T.tile0;
+        return colpart[tt * pstride + (int64_t)slot * m2 + e];
+      };
+      for (; bi + 4 <= T.bi1 + 1; bi += 4) {
+        const float v0 = cp(bi), v1 = cp(bi + 1), v2 = cp(bi + 2), v3 = cp(bi + 3);
+        b += v0; b += v1; b += v2; b += v3;
+      }
+      for (; bi <= T.bi1; ++bi) b += cp(bi);
+    }
+    if (CLOSURE) {
+      sg[e] = a + b;
+    } else if (gEa == gEb) {
+      gEa[(int64_t)c * m2 + e] += a + b;
+    } else {
+      if (c < nA) gEa[(int64_t)c * m2 + e] += a;
+      if (c < nB) gEb[(int64_t)c * m2 + e] += b;
+    }
+  }
+  if (CLOSURE) {
+    __syncthreads();
+    // gPsi = gE[:k,:k];  gMu[r] = sum_s (gE[r][s] + gE[s][r]) mu[s] + gE[r][k] + gE[k][r]   (Fisher-Rao)
+    for (int idx = threadIdx.x; idx < k * (k + 1); idx += 256) {
+      const int r = idx / (k + 1), s = idx % (k + 1);
+      if (s < k) {
+        gPsi[(int64_t)c * k * k + r * k + s] = sg[r * m + s];
+      } else if (fr) {
+        float v = sg[r * m + k] + sg[k * m + r];
+        for (int u = 0; u < k; ++u) v += (sg[r * m + u] + sg[u * m + r]) * Mu[(int64_t)c * k + u];
+        gMu[(int64_t)c * k + r] = v;
+      }
     }
   }
 }
@@ -725,9 +996,7 @@ size_t class_factor_floats(int m, int dist) {
 
 cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W, int32_t* flag, cudaStream_t st) {
   if (C <= 0) return cudaSuccess;
-  const int mp = (m + 1) & ~1;
-  const int ld = (mp > 32 ? 64 : 32) + 1;
-  const int per_warp = (4 * m * ld + 2 * m) * (int)sizeof(float);
+  const int per_warp = factor_scratch_floats(m) * (int)sizeof(float);
   const int nw = warps_for(per_warp);
   const int smem = nw * per_warp;
   static int smem_set[kMaxDevices] = {0};
@@ -741,29 +1010,61 @@ cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W
   return cudaGetLastError();
 }
 
-cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
-                                  int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
-                                  float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
-                                  cudaStream_t st) {
-  const int64_t npairs = pair_end - pair_begin;
-  if (tri && dist_out != nullptr && nA > 0) {
-    const float dv = (dist & SQFA_DIST_SQUARED) ? 0.f : sqrtf(DIST_EPS);  // d(i,i): lambda = 1 exactly
-    fill_diagonal_kernel<<<(nA + 255) / 256, 256, 0, st>>>(dist_out, nA, dv);
+cudaError_t launch_class_prepare(const float* PsiPart, const float* MuPart, int nchunk, float noise, int C, int k,
+                                 int dist, float* Mu, float* E, float* W, int32_t* flag, cudaStream_t st) {
+  if (C <= 0) return cudaSuccess;
+  const int m = ((dist & 15) == SQFA_DIST_FISHER_RAO_LB) ? k + 1 : k;
+  const int per_warp = (factor_scratch_floats(m) + m * m + k) * (int)sizeof(float);
+  const int nw = warps_for(per_warp);
+  const int smem = nw * per_warp;
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(class_prepare_kernel, smem, smem_set);
+    if (e != cudaSuccess) return e;
   }
-  if (npairs <= 0) return cudaGetLastError();
-  if ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) {
-    const unsigned blocks = (unsigned)((npairs + PAIR_WARPS - 1) / PAIR_WARPS);
-    pair_le_kernel<<<blocks, PAIR_WARPS * 32, 0, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
-                                                       dist_out, loss, gEa, gEb);
+  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
+  if (e != cudaSuccess) return e;
+  class_prepare_kernel<<<(C + nw - 1) / nw, nw * 32, smem, st>>>(PsiPart, MuPart, nchunk, noise, C, k, dist, Mu, E, W,
+                                                                  flag);
+  return cudaGetLastError();
+}
+
+// Tile edge: single pairs while the launch has few pairs (every pair gets its own warp: latency), 2 x 2
+// and 4 x 4 tiles for long pair lists (fewer, larger partials). The shared-memory variant (m > 32) and
+// log-Euclidean always use single pairs.
+static int pair_tile_edge(int m, int dist, int64_t npairs) {
+  if ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN || m > 32) return 1;
+  int R = npairs <= 16384 ? 1 : (npairs <= 131072 ? 2 : 4);
+  if (m > 24 && R > 2) R = 2;  // column accumulators are R m^2 floats of shared memory per warp
+  return R;
+}
+
+PairWorkspace pair_workspace(int nA, int nB, int m, int dist, int tri, int64_t pair_begin, int64_t pair_end) {
+  PairWorkspace w;
+  const int64_t npairs = pair_end > pair_begin ? pair_end - pair_begin : 0;
+  w.T = make_pair_tiles(nA, nB, tri, pair_begin, pair_end, pair_tile_edge(m, dist, npairs));
+  const bool le = (dist & 15) == SQFA_DIST_LOG_EUCLIDEAN;
+  const size_t part = le ? (size_t)w.T.ntiles : (size_t)w.T.ntiles * w.T.R * m * m;
+  auto al = [](size_t n) { return (n + 63) & ~size_t(63); };
+  w.rowpart = 0;
+  w.colpart = al(part);
+  w.losspart = w.colpart + (le ? 0 : al(part));
+  w.total_floats = w.losspart + al((size_t)2 * w.T.ntiles) + 64;
+  return w;
+}
+
+static cudaError_t launch_pair_kernel(const PairArgs& A, cudaStream_t st) {
+  const int m = A.m;
+  if (A.T.ntiles <= 0) return cudaSuccess;
+  if ((A.dist & 15) == SQFA_DIST_LOG_EUCLIDEAN) {
+    const unsigned blocks = (unsigned)((A.T.ntiles + PAIR_WARPS - 1) / PAIR_WARPS);
+    pair_le_kernel<<<blocks, PAIR_WARPS * 32, 0, st>>>(A);
     return cudaGetLastError();
   }
   if (m <= 32) {  // register-resident Jacobi
-#define SQFA_PAIR_REG(MPV)                                                                                   \
-  if (((m + 1) & ~1) < MPV)                                                                                    \
-    return launch_pair_reg<MPV, MPV - 2>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD, dist_out, \
-                                         loss, gEa, gEb, eig_out, st);                                          \
-  return launch_pair_reg<MPV, MPV>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD, dist_out, loss, \
-                                   gEa, gEb, eig_out, st)
+#define SQFA_PAIR_REG(MPV)                                                 \
+  if (((m + 1) & ~1) < MPV) return launch_pair_reg<MPV, MPV - 2>(A, st); \
+  return launch_pair_reg<MPV, MPV>(A, st)
     switch ((m + 3) / 4) {
       case 1: SQFA_PAIR_REG(4);
       case 2: SQFA_PAIR_REG(8);
@@ -781,14 +1082,78 @@ cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int 
   const int per_warp = (2 * m * ld + m * m + 3 * m) * (int)sizeof(float);
   const int nw = warps_for(per_warp);
   const int smem = nw * per_warp;
-  const unsigned blocks = (unsigned)((npairs + nw - 1) / nw);
+  const unsigned blocks = (unsigned)((A.T.ntiles + nw - 1) / nw);
   static int smem_set[kMaxDevices] = {0};
   {
     cudaError_t e = ensure_dynamic_smem(pair_ai_kernel, smem, smem_set);
     if (e != cudaSuccess) return e;
   }
-  pair_ai_kernel<<<blocks, nw * 32, smem, st>>>(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD,
-                                                dist_out, loss, gEa, gEb, eig_out);
+  pair_ai_kernel<<<blocks, nw * 32, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
+static PairArgs make_pair_args(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
+                               int64_t pair_begin, int64_t pair_end, float weight, const float* gD, float* dist_out,
+                               float* eig_out, bool want_grad, bool want_loss, float* ws, const PairWorkspace& L) {
+  PairArgs A;
+  A.Wa = Wa; A.Wb = Wb; A.nA = nA; A.nB = nB; A.m = m; A.dist = dist; A.tri = tri;
+  A.pair_begin = pair_begin; A.pair_end = pair_end; A.weight = weight; A.gD = gD;
+  A.dist_out = dist_out; A.eig_out = eig_out;
+  A.rowpart = want_grad ? ws + L.rowpart : nullptr;
+  A.colpart = want_grad ? ws + L.colpart : nullptr;
+  A.losspart = want_loss ? ws + L.losspart : nullptr;
+  A.T = L.T;
+  return A;
+}
+
+cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
+                                  int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
+                                  float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out, float* ws,
+                                  cudaStream_t st) {
+  if (tri && dist_out != nullptr && nA > 0) {
+    const float dv = (dist & SQFA_DIST_SQUARED) ? 0.f : sqrtf(DIST_EPS);  // d(i,i): lambda = 1 exactly
+    fill_diagonal_kernel<<<(nA + 255) / 256, 256, 0, st>>>(dist_out, nA, dv);
+  }
+  if (pair_end <= pair_begin) return cudaGetLastError();
+  const PairWorkspace L = pair_workspace(nA, nB, m, dist, tri, pair_begin, pair_end);
+  const bool want_grad = gEa != nullptr, want_loss = loss != nullptr;
+  const PairArgs A = make_pair_args(Wa, Wb, nA, nB, m, dist, tri, pair_begin, pair_end, weight, gD, dist_out, eig_out,
+                                    want_grad, want_loss, ws, L);
+  cudaError_t e = launch_pair_kernel(A, st);
+  if (e != cudaSuccess) return e;
+  if (!want_grad && !want_loss) return cudaSuccess;
+  const int nC = nA > nB ? nA : nB;
+  const bool le = (dist & 15) == SQFA_DIST_LOG_EUCLIDEAN;
+  if (le && want_grad) le_grad_kernel<<<nC, 256, 0, st>>>(L.T, Wa, Wb, nA, nB, m, A.rowpart, gEa, gEb);
+  pair_reduce_kernel<false><<<nC + 1, 256, 0, st>>>(L.T, nA, nB, m, le ? nullptr : A.rowpart, A.colpart, A.losspart,
+                                                    gEa, gEb, loss, 1.f, nullptr, 0, 0, nullptr, nullptr);
+  return cudaGetLastError();
+}
+
+// The pair stage of the closure: distances of the pairs [pair_begin, pair_end) of the C classes, then
+// per class the reduced dLoss/dE pushed through the adjoint of the embedding -> (gPsi, gMu), and
+// out = {weight * sum d, #non-finite, 0}. Log-Euclidean: the gradient w.r.t. the matrix logarithms is
+// accumulated in gLog (zeroed here) and the caller applies the factorisation's adjoint.
+cudaError_t launch_pair_closure(const float* W, int C, int m, int dist, int64_t pair_begin, int64_t pair_end,
+                                float weight, const float* Mu, int k, float* out, float* gPsi, float* gMu, float* gLog,
+                                float* ws, cudaStream_t st) {
+  const bool le = (dist & 15) == SQFA_DIST_LOG_EUCLIDEAN;
+  const bool fr = (dist & 15) == SQFA_DIST_FISHER_RAO_LB;
+  const PairWorkspace L = pair_workspace(C, C, m, dist, 1, pair_begin, pair_end);
+  const PairArgs A = make_pair_args(W, W, C, C, m, dist, 1, pair_begin, pair_end, weight, nullptr, nullptr, nullptr,
+                                    true, true, ws, L);
+  cudaError_t e = launch_pair_kernel(A, st);
+  if (e != cudaSuccess) return e;
+  if (le) {
+    if ((e = cudaMemsetAsync(gLog, 0, (size_t)C * m * m * sizeof(float), st)) != cudaSuccess) return e;
+    if (L.T.ntiles > 0) le_grad_kernel<<<C, 256, 0, st>>>(L.T, W, W, C, C, m, A.rowpart, gLog, gLog);
+    pair_reduce_kernel<true><<<C + 1, 256, 0, st>>>(L.T, C, C, m, nullptr, nullptr, A.losspart, nullptr, nullptr, out,
+                                                    weight, nullptr, k, 0, nullptr, nullptr);
+    return cudaGetLastError();
+  }
+  pair_reduce_kernel<true><<<C + 1, 256, m * m * sizeof(float), st>>>(L.T, C, C, m, A.rowpart, A.colpart, A.losspart,
+                                                                     nullptr, nullptr, out, weight, Mu, k, fr ? 1 : 0,
+                                                                     gPsi, gMu);
   return cudaGetLastError();
 }
 

@@ -114,88 +114,166 @@ project_stream_kernel(const float* __restrict__ S, const float* __restrict__ F, 
   }
 }
 
-// Row r = (c, f) of T, `tpr` threads per row (a multiple of 32, 256 / tpr rows per block):
-// T[c][f][:] = sum over the row splits of the partial products; Psi[c][f][:] = T[c][f][:] F^T and
-// mu'[c][f] = F[f][:] . m[c] from the same pass. Fixed reduction tree: deterministic.
-template <int KT, int VW>
-__global__ void __launch_bounds__(256)
+// Second stage of the projection, one block per (class, chunk of 128 columns), one warp per filter f:
+//   T[c][f][cols]         = sum over the row splits of the partial products   (fixed order)
+//   PsiPart[c][chunk][f][g] = T[c][f][cols] . F[g][cols]      (this chunk's share of Psi = T F^T)
+//   MuPart[c][chunk][f]     = F[f][cols] . m[c][cols]         (this chunk's share of mu' = F m)
+// The chunk partials are summed per class, in chunk order, by psi_reduce_kernel (stand-alone
+// projection) or by class_prepare_kernel (closure): deterministic, and parallel over C * D / 128
+// blocks instead of one block per row of T.
+constexpr int PF_COLS = 128;
+
+__global__ void __launch_bounds__(1024)
 project_finish_kernel(const float* __restrict__ partial, const float* __restrict__ F, const float* __restrict__ M,
-                      int C, int D, int k, int nsplit, int tpr, float* __restrict__ T, float* __restrict__ Psi,
-                      float* __restrict__ Mu) {
-  __shared__ float red[8][KT + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (256 / tpr) + threadIdx.x / tpr, lt = threadIdx.x % tpr;
-  const bool valid = r < C * k;
-  const int c = valid ? r / k : 0, f = valid ? r % k : 0;
-  float psi[KT];
-#pragma unroll
-  for (int g = 0; g < KT; ++g) psi[g] = 0.f;
-  float mu = 0.f;
-  const int64_t row = (int64_t)r * D, sstride = (int64_t)C * k * D;
-  if (valid) {
-    for (int j = VW * lt; j < D; j += VW * tpr) {
-      if constexpr (VW == 4) {
-        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0, t3 = t0;
-        const float* pj = partial + row + j;
-        int s = 0;
-        for (; s + 4 <= nsplit; s += 4) {  // four independent loads in flight
-          const float4 a0 = *reinterpret_cast<const float4*>(pj + (int64_t)s * sstride);
-          const float4 a1 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 1) * sstride);
-          const float4 a2 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 2) * sstride);
-          const float4 a3 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 3) * sstride);
-          t0.x += a0.x; t0.y += a0.y; t0.z += a0.z; t0.w += a0.w;
-          t1.x += a1.x; t1.y += a1.y; t1.z += a1.z; t1.w += a1.w;
-          t2.x += a2.x; t2.y += a2.y; t2.z += a2.z; t2.w += a2.w;
-          t3.x += a3.x; t3.y += a3.y; t3.z += a3.z; t3.w += a3.w;
-        }
-        for (; s < nsplit; ++s) {
-          const float4 a0 = *reinterpret_cast<const float4*>(pj + (int64_t)s * sstride);
-          t0.x += a0.x; t0.y += a0.y; t0.z += a0.z; t0.w += a0.w;
-        }
-        const float4 t = make_float4((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y),
-                                     (t0.z + t1.z) + (t2.z + t3.z), (t0.w + t1.w) + (t2.w + t3.w));
-        *reinterpret_cast<float4*>(T + row + j) = t;
-#pragma unroll
-        for (int g = 0; g < KT; ++g) {
-          if (g < k) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(F + (int64_t)g * D + j));
-            psi[g] += (t.x * w.x + t.y * w.y) + (t.z * w.z + t.w * w.w);
-          }
-        }
-        if (M != nullptr) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(F + (int64_t)f * D + j));
-          const float4 m = __ldg(reinterpret_cast<const float4*>(M + (int64_t)c * D + j));
-          mu += (w.x * m.x + w.y * m.y) + (w.z * m.z + w.w * m.w);
-        }
-      } else {
-        float t = 0.f;
-        for (int s = 0; s < nsplit; ++s) t += partial[(int64_t)s * sstride + row + j];
-        T[row + j] = t;
-#pragma unroll
-        for (int g = 0; g < KT; ++g)
-          if (g < k) psi[g] += t * __ldg(F + (int64_t)g * D + j);
-        if (M != nullptr) mu += __ldg(F + (int64_t)f * D + j) * __ldg(M + (int64_t)c * D + j);
+                      int C, int D, int k, int nsplit, int vec16, float* __restrict__ T,
+                      float* __restrict__ PsiPart, float* __restrict__ MuPart) {
+  const int c = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;  // blockDim.x = 32 k
+  const int col = chunk * PF_COLS + 4 * lane;
+  const int64_t sstride = (int64_t)C * k * D;
+  const int64_t row = ((int64_t)c * k + f) * D;
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nv = col >= D ? 0 : (D - col >= 4 ? 4 : D - col);  // valid columns of this thread
+  if (vec16) {
+    if (nv == 4) {
+      const float* pj = partial + row + col;
+      int s = 0;
+      for (; s + 4 <= nsplit; s += 4) {  // four independent loads in flight, added in order
+        const float4 a0 = *reinterpret_cast<const float4*>(pj + (int64_t)s * sstride);
+        const float4 a1 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 1) * sstride);
+        const float4 a2 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 2) * sstride);
+        const float4 a3 = *reinterpret_cast<const float4*>(pj + (int64_t)(s + 3) * sstride);
+        t.x += a0.x; t.y += a0.y; t.z += a0.z; t.w += a0.w;
+        t.x += a1.x; t.y += a1.y; t.z += a1.z; t.w += a1.w;
+        t.x += a2.x; t.y += a2.y; t.z += a2.z; t.w += a2.w;
+        t.x += a3.x; t.y += a3.y; t.z += a3.z; t.w += a3.w;
       }
+      for (; s < nsplit; ++s) {
+        const float4 a0 = *reinterpret_cast<const float4*>(pj + (int64_t)s * sstride);
+        t.x += a0.x; t.y += a0.y; t.z += a0.z; t.w += a0.w;
+      }
+      *reinterpret_cast<float4*>(T + row + col) = t;
     }
+  } else {
+    float tv[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < nv; ++q) {
+      for (int s = 0; s < nsplit; ++s) tv[q] += partial[(int64_t)s * sstride + row + col + q];
+      T[row + col + q] = tv[q];
+    }
+    t = make_float4(tv[0], tv[1], tv[2], tv[3]);
   }
-#pragma unroll
-  for (int g = 0; g < KT; ++g) {
-    float a = psi[g];
+  auto load4 = [&](const float* p) {  // 4 columns of a row of F or M, zero beyond D
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec16 && nv == 4) {
+      w = __ldg(reinterpret_cast<const float4*>(p));
+    } else {
+      if (nv > 0) w.x = __ldg(p);
+      if (nv > 1) w.y = __ldg(p + 1);
+      if (nv > 2) w.z = __ldg(p + 2);
+      if (nv > 3) w.w = __ldg(p + 3);
+    }
+    return w;
+  };
+  float* pp = PsiPart + (((int64_t)c * nchunk + chunk) * k + f) * k;
+  for (int g = 0; g < k; ++g) {
+    const float4 w = load4(F + (int64_t)g * D + col);
+    float a = (t.x * w.x + t.y * w.y) + (t.z * w.z + t.w * w.w);
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) red[warp][g] = a;
+    if (lane == 0) pp[g] = a;
   }
-  for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
-  if (lane == 0) red[warp][KT] = mu;
+  if (M != nullptr) {
+    const float4 w = load4(F + (int64_t)f * D + col);
+    const float4 mm = load4(M + (int64_t)c * D + col);
+    float a = (w.x * mm.x + w.y * mm.y) + (w.z * mm.z + w.w * mm.w);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) MuPart[((int64_t)c * nchunk + chunk) * k + f] = a;
+  }
+}
+
+// Psi[c] / Mu[c] = sum over the column chunks, in chunk order (stand-alone projection)
+__global__ void psi_reduce_kernel(const float* __restrict__ PsiPart, const float* __restrict__ MuPart, int C, int k,
+                                  int nchunk, float* __restrict__ Psi, float* __restrict__ Mu) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int per = k * k + k;
+  if (idx >= (int64_t)C * per) return;
+  const int c = (int)(idx / per), e = (int)(idx % per);
+  float a = 0.f;
+  if (e < k * k) {
+    for (int ch = 0; ch < nchunk; ++ch) a += PsiPart[((int64_t)c * nchunk + ch) * k * k + e];
+    Psi[(int64_t)c * k * k + e] = a;
+  } else if (MuPart != nullptr) {
+    for (int ch = 0; ch < nchunk; ++ch) a += MuPart[((int64_t)c * nchunk + ch) * k + (e - k * k)];
+    Mu[(int64_t)c * k + (e - k * k)] = a;
+  }
+}
+
+// Sphere constraint (reference constraints.py:37): F[f] = W[f] / |W[f]|, inv_norm[f] = 1 / |W[f]|.
+// One block per filter, fixed reduction tree.
+__global__ void __launch_bounds__(256)
+constraint_fwd_kernel(const float* __restrict__ Wraw, int D, float* __restrict__ F, float* __restrict__ inv_norm) {
+  __shared__ float red[256];
+  const int f = blockIdx.x;
+  const float* w = Wraw + (int64_t)f * D;
+  float a = 0.f;
+  for (int j = threadIdx.x; j < D; j += 256) a += w[j] * w[j];
+  red[threadIdx.x] = a;
   __syncthreads();
-  if (valid) {  // the warps of a row are contiguous: sum them in order
-    const int w0 = (threadIdx.x / tpr) * (tpr / 32);
-    for (int e = lt; e <= KT; e += tpr) {
-      float a = 0.f;
-      for (int w = 0; w < tpr / 32; ++w) a += red[w0 + w][e];
-      if (e < k) Psi[(int64_t)r * k + e] = a;
-      if (e == KT && M != nullptr) Mu[r] = a;
-    }
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
   }
+  const float nrm = sqrtf(red[0]);
+  for (int j = threadIdx.x; j < D; j += 256) F[(int64_t)f * D + j] = w[j] / nrm;
+  if (threadIdx.x == 0) inv_norm[f] = 1.f / nrm;
+}
+
+// Last kernel of a closure evaluation, one block per filter f:
+//   dF[f] = sum of the class-split partials of the projection adjoint (fixed order),
+//   the constraint's adjoint: sphere  grad[f] = (dF[f] - (dF[f] . F[f]) F[f]) / |W[f]|
+//                             (autograd through constraints.py:37), none: grad[f] = dF[f];
+//   rows f < n_fixed get a zero gradient (FixedFilters detaches them, constraints.py:95-141),
+//   out[2] = max |grad| over all filters (atomicMax on the float bits; order-independent).
+__global__ void __launch_bounds__(256)
+closure_finish_kernel(const float* __restrict__ partial, int D, int k, int csplit, const float* __restrict__ F,
+                      const float* __restrict__ inv_norm, int sphere, int n_fixed, float* __restrict__ grad,
+                      float* __restrict__ out) {
+  __shared__ float red[256];
+  const int f = blockIdx.x;
+  float* g = grad + (int64_t)f * D;
+  float dot = 0.f;
+  for (int j = threadIdx.x; j < D; j += 256) {
+    float a = 0.f;
+    for (int s = 0; s < csplit; ++s) a += partial[((int64_t)s * k + f) * D + j];
+    g[j] = a;  // re-read below by the same thread
+    if (sphere) dot += a * F[(int64_t)f * D + j];
+  }
+  if (sphere) {
+    red[threadIdx.x] = dot;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    dot = red[0];
+    __syncthreads();
+  }
+  const float inv = sphere ? inv_norm[f] : 1.f;
+  float amax = 0.f;
+  for (int j = threadIdx.x; j < D; j += 256) {
+    float v = g[j];
+    if (f < n_fixed) v = 0.f;
+    else if (sphere) v = (v - dot * F[(int64_t)f * D + j]) * inv;
+    g[j] = v;
+    amax = fmaxf(amax, fabsf(v));
+  }
+  red[threadIdx.x] = amax;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  // NaN gradients: fmaxf drops NaN, the loss / non-finite counter carry that information
+  if (threadIdx.x == 0 && out != nullptr) atomicMax(reinterpret_cast<unsigned int*>(out + 2), __float_as_uint(red[0]));
 }
 
 // dF[f][j] = sum_c ( sum_g (gPsi[c][f][g] + gPsi[c][g][f]) T[c][g][j] + gMu[c][f] M[c][j] )
@@ -452,22 +530,12 @@ __global__ void embed_bwd_kernel(const float* __restrict__ gE, const float* __re
 }
 
 template <int KT>
-cudaError_t run_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, int rows, int nsplit,
-                            float* partial, float* T, float* Psi, float* Mu, cudaStream_t st) {
+cudaError_t run_project_stream(const float* S, const float* F, int C, int D, int k, int rows, int nsplit,
+                               float* partial, cudaStream_t st) {
   dim3 grid((D + PS_COLS - 1) / PS_COLS, nsplit, C);
   const int vec16 =
       (D % 4 == 0 && ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0) ? 1 : 0;
   project_stream_kernel<KT><<<grid, PS_THREADS, 0, st>>>(S, F, C, D, k, rows, vec16, partial);
-  int tpr = 32;  // threads per (class, filter) row: about 4 float4 per thread, 32 .. 256
-  while (tpr < 256 && tpr * 16 < D) tpr *= 2;
-  const int rpb = 256 / tpr;
-  const unsigned nb = (unsigned)(((int64_t)C * k + rpb - 1) / rpb);
-  const bool al16 = ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(T) |
-                      reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(M)) & 15) == 0;
-  if (D % 4 == 0 && al16)
-    project_finish_kernel<KT, 4><<<nb, 256, 0, st>>>(partial, F, M, C, D, k, nsplit, tpr, T, Psi, Mu);
-  else
-    project_finish_kernel<KT, 1><<<nb, 256, 0, st>>>(partial, F, M, C, D, k, nsplit, tpr, T, Psi, Mu);
   return cudaGetLastError();
 }
 
@@ -506,34 +574,90 @@ int project_nsplit(int C, int D) {
 
 static size_t project_partial_floats(int C, int D, int k) { return (size_t)project_nsplit(C, D) * C * k * D; }
 
+int project_nchunk(int D) { return (D + PF_COLS - 1) / PF_COLS; }
+static size_t al64(size_t n) { return (n + 63) & ~size_t(63); }
+size_t project_psipart_floats(int C, int D, int k) { return al64((size_t)C * project_nchunk(D) * k * k); }
+size_t project_mupart_floats(int C, int D, int k) { return al64((size_t)C * project_nchunk(D) * k); }
+int project_bwd_csplit(int C, int D) {
+  int csplit = C < 64 ? (C > 0 ? C : 1) : 64;
+  // few column blocks -> more class splits are useful; many -> fewer
+  const int colblocks = (D + 127) / 128;
+  while (csplit > 1 && colblocks * csplit > 2048) csplit >>= 1;
+  return csplit;
+}
+
+// workspace (floats): [ row-split partials | PsiPart | MuPart ] for the forward, [ class-split partials ] for
+// the adjoint (they alias: the two are never live together)
 size_t project_workspace_bytes(int C, int D, int k) {
-  const size_t fwd = project_partial_floats(C, D, k) * sizeof(float);
-  const size_t bwd = (size_t)64 * k * D * sizeof(float);
-  return fwd > bwd ? fwd : bwd;
+  const size_t fwd = al64(project_partial_floats(C, D, k)) + project_psipart_floats(C, D, k) +
+                     project_mupart_floats(C, D, k);
+  const size_t bwd = (size_t)64 * k * D;
+  return (fwd > bwd ? fwd : bwd) * sizeof(float);
+}
+
+// T and the per-chunk partials of Psi / Mu (the closure reduces them inside class_prepare_kernel)
+cudaError_t launch_project_partials(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
+                                    float* partial, float* PsiPart, float* MuPart, cudaStream_t st) {
+  if (C <= 0) return cudaSuccess;
+  const int rows = project_rows_per_split(C, D), nsplit = project_nsplit(C, D);
+  cudaError_t e;
+  if (k <= 4) e = run_project_stream<4>(S, F, C, D, k, rows, nsplit, partial, st);
+  else if (k <= 8) e = run_project_stream<8>(S, F, C, D, k, rows, nsplit, partial, st);
+  else if (k <= 16) e = run_project_stream<16>(S, F, C, D, k, rows, nsplit, partial, st);
+  else e = run_project_stream<32>(S, F, C, D, k, rows, nsplit, partial, st);
+  if (e != cudaSuccess) return e;
+  const int vec16 = (D % 4 == 0 && ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(T) |
+                                     reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(M)) & 15) == 0)
+                        ? 1 : 0;
+  project_finish_kernel<<<dim3(project_nchunk(D), C), 32 * k, 0, st>>>(partial, F, M, C, D, k, nsplit, vec16, T,
+                                                                        PsiPart, MuPart);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
                                float* Psi, float* Mu, float* ws, cudaStream_t st) {
   if (C <= 0) return cudaSuccess;
-  const int rows = project_rows_per_split(C, D), nsplit = project_nsplit(C, D);
-  cudaError_t e;
-  if (k <= 4) e = run_project_fwd<4>(S, M, F, C, D, k, rows, nsplit, ws, T, Psi, Mu, st);
-  else if (k <= 8) e = run_project_fwd<8>(S, M, F, C, D, k, rows, nsplit, ws, T, Psi, Mu, st);
-  else if (k <= 16) e = run_project_fwd<16>(S, M, F, C, D, k, rows, nsplit, ws, T, Psi, Mu, st);
-  else e = run_project_fwd<32>(S, M, F, C, D, k, rows, nsplit, ws, T, Psi, Mu, st);
-  return e;
+  float* PsiPart = ws + al64(project_partial_floats(C, D, k));
+  float* MuPart = PsiPart + project_psipart_floats(C, D, k);
+  cudaError_t e = launch_project_partials(S, M, F, C, D, k, T, ws, PsiPart, M != nullptr ? MuPart : nullptr, st);
+  if (e != cudaSuccess) return e;
+  const int64_t total = (int64_t)C * (k * k + k);
+  psi_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(PsiPart, M != nullptr ? MuPart : nullptr, C, k,
+                                                                     project_nchunk(D), Psi, Mu);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_project_bwd_partials(const float* gPsi, const float* gMu, const float* T, const float* M,
+                                               int C, int D, int k, float* ws, int csplit, cudaStream_t st) {
+  const int colblocks = (D + 127) / 128;
+  const int smem = (k * k + k) * (int)sizeof(float);
+  project_bwd_kernel<<<dim3(colblocks, csplit), 128, smem, st>>>(gPsi, gMu, T, M, C, D, k, csplit, ws);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_project_bwd(const float* gPsi, const float* gMu, const float* T, const float* M, int C, int D,
                                int k, float* dF, float* ws, cudaStream_t st) {
-  int csplit = C < 64 ? (C > 0 ? C : 1) : 64;
-  // few column blocks -> more class splits are useful; many -> fewer
-  const int colblocks = (D + 127) / 128;
-  while (csplit > 1 && colblocks * csplit > 2048) csplit >>= 1;
-  const int smem = (k * k + k) * (int)sizeof(float);
-  project_bwd_kernel<<<dim3(colblocks, csplit), 128, smem, st>>>(gPsi, gMu, T, M, C, D, k, csplit, ws);
+  const int csplit = project_bwd_csplit(C, D);
+  cudaError_t e = launch_project_bwd_partials(gPsi, gMu, T, M, C, D, k, ws, csplit, st);
+  if (e != cudaSuccess) return e;
   const int64_t total = (int64_t)k * D;
   project_bwd_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, D, k, csplit, dF);
+  return cudaGetLastError();
+}
+
+// adjoint of the projection followed by the adjoint of the filter constraint (closure tail)
+cudaError_t launch_project_bwd_constrained(const float* gPsi, const float* gMu, const float* T, const float* M, int C,
+                                           int D, int k, const float* F, const float* inv_norm, int sphere,
+                                           int n_fixed, float* grad, float* out, float* ws, cudaStream_t st) {
+  const int csplit = project_bwd_csplit(C, D);
+  cudaError_t e = launch_project_bwd_partials(gPsi, gMu, T, M, C, D, k, ws, csplit, st);
+  if (e != cudaSuccess) return e;
+  closure_finish_kernel<<<k, 256, 0, st>>>(ws, D, k, csplit, F, inv_norm, sphere, n_fixed, grad, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_constraint_fwd(const float* Wraw, int D, int k, float* F, float* inv_norm, cudaStream_t st) {
+  constraint_fwd_kernel<<<k, 256, 0, st>>>(Wraw, D, F, inv_norm);
   return cudaGetLastError();
 }
 

@@ -56,13 +56,22 @@ cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K
 }  // namespace sqfa
 
 namespace sqfa {
-// ---- project.cu (K4, K6, transform, embedding) ----
+// ---- project.cu (K4, K6, transform, embedding, constraint) ----
 int project_nsplit(int C, int D);
+int project_nchunk(int D);
 size_t project_workspace_bytes(int C, int D, int k);
+size_t project_psipart_floats(int C, int D, int k);
+size_t project_mupart_floats(int C, int D, int k);
+cudaError_t launch_project_partials(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
+                                    float* partial, float* PsiPart, float* MuPart, cudaStream_t st);
 cudaError_t launch_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
                                float* Psi, float* Mu, float* ws, cudaStream_t st);
 cudaError_t launch_project_bwd(const float* gPsi, const float* gMu, const float* T, const float* M, int C, int D,
                                int k, float* dF, float* ws, cudaStream_t st);
+cudaError_t launch_project_bwd_constrained(const float* gPsi, const float* gMu, const float* T, const float* M, int C,
+                                           int D, int k, const float* F, const float* inv_norm, int sphere,
+                                           int n_fixed, float* grad, float* out, float* ws, cudaStream_t st);
+cudaError_t launch_constraint_fwd(const float* Wraw, int D, int k, float* F, float* inv_norm, cudaStream_t st);
 cudaError_t launch_transform(const float* X, int64_t ldx, const float* F, int64_t n, int D, int k, float* Z,
                              cudaStream_t st);
 cudaError_t launch_embed_fwd(const float* Psi, const float* Mu, float noise, int C, int k, int fr, float* E,
@@ -71,22 +80,53 @@ cudaError_t launch_embed_bwd(const float* gE, const float* Mu, int C, int k, int
                              cudaStream_t st);
 
 // ---- pairs.cu (K5) ----
+// A launch of the pair kernels covers the R x R tiles of block rows bi0 .. bi1 of the pair matrix
+// (lower triangle for self distances); local tile t = global tile - tile0.
+struct PairTiles {
+  int R, tri, nbj, bi0, bi1;
+  int64_t tile0, ntiles;
+};
+struct PairArgs {
+  const float* Wa;
+  const float* Wb;
+  int nA, nB, m, dist, tri;
+  int64_t pair_begin, pair_end;
+  float weight;
+  const float* gD;
+  float* dist_out;
+  float* eig_out;
+  float* rowpart;   // [ntiles][R][m*m] per-tile partial gradients of the row classes (LE: one factor per pair)
+  float* colpart;   // [ntiles][R][m*m] ... of the column classes
+  float* losspart;  // [ntiles][2] {sum of distances, non-finite count}
+  PairTiles T;
+};
+struct PairWorkspace {
+  size_t rowpart, colpart, losspart, total_floats;  // offsets in floats
+  PairTiles T;
+};
+PairTiles make_pair_tiles(int nA, int nB, int tri, int64_t pair_begin, int64_t pair_end, int R);
+PairWorkspace pair_workspace(int nA, int nB, int m, int dist, int tri, int64_t pair_begin, int64_t pair_end);
 size_t class_factor_floats(int m, int dist);
 cudaError_t launch_class_factor(const float* E, int C, int m, int dist, float* W, int32_t* flag, cudaStream_t st);
+cudaError_t launch_class_prepare(const float* PsiPart, const float* MuPart, int nchunk, float noise, int C, int k,
+                                 int dist, float* Mu, float* E, float* W, int32_t* flag, cudaStream_t st);
 cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int nB, int m, int dist, int tri,
                                   int64_t pair_begin, int64_t pair_end, float weight, const float* gD,
-                                  float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out,
+                                  float* dist_out, float* loss, float* gEa, float* gEb, float* eig_out, float* ws,
                                   cudaStream_t st);
+cudaError_t launch_pair_closure(const float* W, int C, int m, int dist, int64_t pair_begin, int64_t pair_end,
+                                float weight, const float* Mu, int k, float* out, float* gPsi, float* gMu, float* gLog,
+                                float* ws, cudaStream_t st);
 cudaError_t launch_class_factor_bwd(const float* W, const float* gLog, int C, int m, int dist, float* gE,
                                     cudaStream_t st);
 }  // namespace sqfa
 
 namespace sqfa {
 // ---- closure.cu ----
-size_t fused_loss_workspace_bytes(int C, int D, int k, int dist);
-cudaError_t launch_fused_loss(const float* S, const float* M, const float* F, int C, int D, int k, float noise,
-                              int dist, int64_t pair_begin, int64_t pair_end, float* out, float* dF, float* ws,
-                              cudaStream_t st);
+size_t fused_loss_workspace_bytes(int C, int D, int k, int dist, int64_t pair_begin, int64_t pair_end);
+cudaError_t launch_fused_loss(const float* S, const float* M, const float* filters, int C, int D, int k, float noise,
+                              int dist, int constraint, int n_fixed, int64_t pair_begin, int64_t pair_end, float* out,
+                              float* grad, float* ws, cudaStream_t st);
 }  // namespace sqfa
 
 

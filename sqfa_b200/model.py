@@ -9,6 +9,7 @@ every method returns results on the device of its inputs.
 """
 
 import contextlib
+import os
 
 import torch
 import torch.nn as nn
@@ -42,6 +43,29 @@ _DICT_DISTANCES = {
     distances.fisher_rao_lower_bound: _ops.DIST_FR,
     distances.fisher_rao_lower_bound_sq: _ops.DIST_FR | _ops.SQUARED,
 }
+
+
+_GRAPH_CLOSURE = os.environ.get("SQFA_GRAPH_CLOSURE", "1") != "0"
+
+
+def _capture_graph(launch, device):
+    """Capture one closure evaluation (8 kernel launches from one C call) into a CUDA graph; None if the
+    capture is not possible here (the caller keeps launching directly)."""
+    try:
+        torch.cuda.synchronize(device)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            launch()  # warm-up on the capture stream (sets per-kernel attributes outside the capture)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        with torch.cuda.graph(graph, stream=side):
+            launch()
+        return graph
+    except Exception:  # e.g. capture unsupported in this context
+        torch.cuda.synchronize(device)
+        return None
 
 
 def _stats_to_scatter(statistics):
@@ -246,8 +270,14 @@ class SecondMomentsSQFA(nn.Module):
             return None
         S, M, dist = plan
         group = self._process_group
-        lib = _lib.load()
-        nbytes = lib.sqfa_fused_loss_workspace_bytes(S.shape[0], S.shape[1], self.filters.shape[0], dist)
+        rank, world = 0, 1
+        if group is not None:
+            import torch.distributed as dist_mod
+
+            rank, world = dist_mod.get_rank(group), dist_mod.get_world_size(group)
+        C, D, k = S.shape[0], S.shape[1], self.filters.shape[0]
+        p0, p1 = _ops.shard_pairs(C * (C - 1) // 2, C, rank, world)
+        nbytes = _lib.load().sqfa_fused_loss_workspace_bytes(C, D, k, dist, p0, p1)
         ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=S.device)  # reused by every evaluation
         return lambda: _ops.FusedLoss.apply(self.filters, S, M, noise, dist, group, ws)
 
@@ -273,26 +303,64 @@ class SecondMomentsSQFA(nn.Module):
         S, M, dist = plan
         group = self._process_group
         k, D = p.shape
-        nbytes = _lib.load().sqfa_fused_loss_workspace_bytes(S.shape[0], S.shape[1], k, dist)
-        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=S.device)
+        C = S.shape[0]
         sphere = any(type(m) is Sphere for m in chain)
         n_fixed = max([m.n_row_fixed for m in chain if type(m) is FixedFilters], default=0)
+        lib = _lib.load()
+
+        if group is not None:
+            # pair list sharded over the ranks: [loss, flag, -, dF] of this rank's pairs, ONE all-reduce,
+            # then the (linear) constraint adjoint on every rank
+            import torch.distributed as dist_mod
+
+            rank, world = dist_mod.get_rank(group), dist_mod.get_world_size(group)
+            p0, p1 = _ops.shard_pairs(C * (C - 1) // 2, C, rank, world)
+            ws = torch.empty(max(int(lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist, p0, p1)), 1),
+                             dtype=torch.uint8, device=S.device)
+
+            @torch.no_grad()
+            def run_sharded():
+                W = p.detach()
+                if sphere:
+                    nrm = W.norm(dim=-1, keepdim=True)
+                    F = W / nrm
+                else:
+                    F = W
+                packed = _ops.fused_loss_raw(F, S, M, noise, dist, group, ws)
+                dF = packed[4:].view(k, D)
+                if n_fixed:
+                    dF[:n_fixed] = 0.0  # frozen rows are detached in FixedFilters.forward
+                dW = (dF - (dF * F).sum(dim=-1, keepdim=True) * F) / nrm if sphere else dF
+                p.grad = dW
+                return torch.cat([packed[:2], dW.abs().max().view(1)])
+
+            return run_sharded
+
+        # single device: ONE native call per evaluation (constraint and its adjoint included), all
+        # buffers static, captured in a CUDA graph after the first evaluations
+        P = C * (C - 1) // 2
+        ws = torch.empty(max(int(lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist, 0, P)), 1), dtype=torch.uint8,
+                         device=S.device)
+        out = torch.zeros(_ops.N_OUT, dtype=torch.float32, device=S.device)
+        grad = torch.zeros(k, D, dtype=torch.float32, device=S.device)
+        state = {"calls": 0, "graph": None, "param_ptr": None}
+
+        def launch():
+            _ops.closure_eval_raw(p.detach(), S, M, noise, dist, sphere, n_fixed, out, grad, ws)
 
         @torch.no_grad()
         def run():
-            W = p.detach()
-            if sphere:
-                nrm = W.norm(dim=-1, keepdim=True)
-                F = W / nrm
+            if not p.is_contiguous():
+                raise RuntimeError("filter parameter must be contiguous")
+            state["calls"] += 1
+            if state["graph"] is not None and state["param_ptr"] == p.data_ptr():
+                state["graph"].replay()
             else:
-                F = W
-            packed = _ops.fused_loss_raw(F, S, M, noise, dist, group, ws)
-            dF = packed[2:].view(k, D)
-            if n_fixed:
-                dF[:n_fixed] = 0.0  # frozen rows are detached in FixedFilters.forward
-            dW = (dF - (dF * F).sum(dim=-1, keepdim=True) * F) / nrm if sphere else dF
-            p.grad = dW
-            return torch.cat([packed[:2], dW.abs().max().view(1)])
+                launch()
+                if state["calls"] == 2 and _GRAPH_CLOSURE and state["graph"] is None:
+                    state["graph"], state["param_ptr"] = _capture_graph(launch, S.device), p.data_ptr()
+            p.grad = grad  # static buffer: the optimiser reads it before the next evaluation overwrites it
+            return out
 
         return run
 

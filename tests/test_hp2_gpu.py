@@ -130,6 +130,8 @@ CASES = [
     ("second_moments", 3000, 48, 6, 8, "log_euclidean"),
     ("full", 3000, 40, 5, 32, None),      # m = 33: two Jacobi columns per lane
     ("second_moments", 2000, 784, 10, 4, None),
+    ("full", 10000, 32, 200, 4, None),    # 19 900 pairs: 2 x 2 pair tiles
+    ("second_moments", 10000, 24, 190, 6, "log_euclidean"),
 ]
 
 

@@ -79,10 +79,11 @@ def test_fit_with_device_lbfgs_matches_torch_lbfgs(monkeypatch):
         loss, _ = model.fit(data_statistics=stats, max_epochs=3, atol=0.0, show_progress=False, return_loss=True,
                             max_iter=8)
         out[name] = (loss, model.filters.detach().cpu())
-    # the gradient is accumulated with atomics (run-to-run rounding), L-BFGS amplifies it: loose bounds
-    assert torch.allclose(out["native"][0], out["torch"][0], rtol=1e-3, atol=1e-6)
+    # loss and gradient are deterministic (fixed-order reductions); what differs between the two
+    # optimisers is the summation order inside the dot products of the two-loop recursion
+    assert torch.allclose(out["native"][0], out["torch"][0], rtol=2e-4, atol=1e-6)
     Fa, Fb = out["native"][1], out["torch"][1]
-    assert float((Fa - Fb).norm() / Fb.norm()) < 3e-2
+    assert float((Fa - Fb).norm() / Fb.norm()) < 5e-3
 
 
 @pytest.mark.parametrize("constraint", ["sphere", "none"])
@@ -107,10 +108,40 @@ def test_fit_constraints_direct_closure_vs_autograd(monkeypatch, constraint):
         loss, _ = model.fit(data_statistics=stats, max_epochs=2, atol=0.0, show_progress=False, return_loss=True,
                             max_iter=5)
         runs[mode] = (loss, model.filters.detach().cpu())
-    # the gradient is accumulated with atomics (run-to-run rounding), L-BFGS amplifies it: loose bounds
-    assert torch.allclose(runs["direct"][0], runs["autograd"][0], rtol=1e-3, atol=1e-6)
-    assert float((runs["direct"][1] - runs["autograd"][1]).norm() / runs["autograd"][1].norm()) < 3e-2
+    assert torch.allclose(runs["direct"][0], runs["autograd"][0], rtol=2e-4, atol=1e-6)
+    assert float((runs["direct"][1] - runs["autograd"][1]).norm() / runs["autograd"][1].norm()) < 5e-3
     assert runs["direct"][0][-1] < runs["direct"][0][0]  # the loss went down
     F = runs["direct"][1]
     if constraint == "sphere":
         assert torch.allclose(F.norm(dim=1), torch.ones(3), atol=1e-5)
+
+
+@pytest.mark.parametrize("c,k,kind", [(12, 4, "full"), (200, 8, "full"), (40, 6, "second_moments")])
+def test_closure_and_fit_are_bit_reproducible(c, k, kind):
+    """No floating-point atomics anywhere in the closure: the same inputs give the same bits, through
+    the directly launched closure, its CUDA-graph replay, and a whole fit (C = 200: 19 900 pairs, 2 x 2 pair tiles)."""
+    from conftest import make_class_data
+    from sqfa_b200.model import SQFA, SecondMomentsSQFA
+    from sqfa_b200.statistics import class_statistics
+
+    d = 48
+    X, y = make_class_data(60 * c, d, c, seed=c)
+    stats = class_statistics(X.cuda(), y.cuda())
+    cls = SQFA if kind == "full" else SecondMomentsSQFA
+    F0 = torch.randn(k, d, generator=torch.Generator().manual_seed(k))
+    outs, grads = [], []
+    for _ in range(2):
+        model = cls(n_dim=d, feature_noise=0.01, n_filters=k, filters=F0.clone()).cuda()
+        plan = model._fused_direct_plan(stats)
+        for _ in range(4):  # call 1: direct launch, call 2: capture, calls 3-4: graph replays
+            outs.append(plan().clone())
+            grads.append(model.parametrizations.filters.original.grad.clone())
+    for o, g in zip(outs[1:], grads[1:]):
+        assert torch.equal(o, outs[0]) and torch.equal(g, grads[0])
+    fits = []
+    for _ in range(2):
+        model = cls(n_dim=d, feature_noise=0.01, n_filters=k, filters=F0.clone())
+        loss, _ = model.fit(data_statistics=stats, max_epochs=3, atol=0.0, show_progress=False, return_loss=True,
+                            max_iter=7)
+        fits.append((loss, model.filters.detach().clone()))
+    assert torch.equal(fits[0][0], fits[1][0]) and torch.equal(fits[0][1], fits[1][1])
