@@ -516,9 +516,16 @@ def run_ours(args):
     Xh, yh = X.cpu().pin_memory(), y.cpu().pin_memory()
     nbuf = int(os.environ.get("SQFA_BENCH_E2E_BUFS", "3"))  # buffer sets / streams in flight
     streams = [torch.cuda.Stream(device=dev) for _ in range(nbuf)]
-    out_h = [{key: torch.empty(v.shape, dtype=v.dtype).pin_memory() for key, v in stats.items()} for _ in range(nbuf)]
+    stats_full = stats  # full statistics on the device: input of the fit leg below
+    # with several ranks every rank finalises and downloads ITS share of the classes (shard_output): the
+    # ranks' host buffers together hold the job's result, nothing is computed or copied twice
+    sharded = world > 1
+    probe = S.class_statistics(X, y, group=group, shard_output=sharded)
+    keys = ("means", "covariances", "second_moments")
+    out_h = [{key: torch.empty(probe[key].shape, dtype=probe[key].dtype).pin_memory() for key in keys}
+             for _ in range(nbuf)]
+    del probe
     Xd, yd = [torch.empty_like(X) for _ in range(nbuf)], [torch.empty_like(y) for _ in range(nbuf)]
-    del stats
 
     def upload(i):  # step i's inputs, pinned host -> device, on the stream of its buffer set
         b = i % nbuf
@@ -529,9 +536,9 @@ def run_ours(args):
     def compute_and_download(i):
         b = i % nbuf
         with torch.cuda.stream(streams[b]):
-            st = S.class_statistics(Xd[b], yd[b], group=group)
-            for key, v in st.items():
-                out_h[b][key].copy_(v, non_blocking=True)
+            st = S.class_statistics(Xd[b], yd[b], group=group, shard_output=sharded)
+            for key in keys:
+                out_h[b][key].copy_(st[key], non_blocking=True)
         return st
 
     def e2e_run(k):
@@ -559,14 +566,16 @@ def run_ours(args):
         sync_all()
         e2e_ms.append(e0.elapsed_time(e1))
     e2e_med = sorted(e2e_ms)[1]
-    stats = {key: v.to(dev) for key, v in out_h[(e2e_steps - 1) % nbuf].items()}
     ems = torch.tensor([e2e_med], device=dev)
+    nbytes = torch.tensor([Xh.numel() * 4 + yh.numel() * 8, sum(v.numel() * 4 for v in out_h[0].values())],
+                          dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nbytes)  # whole-job bytes per step: all ranks' uploads and downloads
     e2e_value = n * world * e2e_steps / (float(ems) * 1e-3)
-    h2d = Xh.numel() * 4 + yh.numel() * 8
-    d2h = sum(v.numel() * 4 for v in out_h[0].values())
-    del last, Xd, yd
+    h2d, d2h = int(nbytes[0]), int(nbytes[1])
+    del last, Xd, yd, out_h
+    stats = stats_full
 
     gc.enable()
     peaks = load_peaks()
@@ -578,7 +587,7 @@ def run_ours(args):
     tf32_peak = max(tf32_cublas, peaks["bf16_tflops"] / 2.0)
     # ---- second hot path on the headline config: SQFA fit on the statistics just computed
     fit = fit_leg(stats, d, c, k, dev, None, 1, peaks, n_eval=50, epochs=5, label="configs[1]") if rank == 0 else None
-    del stats, out_h
+    del stats, stats_full
     torch.cuda.empty_cache()
     # ---- second hot path on configs[3] (C = 1000): all ranks, pair list sharded when world > 1
     n4, d4, c4, k4 = CONFIGS["c4"]
@@ -632,7 +641,8 @@ def run_ours(args):
                    "parallelism": PARALLELISM_NOTE.format(world=world) if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "repetitions_ms": [round(x, 2) for x in e2e_ms], "reported": "median repetition",
-                "overlap": f"{nbuf} CUDA streams / buffer sets, inputs of step i+1 uploaded while step i computes and downloads"},
+                "overlap": f"{nbuf} CUDA streams / buffer sets, inputs of step i+1 uploaded while step i computes and downloads",
+                "bytes": "whole job (all ranks); with N > 1 every rank downloads its share of the classes"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "fit": fit, "fit_c4": fit_c4,
         "hp1_table": table, "tf32_peak_measured_tflops": tf32_cublas,

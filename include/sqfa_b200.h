@@ -108,6 +108,16 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
  *              the accumulator truncation bias of the tensor core.
  *   n          number of rows of X (sizes the K split of small problems; no rows beyond the
  *              class offsets are read)
+ *   done, n_groups, reserve_sms
+ *              overlap of a multi-device caller's collective with this kernel: with done != NULL
+ *              (int32 [n_groups], zeroed by the caller) the jobs run in class order, classes are
+ *              split into n_groups contiguous groups (class c belongs to group c n_groups / n_classes)
+ *              and done[g] is incremented once per (job, CTA, epilogue warp) after the job's tile has
+ *              been stored and fenced; when done[g] reaches sqfa_class_gram_group_signals(..., g)
+ *              all tiles of group g are final, so a stream memory operation (cuStreamWaitValue32)
+ *              on ANOTHER stream can release the all-reduce of that group's slice of gram while this
+ *              kernel still computes the next groups. reserve_sms SMs are left out of the grid for
+ *              that collective's kernels. done == NULL: largest class first, all SMs.
  *   ws         sqfa_class_gram_workspace_bytes(n, n_dim, n_classes) bytes (device-side job plan). */
 size_t sqfa_class_gram_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes);
 size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes);
@@ -116,21 +126,12 @@ size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes);
 int64_t sqfa_gram_executed_tile_area(int32_t n_dim);
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
-                    void* ws, size_t ws_bytes, sqfa_stream_t stream);
-
-/* The Gram fused with its all-reduce over NVSwitch: every finished 256 x 256 tile is added with
- * multimem.red (16 bytes per instruction) through `gram_multicast` -- the multicast alias of a
- * buffer that exists at the same offset on every device of the group (e.g. torch symmetric
- * memory) -- so each device's copy receives the partial sums of all devices while the tensor cores
- * are still working on the next tiles; no separate collective. Packed tile layout
- * (sqfa_gram_packed_floats). `gram_local` is this device's own mapping of the same buffer (only
- * used for address arithmetic). The CALLER zero-fills every device's buffer and makes sure (a
- * barrier or any collective) that all devices have done so before any of them calls this, and
- * synchronises the devices again before anyone reads the sums. */
-int sqfa_class_gram_multicast(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                              const float* shift, int64_t n, int32_t n_dim, int32_t n_classes, float* gram_local,
-                              float* gram_multicast, int chain_rows, void* ws, size_t ws_bytes,
-                              sqfa_stream_t stream);
+                    int32_t* done, int32_t n_groups, int32_t reserve_sms, void* ws, size_t ws_bytes,
+                    sqfa_stream_t stream);
+int64_t sqfa_class_gram_group_signals(int64_t n, int32_t n_dim, int32_t n_classes, int32_t n_groups, int32_t group);
+/* Enqueue on `stream` a wait until *flag >= value (device memory; cuStreamWaitValue32): what gates a
+ * collective on the counters above. No kernel is launched, no SM is occupied while waiting. */
+int sqfa_stream_wait_geq(sqfa_stream_t stream, const int32_t* flag, int32_t value);
 
 /* Statistics epilogue (statistics.py:43-47, 84-93, 116, 120-122):
  *   cov[c] = (gram[c] - n_c d d^T) / (n_c - ddof),  d = means[c] - shift[c]  (shift NULL -> d = 0)

@@ -40,14 +40,13 @@ SIGNATURES = {
     "sqfa_class_gram_workspace_bytes": (c_size, [c_i64, c_i32, c_i32]),
     "sqfa_class_gram": (
         c_int,
-        [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_size, c_ptr],
+        [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_i32, c_i32, c_ptr,
+         c_size, c_ptr],
     ),
+    "sqfa_class_gram_group_signals": (c_i64, [c_i64, c_i32, c_i32, c_i32, c_i32]),
+    "sqfa_stream_wait_geq": (c_int, [c_ptr, c_ptr, c_i32]),
     "sqfa_gram_packed_floats": (c_size, [c_i32, c_i32]),
     "sqfa_gram_executed_tile_area": (c_i64, [c_i32]),
-    "sqfa_class_gram_multicast": (
-        c_int,
-        [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_int, c_ptr, c_size, c_ptr],
-    ),
     "sqfa_stats_epilogue_workspace_bytes": (c_size, [c_i32]),
     "sqfa_stats_epilogue": (
         c_int,

@@ -3,11 +3,18 @@ samples are sharded over the ranks of a process group -- the collectives between
 
 Per-class (count, sum x, sum (x - mu)(x - mu)^T) are additive over samples, so every rank
 processes its own rows and three all-reduces make the result global:
-max label -> n_classes, [class sums | class counts] -> global means, Gram partials -> global
-covariances. The local steps are supplied by an `ops` object: `CudaStatsOps` (the sm_100a kernels
-through the C ABI) in the product; the CPU test-suite injects oracle-backed ops to exercise this
-host logic under the gloo backend.
+max label -> n_classes, [class sums | class counts] in ONE buffer -> global means, Gram partials ->
+global covariances. The Gram all-reduce (the only large one) is OVERLAPPED with the Gram kernel: the
+kernel runs its jobs in class order and bumps a device counter per class group when the group's tiles
+are final; a side stream waits on each counter with a stream memory operation (no SM occupied) and
+all-reduces that group's slice of the packed Gram while the tensor cores work on the next groups (a
+few SMs are left out of the Gram grid for NCCL's kernels). The local steps are supplied by an `ops`
+object: `CudaStatsOps` (the sm_100a kernels through the C ABI) in the product; the CPU test-suite
+injects oracle-backed ops to exercise this host logic under the gloo backend.
 """
+
+import ctypes
+import os
 
 import torch
 
@@ -66,10 +73,10 @@ class CudaStatsOps:
         )
         return perm[:n], offsets, counts
 
-    def class_sums(self, X, perm, offsets, C):
+    def class_sums(self, X, perm, offsets, C, out=None):
         lib, dev = self.lib, X.device
         n, D = X.shape
-        sums = torch.empty(C, D, dtype=torch.float32, device=dev)
+        sums = torch.empty(C, D, dtype=torch.float32, device=dev) if out is None else out
         ws_bytes = lib.sqfa_class_sums_workspace_bytes(n, D, C)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         _lib.check(
@@ -113,11 +120,12 @@ class CudaStatsOps:
     def packed_is_smaller(self, D, C):
         return self.lib.sqfa_gram_packed_floats(D, C) < C * D * D  # padding to 256 can outweigh the triangle
 
-    def class_gram(self, X, perm, offsets, centre, C, packed=False):
+    def class_gram(self, X, perm, offsets, centre, C, packed=False, done=None, n_groups=0, reserve_sms=0):
         """Upper triangle of sum_{i in c} (x_i - centre_c)(x_i - centre_c)^T per class (tcgen05).
 
         packed=True returns the flat list of 256 x 256 upper tiles (what ranks all-reduce: about
-        half the bytes of (C, D, D)); `finalize(..., packed=True)` consumes it."""
+        half the bytes of (C, D, D)); `finalize(..., packed=True)` consumes it. `done` (int32
+        [n_groups], zeroed): completion counters per class group, see sqfa_class_gram."""
         lib, dev = self.lib, X.device
         n, D = X.shape
         if packed:
@@ -132,7 +140,8 @@ class CudaStatsOps:
         _lib.check(
             lib.sqfa_class_gram(
                 _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), n, D, C,
-                _lib.ptr(gram), 2 if packed else 0, 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+                _lib.ptr(gram), 2 if packed else 0, 0, _lib.ptr(done), n_groups, reserve_sms, _lib.ptr(ws), ws_bytes,
+                _lib.stream_ptr(dev),
             ),
             "sqfa_class_gram",
         )
@@ -141,73 +150,75 @@ class CudaStatsOps:
             self.gram_events.append(ev)
         return gram
 
-    def multicast_buffer(self, group, C, D, dev):
-        """(buffer, symmetric-memory handle) for the fused Gram + all-reduce: a packed-Gram buffer that
-        sits at the same offset on every rank, with an NVSwitch multicast alias; None unless enabled
-        (SQFA_GRAM_MULTICAST=1) and supported by the platform. Collective: every rank of the group calls it
-        with the same arguments. The buffers are cached per (group, size)."""
-        import os
-
+    def class_gram_overlapped(self, X, perm, offsets, centre, C, group):
+        """Packed Gram partials of this rank, all-reduced over `group` WHILE the kernel runs: classes are
+        split into groups; a side stream waits (stream memory operation) until the kernel has finished a
+        group and all-reduces that group's slice. Returns the reduced packed buffer, valid on the
+        current stream."""
         import torch.distributed as dist
-
-        # Opt-in (SQFA_GRAM_MULTICAST=1). Measured on 2 B200s at c2: 4.39 ms per step against 2.85 ms
-        # with the packed NCCL all-reduce -- the 16-byte multimem.red instructions issued by the four
-        # epilogue warps per CTA are latency-limited and hold up the accumulator hand-over; a bulk
-        # (TMA-sized) push is what this path needs before it can be the default (DESIGN.md section 8).
-        if os.environ.get("SQFA_GRAM_MULTICAST") != "1" or dist.get_world_size(group) < 2:
-            return None
-        numel = self.lib.sqfa_gram_packed_floats(D, C)
-        cache = self.__dict__.setdefault("_mc_cache", {})
-        key = (id(group), numel)
-        if key not in cache:
-            entry = None
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-
-                buf = symm_mem.empty(numel, dtype=torch.float32, device=dev)
-                hdl = symm_mem.rendezvous(buf, group.group_name)
-                ok = int(hdl.multicast_ptr) != 0
-                entry = (buf, hdl)
-            except Exception:  # no symmetric memory on this platform / backend
-                ok = False
-            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # all ranks take the same path
-            cache[key] = entry if int(flag.item()) == 1 else None
-        return cache[key]
-
-    def class_gram_multicast(self, X, perm, offsets, centre, C, buf, multicast_ptr):
-        """This rank's Gram partials, added tile by tile into every rank's `buf` through NVSwitch."""
-        import ctypes
 
         lib, dev = self.lib, X.device
         n, D = X.shape
-        ws_bytes = lib.sqfa_class_gram_workspace_bytes(n, D, C)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(
-            lib.sqfa_class_gram_multicast(
-                _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), n, D, C, _lib.ptr(buf),
-                ctypes.c_void_p(int(multicast_ptr)), 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
-            ),
-            "sqfa_class_gram_multicast",
-        )
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_side", None) is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        G = max(1, min(C, int(os.environ.get("SQFA_GRAM_GROUPS", "5"))))
+        reserve = int(os.environ.get("SQFA_GRAM_RESERVE_SMS", "8"))
+        done = torch.zeros(G, dtype=torch.int32, device=dev)
+        zeroed = torch.cuda.Event()
+        zeroed.record(main)
+        gram = self.class_gram(X, perm, offsets, centre, C, packed=True, done=done, n_groups=G, reserve_sms=reserve)
+        per_class = gram.numel() // C
+        side.wait_event(zeroed)  # the counters are zero before the side stream looks at them
+        gram.record_stream(side)
+        done.record_stream(side)
+        lo = 0
+        for g in range(G):
+            hi = lo
+            while hi < C and (hi * G) // C == g:
+                hi += 1
+            expected = lib.sqfa_class_gram_group_signals(n, D, C, G, g)
+            _lib.check(
+                lib.sqfa_stream_wait_geq(ctypes.c_void_p(side.cuda_stream),
+                                         ctypes.c_void_p(done.data_ptr() + 4 * g), int(expected)),
+                "sqfa_stream_wait_geq",
+            )
+            with torch.cuda.stream(side):
+                dist.all_reduce(gram[lo * per_class : hi * per_class], group=group)
+            lo = hi
+        main.wait_stream(side)
+        return gram
 
-    def finalize(self, gram, means, counts, estimator_id, ddof, want_sm, packed=False):
-        """cov (in place over gram unless it is packed; mirrored), optional OAS shrinkage, second moments."""
+    def finalize(self, gram, means, counts, estimator_id, ddof, want_sm, packed=False, class_range=None):
+        """cov (in place over gram unless it is packed; mirrored), optional OAS shrinkage, second moments.
+        `class_range` (c0, c1): only those classes (a rank finalising its share of a sharded result)."""
         lib, dev = self.lib, gram.device
         C, D = means.shape
-        cov = torch.empty(C, D, D, dtype=torch.float32, device=dev) if packed else gram
-        sm = torch.empty(C, D, D, dtype=torch.float32, device=dev) if want_sm else None
-        ws_bytes = lib.sqfa_stats_epilogue_workspace_bytes(C)
+        c0, c1 = (0, C) if class_range is None else class_range
+        nc = c1 - c0
+        if packed:
+            per_class = gram.numel() // max(C, 1)
+            gram_part = gram[c0 * per_class : c1 * per_class]
+            cov = torch.empty(nc, D, D, dtype=torch.float32, device=dev)
+        else:
+            gram_part = gram[c0:c1]
+            cov = gram_part
+        sm = torch.empty(nc, D, D, dtype=torch.float32, device=dev) if want_sm else None
+        if nc == 0:
+            return cov, sm
+        means_part, counts_part = means[c0:c1], counts[c0:c1]
+        ws_bytes = lib.sqfa_stats_epilogue_workspace_bytes(nc)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(
             lib.sqfa_stats_epilogue(
-                _lib.ptr(gram), _lib.ptr(means), None, _lib.ptr(counts), D, C, estimator_id | (16 if packed else 0),
-                ddof, _lib.ptr(cov), _lib.ptr(sm), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+                _lib.ptr(gram_part), _lib.ptr(means_part), None, _lib.ptr(counts_part), D, nc,
+                estimator_id | (16 if packed else 0), ddof, _lib.ptr(cov), _lib.ptr(sm), _lib.ptr(ws), ws_bytes,
+                _lib.stream_ptr(dev),
             ),
             "sqfa_stats_epilogue",
         )
         return cov, sm
-
 
     def fused(self, X, y, C, estimator_id, ddof, want_sm):
         """All local steps from ONE C call (sqfa_class_statistics): no host work between kernels."""
@@ -238,9 +249,19 @@ def _all_reduce(t, group, op=None):
     dist.all_reduce(t, op=op if op is not None else dist.ReduceOp.SUM, group=group)
 
 
-def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, ddof=1, centre=None, want_sm=True):
+_COUNT_BASE = 1 << 20  # class counts travel as two float32 (hi, lo) next to the class sums: exact below 2^44
+
+
+def class_share(n_classes, rank, world):
+    """Contiguous range of classes whose statistics `rank` finalises when the output is sharded."""
+    return (n_classes * rank) // world, (n_classes * (rank + 1)) // world
+
+
+def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, ddof=1, centre=None, want_sm=True,
+                         shard_output=False):
     """means, covariances, second moments of the labeled rows; with `group`, of the union of the
-    rows held by all ranks (every rank returns the full global result).
+    rows held by all ranks (every rank returns the full global result, or -- `shard_output` -- the
+    means of all classes and the covariances / second moments of its `class_share`).
 
     Two passes over the local rows, like the reference (mean first, then the Gram of the centred
     rows, statistics.py:118-120). `centre` (C, D) overrides the centring vectors.
@@ -266,37 +287,46 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
     ):
         return ops.fused(X, y, C, estimator_id, ddof, want_sm)
     perm, offsets, counts = ops.bucket(y, C)
-    mc = None
-    if group is not None and centre is None and getattr(ops, "multicast_buffer", None) is not None:
-        mc = ops.multicast_buffer(group, C, X.shape[1], X.device)
-        if mc is not None:
-            # zero-filled BEFORE the all-reduce below: that collective cannot complete anywhere until
-            # every rank has contributed, i.e. has passed this point in its stream
-            mc[0].zero_()
-    sums = ops.class_sums(X, perm, offsets, C)
-    class_counts = counts[:C].clone()
+    D = X.shape[1]
     if group is not None:
-        _all_reduce(sums, group)
-        _all_reduce(class_counts, group)
+        # ONE small collective: [class sums | counts / 2^20 | counts mod 2^20] in the dtype of the sums
+        small = torch.empty(C * D + 2 * C, dtype=X.dtype, device=X.device)
+        sums = small[: C * D].view(C, D)
+        local_sums = ops.class_sums(X, perm, offsets, C, out=sums)
+        if local_sums is not sums:  # ops without an `out` argument
+            sums.copy_(local_sums)
+        local = counts[:C]
+        small[C * D : C * D + C] = torch.div(local, _COUNT_BASE, rounding_mode="floor").to(X.dtype)
+        small[C * D + C :] = torch.remainder(local, _COUNT_BASE).to(X.dtype)
+        _all_reduce(small, group)
+        class_counts = (small[C * D : C * D + C].round().to(torch.int64) * _COUNT_BASE
+                        + small[C * D + C :].round().to(torch.int64))
+    else:
+        sums = ops.class_sums(X, perm, offsets, C)
+        class_counts = counts[:C].clone()
     means = ops.class_means(sums, class_counts)
     shift = means if centre is None else centre
-    if mc is not None:
-        # Gram fused with its all-reduce: every finished tile is multimem.red-added into the copy of
-        # every rank while the tensor cores work on the next one; one barrier, no collective
-        buf, hdl = mc
-        ops.class_gram_multicast(X, perm, offsets, shift, C, buf, hdl.multicast_ptr)
-        hdl.barrier()
-        cov, sm = ops.finalize(buf, means, class_counts, estimator_id, ddof, want_sm, packed=True)
-    elif group is not None and getattr(ops, "supports_packed", False) and ops.packed_is_smaller(X.shape[1], C):
-        # the one large collective: partial Gram sums over NVLink, upper 256 x 256 tiles only
+    class_range = None
+    if group is not None and shard_output:
+        import torch.distributed as dist
+
+        class_range = class_share(C, dist.get_rank(group), dist.get_world_size(group))
+    extra = {} if class_range is None else {"class_range": class_range}
+    packed_ok = group is not None and getattr(ops, "supports_packed", False) and ops.packed_is_smaller(D, C)
+    overlap = getattr(ops, "class_gram_overlapped", None) is not None and getattr(ops, "gram_events", None) is None
+    if packed_ok and overlap and os.environ.get("SQFA_GRAM_OVERLAP", "1") != "0":
+        # the one large collective, hidden behind the kernel that produces its input
+        gram = ops.class_gram_overlapped(X, perm, offsets, shift, C, group)
+        cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm, packed=True, **extra)
+    elif packed_ok:
         gram = ops.class_gram(X, perm, offsets, shift, C, packed=True)
         _all_reduce(gram, group)
-        cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm, packed=True)
+        cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm, packed=True, **extra)
     else:
         gram = ops.class_gram(X, perm, offsets, shift, C)
         if group is not None:
             _all_reduce(gram, group)
-        cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm)
+        cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm, **extra)
     return means, cov, sm, (perm, offsets, counts)
 
 

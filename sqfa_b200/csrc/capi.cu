@@ -109,9 +109,11 @@ size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes) {
 
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
-                    void* ws, size_t ws_bytes, sqfa_stream_t stream) {
+                    int32_t* done, int32_t n_groups, int32_t reserve_sms, void* ws, size_t ws_bytes,
+                    sqfa_stream_t stream) {
   if (n_dim <= 0 || n_classes < 0 || offsets == nullptr || gram == nullptr || ws == nullptr || ldx < n_dim ||
-      X == nullptr || perm == nullptr || (accumulate & ~(SQFA_GRAM_ACCUMULATE | SQFA_GRAM_PACKED)))
+      X == nullptr || perm == nullptr || (accumulate & ~(SQFA_GRAM_ACCUMULATE | SQFA_GRAM_PACKED)) ||
+      (done != nullptr && (n_groups <= 0 || n_groups > n_classes)) || reserve_sms < 0)
     return fail_arg(__func__, "bad argument");
   if (n < 0) return fail_arg(__func__, "bad argument");
   if (ws_bytes < sqfa_class_gram_workspace_bytes(n, n_dim, n_classes))
@@ -120,26 +122,40 @@ int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int6
     return fail_arg(__func__, "too many (class, tile) jobs", SQFA_E_UNSUPPORTED);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail_arg(__func__, "no CUDA device");
-  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram, nullptr,
+  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram,
                                                 accumulate & SQFA_GRAM_ACCUMULATE, accumulate & SQFA_GRAM_PACKED,
-                                                chain_rows, ws, sms, S(stream)));
+                                                chain_rows, done, n_groups, reserve_sms, ws, sms, S(stream)));
 }
 
-int sqfa_class_gram_multicast(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                              const float* shift, int64_t n, int32_t n_dim, int32_t n_classes, float* gram_local,
-                              float* gram_multicast, int chain_rows, void* ws, size_t ws_bytes,
-                              sqfa_stream_t stream) {
-  if (n_dim <= 0 || n_classes < 0 || n < 0 || offsets == nullptr || gram_local == nullptr ||
-      gram_multicast == nullptr || ws == nullptr || ldx < n_dim || X == nullptr || perm == nullptr)
-    return fail_arg(__func__, "bad argument");
-  if (ws_bytes < sqfa_class_gram_workspace_bytes(n, n_dim, n_classes))
-    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
-  if ((int64_t)n_classes * sqfa::gram_tiles_per_class(n_dim, nullptr) > (1ll << 30) / 4096)
-    return fail_arg(__func__, "too many (class, tile) jobs", SQFA_E_UNSUPPORTED);
+int64_t sqfa_class_gram_group_signals(int64_t n, int32_t n_dim, int32_t n_classes, int32_t n_groups, int32_t group) {
+  if (n_dim <= 0 || n_classes <= 0 || n_groups <= 0 || n_groups > n_classes || group < 0 || group >= n_groups) return 0;
   const int sms = sm_count_cached();
-  if (sms <= 0) return fail_arg(__func__, "no CUDA device");
-  return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram_local,
-                                                gram_multicast, 1, 1, chain_rows, ws, sms, S(stream)));
+  const int64_t ks = sqfa::gram_ksplit(n < 0 ? 0 : n, n_classes, n_dim, sms > 0 ? sms : 148);
+  int64_t classes = 0;  // classes c with c * n_groups / n_classes == group
+  for (int c = 0; c < n_classes; ++c) classes += ((int64_t)c * n_groups) / n_classes == group ? 1 : 0;
+  return classes * sqfa::gram_tiles_per_class(n_dim, nullptr) * ks * 8;  // 2 CTAs x 4 epilogue warps per job
+}
+
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (no link dependency on libcuda)
+int sqfa_stream_wait_geq(sqfa_stream_t stream, const int32_t* flag, int32_t value) {
+  if (flag == nullptr) return fail_arg(__func__, "bad argument");
+  typedef int (*wait_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+  static wait_fn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || p == nullptr || q != cudaDriverEntryPointSuccess)
+      return fail_arg(__func__, "cuStreamWaitValue32 is not available", SQFA_E_UNSUPPORTED);
+    fn = reinterpret_cast<wait_fn>(p);
+  }
+  const int rc = fn(S(stream), (unsigned long long)reinterpret_cast<uintptr_t>(flag), (unsigned int)value,
+                    0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+  if (rc != 0) {
+    snprintf(g_err, sizeof(g_err), "%s: cuStreamWaitValue32 failed with CUresult %d", __func__, rc);
+    return 1000 + rc;
+  }
+  return 0;
 }
 
 size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes) {
@@ -375,7 +391,8 @@ int sqfa_class_statistics(const float* X, int64_t ldx, const int64_t* labels, in
   if (rc) return rc;
   rc = sqfa_class_means(sums, counts, nullptr, n_dim, n_classes, means, stream);
   if (rc) return rc;
-  rc = sqfa_class_gram(X, ldx, perm, offsets, means, n, n_dim, n_classes, cov, 0, 0, ws_gram, w.gram, stream);
+  rc = sqfa_class_gram(X, ldx, perm, offsets, means, n, n_dim, n_classes, cov, 0, 0, nullptr, 0, 0, ws_gram, w.gram,
+                       stream);
   if (rc) return rc;
   return sqfa_stats_epilogue(cov, means, nullptr, counts, n_dim, n_classes, estimator, ddof, cov, sm, ws_epi, w.epi,
                              stream);

@@ -81,7 +81,9 @@ struct GramParams {
   const int64_t* offsets;
   const float* shift;
   float* gram;
-  float* mc_gram;    // NVSwitch multicast alias of gram (packed layout): tiles are multimem.red-added into every device's copy
+  int32_t* done;     // optional completion counters: done[c G / C] += 1 per (job, CTA, epilogue warp) once the
+  int n_groups;      //   job's tile is stored -- a collective on another stream can be gated on a class group
+  int class_order;   // jobs in class order (so class groups finish in order) instead of largest class first
   const int4* jobs;  // (class, tile row, tile col, K part)
   int njobs;
   int D, C, KS;
@@ -98,12 +100,12 @@ struct GramParams {
 // Job list: classes in descending size, tiles of a class adjacent (they share the gathered rows
 // in L2), K parts innermost.  job = ((rank * T) + t) * KS + ks
 __global__ void __launch_bounds__(1024) gram_plan_kernel(const int64_t* __restrict__ offsets, int C, int TT, int KS,
-                                                          int4* __restrict__ jobs) {
+                                                          int class_order, int4* __restrict__ jobs) {
   const int T = TT * (TT + 1) / 2;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int64_t n_c = offsets[c + 1] - offsets[c];
-    int rank = 0;
-    for (int o = 0; o < C; ++o) {
+    int rank = class_order ? c : 0;
+    for (int o = 0; o < C && !class_order; ++o) {
       const int64_t n_o = offsets[o + 1] - offsets[o];
       rank += (n_o > n_c || (n_o == n_c && o < c)) ? 1 : 0;
     }
@@ -390,6 +392,16 @@ gram_tf32x3_kernel(const GramParams P) {
     const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16);
     const uint32_t acc_empty0 = mapa_u32(smem_u32(&acc_empty_bar), 0);
     uint32_t acc_phase = 0;
+    // job finished as far as this warp is concerned: its stores are visible device-wide before the
+    // group's counter moves (a collective on another stream waits for the counter with a stream
+    // memory operation and then reads the tiles)
+    auto signal_done = [&](int c) {
+      if (P.done != nullptr) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(P.done + (int)(((int64_t)c * P.n_groups) / P.C), 1);
+      }
+    };
     for (int j = pair; j < P.njobs; j += npairs) {
       const JobGeom g = decode_job(P, j);
       // TMEM lane i = 32 q + lane is operand slot i of this CTA -> tile row 4 (i % 32) + i / 32
@@ -408,6 +420,7 @@ gram_tf32x3_kernel(const GramParams P) {
         if (!P.atomic_out && row < D)
           for (int cc = 0; cc < TN2; ++cc)
             if (g.n0 + cc < D) grow[g.n0 + cc] = 0.f;
+        signal_done(g.c);
         continue;
       }
       bool first = true;
@@ -457,7 +470,6 @@ gram_tf32x3_kernel(const GramParams P) {
           // Last chain of the tile: main + running sum + cross terms -> output, 16 bytes at a time.
           // Tile columns 4 s .. 4 s + 3 are accumulator columns s, 32 + s, 64 + s, 96 + s of a
           // 128-column half (the slot permutation), so one chunk reads 4 slots from each quarter.
-          float* const mcrow = P.mc_gram != nullptr ? P.mc_gram + (grow - P.gram) : nullptr;
 #pragma unroll 1
           for (int ch = 0; ch < 16; ++ch) {  // 4 slots from each quarter per chunk (register budget of this role)
             const int half = ch >> 3, s0 = 4 * (ch & 7);
@@ -490,8 +502,7 @@ gram_tf32x3_kernel(const GramParams P) {
                 if (cidx < D) {  // D % 4 == 0: the four columns are all inside
                   const float4 v = make_float4(__uint_as_float(m[0][jj]), __uint_as_float(m[1][jj]),
                                                __uint_as_float(m[2][jj]), __uint_as_float(m[3][jj]));
-                  if (mcrow != nullptr) multimem_red_add_v4(mcrow + cidx, v);
-                  else if (P.atomic_out) red_add_v4(grow + cidx, v);
+                  if (P.atomic_out) red_add_v4(grow + cidx, v);
                   else *reinterpret_cast<float4*>(grow + cidx) = v;
                 }
               }
@@ -522,13 +533,11 @@ gram_tf32x3_kernel(const GramParams P) {
               // accumulator column n = 128 (n / 128) + slot  ->  tile column 128 (n / 128) + 4 (slot % 32) + slot / 32:
               // the 16 columns of this chunk are 16 bytes apart in the output row
               const int gc = g.n0 + (col0 & 128) + 4 * (col0 & 31) + ((col0 & 127) >> 5);
-              float* const mcrow = P.mc_gram != nullptr ? P.mc_gram + (grow - P.gram) : nullptr;
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) {
                 const int cidx = gc + 4 * jj;
                 if (cidx < D) {
-                  if (mcrow != nullptr) multimem_red_add_f32(mcrow + cidx, __uint_as_float(v[jj]));
-                  else if (P.atomic_out) atomicAdd(grow + cidx, __uint_as_float(v[jj]));
+                  if (P.atomic_out) atomicAdd(grow + cidx, __uint_as_float(v[jj]));
                   else grow[cidx] = __uint_as_float(v[jj]);
                 }
               }
@@ -537,6 +546,7 @@ gram_tf32x3_kernel(const GramParams P) {
         }
         first = false;
       }
+      signal_done(g.c);
     }
   }
 
@@ -579,8 +589,9 @@ size_t gram_workspace_bytes(int C, int D, int ksplit_max) {
 }
 
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                               const float* shift, int64_t n, int D, int C, float* gram, float* mc_gram, int accumulate,
-                               int packed, int chain_rows, void* ws, int num_sms, cudaStream_t stream) {
+                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate, int packed,
+                               int chain_rows, int32_t* done, int n_groups, int reserve_sms, void* ws, int num_sms,
+                               cudaStream_t stream) {
   static int smem_set[kMaxDevices] = {0};
   {
     cudaError_t e = ensure_dynamic_smem(gram_tf32x3_kernel, GRAM2_SMEM, smem_set);
@@ -590,28 +601,30 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
   GramParams P;
   int TT = 0;
   const int T = gram_tiles_per_class(D, &TT);
-  P.X = X; P.ldx = ldx; P.n = n; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram; P.mc_gram = mc_gram;
+  P.X = X; P.ldx = ldx; P.n = n; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram;
+  P.done = done; P.n_groups = n_groups > 0 ? n_groups : 1; P.class_order = done != nullptr ? 1 : 0;
   P.jobs = reinterpret_cast<const int4*>(ws);
   P.D = D; P.C = C;
   P.KS = gram_ksplit(n, C, D, num_sms);
   P.njobs = C * T * P.KS;
   const int cr = chain_rows > 0 ? chain_rows : 512;
   P.chain_kb = (cr + BK - 1) / BK;
-  P.atomic_out = (accumulate || P.KS > 1 || mc_gram != nullptr) ? 1 : 0;
+  P.atomic_out = (accumulate || P.KS > 1) ? 1 : 0;
   P.packed = packed ? 1 : 0; P.T = T; P.TT = TT;
   P.vec_ok = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(gram) & 15) == 0);
   static const int env_flags = [] { const char* e = getenv("SQFA_GRAM_FLAGS"); return e ? atoi(e) : 0; }();
   P.flags = env_flags;
   P.vecx = ((ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && !(env_flags & 4)) ? 1 : 0;
   if ((uint64_t)ldx * 4ull >= (1ull << 32)) return cudaErrorInvalidValue;
-  if (P.atomic_out && !accumulate && mc_gram == nullptr) {  // K parts are summed with red.add -> start from zero
-    // (multicast mode: the caller zero-fills every device's buffer before any device starts)
+  if (P.atomic_out && !accumulate) {  // K parts are summed with red.add -> start from zero
     const size_t floats = packed ? (size_t)C * T * TM2 * TN2 : (size_t)C * D * D;
     cudaError_t e = cudaMemsetAsync(gram, 0, floats * sizeof(float), stream);
     if (e != cudaSuccess) return e;
   }
-  gram_plan_kernel<<<1, 1024, 0, stream>>>(offsets, C, TT, P.KS, reinterpret_cast<int4*>(ws));
-  int grid = (num_sms / 2) * 2;
+  gram_plan_kernel<<<1, 1024, 0, stream>>>(offsets, C, TT, P.KS, P.class_order, reinterpret_cast<int4*>(ws));
+  // reserve_sms SMs are left to other streams (the collective that runs while this kernel still computes)
+  const int usable = num_sms - (reserve_sms > 0 ? reserve_sms : 0);
+  int grid = ((usable > 2 ? usable : 2) / 2) * 2;
   if (grid > 2 * P.njobs) grid = 2 * P.njobs;
   gram_tf32x3_kernel<<<grid, GRAM2_THREADS, GRAM2_SMEM, stream>>>(P);
   return cudaGetLastError();

@@ -315,7 +315,16 @@ class_prepare_kernel(const float* __restrict__ PsiPart, const float* __restrict_
   if (fr) {
     for (int r = lane; r < k; r += 32) {
       float a = 0.f;
-      for (int ch = 0; ch < nchunk; ++ch) a += MuPart[((int64_t)c * nchunk + ch) * k + r];
+      const float* mp_ = MuPart + (int64_t)c * nchunk * k + r;
+      int ch = 0;
+      for (; ch + 8 <= nchunk; ch += 8) {
+        float u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u[q] = mp_[(int64_t)(ch + q) * k];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a += u[q];
+      }
+      for (; ch < nchunk; ++ch) a += mp_[(int64_t)ch * k];
       mus[r] = a;
       Mu[(int64_t)c * k + r] = a;
     }
@@ -327,7 +336,16 @@ class_prepare_kernel(const float* __restrict__ PsiPart, const float* __restrict_
     if (r < k && s < k) {
       v = 0.f;
       const float* pp = PsiPart + (int64_t)c * nchunk * k * k + r * k + s;
-      for (int ch = 0; ch < nchunk; ++ch) v += pp[(int64_t)ch * k * k];
+      const int kk = k * k;
+      int ch = 0;
+      for (; ch + 8 <= nchunk; ch += 8) {  // eight loads in flight, added in chunk order
+        float u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u[q] = pp[(int64_t)(ch + q) * kk];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += u[q];
+      }
+      for (; ch < nchunk; ++ch) v += pp[(int64_t)ch * kk];
       if (r == s) v += noise;
       if (fr) v += mus[r] * mus[s];
     } else if (r == k && s == k) {
@@ -501,7 +519,8 @@ pair_ai_kernel(const PairArgs A) {
 // which stays in use for 32 < m <= 64.
 // ------------------------------------------------------------------------------------------------
 template <int MP, int MJ>  // MP: padded size (multiple of 4, shared-memory strides); MJ: even m, the Jacobi width
-__global__ void __launch_bounds__(PAIR_WARPS * 32)
+// 6 blocks of 4 warps per SM: the kernel is issue-bound and needs the warps to hide shuffle / MUFU latency
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 6)
 pair_ai_reg_kernel(const PairArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr int LDT = MP + 1;                                  // odd stride: conflict-free transposed access

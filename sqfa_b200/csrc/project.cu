@@ -233,47 +233,58 @@ constraint_fwd_kernel(const float* __restrict__ Wraw, int D, float* __restrict__
 //                             (autograd through constraints.py:37), none: grad[f] = dF[f];
 //   rows f < n_fixed get a zero gradient (FixedFilters detaches them, constraints.py:95-141),
 //   out[2] = max |grad| over all filters (atomicMax on the float bits; order-independent).
-__global__ void __launch_bounds__(256)
+constexpr int CF_THREADS = 1024;
+
+__device__ __forceinline__ float block_reduce_1024(float v, float* red, bool take_max) {
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = CF_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      red[threadIdx.x] = take_max ? fmaxf(red[threadIdx.x], red[threadIdx.x + o]) : red[threadIdx.x] + red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(CF_THREADS)
 closure_finish_kernel(const float* __restrict__ partial, int D, int k, int csplit, const float* __restrict__ F,
                       const float* __restrict__ inv_norm, int sphere, int n_fixed, float* __restrict__ grad,
                       float* __restrict__ out) {
-  __shared__ float red[256];
+  __shared__ float red[CF_THREADS];
   const int f = blockIdx.x;
   float* g = grad + (int64_t)f * D;
+  const int64_t sstride = (int64_t)k * D;
   float dot = 0.f;
-  for (int j = threadIdx.x; j < D; j += 256) {
+  for (int j = threadIdx.x; j < D; j += CF_THREADS) {
+    const float* p = partial + (int64_t)f * D + j;
     float a = 0.f;
-    for (int s = 0; s < csplit; ++s) a += partial[((int64_t)s * k + f) * D + j];
+    int s = 0;
+    for (; s + 8 <= csplit; s += 8) {  // eight loads in flight, added in split order
+      float u[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) u[q] = p[(int64_t)(s + q) * sstride];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a += u[q];
+    }
+    for (; s < csplit; ++s) a += p[(int64_t)s * sstride];
     g[j] = a;  // re-read below by the same thread
     if (sphere) dot += a * F[(int64_t)f * D + j];
   }
-  if (sphere) {
-    red[threadIdx.x] = dot;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
-    }
-    dot = red[0];
-    __syncthreads();
-  }
+  if (sphere) dot = block_reduce_1024(dot, red, false);
   const float inv = sphere ? inv_norm[f] : 1.f;
   float amax = 0.f;
-  for (int j = threadIdx.x; j < D; j += 256) {
+  for (int j = threadIdx.x; j < D; j += CF_THREADS) {
     float v = g[j];
     if (f < n_fixed) v = 0.f;
     else if (sphere) v = (v - dot * F[(int64_t)f * D + j]) * inv;
     g[j] = v;
     amax = fmaxf(amax, fabsf(v));
   }
-  red[threadIdx.x] = amax;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
-    __syncthreads();
-  }
+  amax = block_reduce_1024(amax, red, true);
   // NaN gradients: fmaxf drops NaN, the loss / non-finite counter carry that information
-  if (threadIdx.x == 0 && out != nullptr) atomicMax(reinterpret_cast<unsigned int*>(out + 2), __float_as_uint(red[0]));
+  if (threadIdx.x == 0 && out != nullptr) atomicMax(reinterpret_cast<unsigned int*>(out + 2), __float_as_uint(amax));
 }
 
 // dF[f][j] = sum_c ( sum_g (gPsi[c][f][g] + gPsi[c][g][f]) T[c][g][j] + gMu[c][f] M[c][j] )
@@ -578,12 +589,15 @@ int project_nchunk(int D) { return (D + PF_COLS - 1) / PF_COLS; }
 static size_t al64(size_t n) { return (n + 63) & ~size_t(63); }
 size_t project_psipart_floats(int C, int D, int k) { return al64((size_t)C * project_nchunk(D) * k * k); }
 size_t project_mupart_floats(int C, int D, int k) { return al64((size_t)C * project_nchunk(D) * k); }
+constexpr int PB_MAX_CSPLIT = 256;
 int project_bwd_csplit(int C, int D) {
-  int csplit = C < 64 ? (C > 0 ? C : 1) : 64;
-  // few column blocks -> more class splits are useful; many -> fewer
+  // enough (column block, class split) blocks to fill the GPU about 8 times over: every block walks its
+  // classes serially (one dependent round of loads per class), so short class lists hide latency
   const int colblocks = (D + 127) / 128;
-  while (csplit > 1 && colblocks * csplit > 2048) csplit >>= 1;
-  return csplit;
+  int csplit = (8 * 148 + colblocks - 1) / colblocks;
+  if (csplit > PB_MAX_CSPLIT) csplit = PB_MAX_CSPLIT;
+  if (csplit > C) csplit = C > 0 ? C : 1;
+  return csplit < 1 ? 1 : csplit;
 }
 
 // workspace (floats): [ row-split partials | PsiPart | MuPart ] for the forward, [ class-split partials ] for
@@ -591,7 +605,7 @@ int project_bwd_csplit(int C, int D) {
 size_t project_workspace_bytes(int C, int D, int k) {
   const size_t fwd = al64(project_partial_floats(C, D, k)) + project_psipart_floats(C, D, k) +
                      project_mupart_floats(C, D, k);
-  const size_t bwd = (size_t)64 * k * D;
+  const size_t bwd = (size_t)PB_MAX_CSPLIT * k * D;
   return (fwd > bwd ? fwd : bwd) * sizeof(float);
 }
 
@@ -652,7 +666,7 @@ cudaError_t launch_project_bwd_constrained(const float* gPsi, const float* gMu, 
   const int csplit = project_bwd_csplit(C, D);
   cudaError_t e = launch_project_bwd_partials(gPsi, gMu, T, M, C, D, k, ws, csplit, st);
   if (e != cudaSuccess) return e;
-  closure_finish_kernel<<<k, 256, 0, st>>>(ws, D, k, csplit, F, inv_norm, sphere, n_fixed, grad, out);
+  closure_finish_kernel<<<k, CF_THREADS, 0, st>>>(ws, D, k, csplit, F, inv_norm, sphere, n_fixed, grad, out);
   return cudaGetLastError();
 }
 

@@ -210,16 +210,6 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
-__device__ __forceinline__ void multimem_red_add_v4(float* mc, float4 v) {
-  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y),
-               "f"(v.z), "f"(v.w)
-               : "memory");
-}
-__device__ __forceinline__ void multimem_red_add_f32(float* mc, float v) {
-  asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
-}
-
-// Register reallocation between warp roles (warpgroup-aligned: all warps of a group of 4 execute it)
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));

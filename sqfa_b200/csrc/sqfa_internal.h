@@ -45,8 +45,9 @@ int64_t gram_executed_tile_area(int D);
 int gram_ksplit(int64_t n, int C, int D, int num_sms);
 size_t gram_workspace_bytes(int C, int D, int ksplit_max);
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
-                              const float* shift, int64_t n, int D, int C, float* gram, float* mc_gram, int accumulate,
-                              int packed, int chain_rows, void* ws, int num_sms, cudaStream_t stream);
+                              const float* shift, int64_t n, int D, int C, float* gram, int accumulate, int packed,
+                              int chain_rows, int32_t* done, int n_groups, int reserve_sms, void* ws, int num_sms,
+                              cudaStream_t stream);
 size_t gram_packed_floats(int D, int C);  // floats of the packed upper-tile list (256 x 256 tiles)
 // ---- umma_probe.cu (test hook) ----
 cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K, int N, int mode, uint32_t lbo,

@@ -68,7 +68,7 @@ def bucket_labels(labels, n_classes=None):
         return ops.bucket(y, int(n_classes))
 
 
-def class_statistics(points, labels, estimator="empirical", keep_on_device=False, group=None):
+def class_statistics(points, labels, estimator="empirical", keep_on_device=False, group=None, shard_output=False):
     """
     Compute the mean, covariance and second moment matrix of each class.
 
@@ -86,7 +86,13 @@ def class_statistics(points, labels, estimator="empirical", keep_on_device=False
         (extension) leave the result on the CUDA device even if `points` lives on the CPU.
     group : torch.distributed process group
         (extension) `points` / `labels` are this rank's shard of the samples; the statistics of the
-        union over all ranks are returned on every rank (three all-reduces, see _stats_driver).
+        union over all ranks are returned on every rank (three all-reduces, the large one overlapped
+        with the Gram kernel, see _stats_driver).
+    shard_output : bool
+        (extension, with `group`) every rank returns the means of all classes but the covariances and
+        second moments of ITS share of the classes only -- rows `class_range[0]:class_range[1]`, the
+        range is added to the dict as "class_range". The ranks' results together are the statistics;
+        nobody computes or moves the same matrix twice.
 
     Returns
     -------
@@ -105,10 +111,17 @@ def class_statistics(points, labels, estimator="empirical", keep_on_device=False
     if y.numel() == 0 and group is None:
         raise RuntimeError("class_statistics: empty input (max() of an empty labels tensor)")
     with torch.cuda.device(dev):
-        means, cov, sm, _ = run_class_statistics(_cuda_ops(), X, y, _ESTIMATORS[estimator], group=group)
+        means, cov, sm, _ = run_class_statistics(_cuda_ops(), X, y, _ESTIMATORS[estimator], group=group,
+                                                 shard_output=shard_output and group is not None)
     stats = {"means": means, "covariances": cov, "second_moments": sm}
     if out_dev != dev and not keep_on_device:
         stats = {k: v.to(out_dev) for k, v in stats.items()}
+    if shard_output and group is not None:
+        import torch.distributed as dist
+
+        from ._stats_driver import class_share
+
+        stats["class_range"] = class_share(means.shape[0], dist.get_rank(group), dist.get_world_size(group))
     return stats
 
 
@@ -189,7 +202,7 @@ class StreamingClassStatistics:
             ws = torch.empty(nb, dtype=torch.uint8, device=dev)
             _lib.check(
                 lib.sqfa_class_gram(_lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(self.shift),
-                                    n, D, C, _lib.ptr(self.gram), 1, 0, _lib.ptr(ws), nb, st),
+                                    n, D, C, _lib.ptr(self.gram), 1, 0, None, 0, 0, _lib.ptr(ws), nb, st),
                 "sqfa_class_gram",
             )
             self.counts += counts[:C]

@@ -25,8 +25,12 @@ class OracleStatsOps:
         offsets = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(counts, 0)])
         return perm, offsets, counts
 
-    def class_sums(self, X, perm, offsets, C):
-        return torch.stack([X[perm[offsets[c]:offsets[c + 1]].long()].sum(0) for c in range(C)])
+    def class_sums(self, X, perm, offsets, C, out=None):
+        sums = torch.stack([X[perm[offsets[c]:offsets[c + 1]].long()].sum(0) for c in range(C)])
+        if out is None:
+            return sums
+        out.copy_(sums)
+        return out
 
     def class_means(self, sums, counts):
         return sums / counts[:, None].to(sums.dtype)
@@ -38,9 +42,10 @@ class OracleStatsOps:
             out.append(Z.T @ Z)
         return torch.stack(out)
 
-    def finalize(self, gram, means, counts, estimator_id, ddof, want_sm):
-        cov = gram / (counts[:, None, None].to(gram.dtype) - ddof)
-        return cov, cov + means[:, :, None] * means[:, None, :]
+    def finalize(self, gram, means, counts, estimator_id, ddof, want_sm, class_range=None):
+        c0, c1 = (0, means.shape[0]) if class_range is None else class_range
+        cov = gram[c0:c1] / (counts[c0:c1, None, None].to(gram.dtype) - ddof)
+        return cov, cov + means[c0:c1, :, None] * means[c0:c1, None, :]
 
 
 def _worker(rank, world, port, ret):
@@ -59,6 +64,10 @@ def _worker(rank, world, port, ret):
     means, cov, sm, _ = run_class_statistics(OracleStatsOps(), X[lo:hi], y[lo:hi], 0, group=dist.group.WORLD)
     if rank == 0:
         ret["means"], ret["cov"], ret["sm"] = means, cov, sm
+    # sharded output: every rank finalises its share of the classes
+    means_s, cov_s, sm_s, _ = run_class_statistics(OracleStatsOps(), X[lo:hi], y[lo:hi], 0, group=dist.group.WORLD,
+                                                   shard_output=True)
+    ret[f"share{rank}"] = (means_s, cov_s, sm_s)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,6 +80,7 @@ def test_sharded_statistics_equal_unsharded():
         ret = mgr.dict()
         mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
         means, cov, sm = ret["means"], ret["cov"], ret["sm"]
+        shares = [ret["share0"], ret["share1"]]
     g = torch.Generator().manual_seed(1)
     X = torch.randn(1000, 7, generator=g, dtype=torch.float64) + 0.5
     y = torch.randint(0, 5, (1000,), generator=g)
@@ -81,3 +91,31 @@ def test_sharded_statistics_equal_unsharded():
     assert torch.allclose(means, ref["means"], rtol=1e-10, atol=1e-12)
     assert torch.allclose(cov, ref["covariances"], rtol=1e-9, atol=1e-12)
     assert torch.allclose(sm, ref["second_moments"], rtol=1e-9, atol=1e-12)
+    # the two ranks' shares, concatenated in rank order, are the full result (classes 0-1 | 2-4)
+    assert shares[0][1].shape[0] == 2 and shares[1][1].shape[0] == 3
+    assert torch.equal(shares[0][0], means) and torch.equal(shares[1][0], means)
+    assert torch.equal(torch.cat([shares[0][1], shares[1][1]]), cov)
+    assert torch.equal(torch.cat([shares[0][2], shares[1][2]]), sm)
+
+
+def test_pair_shards_cover_the_pair_list():
+    """shard_pairs: contiguous, disjoint, complete; cuts fall on rows that are multiples of 4."""
+    from sqfa_b200._ops import shard_pairs
+    from sqfa_b200._stats_driver import class_share
+
+    for C in (2, 5, 10, 19, 100, 1000):
+        P = C * (C - 1) // 2
+        for world in (1, 2, 3, 4, 8):
+            cuts = [shard_pairs(P, C, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == P
+            for (a0, a1), (b0, b1) in zip(cuts[:-1], cuts[1:]):
+                assert a1 == b0 and a0 <= a1
+            for b, e in cuts[:-1]:
+                i = int((1 + (1 + 8 * e) ** 0.5) / 2)  # e = i (i - 1) / 2 for a row i that is a multiple of 4
+                assert i * (i - 1) // 2 == e and (i % 4 == 0 or e == P or e == 0)
+            if C == 1000 and world == 8:  # balanced to a few percent
+                sizes = [e - b for b, e in cuts]
+                assert max(sizes) / min(sizes) < 1.1
+            shares = [class_share(C, r, world) for r in range(world)]
+            assert shares[0][0] == 0 and shares[-1][1] == C
+            assert all(a[1] == b[0] for a, b in zip(shares[:-1], shares[1:]))

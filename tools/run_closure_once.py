@@ -1,7 +1,10 @@
-"""A few fused closure evaluations at a BASELINE config (for ncu launch lists). Usage: run_closure_once.py c2 [reps]"""
+"""A few closure evaluations (the fitting loop's graph-free path) at a BASELINE config, for ncu launch
+lists / captures. Usage: run_closure_once.py c2 [reps] [graph]   (graph: allow CUDA-graph replay)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if not (len(sys.argv) > 3 and sys.argv[3] == "graph"):
+    os.environ["SQFA_GRAPH_CLOSURE"] = "0"  # individual kernel launches are what a profiler should see
 import torch
 from sqfa_b200.model import SQFA
 
@@ -16,10 +19,8 @@ del A
 means = 0.05 * torch.randn(C, D, device=dev, generator=g) / D**0.5
 stats = {"means": means, "covariances": cov}
 model = SQFA(n_dim=D, feature_noise=0.01, n_filters=k).to(dev)
-plan = model._fused_loss_plan(stats)
+plan = model._fused_direct_plan(stats)
 for _ in range(reps):
-    model.zero_grad()
     out = plan()
-    out[0].backward()
 torch.cuda.synchronize()
 print("ok", out.tolist())
