@@ -150,6 +150,29 @@ class CudaStatsOps:
             self.gram_events.append(ev)
         return gram
 
+    def _collective_group(self, group, max_ctas):
+        """Communicator for the overlapped Gram all-reduce: NCCL limited to as many CTAs as SMs are left
+        out of the Gram grid (CTAs beyond that could not start before the Gram kernel ends, and the
+        collective would finish only then). A dedicated group when `group` spans all ranks (creating a
+        group is collective over the default group); otherwise `group` itself."""
+        import torch.distributed as dist
+
+        cache = self.__dict__.setdefault("_coll_groups", {})
+        key = (id(group), max_ctas)
+        if key not in cache:
+            pg = group
+            ctas = int(os.environ.get("SQFA_NCCL_CTAS", str(max_ctas)))
+            if ctas > 0 and dist.get_world_size(group) == dist.get_world_size() and dist.get_backend(group) == "nccl":
+                try:
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.max_ctas = ctas
+                    opts.config.min_ctas = 1
+                    pg = dist.new_group(ranks=list(range(dist.get_world_size())), backend="nccl", pg_options=opts)
+                except Exception:  # older torch / NCCL without per-communicator config
+                    pg = group
+            cache[key] = pg
+        return cache[key]
+
     def class_gram_overlapped(self, X, perm, offsets, centre, C, group):
         """Packed Gram partials of this rank, all-reduced over `group` WHILE the kernel runs: classes are
         split into groups; a side stream waits (stream memory operation) until the kernel has finished a
@@ -165,10 +188,19 @@ class CudaStatsOps:
         side = self._side
         G = max(1, min(C, int(os.environ.get("SQFA_GRAM_GROUPS", "5"))))
         reserve = int(os.environ.get("SQFA_GRAM_RESERVE_SMS", "8"))
+        coll_group = self._collective_group(group, reserve)
         done = torch.zeros(G, dtype=torch.int32, device=dev)
         zeroed = torch.cuda.Event()
         zeroed.record(main)
+        trace = getattr(self, "overlap_trace", None)  # diagnostics: list that receives CUDA events
+        if trace is not None:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(main)
         gram = self.class_gram(X, perm, offsets, centre, C, packed=True, done=done, n_groups=G, reserve_sms=reserve)
+        if trace is not None:
+            t1 = torch.cuda.Event(enable_timing=True)
+            t1.record(main)
+            marks = []
         per_class = gram.numel() // C
         side.wait_event(zeroed)  # the counters are zero before the side stream looks at them
         gram.record_stream(side)
@@ -185,8 +217,14 @@ class CudaStatsOps:
                 "sqfa_stream_wait_geq",
             )
             with torch.cuda.stream(side):
-                dist.all_reduce(gram[lo * per_class : hi * per_class], group=group)
+                dist.all_reduce(gram[lo * per_class : hi * per_class], group=coll_group)
+                if trace is not None:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(side)
+                    marks.append(ev)
             lo = hi
+        if trace is not None:
+            trace.append((t0, t1, marks))
         main.wait_stream(side)
         return gram
 
