@@ -167,6 +167,22 @@ int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K
                           uint32_t lbo, uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
                           uint32_t kstep_bytes, sqfa_stream_t stream);
 
+/* float64 variants (the reference follows the dtype of `points`, statistics.py:28,32-34, and runs its
+ * test-suite in float64): same contracts as the float32 entry points above, label bucketing is shared.
+ * FP64 pipe (DFMA), 64 x 64 upper tiles, every reduction in a fixed order (bit-reproducible); no
+ * workspace. gram is (C, D, D) with the upper triangle defined; cov must not alias gram. */
+int sqfa_class_sums_f64(const double* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                        const double* shift, int64_t n, int32_t n_dim, int32_t n_classes, double* sums,
+                        int accumulate, sqfa_stream_t stream);
+int sqfa_class_means_f64(const double* sums, const int64_t* counts, const double* shift, int32_t n_dim,
+                         int32_t n_classes, double* means, sqfa_stream_t stream);
+int sqfa_class_gram_f64(const double* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                        const double* shift, int64_t n, int32_t n_dim, int32_t n_classes, double* gram,
+                        int accumulate, sqfa_stream_t stream);
+int sqfa_stats_epilogue_f64(const double* gram, const double* means, const double* shift, const int64_t* counts,
+                            int32_t n_dim, int32_t n_classes, int estimator, int ddof, double* cov, double* sm,
+                            sqfa_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * HP2: the per-iteration loss and its backward (model.py:190-220, 508-546; _optim.py:90-96)
  * ------------------------------------------------------------------------------------------- */

@@ -58,6 +58,11 @@ SIGNATURES = {
         [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_i32, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
          c_size, c_ptr],
     ),
+    "sqfa_class_sums_f64": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_ptr]),
+    "sqfa_class_means_f64": (c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
+    "sqfa_class_gram_f64": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_ptr]),
+    "sqfa_stats_epilogue_f64": (
+        c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "sqfa_lbfgs_max_n": (c_i64, []),
     "sqfa_lbfgs_max_history": (c_i32, []),
     "sqfa_lbfgs_direction": (

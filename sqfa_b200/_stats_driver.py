@@ -161,7 +161,9 @@ class CudaStatsOps:
         key = (id(group), max_ctas)
         if key not in cache:
             pg = group
-            ctas = int(os.environ.get("SQFA_NCCL_CTAS", str(max_ctas)))
+            # measured (2 x B200, c2): capping NCCL to the reserved SMs makes the collective 2-4x slower than
+            # letting its CTAs share the few free SMs, so no cap by default (SQFA_NCCL_CTAS=n to set one)
+            ctas = int(os.environ.get("SQFA_NCCL_CTAS", "0"))
             if ctas > 0 and dist.get_world_size(group) == dist.get_world_size() and dist.get_backend(group) == "nccl":
                 try:
                     opts = dist.ProcessGroupNCCL.Options()
@@ -187,7 +189,7 @@ class CudaStatsOps:
             self._side = torch.cuda.Stream(device=dev)
         side = self._side
         G = max(1, min(C, int(os.environ.get("SQFA_GRAM_GROUPS", "5"))))
-        reserve = int(os.environ.get("SQFA_GRAM_RESERVE_SMS", "8"))
+        reserve = int(os.environ.get("SQFA_GRAM_RESERVE_SMS", "4"))
         coll_group = self._collective_group(group, reserve)
         done = torch.zeros(G, dtype=torch.int32, device=dev)
         zeroed = torch.cuda.Event()
@@ -279,6 +281,61 @@ class CudaStatsOps:
             "sqfa_class_statistics",
         )
         return means, cov, sm, (perm, offsets, counts)
+
+
+class CudaStatsOps64(CudaStatsOps):
+    """float64 local steps: DFMA kernels of stats64.cu. Bucketing and the label
+    maximum are dtype-independent and inherited; there is no packed Gram and no one-call fused path."""
+
+    supports_packed = False
+    fused = None
+    class_gram_overlapped = None
+
+    def class_sums(self, X, perm, offsets, C, out=None):
+        n, D = X.shape
+        sums = torch.empty(C, D, dtype=torch.float64, device=X.device) if out is None else out
+        _lib.check(
+            self.lib.sqfa_class_sums_f64(_lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), None, n, D, C,
+                                         _lib.ptr(sums), 0, _lib.stream_ptr(X.device)),
+            "sqfa_class_sums_f64",
+        )
+        return sums
+
+    def class_means(self, sums, counts):
+        C, D = sums.shape
+        means = torch.empty_like(sums)
+        _lib.check(
+            self.lib.sqfa_class_means_f64(_lib.ptr(sums), _lib.ptr(counts), None, D, C, _lib.ptr(means),
+                                          _lib.stream_ptr(sums.device)),
+            "sqfa_class_means_f64",
+        )
+        return means
+
+    def class_gram(self, X, perm, offsets, centre, C, packed=False, **_unused):
+        n, D = X.shape
+        gram = torch.empty(C, D, D, dtype=torch.float64, device=X.device)
+        _lib.check(
+            self.lib.sqfa_class_gram_f64(_lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre),
+                                         n, D, C, _lib.ptr(gram), 0, _lib.stream_ptr(X.device)),
+            "sqfa_class_gram_f64",
+        )
+        return gram
+
+    def finalize(self, gram, means, counts, estimator_id, ddof, want_sm, packed=False, class_range=None):
+        C, D = means.shape
+        c0, c1 = (0, C) if class_range is None else class_range
+        nc = c1 - c0
+        dev = gram.device
+        cov = torch.empty(nc, D, D, dtype=torch.float64, device=dev)
+        sm = torch.empty(nc, D, D, dtype=torch.float64, device=dev) if want_sm else None
+        if nc > 0:
+            _lib.check(
+                self.lib.sqfa_stats_epilogue_f64(_lib.ptr(gram[c0:c1]), _lib.ptr(means[c0:c1]), None,
+                                                 _lib.ptr(counts[c0:c1]), D, nc, estimator_id, ddof, _lib.ptr(cov),
+                                                 _lib.ptr(sm), _lib.stream_ptr(dev)),
+                "sqfa_stats_epilogue_f64",
+            )
+        return cov, sm
 
 
 def _all_reduce(t, group, op=None):

@@ -418,3 +418,46 @@ int sqfa_lbfgs_direction(const float* g, float* prev_g, float* d, float* S_, flo
 }
 
 }  // extern "C"
+
+extern "C" {
+
+// --------------------------------------------------------------------------------- float64 hot path 1
+int sqfa_class_sums_f64(const double* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                        const double* shift, int64_t n, int32_t n_dim, int32_t n_classes, double* sums,
+                        int accumulate, sqfa_stream_t stream) {
+  if (n < 0 || n_dim <= 0 || n_classes < 0 || offsets == nullptr || sums == nullptr ||
+      (n > 0 && (X == nullptr || perm == nullptr)) || ldx < n_dim)
+    return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_class_sums_f64(X, ldx, perm, offsets, shift, n_dim, n_classes, sums, accumulate,
+                                                    S(stream)));
+}
+
+int sqfa_class_means_f64(const double* sums, const int64_t* counts, const double* shift, int32_t n_dim,
+                         int32_t n_classes, double* means, sqfa_stream_t stream) {
+  if (sums == nullptr || counts == nullptr || means == nullptr || n_dim <= 0 || n_classes < 0)
+    return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_class_means_f64(sums, counts, shift, n_dim, n_classes, means, S(stream)));
+}
+
+int sqfa_class_gram_f64(const double* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                        const double* shift, int64_t n, int32_t n_dim, int32_t n_classes, double* gram,
+                        int accumulate, sqfa_stream_t stream) {
+  if (n < 0 || n_dim <= 0 || n_classes < 0 || offsets == nullptr || gram == nullptr ||
+      (n > 0 && (X == nullptr || perm == nullptr)) || ldx < n_dim || (accumulate & ~SQFA_GRAM_ACCUMULATE))
+    return fail_arg(__func__, "bad argument");
+  if (n_classes > 65535) return fail_arg(__func__, "n_classes must be <= 65535", SQFA_E_UNSUPPORTED);
+  return wrap(__func__, sqfa::launch_class_gram_f64(X, ldx, perm, offsets, shift, n_dim, n_classes, gram, accumulate,
+                                                    S(stream)));
+}
+
+int sqfa_stats_epilogue_f64(const double* gram, const double* means, const double* shift, const int64_t* counts,
+                            int32_t n_dim, int32_t n_classes, int estimator, int ddof, double* cov, double* sm,
+                            sqfa_stream_t stream) {
+  if (gram == nullptr || means == nullptr || counts == nullptr || cov == nullptr || cov == gram || n_dim <= 0 ||
+      n_classes < 0 || (estimator != SQFA_EST_EMPIRICAL && estimator != SQFA_EST_OAS) || (ddof != 0 && ddof != 1))
+    return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_stats_epilogue_f64(gram, means, shift, counts, n_dim, n_classes, estimator, ddof,
+                                                        cov, sm, S(stream)));
+}
+
+}  // extern "C"

@@ -139,3 +139,16 @@ cudaError_t launch_lbfgs_direction(const float* g, float* prev_g, float* d, floa
                                    int32_t* meta, int64_t n, int history, float t_prev, int first, float* out,
                                    cudaStream_t stream);
 }  // namespace sqfa
+
+namespace sqfa {
+// ---- stats64.cu (float64 variants of K2a, K2, K3) ----
+cudaError_t launch_class_sums_f64(const double* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                                  const double* shift, int D, int C, double* sums, int accumulate, cudaStream_t st);
+cudaError_t launch_class_means_f64(const double* sums, const int64_t* counts, const double* shift, int D, int C,
+                                   double* means, cudaStream_t st);
+cudaError_t launch_class_gram_f64(const double* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
+                                  const double* shift, int D, int C, double* gram, int accumulate, cudaStream_t st);
+cudaError_t launch_stats_epilogue_f64(const double* gram, const double* means, const double* shift,
+                                      const int64_t* counts, int D, int C, int estimator, int ddof, double* cov,
+                                      double* sm, cudaStream_t st);
+}  // namespace sqfa

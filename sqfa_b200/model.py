@@ -102,11 +102,18 @@ def _check_statistics(data_statistics, needs_dict=False):
         )
 
 
-def _statistics_to(data_statistics, dev):
-    """float32 copy of the statistics on the compute device (no copy if already there)."""
+def _statistics_to(data_statistics, dev, dtype=torch.float32):
+    """The statistics on the compute device in the model's dtype (no copy if already so). float32 models
+    run the native closure; a model converted with `.double()` -- the reference's remedy for NaN / inf
+    distances, _optim.py:28-30 -- keeps float64 statistics and evaluates the closure with float64
+    device-side library calls."""
+
+    def put(t):
+        return t.detach().to(device=dev, dtype=dtype).contiguous()
+
     if isinstance(data_statistics, dict):
-        return {k: _ops.f32c(v, dev) for k, v in data_statistics.items() if isinstance(v, torch.Tensor)}
-    return _ops.f32c(torch.as_tensor(data_statistics), dev)
+        return {k: put(v) for k, v in data_statistics.items() if isinstance(v, torch.Tensor)}
+    return put(torch.as_tensor(data_statistics))
 
 
 class _Transform(torch.autograd.Function):
@@ -262,13 +269,16 @@ class SecondMomentsSQFA(nn.Module):
 
     def _fused_loss_plan(self, data_statistics):
         """Callable evaluating [loss, #non-finite] natively at the current filters, or None."""
-        if not self.filters.is_cuda or self.filters.shape[0] > _ops.MAX_FILTERS:
+        if (not self.filters.is_cuda or self.filters.dtype != torch.float32
+                or self.filters.shape[0] > _ops.MAX_FILTERS):
             return None
         plan = self._fused_inputs(data_statistics)
         noise = self._noise_scalar()
         if plan is None or noise is None:
             return None
         S, M, dist = plan
+        if S.dtype != torch.float32 or (M is not None and M.dtype != torch.float32):
+            return None
         group = self._process_group
         rank, world = 0, 1
         if group is not None:
@@ -301,6 +311,8 @@ class SecondMomentsSQFA(nn.Module):
         if plan is None or noise is None:
             return None
         S, M, dist = plan
+        if S.dtype != torch.float32 or (M is not None and M.dtype != torch.float32):
+            return None
         group = self._process_group
         k, D = p.shape
         C = S.shape[0]
@@ -379,7 +391,7 @@ class SecondMomentsSQFA(nn.Module):
             pca_filters = pca_from_scatter(_stats_to_scatter(data_statistics), n_components)
 
         device = self.filters.device
-        self._install_filters(pca_filters.detach().to(device=device, dtype=torch.float32).contiguous())
+        self._install_filters(pca_filters.detach().to(device=device, dtype=self.filters.dtype).contiguous())
 
     def fit(
         self,
@@ -417,7 +429,7 @@ class SecondMomentsSQFA(nn.Module):
         self._process_group = process_group
         self._last_fit_evaluations = 0
         with torch.cuda.device(dev):
-            stats_dev = _statistics_to(data_statistics, dev)
+            stats_dev = _statistics_to(data_statistics, dev, self.filters.dtype)
             self.to(dev)
             try:
                 loss, training_time = self._fit_on_device(

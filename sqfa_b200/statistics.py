@@ -10,16 +10,22 @@ device of `points`. There is no CPU compute path.
 import torch
 
 from . import _lib
-from ._stats_driver import CudaStatsOps, run_class_statistics
+from ._stats_driver import CudaStatsOps, CudaStatsOps64, run_class_statistics
 
 __all__ = ["class_statistics", "oas_covariance", "pca", "pca_from_scatter"]  # the reference's; extensions below
 
 _ESTIMATORS = {"empirical": 0, "oas": 1}
 _ops_singleton = None
+_ops64_singleton = None
 
 
-def _cuda_ops():
-    global _ops_singleton
+def _cuda_ops(dtype=torch.float32):
+    """The local kernels for the dtype of the points: float32 (tcgen05 3xTF32) or float64 (DFMA)."""
+    global _ops_singleton, _ops64_singleton
+    if dtype == torch.float64:
+        if _ops64_singleton is None:
+            _ops64_singleton = CudaStatsOps64()
+        return _ops64_singleton
     if _ops_singleton is None:
         _ops_singleton = CudaStatsOps()
     return _ops_singleton
@@ -30,8 +36,8 @@ def _as_device_points(points, dev):
         raise TypeError("points must be a torch.Tensor")
     if points.dim() != 2:
         raise ValueError("points must have shape (n_points, n_dim)")
-    if points.dtype != torch.float32:
-        raise TypeError(f"sqfa_b200 kernels compute in float32; got points of dtype {points.dtype}")
+    if points.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"points must be float32 or float64 (the output follows their dtype); got {points.dtype}")
     X = points.detach().to(dev, non_blocking=True)
     if X.stride(1) != 1 or X.stride(0) < X.shape[1]:
         X = X.contiguous()
@@ -77,7 +83,8 @@ def class_statistics(points, labels, estimator="empirical", keep_on_device=False
     Parameters
     ----------
     points : torch.Tensor
-        Data points with shape (n_points, n_dim), float32, on the CPU or a CUDA device.
+        Data points with shape (n_points, n_dim), float32 or float64 (the statistics have the dtype of
+        the points, like the reference's), on the CPU or a CUDA device.
     labels : torch.Tensor
         Class labels of each point with shape (n_points).
     estimator:
@@ -111,7 +118,7 @@ def class_statistics(points, labels, estimator="empirical", keep_on_device=False
     if y.numel() == 0 and group is None:
         raise RuntimeError("class_statistics: empty input (max() of an empty labels tensor)")
     with torch.cuda.device(dev):
-        means, cov, sm, _ = run_class_statistics(_cuda_ops(), X, y, _ESTIMATORS[estimator], group=group,
+        means, cov, sm, _ = run_class_statistics(_cuda_ops(X.dtype), X, y, _ESTIMATORS[estimator], group=group,
                                                  shard_output=shard_output and group is not None)
     stats = {"means": means, "covariances": cov, "second_moments": sm}
     if out_dev != dev and not keep_on_device:
@@ -177,6 +184,8 @@ class StreamingClassStatistics:
         lib, dev, C, D = self.lib, self.dev, self.C, self.D
         X = _as_device_points(points, dev)
         y = _as_device_labels(labels, dev)
+        if X.dtype != torch.float32:
+            raise TypeError("StreamingClassStatistics accumulates float32 chunks")
         if X.shape[1] != D or y.numel() != X.shape[0]:
             raise ValueError("chunk must have shape (n, n_dim) and one label per row")
         n = X.shape[0]
@@ -267,9 +276,9 @@ def _single_class(points, estimator_id, assume_centered):
     n, D = X.shape
     with torch.cuda.device(dev):
         y = torch.zeros(n, dtype=torch.int64, device=dev)
-        centre = torch.zeros(1, D, dtype=torch.float32, device=dev) if assume_centered else None
+        centre = torch.zeros(1, D, dtype=X.dtype, device=dev) if assume_centered else None
         _, cov, _, _ = run_class_statistics(
-            _cuda_ops(), X, y, estimator_id, n_classes=1, ddof=0 if assume_centered else 1, centre=centre,
+            _cuda_ops(X.dtype), X, y, estimator_id, n_classes=1, ddof=0 if assume_centered else 1, centre=centre,
             want_sm=False,
         )
     cov = cov[0]

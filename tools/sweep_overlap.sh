@@ -1,0 +1,7 @@
+run() { env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NPROC:-2} --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) tools/diag_overlap.py 2>&1 | grep -E "world|gram kernel|Error|error" ; }
+run SQFA_GRAM_OVERLAP=0
+run SQFA_GRAM_RESERVE_SMS=4
+run SQFA_GRAM_RESERVE_SMS=4 SQFA_GRAM_GROUPS=10
+run SQFA_GRAM_RESERVE_SMS=2 SQFA_GRAM_GROUPS=10
+run SQFA_GRAM_RESERVE_SMS=8 SQFA_GRAM_GROUPS=10
+run SQFA_GRAM_RESERVE_SMS=6 SQFA_GRAM_GROUPS=5
