@@ -189,7 +189,7 @@ class CudaStatsOps:
             self._side = torch.cuda.Stream(device=dev)
         side = self._side
         G = max(1, min(C, int(os.environ.get("SQFA_GRAM_GROUPS", "5"))))
-        reserve = int(os.environ.get("SQFA_GRAM_RESERVE_SMS", "4"))
+        reserve = int(os.environ.get("SQFA_GRAM_RESERVE_SMS", "8"))
         coll_group = self._collective_group(group, reserve)
         done = torch.zeros(G, dtype=torch.int32, device=dev)
         zeroed = torch.cuda.Event()
@@ -409,7 +409,11 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
     extra = {} if class_range is None else {"class_range": class_range}
     packed_ok = group is not None and getattr(ops, "supports_packed", False) and ops.packed_is_smaller(D, C)
     overlap = getattr(ops, "class_gram_overlapped", None) is not None and getattr(ops, "gram_events", None) is None
-    if packed_ok and overlap and os.environ.get("SQFA_GRAM_OVERLAP", "1") != "0":
+    # Opt-in (SQFA_GRAM_OVERLAP=1). Measured on 2 x B200 at c2 (tools/sweep_overlap.sh): NCCL's kernels only
+    # start once >= 8 SMs are free, leaving 8 SMs out of the Gram grid costs the Gram a whole extra round of
+    # tiles (+0.19 ms of 2.0), and the all-reduce progresses at ~45 GB/s on those few SMs -- the step comes
+    # out within +-0.06 ms of the serialised version (2.82 vs 2.90 and 2.98 vs 2.92 ms on two boxes).
+    if packed_ok and overlap and os.environ.get("SQFA_GRAM_OVERLAP", "0") == "1":
         # the one large collective, hidden behind the kernel that produces its input
         gram = ops.class_gram_overlapped(X, perm, offsets, shift, C, group)
         cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm, packed=True, **extra)

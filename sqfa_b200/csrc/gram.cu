@@ -123,14 +123,15 @@ struct JobGeom {
   int kb0, kb1;
 };
 
+template <int TM, int TN>
 __device__ __forceinline__ JobGeom decode_job(const GramParams& P, int j) {
   const int4 jb = __ldg(P.jobs + j);
   JobGeom g;
   g.c = jb.x;
-  g.m0 = jb.y * TM2;
-  g.n0 = jb.z * TN2;
-  g.n_eff = TN2;  // full N: the slot permutation spreads a tile's columns over all 128 slots of a CTA
-  g.nh = TN2 / 2;
+  g.m0 = jb.y * TM;
+  g.n0 = jb.z * TN;
+  g.n_eff = TN;  // full N: the slot permutation spreads a tile's columns over all 128 slots of a CTA
+  g.nh = TN / 2;
   g.diag = (jb.y == jb.z) && !(P.flags & 1);
   g.row_begin = P.offsets[g.c];
   g.n_c = P.offsets[g.c + 1] - g.row_begin;
@@ -140,8 +141,15 @@ __device__ __forceinline__ JobGeom decode_job(const GramParams& P, int j) {
   return g;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GRAM2_THREADS, 1)
-gram_tf32x3_kernel(const GramParams P) {
+// PAIR = true : tcgen05.mma.cta_group::2, a 256 x 256 tile over a cluster of two CTAs (the general kernel)
+// PAIR = false: tcgen05.mma.cta_group::1, ONE CTA computes a 128 x TN tile (TN = 128): the variant for
+//               n_dim <= 128, where a class has a single (diagonal) tile and a 256 x 256 tile would execute
+//               (256 / D)^2 times the useful MMA work. A launch without cluster dimensions is a cluster of
+//               one CTA, so the cluster-window barrier addressing below is valid in both variants.
+template <bool PAIR, int TN>
+__device__ __forceinline__ void gram_body(const GramParams& P) {
+  constexpr int TM = PAIR ? 256 : 128;
+  constexpr int NCTA = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* run = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES);  // [256 cols][128 rows]
@@ -153,19 +161,22 @@ gram_tf32x3_kernel(const GramParams P) {
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES2; ++s) {
-      mbar_init(&full_bar[s], 2 * PROD_WARPS2);
+      mbar_init(&full_bar[s], NCTA * PROD_WARPS2);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_full_bar, 1);
-    mbar_init(&acc_empty_bar, 2 * EPI_WARPS2);
+    mbar_init(&acc_empty_bar, NCTA * EPI_WARPS2);
     mbar_fence_init();
   }
-  if (warp == MMA_WARP2) tmem_alloc_2cta<TMEM_COLS2>(&s_tmem_base);
+  if (warp == MMA_WARP2) {
+    if constexpr (PAIR) tmem_alloc_2cta<TMEM_COLS2>(&s_tmem_base);
+    else tmem_alloc<TMEM_COLS2>(&s_tmem_base);
+  }
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives remotely
@@ -173,7 +184,7 @@ gram_tf32x3_kernel(const GramParams P) {
   const uint32_t tmem_base = s_tmem_base;
 
   const int D = P.D;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pair = PAIR ? (blockIdx.x >> 1) : blockIdx.x, npairs = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   // Registers: 13 warps put 4 warps on one SM sub-partition, so the launch gets 128 per thread.
   // The MMA and epilogue warps (warpgroups 2, 3) give some back and the producers (warpgroups 0, 1)
@@ -192,7 +203,7 @@ gram_tf32x3_kernel(const GramParams P) {
     const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's barriers, cluster window
     const bool vecx = P.vecx != 0;
     for (int j = pair; j < P.njobs; j += npairs) {
-      const JobGeom g = decode_job(P, j);
+      const JobGeom g = decode_job<TM, TN>(P, j);
       const int kb0 = g.kb0, kb1 = g.kb1;
       const int64_t n_c = g.n_c;
       if (g.diag && !isA) {
@@ -323,8 +334,16 @@ gram_tf32x3_kernel(const GramParams P) {
     if (leader) {
       uint32_t stage = 0, phase = 0, chain_phase = 0;
       for (int j = pair; j < P.njobs; j += npairs) {
-        const JobGeom g = decode_job(P, j);
-        const uint32_t idesc = make_idesc_tf32(TM2, (uint32_t)g.n_eff, 0, 0);
+        const JobGeom g = decode_job<TM, TN>(P, j);
+        const uint32_t idesc = make_idesc_tf32(TM, (uint32_t)g.n_eff, 0, 0);
+        auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+          if constexpr (PAIR) umma_tf32_ss_2cta(d, da, db, idesc, acc);
+          else umma_tf32_ss(d, da, db, idesc, acc);
+        };
+        auto commit = [&](uint64_t* bar) {
+          if constexpr (PAIR) umma_commit_2cta(bar, 3);
+          else umma_commit(bar);
+        };
         // cross terms (small accumulator) / hi*hi (main accumulator) of one stage
         auto issue_stage = [&](uint32_t stg, bool cross, bool mainp, int kb, int cb) {
           const uint32_t st = smem_u32(smem + stg * STAGE2_BYTES);
@@ -339,12 +358,12 @@ gram_tf32x3_kernel(const GramParams P) {
             const uint64_t dB_lo = make_smem_desc(b_lo + ko, OP_LBO, OP_SBO2, 0);
             if (cross) {
               const uint32_t acc_small = (kb > g.kb0 || k8 > 0) ? 1u : 0u;  // zeroed once per job
-              umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_lo, dB_hi, idesc, acc_small);
-              umma_tf32_ss_2cta(tmem_base + TMEM_SMALL2, dA_hi, dB_lo, idesc, 1u);
+              mma(tmem_base + TMEM_SMALL2, dA_lo, dB_hi, acc_small);
+              mma(tmem_base + TMEM_SMALL2, dA_hi, dB_lo, 1u);
             }
             if (mainp) {
               const uint32_t acc_main = (kb > cb || k8 > 0) ? 1u : 0u;  // zeroed at every chain start
-              umma_tf32_ss_2cta(tmem_base, dA_hi, dB_hi, idesc, acc_main);
+              mma(tmem_base, dA_hi, dB_hi, acc_main);
             }
           }
         };
@@ -376,8 +395,8 @@ gram_tf32x3_kernel(const GramParams P) {
             }
             if (elect_one()) {
               issue_stage(stage, !crossed, true, kb, cb);
-              umma_commit_2cta(&empty_bar[stage], 3);
-              if (kb == ce - 1) umma_commit_2cta(&acc_full_bar, 3);
+              commit(&empty_bar[stage]);
+              if (kb == ce - 1) commit(&acc_full_bar);
             }
             __syncwarp();
             if (++stage == STAGES2) { stage = 0; phase ^= 1; }
@@ -403,22 +422,22 @@ gram_tf32x3_kernel(const GramParams P) {
       }
     };
     for (int j = pair; j < P.njobs; j += npairs) {
-      const JobGeom g = decode_job(P, j);
+      const JobGeom g = decode_job<TM, TN>(P, j);
       // TMEM lane i = 32 q + lane is operand slot i of this CTA -> tile row 4 (i % 32) + i / 32
       const int row = g.m0 + 128 * (int)rank + 4 * lane + q;
       // output row pointer, indexed by the GLOBAL column: full (C, D, D) layout, or the packed
       // tile list (what a multi-device caller all-reduces: upper tiles only)
       float* grow;
       if (P.packed) {
-        const int tm = g.m0 / TM2, tn = g.n0 / TN2;
+        const int tm = g.m0 / TM, tn = g.n0 / TN;
         const int64_t t = (int64_t)tm * P.TT - (int64_t)tm * (tm - 1) / 2 + (tn - tm);
-        grow = P.gram + (((int64_t)g.c * P.T + t) * TM2 + (row - g.m0)) * TN2 - g.n0;
+        grow = P.gram + (((int64_t)g.c * P.T + t) * TM + (row - g.m0)) * TN - g.n0;
       } else {
         grow = P.gram + ((int64_t)g.c * D + row) * D;
       }
       if (g.kb1 <= g.kb0) {  // empty class / empty K part: the tile contribution is exactly zero
         if (!P.atomic_out && row < D)
-          for (int cc = 0; cc < TN2; ++cc)
+          for (int cc = 0; cc < TN; ++cc)
             if (g.n0 + cc < D) grow[g.n0 + cc] = 0.f;
         signal_done(g.c);
         continue;
@@ -452,12 +471,12 @@ gram_tf32x3_kernel(const GramParams P) {
             }
           };
 #pragma unroll
-          for (int c = 0; c < TN2 / 32; c += 2) {
+          for (int c = 0; c < TN / 32; c += 2) {
             tmem_ld_wait();
             tmem_ld_32x32b_x32(tq + (uint32_t)(32 * (c + 1)), vb);
             add_chunk(c, va);
             tmem_ld_wait();
-            if (c + 2 < TN2 / 32) {
+            if (c + 2 < TN / 32) {
               tmem_ld_32x32b_x32(tq + (uint32_t)(32 * (c + 2)), va);
             } else {  // main accumulator fully read: hand it back to the MMA warp
               tc_fence_before_sync();
@@ -471,7 +490,7 @@ gram_tf32x3_kernel(const GramParams P) {
           // Tile columns 4 s .. 4 s + 3 are accumulator columns s, 32 + s, 64 + s, 96 + s of a
           // 128-column half (the slot permutation), so one chunk reads 4 slots from each quarter.
 #pragma unroll 1
-          for (int ch = 0; ch < 16; ++ch) {  // 4 slots from each quarter per chunk (register budget of this role)
+          for (int ch = 0; ch < TN / 16; ++ch) {  // 4 slots from each quarter per chunk (register budget of this role)
             const int half = ch >> 3, s0 = 4 * (ch & 7);
             uint32_t m[4][4], w[4][4];
 #pragma unroll
@@ -481,7 +500,7 @@ gram_tf32x3_kernel(const GramParams P) {
               tmem_ld_32x32b_x4(tq + TMEM_SMALL2 + col, w[qd]);
             }
             tmem_ld_wait();
-            if (ch == 15) {  // both accumulators read: the next job may start
+            if (ch == TN / 16 - 1) {  // both accumulators read: the next job may start
               tc_fence_before_sync();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster(acc_empty0);
@@ -510,12 +529,12 @@ gram_tf32x3_kernel(const GramParams P) {
           }
         } else {
 #pragma unroll 1
-          for (int col0 = 0; col0 < TN2; col0 += 16) {
+          for (int col0 = 0; col0 < TN; col0 += 16) {
             uint32_t v[16], w[16];
             tmem_ld_32x32b_x16(tq + (uint32_t)col0, v);
             tmem_ld_32x32b_x16(tq + TMEM_SMALL2 + (uint32_t)col0, w);
             tmem_ld_wait();
-            if (col0 + 16 >= TN2) {  // both accumulators read: the next job may start
+            if (col0 + 16 >= TN) {  // both accumulators read: the next job may start
               tc_fence_before_sync();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster(acc_empty0);
@@ -552,8 +571,19 @@ gram_tf32x3_kernel(const GramParams P) {
 
   tc_fence_before_sync();
   cluster_sync_all();
-  if (warp == MMA_WARP2) tmem_dealloc_2cta<TMEM_COLS2>(tmem_base);
+  if (warp == MMA_WARP2) {
+    if constexpr (PAIR) tmem_dealloc_2cta<TMEM_COLS2>(tmem_base);
+    else tmem_dealloc<TMEM_COLS2>(tmem_base);
+  }
 }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GRAM2_THREADS, 1)
+gram_tf32x3_kernel(const GramParams P) { gram_body<true, TN2>(P); }
+
+constexpr int TN1 = 128;  // tile edge of the single-CTA variant
+constexpr int GRAM1_SMEM = STAGES2 * STAGE2_BYTES + 128 * TN1 * 4 + 1024;
+__global__ void __launch_bounds__(GRAM2_THREADS, 1)
+gram_tf32x3_small_kernel(const GramParams P) { gram_body<false, TN1>(P); }
 
 }  // namespace
 
@@ -567,9 +597,26 @@ int gram_tiles_per_class(int D, int* TT_out) {
   return TT * (TT + 1) / 2;
 }
 
+// n_dim <= 128: the single-CTA variant (one 128 x 128 tile per class) unless the packed layout is asked for
+static bool gram_use_small(int D, int packed) { return D <= TN1 && !packed; }
+
 // Accumulator area (rows x columns) the tensor cores execute per sample for one class: every tile that
-// intersects the upper triangle is a full TM2 x TN2 MMA, whatever part of it lies beyond D.
-int64_t gram_executed_tile_area(int D) { return (int64_t)gram_tiles_per_class(D, nullptr) * TM2 * TN2; }
+// intersects the upper triangle is a full MMA tile, whatever part of it lies beyond D.
+int64_t gram_executed_tile_area(int D) {
+  if (gram_use_small(D, 0)) return (int64_t)128 * TN1;
+  return (int64_t)gram_tiles_per_class(D, nullptr) * TM2 * TN2;
+}
+
+// K parts per class for the single-CTA variant: about three jobs per SM, at least 256 samples per part
+int gram_ksplit_small(int64_t n, int C, int num_sms) {
+  if (C <= 0) return 1;
+  int64_t ks = (3 * (int64_t)num_sms + C - 1) / C;
+  const int64_t avg = n / C;
+  const int64_t cap = avg / 256 > 1 ? avg / 256 : 1;
+  if (ks > cap) ks = cap;
+  if (ks > 64) ks = 64;
+  return (int)(ks < 1 ? 1 : ks);
+}
 
 // K parts per tile so that small problems still fill the CTA pairs
 int gram_ksplit(int64_t n, int C, int D, int num_sms) {
@@ -585,27 +632,33 @@ int gram_ksplit(int64_t n, int C, int D, int num_sms) {
 }
 
 size_t gram_workspace_bytes(int C, int D, int ksplit_max) {
-  return (size_t)C * gram_tiles_per_class(D, nullptr) * (ksplit_max > 0 ? ksplit_max : 1) * sizeof(int4) + 256;
+  // the job plan of either variant (the single-CTA variant splits K up to 64 ways)
+  const size_t pair = (size_t)C * gram_tiles_per_class(D, nullptr) * (ksplit_max > 0 ? ksplit_max : 1);
+  const size_t small = D <= TN1 ? (size_t)C * 64 : 0;
+  return (pair > small ? pair : small) * sizeof(int4) + 256;
 }
 
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
                                const float* shift, int64_t n, int D, int C, float* gram, int accumulate, int packed,
                                int chain_rows, int32_t* done, int n_groups, int reserve_sms, void* ws, int num_sms,
                                cudaStream_t stream) {
-  static int smem_set[kMaxDevices] = {0};
+  const bool small = gram_use_small(D, packed);
+  static int smem_set[kMaxDevices] = {0}, smem_set1[kMaxDevices] = {0};
   {
-    cudaError_t e = ensure_dynamic_smem(gram_tf32x3_kernel, GRAM2_SMEM, smem_set);
+    cudaError_t e = small ? ensure_dynamic_smem(gram_tf32x3_small_kernel, GRAM1_SMEM, smem_set1)
+                          : ensure_dynamic_smem(gram_tf32x3_kernel, GRAM2_SMEM, smem_set);
     if (e != cudaSuccess) return e;
   }
   if (C <= 0) return cudaSuccess;
   GramParams P;
   int TT = 0;
-  const int T = gram_tiles_per_class(D, &TT);
+  int T = gram_tiles_per_class(D, &TT);
+  if (small) { TT = 1; T = 1; }
   P.X = X; P.ldx = ldx; P.n = n; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram;
   P.done = done; P.n_groups = n_groups > 0 ? n_groups : 1; P.class_order = done != nullptr ? 1 : 0;
   P.jobs = reinterpret_cast<const int4*>(ws);
   P.D = D; P.C = C;
-  P.KS = gram_ksplit(n, C, D, num_sms);
+  P.KS = small ? gram_ksplit_small(n, C, num_sms) : gram_ksplit(n, C, D, num_sms);
   P.njobs = C * T * P.KS;
   const int cr = chain_rows > 0 ? chain_rows : 512;
   P.chain_kb = (cr + BK - 1) / BK;
@@ -624,6 +677,12 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
   gram_plan_kernel<<<1, 1024, 0, stream>>>(offsets, C, TT, P.KS, P.class_order, reinterpret_cast<int4*>(ws));
   // reserve_sms SMs are left to other streams (the collective that runs while this kernel still computes)
   const int usable = num_sms - (reserve_sms > 0 ? reserve_sms : 0);
+  if (small) {
+    int grid = usable > 1 ? usable : 1;
+    if (grid > P.njobs) grid = P.njobs;
+    gram_tf32x3_small_kernel<<<grid, GRAM2_THREADS, GRAM1_SMEM, stream>>>(P);
+    return cudaGetLastError();
+  }
   int grid = ((usable > 2 ? usable : 2) / 2) * 2;
   if (grid > 2 * P.njobs) grid = 2 * P.njobs;
   gram_tf32x3_kernel<<<grid, GRAM2_THREADS, GRAM2_SMEM, stream>>>(P);
