@@ -56,6 +56,9 @@ typedef void* sqfa_stream_t; /* cudaStream_t */
 #define SQFA_DIST_SQUARED 16
 
 int sqfa_version(void);
+/* hash of the sources the library was built from (sqfa_b200/build.py); loaders compare it with the
+ * sources they ship with and refuse a stale build */
+const char* sqfa_build_id(void);
 const char* sqfa_last_error(void);
 /* number of SMs of the current device (grid sizing); <= 0 on failure */
 int sqfa_device_sm_count(void);
@@ -160,12 +163,6 @@ int sqfa_class_statistics(const float* X, int64_t ldx, const int64_t* labels, in
                           int32_t n_classes, int estimator, int ddof, float* means, float* cov, float* sm,
                           int64_t* counts, int64_t* offsets, int32_t* perm, void* ws, size_t ws_bytes,
                           sqfa_stream_t stream);
-
-/* Test hook: D[128 x N] = A^T B through one tcgen05.mma chain with a caller-chosen operand
- * layout / descriptor (pins the UMMA layout assumptions of sqfa_class_gram on hardware). */
-int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K, int32_t N, int32_t mode,
-                          uint32_t lbo, uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
-                          uint32_t kstep_bytes, sqfa_stream_t stream);
 
 /* float64 variants (the reference follows the dtype of `points`, statistics.py:28,32-34, and runs its
  * test-suite in float64): same contracts as the float32 entry points above, label bucketing is shared.

@@ -26,6 +26,7 @@ c_int = ctypes.c_int
 # name -> (restype, argtypes); mirrors include/sqfa_b200.h one to one
 SIGNATURES = {
     "sqfa_version": (c_int, []),
+    "sqfa_build_id": (ctypes.c_char_p, []),
     "sqfa_last_error": (ctypes.c_char_p, []),
     "sqfa_device_sm_count": (c_int, []),
     "sqfa_label_max": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
@@ -68,10 +69,6 @@ SIGNATURES = {
     "sqfa_lbfgs_direction": (
         c_int,
         [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i32, ctypes.c_float, c_int, c_ptr, c_ptr],
-    ),
-    "sqfa_debug_umma_probe": (
-        c_int,
-        [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_u32, c_u32, c_u32, c_u32, c_u32, c_u32, c_ptr],
     ),
     "sqfa_project_workspace_bytes": (c_size, [c_i32, c_i32, c_i32]),
     "sqfa_project_fwd": (
@@ -132,6 +129,17 @@ def load():
         fn.restype = restype
         fn.argtypes = argtypes
     lib.sqfa_missing_symbols = tuple(missing)
+    if "sqfa_build_id" not in missing and os.environ.get("SQFA_ALLOW_STALE_LIB") != "1":
+        # a library built from other sources than the ones next to it would be tested / run silently
+        from . import build as _build
+
+        want = _build.source_build_id()
+        have = lib.sqfa_build_id().decode()
+        if want is not None and have != want:
+            raise SqfaNativeError(
+                f"{LIB_PATH} was built from different sources (build id {have}, sources {want}); "
+                "rebuild it with `python -m sqfa_b200.build`"
+            )
     _lib = lib
     return lib
 

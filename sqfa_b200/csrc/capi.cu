@@ -39,7 +39,12 @@ int sm_count_cached() {
 
 extern "C" {
 
-int sqfa_version(void) { return 100; }
+#ifndef SQFA_BUILD_ID
+#define SQFA_BUILD_ID "unknown"
+#endif
+
+int sqfa_version(void) { return 200; }
+const char* sqfa_build_id(void) { return SQFA_BUILD_ID; }
 const char* sqfa_last_error(void) { return g_err; }
 int sqfa_device_sm_count(void) { return sm_count_cached(); }
 
@@ -175,16 +180,6 @@ int sqfa_stats_epilogue(const float* gram, const float* means, const float* shif
     return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
   return wrap(__func__, sqfa::launch_stats_epilogue(gram, packed, means, shift, counts, n_dim, n_classes, estimator,
                                                     ddof, cov, sm, ws, S(stream)));
-}
-
-int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K, int32_t N, int32_t mode,
-                          uint32_t lbo, uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
-                          uint32_t kstep_bytes, sqfa_stream_t stream) {
-  if (A == nullptr || B == nullptr || Dout == nullptr || K <= 0 || K % 8 != 0 || K > 64 || N < 16 || N > 256 ||
-      N % 32 != 0)
-    return fail_arg(__func__, "bad argument");
-  return wrap(__func__, sqfa::launch_umma_probe(A, B, Dout, K, N, mode, lbo, sbo, layout_type, a_major, b_major,
-                                                kstep_bytes, S(stream)));
 }
 
 }  // extern "C"

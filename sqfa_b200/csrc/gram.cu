@@ -97,8 +97,9 @@ struct GramParams {
                      // 4 = scalar loads, 8 = no early cross-term MMAs during a chain drain
 };
 
-// Job list: classes in descending size, tiles of a class adjacent (they share the gathered rows
-// in L2), K parts innermost.  job = ((rank * T) + t) * KS + ks
+// Job list: classes in descending size; within a class the K parts, and within a K part its tiles:
+// the CTA pairs that run concurrently work on the tiles of the SAME rows, which they share in L2.
+// job = ((rank * KS) + ks) * T + t
 __global__ void __launch_bounds__(1024) gram_plan_kernel(const int64_t* __restrict__ offsets, int C, int TT, int KS,
                                                           int class_order, int4* __restrict__ jobs) {
   const int T = TT * (TT + 1) / 2;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(1024) gram_plan_kernel(const int64_t* __restri
     int t = 0;
     for (int tm = 0; tm < TT; ++tm)
       for (int tn = tm; tn < TT; ++tn, ++t)
-        for (int ks = 0; ks < KS; ++ks) jobs[((int64_t)rank * T + t) * KS + ks] = make_int4(c, tm, tn, ks);
+        for (int ks = 0; ks < KS; ++ks) jobs[((int64_t)rank * KS + ks) * T + t] = make_int4(c, tm, tn, ks);
   }
 }
 
@@ -607,10 +608,12 @@ int64_t gram_executed_tile_area(int D) {
   return (int64_t)gram_tiles_per_class(D, nullptr) * TM2 * TN2;
 }
 
-// K parts per class for the single-CTA variant: about three jobs per SM, at least 256 samples per part
+// K parts per class for the single-CTA variant: ONE round of jobs (a job's fixed cost -- cold load
+// pipeline, accumulator drain, 64 KB of red.add -- is as long as 500 samples of MMA work; measured on c3:
+// 380 jobs of 526 samples ran at 24 % tensor-pipe activity), at least 256 samples per part
 int gram_ksplit_small(int64_t n, int C, int num_sms) {
   if (C <= 0) return 1;
-  int64_t ks = (3 * (int64_t)num_sms + C - 1) / C;
+  int64_t ks = num_sms / C;
   const int64_t avg = n / C;
   const int64_t cap = avg / 256 > 1 ? avg / 256 : 1;
   if (ks > cap) ks = cap;
@@ -620,9 +623,27 @@ int gram_ksplit_small(int64_t n, int C, int num_sms) {
 
 // K parts per tile so that small problems still fill the CTA pairs
 int gram_ksplit(int64_t n, int C, int D, int num_sms) {
-  const int64_t tiles = (int64_t)C * gram_tiles_per_class(D, nullptr);
+  const int T = gram_tiles_per_class(D, nullptr);
+  const int64_t tiles = (int64_t)C * T;
   const int pairs = num_sms / 2 > 0 ? num_sms / 2 : 1;
-  if (tiles >= 6 * (int64_t)pairs || tiles <= 0) return 1;
+  if (tiles <= 0) return 1;
+  if (tiles >= 6 * (int64_t)pairs) {
+    // Enough tiles to fill the GPU. A tile reads the rows of its class once per column slab, and the
+    // tiles of a class re-read them: free while the concurrently running (class, K part) groups fit in
+    // the 126 MB L2, HBM-bound otherwise (measured on the c5 shard, 125 000 rows x 4 KB per class:
+    // 5x the algorithmic traffic, 3.3 TB/s). Large classes are therefore cut into K parts whose rows
+    // -- times the number of groups in flight -- stay L2-resident; parts are summed with red.add.
+    const int64_t avg = C > 0 ? n / C : n;
+    const double groups_in_flight = (double)pairs / T > 1.0 ? (double)pairs / T : 1.0;
+    const double part_bytes = 96e6 / groups_in_flight;
+    const double class_bytes = (double)avg * D * 4.0;
+    if (class_bytes <= part_bytes) return 1;
+    int64_t ks = (int64_t)(class_bytes / part_bytes + 0.999);
+    const int64_t cap = avg / 2048 > 1 ? avg / 2048 : 1;  // keep >= 2048 samples per part (epilogue amortised)
+    if (ks > cap) ks = cap;
+    if (ks > 64) ks = 64;
+    return (int)(ks < 1 ? 1 : ks);
+  }
   int64_t ks = (4 * (int64_t)pairs + tiles - 1) / tiles;
   const int64_t avg = C > 0 ? n / C : n;
   const int64_t cap = avg / 512 > 1 ? avg / 512 : 1;  // keep >= 512 samples per part

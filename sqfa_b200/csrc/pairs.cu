@@ -364,10 +364,95 @@ class_prepare_kernel(const float* __restrict__ PsiPart, const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // pair kernel, affine-invariant family (AI, FR lower bound): one warp per pair
 // ------------------------------------------------------------------------------------------------
+// Column stride (floats) of the column-contiguous matrices of the shared-memory variant: a multiple
+// of 4 whose quarter is odd, so that 16-byte accesses of 8 lanes to 8 different columns hit 8 different
+// bank groups (conflict-free LDS.128 / STS.128).
+__host__ __device__ inline int pair_col_stride(int m) {
+  int m4 = (m + 3) >> 2;
+  if ((m4 & 1) == 0) ++m4;
+  return 4 * m4;
+}
+
+// One-sided Jacobi on the mp (even) columns of a matrix stored column-contiguous (column p at
+// A + p * ldc, entries >= m are zero). Lane t < mp / 2 owns ONE COLUMN PAIR per round of the round-robin
+// schedule: it loads both columns into registers (16-byte loads), forms the three dot products and the
+// rotation, and writes both columns back in place -- no other lane touches them in that round, so there
+// is no double buffer, no shuffle and no redundant dot product. M4 = float4s per column the registers
+// are sized for.
+template <int M4>
+__device__ void warp_jacobi_cols(float* A, int m, int mp, int ldc, int lane) {
+  const int n1 = mp - 1, np = mp >> 1;
+  const int m4 = (m + 3) >> 2;
+  for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+    bool rotated = false;
+    for (int r = 0; r < n1; ++r) {
+      if (lane < np) {
+        // circle method: the fixed player n1 meets r; the others meet their mirror image around r
+        int p, q;
+        if (lane == 0) {
+          p = n1; q = r;
+        } else {
+          p = r + lane; if (p >= n1) p -= n1;
+          q = r - lane; if (q < 0) q += n1;
+        }
+        const int lo = p < q ? p : q, hi = p < q ? q : p;
+        float4* xp = reinterpret_cast<float4*>(A + lo * ldc);
+        float4* yp = reinterpret_cast<float4*>(A + hi * ldc);
+        float4 x[M4], y[M4];
+        float2 aa = make_float2(0.f, 0.f), bb = aa, ab = aa;
+#pragma unroll
+        for (int i = 0; i < M4; ++i) {
+          if (i < m4) {
+            x[i] = xp[i];
+            y[i] = yp[i];
+            const float2 x0 = make_float2(x[i].x, x[i].y), x1 = make_float2(x[i].z, x[i].w);
+            const float2 y0 = make_float2(y[i].x, y[i].y), y1 = make_float2(y[i].z, y[i].w);
+            aa = __ffma2_rn(x0, x0, aa); aa = __ffma2_rn(x1, x1, aa);
+            bb = __ffma2_rn(y0, y0, bb); bb = __ffma2_rn(y1, y1, bb);
+            ab = __ffma2_rn(x0, y0, ab); ab = __ffma2_rn(x1, y1, ab);
+          }
+        }
+        const float alpha = aa.x + aa.y, beta = bb.x + bb.y, gamma = ab.x + ab.y;
+        const float g2 = gamma * gamma, scale = alpha * beta;
+        if (g2 > (JACOBI_TOL * JACOBI_TOL) * scale && alpha > 0.f && beta > 0.f) {
+          // same rules as the register kernel: approximate reciprocal / square root for the angle, and
+          // a sweep whose rotations were all below JACOBI_LAST is the last one
+          const float zeta = (beta - alpha) * rcp_approx(2.f * gamma);
+          const float tt = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
+          const float cs = rsqrtf(fmaf(tt, tt, 1.f)), sn = cs * tt;
+          rotated = rotated || g2 > (JACOBI_LAST * JACOBI_LAST) * scale;
+          const float2 c2 = make_float2(cs, cs), s2 = make_float2(sn, sn), ns2 = make_float2(-sn, -sn);
+#pragma unroll
+          for (int i = 0; i < M4; ++i) {
+            if (i < m4) {  // x' = c x - s y, y' = s x + c y
+              const float2 x0 = make_float2(x[i].x, x[i].y), x1 = make_float2(x[i].z, x[i].w);
+              const float2 y0 = make_float2(y[i].x, y[i].y), y1 = make_float2(y[i].z, y[i].w);
+              const float2 nx0 = __ffma2_rn(c2, x0, __fmul2_rn(ns2, y0)), nx1 = __ffma2_rn(c2, x1, __fmul2_rn(ns2, y1));
+              const float2 ny0 = __ffma2_rn(c2, y0, __fmul2_rn(s2, x0)), ny1 = __ffma2_rn(c2, y1, __fmul2_rn(s2, x1));
+              xp[i] = make_float4(nx0.x, nx0.y, nx1.x, nx1.y);
+              yp[i] = make_float4(ny0.x, ny0.y, ny1.x, ny1.y);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, rotated)) break;
+  }
+}
+
+// floats of per-warp scratch of the shared-memory pair kernel
+__host__ __device__ inline int pair_smem_floats(int m) {
+  const int mp = (m + 1) & ~1, ldc = pair_col_stride(m);
+  return mp * ldc + m * ldc + ((m * m + 3) & ~3) + 4 * ((m + 3) & ~3);
+}
+
+template <int M4>
 __global__ void __launch_bounds__(PAIR_WARPS * 32)
 pair_ai_kernel(const PairArgs A) {
-  // shared-memory variant (32 < m <= 64): tiles are single pairs (R = 1), tile (bi, bj) = pair (i, j)
-  extern __shared__ float smem[];
+  // shared-memory variant (32 < m <= 64): tiles are single pairs (R = 1), tile (bi, bj) = pair (i, j).
+  // Matrices are column-contiguous: column q of A = (L_j^-1 L_i)^T at bufA + q * ldc.
+  extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (t >= A.T.ntiles) return;
@@ -377,15 +462,15 @@ pair_ai_kernel(const PairArgs A) {
   const bool active = pair_in_launch(i, j, A.nA, nB, tri, A.pair_begin, A.pair_end);
   const bool want_grad = A.rowpart != nullptr;
   const int mp = (m + 1) & ~1;
-  const int ld = (mp > 32 ? 64 : 32) + 1;
-  const int nslot = (mp + 31) >> 5;
-  const int per_warp = 2 * m * ld + m * m + 3 * m;
-  float* bufA = smem + (size_t)warp * per_warp;
-  float* bufB = bufA + m * ld;
-  float* Ls = bufB + m * ld;   // m x m, row stride m: L_i, later L_i^-1, later Zj
-  float* ci = Ls + m * m;      // per-eigenvalue coefficients
-  float* cj = ci + m;
-  float* lamv = cj + m;
+  const int ldc = pair_col_stride(m);
+  const int nslot = (m + 31) >> 5;
+  const int mpad = (m + 3) & ~3;
+  float* bufA = smem + (size_t)warp * pair_smem_floats(m);  // [mp][ldc]  columns of A, then of A_f
+  float* bufY = bufA + mp * ldc;                            // [m][ldc]   Linv_j^T (staging), later columns of Y
+  float* Ls = bufY + m * ldc;                               // [m][m]     L_i, later L_i^-1
+  float* ci = Ls + ((m * m + 3) & ~3);                      // per-eigenvalue coefficients
+  float* cj = ci + mpad;
+  float* lamv = cj + mpad;
   float dval = 0.f, bad = 0.f;
   float* gi = want_grad ? A.rowpart + t * m * m : nullptr;
   float* gj = want_grad ? A.colpart + t * m * m : nullptr;
@@ -395,35 +480,34 @@ pair_ai_kernel(const PairArgs A) {
   if (active) {
     const float* Wi = A.Wa + (int64_t)i * 2 * m * m;
     const float* Wj = A.Wb + (int64_t)j * 2 * m * m;
-    // stage L_i (row-major) and L_j^-1 transposed: bufB[r][q] = Linv_j[q][r]
+    // stage L_i (row-major) and L_j^-1 transposed (bufY[r][q] = Linv_j[q][r], row stride ldc); zero A
+    for (int idx = lane; idx < mp * ldc; idx += 32) bufA[idx] = 0.f;
     for (int idx = lane; idx < m * m; idx += 32) {
       Ls[idx] = Wi[idx];
       const int q = idx / m, r = idx % m;
-      bufB[r * ld + q] = Wj[m * m + idx];
+      bufY[r * ldc + q] = Wj[m * m + idx];
     }
     __syncwarp();
-    // A[s][q] = B[q][s] = sum_{r >= s} Linv_j[q][r] L_i[r][s];  columns >= m are zero (dummy players)
+    // column q of A: A[s][q] = sum_{r >= s} Linv_j[q][r] L_i[r][s]   (column mp - 1 > m - 1 stays zero)
     for (int tt = 0; tt < nslot; ++tt) {
       const int q = lane + 32 * tt;
-      if (q < ld - 1) {
+      if (q < m) {
         for (int s = 0; s < m; ++s) {
           float a = 0.f;
-          if (q < m)
-            for (int r = s; r < m; ++r) a += bufB[r * ld + q] * Ls[r * m + s];
-          bufA[s * ld + q] = a;
+          for (int r = s; r < m; ++r) a += bufY[r * ldc + q] * Ls[r * m + s];
+          bufA[q * ldc + s] = a;
         }
       }
     }
     __syncwarp();
-    float* Af = warp_jacobi(bufA, bufB, m, mp, ld, lane);
-    float* Yb = (Af == bufA) ? bufB : bufA;
+    warp_jacobi_cols<M4>(bufA, m, mp, ldc, lane);
     // eigenvalues and the distance
     float d2 = 0.f;
     for (int tt = 0; tt < nslot; ++tt) {
       const int q = lane + 32 * tt;
       if (q < m) {
         float n2 = 0.f;
-        for (int s = 0; s < m; ++s) n2 += Af[s * ld + q] * Af[s * ld + q];
+        for (int s = 0; s < m; ++s) n2 += bufA[q * ldc + s] * bufA[q * ldc + s];
         const float ll = logf(n2);
         d2 += ll * ll;
         ci[q] = 2.f * ll / n2;
@@ -457,7 +541,7 @@ pair_ai_kernel(const PairArgs A) {
       if (A.gD != nullptr)
         w *= tri ? (A.gD[(int64_t)i * nB + j] + A.gD[(int64_t)j * nB + i]) : A.gD[(int64_t)i * nB + j];
       __syncwarp();
-      // Y = L_i^-T A_f : Y[r][q] = sum_{s >= r} Linv_i[s][r] A_f[s][q]
+      // column q of Y = L_i^-T A_f : Y[r][q] = sum_{s >= r} Linv_i[s][r] A_f[s][q]
       for (int idx = lane; idx < m * m; idx += 32) Ls[idx] = Wi[m * m + idx];
       __syncwarp();
       for (int tt = 0; tt < nslot; ++tt) {
@@ -465,39 +549,26 @@ pair_ai_kernel(const PairArgs A) {
         if (q < m) {
           for (int r = 0; r < m; ++r) {
             float v = 0.f;
-            for (int s = r; s < m; ++s) v += Ls[s * m + r] * Af[s * ld + q];
-            Yb[r * ld + q] = v;
+            for (int s = r; s < m; ++s) v += Ls[s * m + r] * bufA[q * ldc + s];
+            bufY[q * ldc + r] = v;
           }
         }
       }
       __syncwarp();
-      // Zi = Y diag(w ci) -> over A_f's buffer, Zj = Y diag(w cj) -> Ls (row stride m)
-      for (int tt = 0; tt < nslot; ++tt) {
-        const int q = lane + 32 * tt;
-        if (q < m) {
-          const float a = w * ci[q], b = w * cj[q];
-          for (int r = 0; r < m; ++r) {
-            const float y = Yb[r * ld + q];
-            Af[r * ld + q] = a * y;
-            Ls[r * m + q] = b * y;
-          }
-        }
-      }
-      __syncwarp();
-      // G_i[r][s] = sum_q Zi[r][q] Y[s][q],  G_j[r][s] = sum_q Zj[r][q] Y[s][q];  lane <-> column s;
-      // stored as this pair's partials (plain stores)
+      // G_i[r][s] = sum_q (w ci_q) Y[r][q] Y[s][q],  G_j[r][s] = sum_q (w cj_q) Y[r][q] Y[s][q];
+      // lane <-> column s; stored as this pair's partials (plain stores)
       for (int tt = 0; tt < nslot; ++tt) {
         const int s = lane + 32 * tt;
         if (s < m) {
           for (int r = 0; r < m; ++r) {
             float a = 0.f, b = 0.f;
             for (int q = 0; q < m; ++q) {
-              const float y = Yb[s * ld + q];
-              a += Af[r * ld + q] * y;
-              b += Ls[r * m + q] * y;
+              const float yy = bufY[q * ldc + r] * bufY[q * ldc + s];
+              a += ci[q] * yy;
+              b += cj[q] * yy;
             }
-            gi[r * m + s] = a;
-            gj[r * m + s] = b;
+            gi[r * m + s] = w * a;
+            gj[r * m + s] = w * b;
           }
         }
       }
@@ -1096,18 +1167,20 @@ static cudaError_t launch_pair_kernel(const PairArgs& A, cudaStream_t st) {
     }
 #undef SQFA_PAIR_REG
   }
-  const int mp = (m + 1) & ~1;
-  const int ld = (mp > 32 ? 64 : 32) + 1;
-  const int per_warp = (2 * m * ld + m * m + 3 * m) * (int)sizeof(float);
+  const int per_warp = pair_smem_floats(m) * (int)sizeof(float);
   const int nw = warps_for(per_warp);
   const int smem = nw * per_warp;
   const unsigned blocks = (unsigned)((A.T.ntiles + nw - 1) / nw);
-  static int smem_set[kMaxDevices] = {0};
-  {
-    cudaError_t e = ensure_dynamic_smem(pair_ai_kernel, smem, smem_set);
+  static int smem_set12[kMaxDevices] = {0}, smem_set17[kMaxDevices] = {0};
+  if (m <= 48) {
+    cudaError_t e = ensure_dynamic_smem(pair_ai_kernel<12>, smem, smem_set12);
     if (e != cudaSuccess) return e;
+    pair_ai_kernel<12><<<blocks, nw * 32, smem, st>>>(A);
+  } else {
+    cudaError_t e = ensure_dynamic_smem(pair_ai_kernel<17>, smem, smem_set17);
+    if (e != cudaSuccess) return e;
+    pair_ai_kernel<17><<<blocks, nw * 32, smem, st>>>(A);
   }
-  pair_ai_kernel<<<blocks, nw * 32, smem, st>>>(A);
   return cudaGetLastError();
 }
 

@@ -49,11 +49,6 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
                               int chain_rows, int32_t* done, int n_groups, int reserve_sms, void* ws, int num_sms,
                               cudaStream_t stream);
 size_t gram_packed_floats(int D, int C);  // floats of the packed upper-tile list (256 x 256 tiles)
-// ---- umma_probe.cu (test hook) ----
-cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K, int N, int mode, uint32_t lbo,
-                              uint32_t sbo, uint32_t layout_type, uint32_t a_major, uint32_t b_major,
-                              uint32_t kstep_bytes, cudaStream_t stream);
-
 }  // namespace sqfa
 
 namespace sqfa {

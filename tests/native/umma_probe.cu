@@ -1,6 +1,7 @@
-// Test hook that pins the tcgen05 operand-layout assumptions of the Gram kernel on hardware:
-// one CTA, D[128 x N] = A^T B through one tcgen05.mma chain with a caller-chosen shared-memory
-// layout / descriptor. Used by tests/test_hp1_gpu.py and tools/umma_probe.py, not by the product.
+// TEST-ONLY object (built into tests/native/libsqfa_probe.so, not part of libsqfa_b200.so or its header).
+// Pins the tcgen05 operand-layout assumptions of the Gram kernel on hardware: one CTA,
+// D[128 x N] = A^T B through one tcgen05.mma chain with a caller-chosen shared-memory layout /
+// descriptor. Used by tests/test_hp1_gpu.py and tools/umma_probe.py.
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -141,3 +142,13 @@ cudaError_t launch_umma_probe(const float* A, const float* B, float* Dout, int K
 }
 
 }  // namespace sqfa
+
+extern "C" int sqfa_debug_umma_probe(const float* A, const float* B, float* Dout, int32_t K, int32_t N, int32_t mode,
+                                     uint32_t lbo, uint32_t sbo, uint32_t layout_type, uint32_t a_major,
+                                     uint32_t b_major, uint32_t kstep_bytes, void* stream) {
+  if (A == nullptr || B == nullptr || Dout == nullptr || K <= 0 || K % 8 != 0 || K > 64 || N < 16 || N > 256 ||
+      N % 32 != 0)
+    return -1;
+  return (int)sqfa::launch_umma_probe(A, B, Dout, K, N, mode, lbo, sbo, layout_type, a_major, b_major, kstep_bytes,
+                                      static_cast<cudaStream_t>(stream));
+}

@@ -1,5 +1,7 @@
 """GPU parity of hot path 1 (class_statistics) against the CPU oracle, through the C ABI."""
 
+import os
+
 import pytest
 import torch
 
@@ -12,9 +14,16 @@ TOL = 1e-5  # north_star: class means and second moments within 1e-5 relative (f
 
 
 def _probe(K, N):
-    from sqfa_b200 import _lib
+    """D[128 x N] = A^T B through the test-only probe library (tests/native/umma_probe.cu)."""
+    import ctypes
 
-    lib = _lib.load()
+    from sqfa_b200 import _lib, build
+
+    path = build.PROBE_LIB if os.path.exists(build.PROBE_LIB) else build.build_probe()
+    lib = ctypes.CDLL(path)
+    u32, i32, ptr = ctypes.c_uint32, ctypes.c_int32, ctypes.c_void_p
+    lib.sqfa_debug_umma_probe.restype = ctypes.c_int
+    lib.sqfa_debug_umma_probe.argtypes = [ptr, ptr, ptr, i32, i32, i32, u32, u32, u32, u32, u32, u32, ptr]
     g = torch.Generator().manual_seed(1)
     A = torch.randint(-4, 5, (K, 128), generator=g).float().cuda()
     B = torch.randint(-4, 5, (K, N), generator=g).float().cuda()

@@ -18,9 +18,14 @@ sys.path.insert(0, ROOT)
 def run_one(cfg):
     import torch
 
-    from sqfa_b200 import _lib
+    import ctypes
 
-    lib = _lib.load()
+    from sqfa_b200 import _lib, build
+
+    lib = ctypes.CDLL(build.PROBE_LIB if os.path.exists(build.PROBE_LIB) else build.build_probe())
+    u32, i32, ptr = ctypes.c_uint32, ctypes.c_int32, ctypes.c_void_p
+    lib.sqfa_debug_umma_probe.restype = ctypes.c_int
+    lib.sqfa_debug_umma_probe.argtypes = [ptr, ptr, ptr, i32, i32, i32, u32, u32, u32, u32, u32, u32, ptr]
     K, N = cfg["K"], cfg["N"]
     g = torch.Generator().manual_seed(1)
     A = torch.randint(-4, 5, (K, 128), generator=g).float().cuda()
