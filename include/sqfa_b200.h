@@ -281,6 +281,24 @@ int sqfa_closure_eval(const float* S, const float* M, const float* raw_filters, 
                       int64_t pair_begin, int64_t pair_end, float* out, float* grad, void* ws, size_t ws_bytes,
                       sqfa_stream_t stream);
 
+/* Plug-in distances between Gaussians that use the mean covariance of the pair (distances.py:240-432),
+ * one warp per pair (Cholesky of (Sigma_a + Sigma_b) / 2 in shared memory), all n_a * n_b pairs:
+ *   SQFA_GAUSS_MAHALANOBIS_SQ  d^T M^-1 d                                             (:283-330)
+ *   SQFA_GAUSS_BHATTACHARYYA   d^T M^-1 d / 8 + (logdet M - (logdet Sa + logdet Sb) / 2) / 2   (:240-280)
+ * (mahalanobis :333-361, hellinger :364-393 and fisher_rao_same_cov :396-432 are scalar maps of these.)
+ *   forward : gD == NULL, dist_out [n_a][n_b]
+ *   backward: gD [n_a][n_b] = upstream gradient; g_sigma_a [n_a][k][k], g_mu_a [n_a][k], g_sigma_b, g_mu_b are
+ *             OVERWRITTEN with the analytic gradients (per-pair partials in ws, summed per class in a fixed
+ *             order); dist_out may be NULL.
+ *   flag [1] or NULL: set to 1 if some matrix was not positive definite. k <= SQFA_MAX_M. */
+#define SQFA_GAUSS_MAHALANOBIS_SQ 0
+#define SQFA_GAUSS_BHATTACHARYYA 1
+size_t sqfa_gauss_pair_workspace_bytes(int32_t n_a, int32_t n_b, int32_t k, int32_t want_grad);
+int sqfa_gauss_pair_distances(const float* mu_a, const float* sigma_a, const float* mu_b, const float* sigma_b,
+                              int32_t n_a, int32_t n_b, int32_t k, int32_t mode, const float* gD, float* dist_out,
+                              float* g_sigma_a, float* g_mu_a, float* g_sigma_b, float* g_mu_b, void* ws,
+                              size_t ws_bytes, int32_t* flag, sqfa_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Optimiser support (reference: torch.optim.LBFGS driven by fitting_loop, _optim.py:78-96)
  * ------------------------------------------------------------------------------------------- */

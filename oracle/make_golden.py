@@ -72,6 +72,11 @@ def main():
         le_sq_aa=D.log_euclidean_sq(A, A), le_aa=D.log_euclidean(A, A),
         fr_sq_ab=D.fisher_rao_lower_bound_sq(sa, sb), fr_ab=D.fisher_rao_lower_bound(sa, sb),
         fr_sq_aa=D.fisher_rao_lower_bound_sq(sa, sa), fr_aa=D.fisher_rao_lower_bound(sa, sa),
+        # plug-in distances between Gaussians (distances.py:240-432)
+        bhatt_ab=D.bhattacharyya(sa, sb), bhatt_aa=D.bhattacharyya(sa, sa),
+        maha_sq_ab=D.mahalanobis_sq(sa, sb), maha_ab=D.mahalanobis(sa, sb), maha_sq_aa=D.mahalanobis_sq(sa, sa),
+        hell_ab=D.hellinger(sa, sb), hell_aa=D.hellinger(sa, sa),
+        frsc_ab=D.fisher_rao_same_cov(sa, sb), frsc_aa=D.fisher_rao_same_cov(sa, sa),
     )
 
     # ---- HP2: the closure (loss + gradient) and a converged fit, both model kinds

@@ -186,6 +186,49 @@ def fisher_rao_lower_bound(stats_a, stats_b):
     return torch.sqrt(fisher_rao_lower_bound_sq(stats_a, stats_b) + EPSILON)
 
 
+def _pair_mean_cov(stats_a, stats_b):
+    mu_a, mu_b = stats_a["means"], stats_b["means"]
+    cov_a, cov_b = stats_a["covariances"], stats_b["covariances"]
+    if mu_a.dim() == 1:
+        mu_a = mu_a.unsqueeze(0)
+    if mu_b.dim() == 1:
+        mu_b = mu_b.unsqueeze(0)
+    if cov_a.dim() == 2:
+        cov_a = cov_a.unsqueeze(0)
+    if cov_b.dim() == 2:
+        cov_b = cov_b.unsqueeze(0)
+    return mu_a[:, None] - mu_b[None, :], (cov_a[:, None] + cov_b[None, :]) / 2, cov_a, cov_b
+
+
+def mahalanobis_sq(stats_a, stats_b):
+    """distances.py:283-330: d^T ((Sigma_a + Sigma_b) / 2)^-1 d for every pair (not squeezed)."""
+    diff, mean_cov, _, _ = _pair_mean_cov(stats_a, stats_b)
+    return torch.einsum("ijk,ijkl,ijl->ij", diff, torch.linalg.inv(mean_cov), diff)  # :323-329
+
+
+def mahalanobis(stats_a, stats_b):
+    """distances.py:333-361"""
+    return torch.sqrt(mahalanobis_sq(stats_a, stats_b) + EPSILON)
+
+
+def bhattacharyya(stats_a, stats_b):
+    """distances.py:240-280: maha / 8 + (logdet mean_cov - (logdet A + logdet B) / 2) / 2, squeezed."""
+    diff, mean_cov, cov_a, cov_b = _pair_mean_cov(stats_a, stats_b)
+    term1 = torch.einsum("ijk,ijkl,ijl->ij", diff, torch.linalg.inv(mean_cov), diff)  # :268-270
+    term2 = torch.logdet(mean_cov) - (torch.logdet(cov_a)[:, None] + torch.logdet(cov_b)[None, :]) * 0.5  # :272-276
+    return torch.squeeze(term1 / 8 + term2 * 0.5)  # :278-280
+
+
+def hellinger(stats_a, stats_b):
+    """distances.py:364-393"""
+    return torch.sqrt(1 - torch.exp(-bhattacharyya(stats_a, stats_b)) + EPSILON)
+
+
+def fisher_rao_same_cov(stats_a, stats_b):
+    """distances.py:396-432"""
+    return 2.0**0.5 * torch.acosh(1 + mahalanobis_sq(stats_a, stats_b) / 4)
+
+
 # ------------------------------------------------------------------------------------------------
 # HP2: model forward and the closure loss
 # ------------------------------------------------------------------------------------------------

@@ -91,6 +91,12 @@ SIGNATURES = {
          c_ptr, c_ptr, c_size, c_ptr],
     ),
     "sqfa_class_factor_bwd": (c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
+    "sqfa_gauss_pair_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32]),
+    "sqfa_gauss_pair_distances": (
+        c_int,
+        [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size,
+         c_ptr, c_ptr],
+    ),
     "sqfa_fused_loss_workspace_bytes": (c_size, [c_i32, c_i32, c_i32, c_i32, c_i64, c_i64]),
     "sqfa_fused_loss": (
         c_int,

@@ -254,6 +254,56 @@ class PairDistance(torch.autograd.Function):
         return ga, gb, None, None
 
 
+GAUSS_MAHA_SQ = 0  # SQFA_GAUSS_MAHALANOBIS_SQ
+GAUSS_BHATT = 1  # SQFA_GAUSS_BHATTACHARYYA
+
+
+def gauss_pairs_raw(mu_a, sig_a, mu_b, sig_b, mode, gD=None):
+    """Mean-covariance distances between Gaussians (Mahalanobis^2 / Bhattacharyya), all n_a x n_b pairs.
+    Forward (gD None): returns D (n_a, n_b). Backward: returns (g_sig_a, g_mu_a, g_sig_b, g_mu_b)."""
+    lib = _lib.load()
+    dev = mu_a.device
+    n_a, k = mu_a.shape
+    n_b = mu_b.shape[0]
+    grad = gD is not None
+    nbytes = lib.sqfa_gauss_pair_workspace_bytes(n_a, n_b, k, 1 if grad else 0)
+    ws = _ws(nbytes, dev)
+    if grad:
+        out = (torch.empty(n_a, k, k, dtype=torch.float32, device=dev), torch.empty(n_a, k, dtype=torch.float32, device=dev),
+               torch.empty(n_b, k, k, dtype=torch.float32, device=dev), torch.empty(n_b, k, dtype=torch.float32, device=dev))
+        D = None
+    else:
+        out = (None, None, None, None)
+        D = torch.empty(n_a, n_b, dtype=torch.float32, device=dev)
+    _lib.check(
+        lib.sqfa_gauss_pair_distances(
+            _lib.ptr(mu_a), _lib.ptr(sig_a), _lib.ptr(mu_b), _lib.ptr(sig_b), n_a, n_b, k, mode, _lib.ptr(gD), _lib.ptr(D),
+            _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(ws), nbytes, None,
+            _lib.stream_ptr(dev),
+        ),
+        "sqfa_gauss_pair_distances",
+    )
+    return out if grad else D
+
+
+class GaussPairDistance(torch.autograd.Function):
+    """D[a, b] = mahalanobis_sq or bhattacharyya between the Gaussians (mu_a, Sigma_a) and (mu_b, Sigma_b)
+    (reference distances.py:240-330), one warp per pair, analytic backward (second launch)."""
+
+    @staticmethod
+    def forward(ctx, mu_a, sig_a, mu_b, sig_b, mode):
+        args = [t.contiguous().float() for t in (mu_a, sig_a, mu_b, sig_b)]
+        ctx.save_for_backward(*args)
+        ctx.mode = mode
+        return gauss_pairs_raw(*args, mode)
+
+    @staticmethod
+    def backward(ctx, gD):
+        mu_a, sig_a, mu_b, sig_b = ctx.saved_tensors
+        g_sig_a, g_mu_a, g_sig_b, g_mu_b = gauss_pairs_raw(mu_a, sig_a, mu_b, sig_b, ctx.mode, gD.contiguous().float())
+        return g_mu_a, g_sig_a, g_mu_b, g_sig_b, None
+
+
 N_OUT = 3  # [loss, number of non-finite pair distances, max |gradient|]
 
 

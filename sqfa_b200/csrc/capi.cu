@@ -456,3 +456,31 @@ int sqfa_stats_epilogue_f64(const double* gram, const double* means, const doubl
 }
 
 }  // extern "C"
+
+extern "C" {
+
+// ------------------------------------------------------------- plug-in distances between Gaussians
+size_t sqfa_gauss_pair_workspace_bytes(int32_t n_a, int32_t n_b, int32_t k, int32_t want_grad) {
+  if (n_a <= 0 || n_b <= 0 || k <= 0) return 1024;
+  return sqfa::gauss_workspace_floats(n_a, n_b, k, want_grad) * sizeof(float);
+}
+
+int sqfa_gauss_pair_distances(const float* mu_a, const float* sigma_a, const float* mu_b, const float* sigma_b,
+                              int32_t n_a, int32_t n_b, int32_t k, int32_t mode, const float* gD, float* dist_out,
+                              float* g_sigma_a, float* g_mu_a, float* g_sigma_b, float* g_mu_b, void* ws,
+                              size_t ws_bytes, int32_t* flag, sqfa_stream_t stream) {
+  const bool grad = gD != nullptr;
+  if (mu_a == nullptr || sigma_a == nullptr || mu_b == nullptr || sigma_b == nullptr || n_a < 0 || n_b < 0 || k <= 0 ||
+      (mode != SQFA_GAUSS_MAHALANOBIS_SQ && mode != SQFA_GAUSS_BHATTACHARYYA) || ws == nullptr ||
+      (!grad && dist_out == nullptr) ||
+      (grad && (g_sigma_a == nullptr || g_mu_a == nullptr || g_sigma_b == nullptr || g_mu_b == nullptr)))
+    return fail_arg(__func__, "bad argument");
+  if (k > SQFA_MAX_M) return fail_arg(__func__, "k exceeds SQFA_MAX_M", SQFA_E_UNSUPPORTED);
+  if (ws_bytes < sqfa_gauss_pair_workspace_bytes(n_a, n_b, k, grad ? 1 : 0))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_gauss_pairs(mu_a, sigma_a, mu_b, sigma_b, n_a, n_b, k, mode, gD, dist_out,
+                                                 g_sigma_a, g_mu_a, g_sigma_b, g_mu_b, static_cast<float*>(ws), flag,
+                                                 S(stream)));
+}
+
+}  // extern "C"

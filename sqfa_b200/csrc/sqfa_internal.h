@@ -147,3 +147,11 @@ cudaError_t launch_stats_epilogue_f64(const double* gram, const double* means, c
                                       const int64_t* counts, int D, int C, int estimator, int ddof, double* cov,
                                       double* sm, cudaStream_t st);
 }  // namespace sqfa
+
+namespace sqfa {
+// ---- gauss.cu (mean-covariance distances between Gaussians: Mahalanobis, Bhattacharyya) ----
+size_t gauss_workspace_floats(int nA, int nB, int k, int want_grad);
+cudaError_t launch_gauss_pairs(const float* muA, const float* SigA, const float* muB, const float* SigB, int nA,
+                               int nB, int k, int mode, const float* gD, float* dist_out, float* gSigA, float* gMuA,
+                               float* gSigB, float* gMuB, float* ws, int32_t* flag_out, cudaStream_t st);
+}  // namespace sqfa

@@ -5,8 +5,9 @@ The three distance families SQFA optimises (affine-invariant, its Calvo-Oller / 
 lower-bound use on embedded Gaussians, log-Euclidean; reference distances.py:46-237) run in the
 warp-per-pair Jacobi kernels and are differentiable through analytic backward passes. The other
 distances of the reference (Bhattacharyya, Mahalanobis, Hellinger, Fisher-Rao with shared
-covariance) are alternative `distance_fun` plug-ins outside the hot path (SURVEY.md section 2);
-they are provided as plain device-side torch compositions so the namespace stays complete.
+covariance; alternative `distance_fun` plug-ins) run in a warp-per-pair
+Cholesky kernel with an analytic backward. float64 inputs and matrices above 64 x 64 take the
+reference's own composition with device-side library calls, in the dtype of the inputs.
 """
 
 import torch
@@ -150,27 +151,40 @@ def fisher_rao_lower_bound(statistics_A, statistics_B):
 
 
 # ------------------------------------------------------------------------------------------------
-# Plug-in distances outside the hot path (reference distances.py:240-432): device-side torch.
+# The reference's other distance_fun plug-ins (distances.py:240-432): distances between Gaussians under
+# the MEAN covariance of the pair. Native: one warp per pair (Cholesky of the mean covariance), analytic
+# backward; mahalanobis, hellinger and fisher_rao_same_cov are scalar maps of the two kernels' outputs.
 # ------------------------------------------------------------------------------------------------
-def bhattacharyya(statistics_A, statistics_B):
-    """Bhattacharyya distance between Gaussians (reference distances.py:240-280)."""
+def _gauss_pairs(statistics_A, statistics_B, mode):
+    """(n_a, n_b) matrix of mahalanobis_sq / bhattacharyya values (not squeezed)."""
     mu_a, mu_b = _unsq_mean(statistics_A["means"]), _unsq_mean(statistics_B["means"])
     cov_a, cov_b = _batch3(statistics_A["covariances"]), _batch3(statistics_B["covariances"])
-    mean_cov = 0.5 * (cov_a[:, None] + cov_b[None])
-    diff = mu_a[:, None] - mu_b[None]
-    maha = torch.einsum("abi,abij,abj->ab", diff, torch.linalg.inv(mean_cov), diff)
-    logdet = torch.logdet(mean_cov) - 0.5 * (torch.logdet(cov_a)[:, None] + torch.logdet(cov_b)[None])
-    return torch.squeeze(0.125 * maha + 0.5 * logdet)
+    ref = statistics_A["means"]
+    dev = _lib.compute_device(mu_a, cov_a, mu_b, cov_b)
+    native = all(t.dtype == torch.float32 for t in (mu_a, mu_b, cov_a, cov_b)) and cov_a.shape[-1] <= _ops.MAX_M
+    with torch.cuda.device(dev):
+        mu_a, mu_b, cov_a, cov_b = (t.to(dev) for t in (mu_a, mu_b, cov_a, cov_b))
+        if native:
+            D = _ops.GaussPairDistance.apply(mu_a, cov_a, mu_b, cov_b, mode)
+        else:  # float64 / large matrices: the reference's composition with device-side library calls
+            mean_cov = 0.5 * (cov_a[:, None] + cov_b[None])
+            diff = mu_a[:, None] - mu_b[None]
+            D = torch.einsum("abi,abij,abj->ab", diff, torch.linalg.inv(mean_cov), diff)
+            if mode == _ops.GAUSS_BHATT:
+                logdet = torch.logdet(mean_cov) - 0.5 * (torch.logdet(cov_a)[:, None] + torch.logdet(cov_b)[None])
+                D = 0.125 * D + 0.5 * logdet
+    return D.to(device=ref.device, dtype=ref.dtype)
+
+
+def bhattacharyya(statistics_A, statistics_B):
+    """Bhattacharyya distance between Gaussians (reference distances.py:240-280)."""
+    return torch.squeeze(_gauss_pairs(statistics_A, statistics_B, _ops.GAUSS_BHATT))
 
 
 def mahalanobis_sq(statistics_A, statistics_B):
-    """Squared Mahalanobis distance under the pairwise mean covariance (reference
-    distances.py:283-330)."""
-    mu_a, mu_b = _unsq_mean(statistics_A["means"]), _unsq_mean(statistics_B["means"])
-    cov_a, cov_b = _batch3(statistics_A["covariances"]), _batch3(statistics_B["covariances"])
-    mean_cov_inv = torch.linalg.inv(0.5 * (cov_a[:, None] + cov_b[None]))
-    diff = mu_a[:, None] - mu_b[None]
-    return torch.squeeze(torch.einsum("abi,abij,abj->ab", diff, mean_cov_inv, diff))
+    """Squared Mahalanobis distance under the pairwise mean covariance, shape (n_a, n_b) (reference
+    distances.py:283-330; not squeezed, like the reference)."""
+    return _gauss_pairs(statistics_A, statistics_B, _ops.GAUSS_MAHA_SQ)
 
 
 def mahalanobis(statistics_A, statistics_B):

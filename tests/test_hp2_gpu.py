@@ -1,6 +1,8 @@
 """GPU parity of hot path 2 (projection, pairwise SPD distances, fused loss + analytic backward, fit)
 against the CPU oracle, through the Python host API that sits on the C ABI."""
 
+import os
+
 import pytest
 import torch
 
@@ -369,3 +371,102 @@ def test_large_and_double_inputs_take_the_composed_path():
     assert got.dtype == torch.float64 and rel_err(got, O.fisher_rao_lower_bound(sd, sd)) < 1e-8
     lam = Ln.generalized_eigenvalues(A6.cuda(), B6.cuda())
     assert lam.dtype == torch.float64 and rel_err(lam, O.generalized_eigenvalues(A6, B6)) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's other distance_fun plug-ins (distances.py:240-432): native warp-per-pair kernels
+# ------------------------------------------------------------------------------------------------
+PLUGINS = ("bhattacharyya", "mahalanobis_sq", "mahalanobis", "hellinger", "fisher_rao_same_cov")
+
+
+def test_plugin_distances_golden():
+    import numpy as np
+
+    from sqfa_b200 import distances as Dn
+
+    with np.load(os.path.join(os.path.dirname(__file__), "golden", "distances.npz")) as z:
+        g = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+    sa = {"means": g["mu_a"].float().cuda(), "covariances": g["A"].float().cuda()}
+    sb = {"means": g["mu_b"].float().cuda(), "covariances": g["B"].float().cuda()}
+    for name, key in (("bhattacharyya", "bhatt"), ("hellinger", "hell"), ("fisher_rao_same_cov", "frsc"),
+                      ("mahalanobis_sq", "maha_sq")):
+        got = getattr(Dn, name)(sa, sb)
+        assert got.shape == g[key + "_ab"].shape, name
+        assert rel_err(got, g[key + "_ab"]) < 1e-4, name
+    assert rel_err(Dn.mahalanobis(sa, sb), g["maha_ab"]) < 1e-4
+    i, j = torch.tril_indices(5, 5, -1)
+    assert rel_err(Dn.bhattacharyya(sa, sa)[i, j], g["bhatt_aa"][i, j]) < 1e-4
+    assert rel_err(Dn.mahalanobis_sq(sa, sa)[i, j], g["maha_sq_aa"][i, j]) < 1e-4
+    # float64 inputs: float64 results through the composed path
+    sa64 = {"means": g["mu_a"].cuda(), "covariances": g["A"].cuda()}
+    sb64 = {"means": g["mu_b"].cuda(), "covariances": g["B"].cuda()}
+    got = Dn.bhattacharyya(sa64, sb64)
+    assert got.dtype == torch.float64 and rel_err(got, g["bhatt_ab"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", PLUGINS)
+@pytest.mark.parametrize("na,nb,k", [(1, 1, 2), (5, 3, 4), (7, 7, 9), (40, 3, 17), (3, 2, 40)])
+def test_plugin_distances_match_oracle_with_gradients(name, na, nb, k):
+    """values and d/d(means, covariances) against fp64 autograd through the reference's formulas
+    (torch.linalg.inv / logdet), for A != B and for A is B."""
+    from sqfa_b200 import distances as Dn
+
+    g = torch.Generator().manual_seed(na * 100 + nb * 10 + k)
+    A, B = sample_spd(na, k, seed=k), sample_spd(nb, k, seed=k + 1)
+    mu_a = torch.randn(na, k, generator=g, dtype=torch.float64)
+    mu_b = torch.randn(nb, k, generator=g, dtype=torch.float64)
+    Wt = torch.randn(na, nb, generator=g, dtype=torch.float64)
+
+    def run(fun, tensors, weights):
+        leaves = [t.clone().requires_grad_(True) for t in tensors]
+        sa = {"means": leaves[0], "covariances": leaves[1]}
+        sb = {"means": leaves[2], "covariances": leaves[3]}
+        D = fun(sa, sb)
+        (D.reshape(na, nb) * weights.to(D)).sum().backward()
+        return D.detach(), [t.grad for t in leaves]
+
+    D_ref, g_ref = run(getattr(O, name), (mu_a, A, mu_b, B), Wt)
+    D_got, g_got = run(getattr(Dn, name), tuple(t.float().cuda() for t in (mu_a, A, mu_b, B)), Wt)
+    assert D_got.shape == D_ref.shape
+    assert rel_err(D_got, D_ref) < 1e-4
+    for a, b in zip(g_got, g_ref):
+        b = 0.5 * (b + b.transpose(-2, -1)) if b.dim() == 3 else b
+        a = 0.5 * (a + a.transpose(-2, -1)) if a.dim() == 3 else a
+        assert rel_err(a, b) < 1e-3
+    if na == nb:  # the same statistics on both sides
+        leaves = [mu_a.float().cuda().requires_grad_(True), A.float().cuda().requires_grad_(True)]
+        s = {"means": leaves[0], "covariances": leaves[1]}
+        D = getattr(Dn, name)(s, s)
+        l64 = [mu_a.clone().requires_grad_(True), A.clone().requires_grad_(True)]
+        s64 = {"means": l64[0], "covariances": l64[1]}
+        D64 = getattr(O, name)(s64, s64)
+        off = ~torch.eye(na, dtype=torch.bool)
+        if na > 1:
+            (D.reshape(na, na)[off.cuda()] * Wt[off].float().cuda()).sum().backward()
+            (D64.reshape(na, na)[off] * Wt[off]).sum().backward()
+            assert rel_err(leaves[0].grad, l64[0].grad) < 1e-3
+            assert rel_err(0.5 * (leaves[1].grad + leaves[1].grad.transpose(1, 2)),
+                           0.5 * (l64[1].grad + l64[1].grad.transpose(1, 2))) < 1e-3
+
+
+def test_fit_with_plugin_distance():
+    """SQFA.fit with distance_fun=bhattacharyya: losses of a short fit against the oracle in fp64."""
+    from sqfa_b200 import distances as Dn
+    from sqfa_b200.model import SQFA
+
+    n, d, c, k = 3000, 20, 5, 3
+    stats = stats_for(n, d, c, seed=31)
+    F0 = torch.randn(k, d, generator=torch.Generator().manual_seed(4))
+    loss64, grad64, _ = O.loss_and_grad("full", stats, F0.double(), noise=0.01, distance=O.bhattacharyya)
+    model = SQFA(n_dim=d, feature_noise=0.01, n_filters=k, filters=F0.clone(), distance_fun=Dn.bhattacharyya).cuda()
+    dmat = model.get_class_distances(to_f32_cuda(stats), regularized=True)
+    i, j = torch.tril_indices(c, c, -1)
+    loss = -dmat[i, j].mean()
+    loss.backward()
+    assert abs(float(loss) - float(loss64)) < DIST_TOL * abs(float(loss64))
+    assert rel_err(model.parametrizations.filters.original.grad, grad64) < GRAD_TOL
+    _, losses_o, _ = O.fit_lbfgs("full", stats, F0.double(), noise=0.01, distance=O.bhattacharyya, max_epochs=2, max_iter=5)
+    model = SQFA(n_dim=d, feature_noise=0.01, n_filters=k, filters=F0.clone(), distance_fun=Dn.bhattacharyya)
+    losses, _ = model.fit(data_statistics={kk: v.float() for kk, v in stats.items()}, max_epochs=2,
+                          show_progress=False, return_loss=True, max_iter=5)
+    assert torch.allclose(losses.double(), losses_o.double(), rtol=1e-3)

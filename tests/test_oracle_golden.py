@@ -89,3 +89,16 @@ def test_fit_golden(tag, kind):
     assert abs(float(losses[-1]) - float(ref_losses[-1])) < 1e-5
     assert abs(float(losses[0]) - float(ref_losses[0])) < 1e-6  # loss lists are stored in float32
     assert O.subspace_angle(F, g[tag + "_fit_filters"]) < 2e-3
+
+
+def test_plugin_distances_golden():
+    """The reference's other distance_fun plug-ins (distances.py:240-432): oracle vs the real reference."""
+    g = load("distances.npz")
+    sa = {"means": g["mu_a"], "covariances": g["A"]}
+    sb = {"means": g["mu_b"], "covariances": g["B"]}
+    for name, key in (("bhattacharyya", "bhatt"), ("hellinger", "hell"), ("fisher_rao_same_cov", "frsc")):
+        assert close(getattr(O, name)(sa, sb), g[key + "_ab"], 1e-10), name
+        assert close(getattr(O, name)(sa, sa), g[key + "_aa"], 1e-9), name
+    assert close(O.mahalanobis_sq(sa, sb), g["maha_sq_ab"], 1e-10)
+    assert close(O.mahalanobis_sq(sa, sa), g["maha_sq_aa"], 1e-10)
+    assert close(O.mahalanobis(sa, sb), g["maha_ab"], 1e-10)
