@@ -433,7 +433,8 @@ def test_plugin_distances_match_oracle_with_gradients(name, na, nb, k):
         b = 0.5 * (b + b.transpose(-2, -1)) if b.dim() == 3 else b
         a = 0.5 * (a + a.transpose(-2, -1)) if a.dim() == 3 else a
         assert rel_err(a, b) < 1e-3
-    if na == nb:  # the same statistics on both sides
+    # (fisher_rao_same_cov: d acosh(1 + x / 4) / dx is infinite at the diagonal's x = 0, in the reference too)
+    if na == nb and name != "fisher_rao_same_cov":  # the same statistics on both sides
         leaves = [mu_a.float().cuda().requires_grad_(True), A.float().cuda().requires_grad_(True)]
         s = {"means": leaves[0], "covariances": leaves[1]}
         D = getattr(Dn, name)(s, s)
