@@ -100,10 +100,10 @@ struct GramParams {
 // Job list: classes in descending size; within a class the K parts, and within a K part its tiles:
 // the CTA pairs that run concurrently work on the tiles of the SAME rows, which they share in L2.
 // job = ((rank * KS) + ks) * T + t
-__global__ void __launch_bounds__(1024) gram_plan_kernel(const int64_t* __restrict__ offsets, int C, int TT, int KS,
-                                                          int class_order, int4* __restrict__ jobs) {
+__global__ void __launch_bounds__(256) gram_plan_kernel(const int64_t* __restrict__ offsets, int C, int TT, int KS,
+                                                         int class_order, int4* __restrict__ jobs) {
   const int T = TT * (TT + 1) / 2;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     const int64_t n_c = offsets[c + 1] - offsets[c];
     int rank = class_order ? c : 0;
     for (int o = 0; o < C && !class_order; ++o) {
@@ -199,26 +199,25 @@ __device__ __forceinline__ void gram_body(const GramParams& P) {
     const bool isA = (warp & 1) == 0;
     const int quad = warp >> 1;  // samples 4 quad .. 4 quad + 3 of a stage = K-major chunk `quad`
     // chunk of slot 32 j + lane in k-chunk `quad`:  quad * 2048 + j * 512 + (lane / 8) * 128 + (lane % 8) * 16
-    const uint32_t hi_base = smem_u32(smem) + (isA ? 0 : 2 * OP_BYTES) + quad * OP_LBO + (lane >> 3) * 128 + (lane & 7) * 16;
-    const uint32_t lo_base = hi_base + OP_BYTES;  // 32-bit shared addresses: no 64-bit math in the loop
+    const uint32_t hi_A = smem_u32(smem) + quad * OP_LBO + (lane >> 3) * 128 + (lane & 7) * 16;  // A operand buffers
+    const uint32_t hi_B = hi_A + 2 * OP_BYTES;                                                    // B operand buffers
     const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's barriers, cluster window
     const bool vecx = P.vecx != 0;
     for (int j = pair; j < P.njobs; j += npairs) {
       const JobGeom g = decode_job<TM, TN>(P, j);
       const int kb0 = g.kb0, kb1 = g.kb1;
       const int64_t n_c = g.n_c;
-      if (g.diag && !isA) {
-        // diagonal tile: the MMA reads this CTA's A buffers as its B half; the B warps only keep
-        // the barrier protocol going (arrival counts are fixed)
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
-          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
-        }
-        continue;
-      }
-      const int col = (isA ? g.m0 : g.n0) + 128 * (int)rank + 4 * lane;  // first of this thread's 4 columns
+      // Diagonal tile: the MMA reads this CTA's A buffers as its B half, so there is no B operand to
+      // produce. The A and the B warp of a sample quad then SHARE the A operand: the A warp produces
+      // the even stages of the job, the B warp the odd ones (each only keeps the barrier protocol going
+      // on the other's stages). Twice the global loads in flight per stage period: diagonal tiles --
+      // every tile of the single-CTA variant, 40-67 % of the tiles at D = 512 ... 1024 -- were bound by
+      // load latency with four loading warps (ncu: stall_long_sb, tensor pipe 29 % at D = 104).
+      const bool share = g.diag;
+      const bool asA = isA || share;
+      const uint32_t hi_base = asA ? hi_A : hi_B;
+      const uint32_t lo_base = hi_base + OP_BYTES;  // 32-bit shared addresses: no 64-bit math in the loop
+      const int col = (asA ? g.m0 : g.n0) + 128 * (int)rank + 4 * lane;  // first of this thread's 4 columns
       const int ncol = col >= D ? 0 : (D - col >= 4 ? 4 : D - col);      // how many of them exist
       float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
       if (P.shift != nullptr && ncol > 0) {
@@ -236,8 +235,11 @@ __device__ __forceinline__ void gram_body(const GramParams& P) {
       // per-load branches); scalar loads only in the last column tile of a D not divisible by 4
       const bool fastw = __all_sync(0xffffffffu, vecx && (ncol == 4 || ncol == 0));
 
-      auto produce = [&](auto fast_tag) {
+      auto produce = [&](auto fast_tag, auto share_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
+        constexpr bool SHARE = decltype(share_tag)::value;
+        constexpr int S = SHARE ? 2 : 1;          // stride between the stages this warp produces
+        const int off = (SHARE && !isA) ? 1 : 0;  // its first stage, relative to kb0
         // Register pipeline. ptxas tracks every global load of this loop on ONE scoreboard, so the
         // first use of any loaded value waits for ALL loads in flight (ncu: the per-slot prefetch
         // of the previous version waited for the refill issued one stage earlier). The loop is
@@ -254,7 +256,15 @@ __device__ __forceinline__ void gram_body(const GramParams& P) {
           return ldg_nc_u32(P.perm + max(min(idx, P.n - 1), (int64_t)0));
         };
         uint32_t rowreg[GB];
-        auto issue = [&](int kb, b128_t(&b)[GB][4]) {  // loads of stages kb .. kb + GB - 1
+        int ring_kb = kb0;  // stage index the shared-memory ring position (stage, phase) stands for
+        auto skip_stage = [&]() {  // a stage some other warp produces: keep the arrival counts going
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+          ++ring_kb;
+        };
+        auto issue = [&](int kb, b128_t(&b)[GB][4]) {  // loads of stages kb, kb + S, .. kb + (GB - 1) S
 #pragma unroll
           for (int u = 0; u < GB; ++u) {
 #pragma unroll
@@ -276,7 +286,7 @@ __device__ __forceinline__ void gram_body(const GramParams& P) {
             }
           }
 #pragma unroll
-          for (int u = 0; u < GB; ++u) rowreg[u] = load_row(kb + GB + u);  // ids of the NEXT batch
+          for (int u = 0; u < GB; ++u) rowreg[u] = load_row(kb + S * (GB + u));  // ids of the NEXT batch
         };
         auto put = [&](uint32_t hp, uint32_t lp, float x0, float x1, float x2, float x3) {
           float4 h, l;
@@ -288,6 +298,10 @@ __device__ __forceinline__ void gram_body(const GramParams& P) {
           st_shared_v4(lp, l);
         };
         auto consume = [&](int kb, const b128_t(&bq)[4]) {
+          if constexpr (SHARE) {
+            while (ring_kb < kb) skip_stage();
+            ++ring_kb;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           float4 b[4];
 #pragma unroll
@@ -315,20 +329,27 @@ __device__ __forceinline__ void gram_body(const GramParams& P) {
         // then the loads of the next batch into the other register set, then the remaining stages
         auto batch = [&](int kb, b128_t(&cur)[GB][4], b128_t(&nxt)[GB][4]) {
           if (kb < kb1) consume(kb, cur[0]);
-          issue(kb + GB, nxt);  // unconditional: stages past the end re-read valid rows, never consumed
+          issue(kb + S * GB, nxt);  // unconditional: stages past the end re-read valid rows, never consumed
 #pragma unroll
           for (int u = 1; u < GB; ++u)
-            if (kb + u < kb1) consume(kb + u, cur[u]);
+            if (kb + S * u < kb1) consume(kb + S * u, cur[u]);
         };
 #pragma unroll
-        for (int u = 0; u < GB; ++u) rowreg[u] = load_row(kb0 + u);
-        issue(kb0, bufA);
-        for (int kb = kb0; kb < kb1; kb += 2 * GB) {
+        for (int u = 0; u < GB; ++u) rowreg[u] = load_row(kb0 + off + S * u);
+        issue(kb0 + off, bufA);
+        for (int kb = kb0 + off; kb < kb1; kb += 2 * GB * S) {
           batch(kb, bufA, bufB);
-          batch(kb + GB, bufB, bufA);
+          batch(kb + GB * S, bufB, bufA);
+        }
+        if constexpr (SHARE) {
+          while (ring_kb < kb1) skip_stage();  // trailing stages of the other warp
         }
       };
-      if (fastw) produce(std::true_type{}); else produce(std::false_type{});
+      if (share) {
+        if (fastw) produce(std::true_type{}, std::true_type{}); else produce(std::false_type{}, std::true_type{});
+      } else {
+        if (fastw) produce(std::true_type{}, std::false_type{}); else produce(std::false_type{}, std::false_type{});
+      }
     }
   } else if (warp == MMA_WARP2) {
     // =========================== MMA issuer (leader CTA only) ===========================
@@ -695,7 +716,8 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
     cudaError_t e = cudaMemsetAsync(gram, 0, floats * sizeof(float), stream);
     if (e != cudaSuccess) return e;
   }
-  gram_plan_kernel<<<1, 1024, 0, stream>>>(offsets, C, TT, P.KS, P.class_order, reinterpret_cast<int4*>(ws));
+  gram_plan_kernel<<<(C + 255) / 256, 256, 0, stream>>>(offsets, C, TT, P.KS, P.class_order,
+                                                        reinterpret_cast<int4*>(ws));
   // reserve_sms SMs are left to other streams (the collective that runs while this kernel still computes)
   const int usable = num_sms - (reserve_sms > 0 ? reserve_sms : 0);
   if (small) {

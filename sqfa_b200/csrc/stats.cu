@@ -24,22 +24,35 @@ __device__ __forceinline__ float4 f4add(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
+// threads of a block that share one row (each owns 4 columns): 256 for D >= 1024, fewer for small D so
+// that the remaining threads of the block form ROW LANES (D = 104: 32 threads per row, 8 row lanes --
+// with one row lane, 230 of 256 threads had no column and the kernel ran at 1.6 TB/s)
+__host__ __device__ inline int sums_threads_per_row(int D) {
+  int tpr = 32;
+  while (tpr < SUM_THREADS && tpr * 4 < D) tpr <<= 1;
+  return tpr;
+}
+
 // partial[c][split][D] = sum over the split's rows of (x - shift_c)
 __global__ void __launch_bounds__(SUM_THREADS)
 class_sums_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ perm,
                   const int64_t* __restrict__ offsets, const float* __restrict__ shift, int D, int nsplit,
                   float* __restrict__ partial, int vec_ok) {
+  __shared__ float4 red[SUM_THREADS];
+  const int tpr = sums_threads_per_row(D), nlanes = SUM_THREADS / tpr;
+  const int rlane = threadIdx.x / tpr, tcol = threadIdx.x % tpr;
   const int c = blockIdx.z;
   const int split = blockIdx.y;
   const int64_t begin = offsets[c];
   const int64_t n_c = offsets[c + 1] - begin;
-  const int64_t k0 = (n_c * split) / nsplit;
-  const int64_t k1 = (n_c * (split + 1)) / nsplit;
-  const int col = (blockIdx.x * SUM_THREADS + threadIdx.x) * 4;
-  if (col >= D) return;
+  const int64_t s0 = (n_c * split) / nsplit, s1 = (n_c * (split + 1)) / nsplit;
+  // the split's rows are cut into one contiguous piece per row lane
+  const int64_t k0 = s0 + ((s1 - s0) * rlane) / nlanes, k1 = s0 + ((s1 - s0) * (rlane + 1)) / nlanes;
+  const int col = (blockIdx.x * tpr + tcol) * 4;
+  const bool live = col < D;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool full = vec_ok && (col + 4 <= D);
-  if (shift != nullptr) {
+  if (shift != nullptr && live) {
     const float* sh = shift + (int64_t)c * D + col;
     s.x = sh[0];
     if (col + 1 < D) s.y = sh[1];
@@ -47,7 +60,7 @@ class_sums_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
     if (col + 3 < D) s.w = sh[3];
   }
   float4 outer = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t kb = k0; kb < k1; kb += SUM_BLOCK_ROWS) {
+  for (int64_t kb = k0; kb < k1 && live; kb += SUM_BLOCK_ROWS) {
     const int64_t ke = kb + SUM_BLOCK_ROWS < k1 ? kb + SUM_BLOCK_ROWS : k1;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     int64_t k = kb;
@@ -78,6 +91,13 @@ class_sums_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
     }
     outer = f4add(outer, f4add(f4add(a0, a1), f4add(a2, a3)));
   }
+  if (nlanes > 1) {  // row lanes of a column group are added in lane order: deterministic
+    red[threadIdx.x] = outer;
+    __syncthreads();
+    if (rlane != 0) return;
+    for (int r = 1; r < nlanes; ++r) outer = f4add(outer, red[r * tpr + tcol]);
+  }
+  if (!live) return;
   float* out = partial + ((int64_t)c * nsplit + split) * D + col;
   out[0] = outer.x;
   if (col + 1 < D) out[1] = outer.y;
@@ -350,10 +370,11 @@ oas_apply_kernel(const double* __restrict__ partial, const float* __restrict__ m
 }  // namespace
 
 int class_sums_splits(int64_t n, int C, int D, int num_sms) {
-  const int colblocks = (D + SUM_THREADS * 4 - 1) / (SUM_THREADS * 4);
+  const int tpr = sums_threads_per_row(D);
+  const int colblocks = (D + tpr * 4 - 1) / (tpr * 4);
   int64_t want = (8ll * num_sms + (int64_t)colblocks * C - 1) / ((int64_t)colblocks * (C > 0 ? C : 1));
   const int64_t avg = C > 0 ? n / C : n;
-  int64_t cap = avg / 64;  // keep >= 64 rows per split
+  int64_t cap = avg / (64 * (SUM_THREADS / tpr));  // keep >= 64 rows per row lane
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   if (want > 4096) want = 4096;
@@ -366,7 +387,8 @@ cudaError_t launch_class_sums(const float* X, int64_t ldx, const int32_t* perm, 
   (void)n;
   if (C <= 0 || D <= 0) return cudaSuccess;
   const int vec_ok = (D % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  dim3 grid((D + SUM_THREADS * 4 - 1) / (SUM_THREADS * 4), nsplit, C);
+  const int tpr = sums_threads_per_row(D);
+  dim3 grid((D + tpr * 4 - 1) / (tpr * 4), nsplit, C);
   class_sums_kernel<<<grid, SUM_THREADS, 0, stream>>>(X, ldx, perm, offsets, shift, D, nsplit, partial_ws, vec_ok);
   const int64_t total = (int64_t)C * D;
   class_sums_finalize_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(partial_ws, nsplit, D, C, sums,
