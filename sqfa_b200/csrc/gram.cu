@@ -94,7 +94,8 @@ struct GramParams {
   int vec_ok;
   int vecx;          // rows of X are 16-byte aligned: LDG.128
   int flags;         // tuning switches (env SQFA_GRAM_FLAGS): 1 = no A-as-B reuse on diagonal tiles,
-                     // 4 = scalar loads, 8 = no early cross-term MMAs during a chain drain
+                     // 2 = A / B producer warps share the A operand of diagonal tiles, 4 = scalar loads,
+                     // 8 = no early cross-term MMAs during a chain drain
 };
 
 // Job list: classes in descending size; within a class the K parts, and within a K part its tiles:
@@ -208,12 +209,20 @@ __device__ __forceinline__ void gram_body(const GramParams& P) {
       const int kb0 = g.kb0, kb1 = g.kb1;
       const int64_t n_c = g.n_c;
       // Diagonal tile: the MMA reads this CTA's A buffers as its B half, so there is no B operand to
-      // produce. The A and the B warp of a sample quad then SHARE the A operand: the A warp produces
-      // the even stages of the job, the B warp the odd ones (each only keeps the barrier protocol going
-      // on the other's stages). Twice the global loads in flight per stage period: diagonal tiles --
-      // every tile of the single-CTA variant, 40-67 % of the tiles at D = 512 ... 1024 -- were bound by
-      // load latency with four loading warps (ncu: stall_long_sb, tensor pipe 29 % at D = 104).
-      const bool share = g.diag;
+      // produce and the B warps only keep the barrier protocol going. Experiment (SQFA_GRAM_FLAGS & 2):
+      // the A and the B warp of a sample quad SHARE the A operand, the A warp producing the even stages
+      // of the job and the B warp the odd ones -- twice the global loads in flight on diagonal tiles.
+      // Measured: c5 shard 77.0 -> 73.0 ms, c4 2.20 -> 2.43 ms, c2 / c3 unchanged; off by default.
+      const bool share = g.diag && (P.flags & 2);
+      if (g.diag && !isA && !share) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(full0 + stage * 8);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       const bool asA = isA || share;
       const uint32_t hi_base = asA ? hi_A : hi_B;
       const uint32_t lo_base = hi_base + OP_BYTES;  // 32-bit shared addresses: no 64-bit math in the loop

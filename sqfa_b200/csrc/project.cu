@@ -567,23 +567,67 @@ cudaError_t run_transform(const float* X, int64_t ldx, const float* F, int64_t n
 
 }  // namespace
 
-// Rows of S per block: as many as fit the F^T tile, fewer when the grid would not fill the GPU
-// (about 8 blocks of 128 threads per SM), never fewer than 64.
-int project_rows_per_split(int C, int D) {
+// Resident blocks of project_stream_kernel<KT> per device (occupancy query, cached per device)
+template <int KT>
+static int project_stream_capacity() {
+  static int cap[kMaxDevices] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148 * 6;
+  if (cap[dev] == 0) {
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_stream_kernel<KT>, PS_THREADS, 0) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || per_sm <= 0 || sms <= 0)
+      return 148 * 6;
+    cap[dev] = per_sm * sms;
+  }
+  return cap[dev];
+}
+
+static int project_capacity(int k) {
+  if (k <= 4) return project_stream_capacity<4>();
+  if (k <= 8) return project_stream_capacity<8>();
+  if (k <= 16) return project_stream_capacity<16>();
+  return project_stream_capacity<32>();
+}
+
+// Row splits of the streaming pass. The grid is (column blocks x splits x classes); what costs time is
+// a last wave of blocks that fills a fraction of the GPU (c4 with one split: 1000 blocks on 888 resident
+// slots = 1.13 waves, 56 % wave efficiency) and, against it, the partial products every split writes and
+// the finish kernel reads back (2 nsplit k / D of the bytes of S). Choose the split count that maximises
+// wave efficiency / (1 + partial traffic), with at least 64 rows per split and at most PS_MAXROWS.
+int project_nsplit(int C, int D, int k) {
   const int64_t colblocks = (D + PS_COLS - 1) / PS_COLS;
-  const int64_t want = (8 * 148 + colblocks * C - 1) / (colblocks * (C > 0 ? C : 1));  // splits wanted
-  int rows = (int)((D + want - 1) / (want > 0 ? want : 1));
+  const int64_t per_split = colblocks * (C > 0 ? C : 1);
+  const int64_t cap = project_capacity(k);
+  const int min_split = (D + PS_MAXROWS - 1) / PS_MAXROWS;
+  int max_split = D / 64 > min_split ? D / 64 : min_split;
+  if (max_split > 256) max_split = 256;
+  int best = min_split;
+  double best_score = -1.0;
+  for (int n = min_split; n <= max_split; ++n) {
+    const int64_t blocks = per_split * n;
+    const int64_t waves = (blocks + cap - 1) / cap;
+    const double eff = (double)blocks / (double)(waves * cap);
+    const double score = eff / (1.0 + 2.0 * n * k / (double)D);
+    if (score > best_score * 1.001) { best_score = score; best = n; }  // ties: fewer splits
+  }
+  return best;
+}
+int project_rows_per_split(int C, int D, int k) {
+  const int n = project_nsplit(C, D, k);
+  int rows = (D + n - 1) / n;
   rows = (rows + 7) & ~7;
-  if (rows < 64) rows = 64;
   if (rows > PS_MAXROWS) rows = PS_MAXROWS;
   return rows;
 }
-int project_nsplit(int C, int D) {
-  const int rows = project_rows_per_split(C, D);
+static int project_nsplit_actual(int C, int D, int k) {
+  const int rows = project_rows_per_split(C, D, k);
   return (D + rows - 1) / rows;
 }
 
-static size_t project_partial_floats(int C, int D, int k) { return (size_t)project_nsplit(C, D) * C * k * D; }
+static size_t project_partial_floats(int C, int D, int k) {
+  return (size_t)project_nsplit_actual(C, D, k) * C * k * D;
+}
 
 int project_nchunk(int D) { return (D + PF_COLS - 1) / PF_COLS; }
 static size_t al64(size_t n) { return (n + 63) & ~size_t(63); }
@@ -613,7 +657,7 @@ size_t project_workspace_bytes(int C, int D, int k) {
 cudaError_t launch_project_partials(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
                                     float* partial, float* PsiPart, float* MuPart, cudaStream_t st) {
   if (C <= 0) return cudaSuccess;
-  const int rows = project_rows_per_split(C, D), nsplit = project_nsplit(C, D);
+  const int rows = project_rows_per_split(C, D, k), nsplit = project_nsplit_actual(C, D, k);
   cudaError_t e;
   if (k <= 4) e = run_project_stream<4>(S, F, C, D, k, rows, nsplit, partial, st);
   else if (k <= 8) e = run_project_stream<8>(S, F, C, D, k, rows, nsplit, partial, st);

@@ -53,7 +53,7 @@ size_t gram_packed_floats(int D, int C);  // floats of the packed upper-tile lis
 
 namespace sqfa {
 // ---- project.cu (K4, K6, transform, embedding, constraint) ----
-int project_nsplit(int C, int D);
+int project_nsplit(int C, int D, int k);
 int project_nchunk(int D);
 size_t project_workspace_bytes(int C, int D, int k);
 size_t project_psipart_floats(int C, int D, int k);
