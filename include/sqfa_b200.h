@@ -114,13 +114,20 @@ int sqfa_class_means(const float* sums, const int64_t* counts, const float* shif
  *   done, n_groups, reserve_sms
  *              overlap of a multi-device caller's collective with this kernel: with done != NULL
  *              (int32 [n_groups], zeroed by the caller) the jobs run in class order, classes are
- *              split into n_groups contiguous groups (class c belongs to group c n_groups / n_classes)
+ *              split into n_groups contiguous groups (class c belongs to group c n_groups / n_classes;
+ *              groups may be empty when n_groups > n_classes)
  *              and done[g] is incremented once per (job, CTA, epilogue warp) after the job's tile has
  *              been stored and fenced; when done[g] reaches sqfa_class_gram_group_signals(..., g)
  *              all tiles of group g are final, so a stream memory operation (cuStreamWaitValue32)
  *              on ANOTHER stream can release the all-reduce of that group's slice of gram while this
  *              kernel still computes the next groups. reserve_sms SMs are left out of the grid for
  *              that collective's kernels. done == NULL: largest class first, all SMs.
+ *   first_class
+ *              with done != NULL the class order starts at this class and wraps around
+ *              (first_class, ..., C - 1, 0, ..., first_class - 1): a rank that pushes every finished
+ *              group to the group's owner (sqfa_peer_push) runs the classes it owns itself LAST, so
+ *              its last transfer hides behind its own remaining work and the ranks' transfers are
+ *              staggered over different peers. 0 otherwise.
  *   ws         sqfa_class_gram_workspace_bytes(n, n_dim, n_classes) bytes (device-side job plan). */
 size_t sqfa_class_gram_workspace_bytes(int64_t n, int32_t n_dim, int32_t n_classes);
 size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes);
@@ -129,8 +136,8 @@ size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes);
 int64_t sqfa_gram_executed_tile_area(int32_t n_dim);
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
-                    int32_t* done, int32_t n_groups, int32_t reserve_sms, void* ws, size_t ws_bytes,
-                    sqfa_stream_t stream);
+                    int32_t* done, int32_t n_groups, int32_t first_class, int32_t reserve_sms, void* ws,
+                    size_t ws_bytes, sqfa_stream_t stream);
 int64_t sqfa_class_gram_group_signals(int64_t n, int32_t n_dim, int32_t n_classes, int32_t n_groups, int32_t group);
 /* Enqueue on `stream` a wait until *flag >= value (device memory; cuStreamWaitValue32): what gates a
  * collective on the counters above. No kernel is launched, no SM is occupied while waiting. */
@@ -147,6 +154,23 @@ size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes);
 int sqfa_stats_epilogue(const float* gram, const float* means, const float* shift, const int64_t* counts,
                         int32_t n_dim, int32_t n_classes, int estimator, int ddof, float* cov, float* sm, void* ws,
                         size_t ws_bytes, sqfa_stream_t stream);
+
+/* Reduce-scatter of the Gram partials by class, fused into the producer and the consumer instead of a
+ * collective kernel ("ReduceScatter by class"): every rank computes the packed
+ * partial Gram of ALL classes from its rows (sqfa_class_gram with completion counters); as soon as the
+ * classes owned by rank g are final, the copy engine pushes that slice into slot [source rank] of rank
+ * g's receive buffer (peer-mapped memory; sqfa_peer_push behind sqfa_stream_wait_geq on a side stream:
+ * no SM is used, the tensor cores keep working on the next group); after one barrier each rank runs
+ *   sqfa_stats_epilogue_reduce: cov[c] = (sum_s partial_s[c] - n_c d d^T) / (n_c - ddof), ...
+ * over ITS classes only, reading source s from `peer_slots + s * slot_stride` (s != self) or from its own
+ * packed buffer `gram` (s == self), summed in ascending s (bit-reproducible). All buffers hold the
+ * packed tile layout of SQFA_GRAM_PACKED for `n_classes` (the classes this rank owns). */
+int sqfa_stats_epilogue_reduce(const float* gram, const float* peer_slots, int64_t slot_stride, int32_t n_sources,
+                               int32_t self, const float* means, const float* shift, const int64_t* counts,
+                               int32_t n_dim, int32_t n_classes, int estimator, int ddof, float* cov, float* sm,
+                               void* ws, size_t ws_bytes, sqfa_stream_t stream);
+/* cudaMemcpyAsync(dst, src, bytes) on `stream` (copy engine; dst may be peer-mapped device memory). */
+int sqfa_peer_push(void* dst, const void* src, size_t bytes, sqfa_stream_t stream);
 
 /* class_statistics in ONE call (statistics.py:8-54) for n rows resident on one device: bucket the
  * labels, per-class sums and means, Gram of the rows centred by their class mean, epilogue. It is

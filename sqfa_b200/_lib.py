@@ -41,8 +41,8 @@ SIGNATURES = {
     "sqfa_class_gram_workspace_bytes": (c_size, [c_i64, c_i32, c_i32]),
     "sqfa_class_gram": (
         c_int,
-        [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_i32, c_i32, c_ptr,
-         c_size, c_ptr],
+        [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_int, c_int, c_ptr, c_i32, c_i32, c_i32,
+         c_ptr, c_size, c_ptr],
     ),
     "sqfa_class_gram_group_signals": (c_i64, [c_i64, c_i32, c_i32, c_i32, c_i32]),
     "sqfa_stream_wait_geq": (c_int, [c_ptr, c_ptr, c_i32]),
@@ -53,6 +53,12 @@ SIGNATURES = {
         c_int,
         [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_int, c_int, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
     ),
+    "sqfa_stats_epilogue_reduce": (
+        c_int,
+        [c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_int, c_int, c_ptr, c_ptr, c_ptr,
+         c_size, c_ptr],
+    ),
+    "sqfa_peer_push": (c_int, [c_ptr, c_ptr, c_size, c_ptr]),
     "sqfa_class_statistics_workspace_bytes": (c_size, [c_i64, c_i32, c_i32]),
     "sqfa_class_statistics": (
         c_int,

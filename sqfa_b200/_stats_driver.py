@@ -4,12 +4,16 @@ samples are sharded over the ranks of a process group -- the collectives between
 Per-class (count, sum x, sum (x - mu)(x - mu)^T) are additive over samples, so every rank
 processes its own rows and three all-reduces make the result global:
 max label -> n_classes, [class sums | class counts] in ONE buffer -> global means, Gram partials ->
-global covariances. The Gram all-reduce (the only large one) is OVERLAPPED with the Gram kernel: the
-kernel runs its jobs in class order and bumps a device counter per class group when the group's tiles
-are final; a side stream waits on each counter with a stream memory operation (no SM occupied) and
-all-reduces that group's slice of the packed Gram while the tensor cores work on the next groups (a
-few SMs are left out of the Gram grid for NCCL's kernels). The local steps are supplied by an `ops`
-object: `CudaStatsOps` (the sm_100a kernels through the C ABI) in the product; the CPU test-suite
+global covariances. The Gram exchange is the only large one. When every rank keeps only its share of
+the classes (`shard_output`), it is a reduce-scatter by class FUSED into the Gram kernel and the
+epilogue (`class_gram_peer_reduce`): the kernel runs the classes group by group (one group per owner
+rank, the rank's own group last) and bumps a device counter when a group's tiles are final; a side
+stream waits on the counter with a stream memory operation and the COPY ENGINE pushes the group's
+tiles over NVLink into the owner's peer-mapped receive slot while the tensor cores work on the next
+group -- no SM, no collective kernel; after one barrier the owner's epilogue sums the slots in rank
+order. With replicated output the packed Gram is all-reduced by NCCL behind the kernel (an overlapped
+NCCL variant exists, measured not to pay). The local steps are supplied by an
+`ops` object: `CudaStatsOps` (the sm_100a kernels through the C ABI) in the product; the CPU test-suite
 injects oracle-backed ops to exercise this host logic under the gloo backend.
 """
 
@@ -120,7 +124,8 @@ class CudaStatsOps:
     def packed_is_smaller(self, D, C):
         return self.lib.sqfa_gram_packed_floats(D, C) < C * D * D  # padding to 256 can outweigh the triangle
 
-    def class_gram(self, X, perm, offsets, centre, C, packed=False, done=None, n_groups=0, reserve_sms=0):
+    def class_gram(self, X, perm, offsets, centre, C, packed=False, done=None, n_groups=0, reserve_sms=0,
+                   first_class=0):
         """Upper triangle of sum_{i in c} (x_i - centre_c)(x_i - centre_c)^T per class (tcgen05).
 
         packed=True returns the flat list of 256 x 256 upper tiles (what ranks all-reduce: about
@@ -140,7 +145,8 @@ class CudaStatsOps:
         _lib.check(
             lib.sqfa_class_gram(
                 _lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(centre), n, D, C,
-                _lib.ptr(gram), 2 if packed else 0, 0, _lib.ptr(done), n_groups, reserve_sms, _lib.ptr(ws), ws_bytes,
+                _lib.ptr(gram), 2 if packed else 0, 0, _lib.ptr(done), n_groups, first_class, reserve_sms, _lib.ptr(ws),
+                ws_bytes,
                 _lib.stream_ptr(dev),
             ),
             "sqfa_class_gram",
@@ -230,6 +236,117 @@ class CudaStatsOps:
         main.wait_stream(side)
         return gram
 
+    # ---- reduce-scatter by class fused into the Gram kernel and the epilogue (peer-mapped memory) ----
+    PEER_SETS = 2  # receive-slot sets, used alternately by consecutive calls
+
+    def peer_acquire(self, D, C, group):
+        """Receive slots for the Gram partials of this rank's classes, one per source rank, mapped into
+        every peer's address space (torch symmetric memory: CUDA IPC / fabric handles exchanged through
+        the group's store). Collective on first use for a (D, C, group). Returns None when peer mapping
+        is unavailable (the caller then all-reduces with NCCL). Also makes the current stream wait until
+        the epilogue that last read the slot set handed out has finished (with the collective that
+        follows on this stream that orders every peer's next push after it)."""
+        import torch.distributed as dist
+
+        if os.environ.get("SQFA_PEER_REDUCE", "1") != "1":
+            return None
+        cache = self.__dict__.setdefault("_peer_states", {})
+        dev = torch.device("cuda", torch.cuda.current_device())
+        key = (D, C, id(group), dev.index)
+        st = cache.get(key)
+        if st is None:
+            W, r = dist.get_world_size(group), dist.get_rank(group)
+            per_class = self.lib.sqfa_gram_packed_floats(D, C) // C
+            shares = [class_share(C, q, W) for q in range(W)]
+            stride = max(hi - lo for lo, hi in shares) * per_class
+            st = {"ok": False}
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                buf = symm_mem.empty(self.PEER_SETS * W * stride, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, group.group_name)
+                peers = [hdl.get_buffer(q, (self.PEER_SETS * W * stride,), torch.float32) for q in range(W)]
+                st = {"ok": True, "buf": buf, "hdl": hdl, "peers": peers, "W": W, "rank": r, "shares": shares,
+                      "per_class": per_class, "stride": stride, "next": 0, "free": [None] * self.PEER_SETS,
+                      "side": torch.cuda.Stream(device=dev), "token": torch.zeros(1, device=dev)}
+            except Exception as e:  # no peer access between these devices / torch without symmetric memory
+                st["why"] = repr(e)
+            # all ranks take the same path: one rank without peer mapping sends everyone to NCCL
+            ok = torch.tensor([1.0 if st["ok"] else 0.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            st["ok"] = bool(ok.item() > 0)
+            cache[key] = st
+        if not st["ok"]:
+            return None
+        k = st["next"]
+        st["next"] = (k + 1) % self.PEER_SETS
+        if st["free"][k] is not None:
+            torch.cuda.current_stream(dev).wait_event(st["free"][k])
+        return {"state": st, "set": k}
+
+    def class_gram_peer_reduce(self, X, perm, offsets, centre, C, group, lease):
+        """This rank's packed Gram partials of all classes; every group of classes is pushed to its owner's
+        slot [this rank] as soon as the kernel has finished it. Returns the local packed buffer; after the
+        call the current stream has passed a barrier behind which all peers' pushes to this rank landed."""
+        import torch.distributed as dist
+
+        lib, dev = self.lib, X.device
+        n, D = X.shape
+        st, k = lease["state"], lease["set"]
+        W, r, shares, per_class, stride = st["W"], st["rank"], st["shares"], st["per_class"], st["stride"]
+        main, side = torch.cuda.current_stream(dev), st["side"]
+        done = torch.zeros(W, dtype=torch.int32, device=dev)
+        zeroed = torch.cuda.Event()
+        zeroed.record(main)
+        own_lo, own_hi = shares[r]
+        # class order: the groups of ranks r+1, r+2, ... and this rank's own classes last
+        gram = self.class_gram(X, perm, offsets, centre, C, packed=True, done=done, n_groups=W,
+                               first_class=own_hi % C)
+        side.wait_event(zeroed)
+        gram.record_stream(side)
+        done.record_stream(side)
+        set_base = k * W * stride
+        for g, lo, hi in peer_push_schedule(r, W, shares):
+            expected = lib.sqfa_class_gram_group_signals(n, D, C, W, g)
+            _lib.check(lib.sqfa_stream_wait_geq(ctypes.c_void_p(side.cuda_stream),
+                                                ctypes.c_void_p(done.data_ptr() + 4 * g), int(expected)),
+                       "sqfa_stream_wait_geq")
+            dst = st["peers"][g].data_ptr() + 4 * (set_base + r * stride)
+            src = gram.data_ptr() + 4 * lo * per_class
+            _lib.check(lib.sqfa_peer_push(ctypes.c_void_p(dst), ctypes.c_void_p(src), 4 * (hi - lo) * per_class,
+                                          ctypes.c_void_p(side.cuda_stream)), "sqfa_peer_push")
+        main.wait_stream(side)
+        # barrier: a rank enters after its pushes completed, and leaves after everyone entered
+        dist.all_reduce(st["token"], group=group)
+        return gram
+
+    def finalize_peer(self, gram, means, counts, estimator_id, ddof, want_sm, lease):
+        """Epilogue over this rank's classes: sum of the W partials (own packed tiles + received slots)."""
+        lib, dev = self.lib, gram.device
+        st, k = lease["state"], lease["set"]
+        W, r, per_class, stride = st["W"], st["rank"], st["per_class"], st["stride"]
+        C, D = means.shape
+        c0, c1 = st["shares"][r]
+        nc = c1 - c0
+        cov = torch.empty(nc, D, D, dtype=torch.float32, device=dev)
+        sm = torch.empty(nc, D, D, dtype=torch.float32, device=dev) if want_sm else None
+        if nc > 0:
+            ws_bytes = lib.sqfa_stats_epilogue_workspace_bytes(nc)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            slots = st["buf"].data_ptr() + 4 * k * W * stride
+            _lib.check(
+                lib.sqfa_stats_epilogue_reduce(
+                    ctypes.c_void_p(gram.data_ptr() + 4 * c0 * per_class), ctypes.c_void_p(slots), stride, W, r,
+                    _lib.ptr(means[c0:c1]), None, _lib.ptr(counts[c0:c1]), D, nc, estimator_id, ddof, _lib.ptr(cov),
+                    _lib.ptr(sm), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev),
+                ),
+                "sqfa_stats_epilogue_reduce",
+            )
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        st["free"][k] = ev
+        return cov, sm
+
     def finalize(self, gram, means, counts, estimator_id, ddof, want_sm, packed=False, class_range=None):
         """cov (in place over gram unless it is packed; mirrored), optional OAS shrinkage, second moments.
         `class_range` (c0, c1): only those classes (a rank finalising its share of a sharded result)."""
@@ -290,6 +407,7 @@ class CudaStatsOps64(CudaStatsOps):
     supports_packed = False
     fused = None
     class_gram_overlapped = None
+    peer_acquire = None
 
     def class_sums(self, X, perm, offsets, C, out=None):
         n, D = X.shape
@@ -348,8 +466,22 @@ _COUNT_BASE = 1 << 20  # class counts travel as two float32 (hi, lo) next to the
 
 
 def class_share(n_classes, rank, world):
-    """Contiguous range of classes whose statistics `rank` finalises when the output is sharded."""
-    return (n_classes * rank) // world, (n_classes * (rank + 1)) // world
+    """Contiguous range of classes whose statistics `rank` finalises when the output is sharded: the
+    classes c with c * world // n_classes == rank (the grouping of the Gram kernel's completion counters)."""
+    return -((-n_classes * rank) // world), -((-n_classes * (rank + 1)) // world)
+
+
+def peer_push_schedule(rank, world, shares):
+    """Order in which `rank` pushes class groups to their owners in the fused reduce-scatter: the groups of
+    ranks rank+1, rank+2, ... (the order the Gram kernel finishes them in, its own group runs last and is
+    not pushed). At every step the ranks address pairwise different peers."""
+    out = []
+    for step in range(1, world):
+        g = (rank + step) % world
+        lo, hi = shares[g]
+        if hi > lo:
+            out.append((g, lo, hi))
+    return out
 
 
 def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, ddof=1, centre=None, want_sm=True,
@@ -383,6 +515,11 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
         return ops.fused(X, y, C, estimator_id, ddof, want_sm)
     perm, offsets, counts = ops.bucket(y, C)
     D = X.shape[1]
+    lease = None
+    if (group is not None and shard_output and centre is None and getattr(ops, "peer_acquire", None) is not None
+            and getattr(ops, "supports_packed", False) and ops.packed_is_smaller(D, C)
+            and getattr(ops, "gram_events", None) is None):
+        lease = ops.peer_acquire(D, C, group)  # before the collective below (see peer_acquire)
     if group is not None:
         # ONE small collective: [class sums | counts / 2^20 | counts mod 2^20] in the dtype of the sums
         small = torch.empty(C * D + 2 * C, dtype=X.dtype, device=X.device)
@@ -413,7 +550,11 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
     # start once >= 8 SMs are free, leaving 8 SMs out of the Gram grid costs the Gram a whole extra round of
     # tiles (+0.19 ms of 2.0), and the all-reduce progresses at ~45 GB/s on those few SMs -- the step comes
     # out within +-0.06 ms of the serialised version (2.82 vs 2.90 and 2.98 vs 2.92 ms on two boxes).
-    if packed_ok and overlap and os.environ.get("SQFA_GRAM_OVERLAP", "0") == "1":
+    if lease is not None:
+        # reduce-scatter by class fused into the Gram kernel (copy-engine pushes) and the epilogue
+        gram = ops.class_gram_peer_reduce(X, perm, offsets, shift, C, group, lease)
+        cov, sm = ops.finalize_peer(gram, means, class_counts, estimator_id, ddof, want_sm, lease)
+    elif packed_ok and overlap and os.environ.get("SQFA_GRAM_OVERLAP", "0") == "1":
         # the one large collective, hidden behind the kernel that produces its input
         gram = ops.class_gram_overlapped(X, perm, offsets, shift, C, group)
         cov, sm = ops.finalize(gram, means, class_counts, estimator_id, ddof, want_sm, packed=True, **extra)

@@ -114,11 +114,12 @@ size_t sqfa_gram_packed_floats(int32_t n_dim, int32_t n_classes) {
 
 int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets, const float* shift,
                     int64_t n, int32_t n_dim, int32_t n_classes, float* gram, int accumulate, int chain_rows,
-                    int32_t* done, int32_t n_groups, int32_t reserve_sms, void* ws, size_t ws_bytes,
-                    sqfa_stream_t stream) {
+                    int32_t* done, int32_t n_groups, int32_t first_class, int32_t reserve_sms, void* ws,
+                    size_t ws_bytes, sqfa_stream_t stream) {
   if (n_dim <= 0 || n_classes < 0 || offsets == nullptr || gram == nullptr || ws == nullptr || ldx < n_dim ||
       X == nullptr || perm == nullptr || (accumulate & ~(SQFA_GRAM_ACCUMULATE | SQFA_GRAM_PACKED)) ||
-      (done != nullptr && (n_groups <= 0 || n_groups > n_classes)) || reserve_sms < 0)
+      (done != nullptr && (n_groups <= 0 || n_groups > 65536)) || reserve_sms < 0 || first_class < 0 ||
+      (first_class > 0 && (done == nullptr || first_class >= n_classes)))
     return fail_arg(__func__, "bad argument");
   if (n < 0) return fail_arg(__func__, "bad argument");
   if (ws_bytes < sqfa_class_gram_workspace_bytes(n, n_dim, n_classes))
@@ -129,11 +130,12 @@ int sqfa_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int6
   if (sms <= 0) return fail_arg(__func__, "no CUDA device");
   return wrap(__func__, sqfa::launch_class_gram(X, ldx, perm, offsets, shift, n, n_dim, n_classes, gram,
                                                 accumulate & SQFA_GRAM_ACCUMULATE, accumulate & SQFA_GRAM_PACKED,
-                                                chain_rows, done, n_groups, reserve_sms, ws, sms, S(stream)));
+                                                chain_rows, done, n_groups, first_class, reserve_sms, ws, sms,
+                                                S(stream)));
 }
 
 int64_t sqfa_class_gram_group_signals(int64_t n, int32_t n_dim, int32_t n_classes, int32_t n_groups, int32_t group) {
-  if (n_dim <= 0 || n_classes <= 0 || n_groups <= 0 || n_groups > n_classes || group < 0 || group >= n_groups) return 0;
+  if (n_dim <= 0 || n_classes <= 0 || n_groups <= 0 || n_groups > 65536 || group < 0 || group >= n_groups) return 0;
   const int sms = sm_count_cached();
   const int64_t ks = sqfa::gram_ksplit(n < 0 ? 0 : n, n_classes, n_dim, sms > 0 ? sms : 148);
   int64_t classes = 0;  // classes c with c * n_groups / n_classes == group
@@ -180,6 +182,30 @@ int sqfa_stats_epilogue(const float* gram, const float* means, const float* shif
     return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
   return wrap(__func__, sqfa::launch_stats_epilogue(gram, packed, means, shift, counts, n_dim, n_classes, estimator,
                                                     ddof, cov, sm, ws, S(stream)));
+}
+
+int sqfa_stats_epilogue_reduce(const float* gram, const float* peer_slots, int64_t slot_stride, int32_t n_sources,
+                               int32_t self, const float* means, const float* shift, const int64_t* counts,
+                               int32_t n_dim, int32_t n_classes, int estimator, int ddof, float* cov, float* sm,
+                               void* ws, size_t ws_bytes, sqfa_stream_t stream) {
+  if (gram == nullptr || peer_slots == nullptr || means == nullptr || counts == nullptr || cov == nullptr ||
+      n_dim <= 0 || n_classes < 0 || n_sources < 1 || n_sources > 64 || self < 0 || self >= n_sources ||
+      slot_stride < (int64_t)sqfa::gram_packed_floats(n_dim, n_classes) ||
+      (estimator != SQFA_EST_EMPIRICAL && estimator != SQFA_EST_OAS) || (ddof != 0 && ddof != 1))
+    return fail_arg(__func__, "bad argument");
+  if (estimator == SQFA_EST_OAS && (ws == nullptr || ws_bytes < sqfa::stats_epilogue_workspace_bytes(n_classes)))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_stats_epilogue(gram, 1, means, shift, counts, n_dim, n_classes, estimator, ddof,
+                                                    cov, sm, ws, S(stream),
+                                                    sqfa::GramSources{peer_slots, slot_stride, n_sources, self}));
+}
+
+// Copy-engine push: no kernel, no SM. With `dst` a peer-mapped address (CUDA IPC / symmetric memory) the
+// bytes travel over NVLink while this device's SMs keep computing.
+int sqfa_peer_push(void* dst, const void* src, size_t bytes, sqfa_stream_t stream) {
+  if ((dst == nullptr || src == nullptr) && bytes > 0) return fail_arg(__func__, "bad argument");
+  if (bytes == 0) return 0;
+  return wrap(__func__, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, S(stream)));
 }
 
 }  // extern "C"
@@ -386,8 +412,8 @@ int sqfa_class_statistics(const float* X, int64_t ldx, const int64_t* labels, in
   if (rc) return rc;
   rc = sqfa_class_means(sums, counts, nullptr, n_dim, n_classes, means, stream);
   if (rc) return rc;
-  rc = sqfa_class_gram(X, ldx, perm, offsets, means, n, n_dim, n_classes, cov, 0, 0, nullptr, 0, 0, ws_gram, w.gram,
-                       stream);
+  rc = sqfa_class_gram(X, ldx, perm, offsets, means, n, n_dim, n_classes, cov, 0, 0, nullptr, 0, 0, 0, ws_gram,
+                       w.gram, stream);
   if (rc) return rc;
   return sqfa_stats_epilogue(cov, means, nullptr, counts, n_dim, n_classes, estimator, ddof, cov, sm, ws_epi, w.epi,
                              stream);

@@ -84,6 +84,7 @@ struct GramParams {
   int32_t* done;     // optional completion counters: done[c G / C] += 1 per (job, CTA, epilogue warp) once the
   int n_groups;      //   job's tile is stored -- a collective on another stream can be gated on a class group
   int class_order;   // jobs in class order (so class groups finish in order) instead of largest class first
+  int first_class;   // class order starts here and wraps around (a rank's own classes can be made to run last)
   const int4* jobs;  // (class, tile row, tile col, K part)
   int njobs;
   int D, C, KS;
@@ -102,11 +103,11 @@ struct GramParams {
 // the CTA pairs that run concurrently work on the tiles of the SAME rows, which they share in L2.
 // job = ((rank * KS) + ks) * T + t
 __global__ void __launch_bounds__(256) gram_plan_kernel(const int64_t* __restrict__ offsets, int C, int TT, int KS,
-                                                         int class_order, int4* __restrict__ jobs) {
+                                                         int class_order, int first_class, int4* __restrict__ jobs) {
   const int T = TT * (TT + 1) / 2;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     const int64_t n_c = offsets[c + 1] - offsets[c];
-    int rank = class_order ? c : 0;
+    int rank = class_order ? (c - first_class + C) % C : 0;
     for (int o = 0; o < C && !class_order; ++o) {
       const int64_t n_o = offsets[o + 1] - offsets[o];
       rank += (n_o > n_c || (n_o == n_c && o < c)) ? 1 : 0;
@@ -691,8 +692,8 @@ size_t gram_workspace_bytes(int C, int D, int ksplit_max) {
 
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
                                const float* shift, int64_t n, int D, int C, float* gram, int accumulate, int packed,
-                               int chain_rows, int32_t* done, int n_groups, int reserve_sms, void* ws, int num_sms,
-                               cudaStream_t stream) {
+                               int chain_rows, int32_t* done, int n_groups, int first_class, int reserve_sms, void* ws,
+                               int num_sms, cudaStream_t stream) {
   const bool small = gram_use_small(D, packed);
   static int smem_set[kMaxDevices] = {0}, smem_set1[kMaxDevices] = {0};
   {
@@ -707,6 +708,7 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
   if (small) { TT = 1; T = 1; }
   P.X = X; P.ldx = ldx; P.n = n; P.perm = perm; P.offsets = offsets; P.shift = shift; P.gram = gram;
   P.done = done; P.n_groups = n_groups > 0 ? n_groups : 1; P.class_order = done != nullptr ? 1 : 0;
+  P.first_class = (P.class_order && first_class > 0 && first_class < C) ? first_class : 0;
   P.jobs = reinterpret_cast<const int4*>(ws);
   P.D = D; P.C = C;
   P.KS = small ? gram_ksplit_small(n, C, num_sms) : gram_ksplit(n, C, D, num_sms);
@@ -725,7 +727,7 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
     cudaError_t e = cudaMemsetAsync(gram, 0, floats * sizeof(float), stream);
     if (e != cudaSuccess) return e;
   }
-  gram_plan_kernel<<<(C + 255) / 256, 256, 0, stream>>>(offsets, C, TT, P.KS, P.class_order,
+  gram_plan_kernel<<<(C + 255) / 256, 256, 0, stream>>>(offsets, C, TT, P.KS, P.class_order, P.first_class,
                                                         reinterpret_cast<int4*>(ws));
   // reserve_sms SMs are left to other streams (the collective that runs while this kernel still computes)
   const int usable = num_sms - (reserve_sms > 0 ? reserve_sms : 0);

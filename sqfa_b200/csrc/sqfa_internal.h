@@ -35,9 +35,17 @@ cudaError_t launch_class_sums(const float* X, int64_t ldx, const int32_t* perm, 
 cudaError_t launch_class_means(const float* sums, const int64_t* counts, const float* shift, int D, int C,
                                float* means, cudaStream_t stream);
 size_t stats_epilogue_workspace_bytes(int C);
+// Partial Grams of the same classes held in several buffers (a rank's own packed tiles + the slots its
+// peers pushed theirs into): source s is `gram` for s == self, else peers + s * stride. Summed in order.
+struct GramSources {
+  const float* peers;
+  int64_t stride;  // floats between the slots of consecutive source ranks
+  int n_src;       // 0 / 1: `gram` alone
+  int self;
+};
 cudaError_t launch_stats_epilogue(const float* gram, int packed, const float* means, const float* shift,
                                   const int64_t* counts, int D, int C, int estimator, int ddof, float* cov, float* sm,
-                                  void* ws, cudaStream_t stream);
+                                  void* ws, cudaStream_t stream, GramSources src = GramSources{nullptr, 0, 0, 0});
 
 // ---- gram.cu (K2: tcgen05 cta_group::2 Gram on CTA pairs) ----
 int gram_tiles_per_class(int D, int* TT_out);
@@ -46,8 +54,8 @@ int gram_ksplit(int64_t n, int C, int D, int num_sms);
 size_t gram_workspace_bytes(int C, int D, int ksplit_max);
 cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, const int64_t* offsets,
                               const float* shift, int64_t n, int D, int C, float* gram, int accumulate, int packed,
-                              int chain_rows, int32_t* done, int n_groups, int reserve_sms, void* ws, int num_sms,
-                              cudaStream_t stream);
+                              int chain_rows, int32_t* done, int n_groups, int first_class, int reserve_sms, void* ws,
+                              int num_sms, cudaStream_t stream);
 size_t gram_packed_floats(int D, int C);  // floats of the packed upper-tile list (256 x 256 tiles)
 }  // namespace sqfa
 

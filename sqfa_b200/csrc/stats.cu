@@ -150,7 +150,7 @@ __device__ __forceinline__ const float* gram_elem(const float* gram, int packed,
 __global__ void __launch_bounds__(256)
 stats_epilogue_kernel(const float* gram, int packed, const float* __restrict__ means,
                       const float* __restrict__ shift, const int64_t* __restrict__ counts, int D, int NT, int ddof,
-                      float* cov, float* sm) {
+                      float* cov, float* sm, const GramSources src) {
   __shared__ float s_cov[32][33];
   __shared__ float s_mu_i[32], s_mu_j[32], s_d_i[32], s_d_j[32];
   const int c = blockIdx.y;
@@ -178,7 +178,14 @@ stats_epilogue_kernel(const float* gram, int packed, const float* __restrict__ m
     const int r = ti * 32 + rr, q = tj * 32 + tx;
     float v = 0.f;
     if (r < D && q < D) {
-      float g = *gram_elem(gram, packed, c, D, r, q);
+      float g;
+      if (src.n_src <= 1) {
+        g = *gram_elem(gram, packed, c, D, r, q);
+      } else {  // fixed order over the source ranks: the result does not depend on arrival order
+        g = 0.f;
+        for (int s = 0; s < src.n_src; ++s)
+          g += *gram_elem(s == src.self ? gram : src.peers + s * src.stride, packed, c, D, r, q);
+      }
       if (shift != nullptr) g -= n * s_d_i[rr] * s_d_j[tx];
       v = g / nm1;
     }
@@ -215,7 +222,7 @@ stats_epilogue_kernel(const float* gram, int packed, const float* __restrict__ m
 __global__ void __launch_bounds__(256)
 stats_epilogue_v4_kernel(const float* gram, int packed, const float* __restrict__ means,
                          const float* __restrict__ shift, const int64_t* __restrict__ counts, int D, int NT, int ddof,
-                         float* cov, float* sm) {
+                         float* cov, float* sm, const GramSources src) {
   __shared__ float s_cov[64][65];
   __shared__ float s_mu_i[64], s_mu_j[64], s_d_i[64], s_d_j[64];
   const int c = blockIdx.y;
@@ -244,7 +251,15 @@ stats_epilogue_v4_kernel(const float* gram, int packed, const float* __restrict_
     const int r = ti * 64 + rr;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < D && q0 < D) {
-      g = *reinterpret_cast<const float4*>(gram_elem(gram, packed, c, D, r, q0));
+      if (src.n_src <= 1) {
+        g = *reinterpret_cast<const float4*>(gram_elem(gram, packed, c, D, r, q0));
+      } else {  // all sources' loads in flight, then one fixed-order sum
+        for (int s = 0; s < src.n_src; ++s) {
+          const float4 v = *reinterpret_cast<const float4*>(
+              gram_elem(s == src.self ? gram : src.peers + s * src.stride, packed, c, D, r, q0));
+          g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+        }
+      }
       if (shift != nullptr) {
         const float a = n * s_d_i[rr];
         g.x -= a * s_d_j[4 * tx]; g.y -= a * s_d_j[4 * tx + 1];
@@ -408,18 +423,19 @@ size_t stats_epilogue_workspace_bytes(int C) { return (size_t)(C > 0 ? C : 1) * 
 
 cudaError_t launch_stats_epilogue(const float* gram, int packed, const float* means, const float* shift,
                                   const int64_t* counts, int D, int C, int estimator, int ddof, float* cov, float* sm,
-                                  void* ws, cudaStream_t stream) {
+                                  void* ws, cudaStream_t stream, GramSources src) {
   if (C <= 0 || D <= 0) return cudaSuccess;
   const bool al16 = ((reinterpret_cast<uintptr_t>(gram) | reinterpret_cast<uintptr_t>(cov) |
-                      reinterpret_cast<uintptr_t>(sm)) & 15) == 0;
+                      reinterpret_cast<uintptr_t>(sm) | reinterpret_cast<uintptr_t>(src.peers) |
+                      (uintptr_t)((src.stride & 3) * 4)) & 15) == 0;
   if (D % 4 == 0 && al16) {
     const int NT = (D + 63) / 64;
     stats_epilogue_v4_kernel<<<dim3(NT * (NT + 1) / 2, C), 256, 0, stream>>>(gram, packed, means, shift, counts, D, NT,
-                                                                             ddof, cov, sm);
+                                                                             ddof, cov, sm, src);
   } else {
     const int NT = (D + 31) / 32;
     stats_epilogue_kernel<<<dim3(NT * (NT + 1) / 2, C), 256, 0, stream>>>(gram, packed, means, shift, counts, D, NT, ddof,
-                                                                          cov, sm);
+                                                                          cov, sm, src);
   }
   if (estimator == 1) {
     double* partial = static_cast<double*>(ws);

@@ -211,7 +211,7 @@ class StreamingClassStatistics:
             ws = torch.empty(nb, dtype=torch.uint8, device=dev)
             _lib.check(
                 lib.sqfa_class_gram(_lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(self.shift),
-                                    n, D, C, _lib.ptr(self.gram), 1, 0, None, 0, 0, _lib.ptr(ws), nb, st),
+                                    n, D, C, _lib.ptr(self.gram), 1, 0, None, 0, 0, 0, _lib.ptr(ws), nb, st),
                 "sqfa_class_gram",
             )
             self.counts += counts[:C]

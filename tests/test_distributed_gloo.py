@@ -91,8 +91,8 @@ def test_sharded_statistics_equal_unsharded():
     assert torch.allclose(means, ref["means"], rtol=1e-10, atol=1e-12)
     assert torch.allclose(cov, ref["covariances"], rtol=1e-9, atol=1e-12)
     assert torch.allclose(sm, ref["second_moments"], rtol=1e-9, atol=1e-12)
-    # the two ranks' shares, concatenated in rank order, are the full result (classes 0-1 | 2-4)
-    assert shares[0][1].shape[0] == 2 and shares[1][1].shape[0] == 3
+    # the two ranks' shares, concatenated in rank order, are the full result (classes 0-2 | 3-4)
+    assert shares[0][1].shape[0] == 3 and shares[1][1].shape[0] == 2
     assert torch.equal(shares[0][0], means) and torch.equal(shares[1][0], means)
     assert torch.equal(torch.cat([shares[0][1], shares[1][1]]), cov)
     assert torch.equal(torch.cat([shares[0][2], shares[1][2]]), sm)
@@ -119,3 +119,24 @@ def test_pair_shards_cover_the_pair_list():
             shares = [class_share(C, r, world) for r in range(world)]
             assert shares[0][0] == 0 and shares[-1][1] == C
             assert all(a[1] == b[0] for a, b in zip(shares[:-1], shares[1:]))
+            # a rank's share is the class group of the Gram kernel's completion counter `rank`
+            for r, (lo, hi) in enumerate(shares):
+                assert all((c * world) // C == r for c in range(lo, hi))
+
+
+def test_peer_push_schedule_is_staggered_and_complete():
+    """Fused reduce-scatter: every rank pushes every non-empty foreign group exactly once, never its own, and
+    at each step the destinations of the ranks are pairwise different (no peer is hit by two pushes)."""
+    from sqfa_b200._stats_driver import class_share, peer_push_schedule
+
+    for C in (3, 10, 19, 1000):
+        for world in (2, 4, 8):
+            shares = [class_share(C, r, world) for r in range(world)]
+            for r in range(world):
+                sched = peer_push_schedule(r, world, shares)
+                assert [g for g, _, _ in sched] == [g for g in [(r + s) % world for s in range(1, world)]
+                                                    if shares[g][1] > shares[g][0]]
+                assert all((lo, hi) == shares[g] for g, lo, hi in sched) and r not in [g for g, _, _ in sched]
+            for step in range(1, world):
+                dests = [(r + step) % world for r in range(world)]
+                assert len(set(dests)) == world

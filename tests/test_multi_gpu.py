@@ -58,6 +58,48 @@ def _worker(rank, world, port, out_dir):
                                    estimator="oas", group=dist.group.WORLD)
         res["stats_oas_absent_class"] = float((part2["covariances"] - full2["covariances"]).norm()
                                               / full2["covariances"].norm())
+        # ---- HP1, sharded output: reduce-scatter by class fused into the Gram kernel (copy-engine pushes into
+        # peer-mapped slots) and the epilogue; against the single-GPU result, against the NCCL all-reduce
+        # path, bit-reproducible, over several calls (slot sets alternate) and from two streams
+        n, d, c = 9001, 512, 12  # D = 512: the packed tile list is smaller than (C, D, D), the layout both paths move
+        X, y = make_class_data(n, d, c, seed=4)
+        X = X / (X.std() * d**0.5)
+        full = S.class_statistics(X.cuda(), y.cuda())
+        Xs, ys = X[cut[rank]:cut[rank + 1]].cuda(), y[cut[rank]:cut[rank + 1]].cuda()
+        sh = S.class_statistics(Xs, ys, group=dist.group.WORLD, shard_output=True)
+        lo, hi = sh["class_range"]
+        ops = S._cuda_ops()
+        states = getattr(ops, "_peer_states", {})
+        res["peer_path_used"] = float(any(st.get("ok") for st in states.values()))
+        res["peer_why"] = ";".join(st.get("why", "") for st in states.values())
+        res["peer_means"] = float((sh["means"] - full["means"]).norm() / full["means"].norm())
+        for key in ("covariances", "second_moments"):
+            res["peer_" + key] = float((sh[key] - full[key][lo:hi]).norm() / full[key][lo:hi].norm())
+        again = [S.class_statistics(Xs, ys, group=dist.group.WORLD, shard_output=True) for _ in range(3)]
+        res["peer_reproducible"] = float(all(torch.equal(a["covariances"], sh["covariances"]) for a in again))
+        other = torch.cuda.Stream()
+        other.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(other):
+            on_other = S.class_statistics(Xs, ys, group=dist.group.WORLD, shard_output=True)
+        on_main = S.class_statistics(Xs, ys, estimator="oas", group=dist.group.WORLD, shard_output=True)
+        torch.cuda.synchronize()
+        res["peer_two_streams"] = float(torch.equal(on_other["covariances"], sh["covariances"]))
+        full_oas = S.class_statistics(X.cuda(), y.cuda(), estimator="oas")
+        res["peer_oas"] = float((on_main["covariances"] - full_oas["covariances"][lo:hi]).norm()
+                                / full_oas["covariances"][lo:hi].norm())
+        os.environ["SQFA_PEER_REDUCE"] = "0"
+        nccl = S.class_statistics(Xs, ys, group=dist.group.WORLD, shard_output=True)
+        os.environ["SQFA_PEER_REDUCE"] = "1"
+        res["peer_vs_nccl"] = float((nccl["covariances"] - sh["covariances"]).norm() / sh["covariances"].norm())
+        # fewer classes than ranks would own (C = 1 on 2 ranks: rank 1 owns nothing)
+        y1 = torch.zeros_like(ys)
+        one = S.class_statistics(Xs, y1, group=dist.group.WORLD, shard_output=True)
+        full1 = S.class_statistics(X.cuda(), torch.zeros_like(y).cuda())
+        lo1, hi1 = one["class_range"]
+        res["peer_one_class_rows"] = float(one["covariances"].shape[0] == hi1 - lo1)
+        if hi1 > lo1:
+            res["peer_one_class"] = float((one["covariances"] - full1["covariances"][lo1:hi1]).norm()
+                                          / full1["covariances"][lo1:hi1].norm())
         # ---- HP2: pair list sharded. C = 40 -> 780 pairs
         n, d, c, k = 12000, 64, 40, 6
         X, y = make_class_data(n, d, c, seed=9)
@@ -103,6 +145,11 @@ def test_sharded_statistics_and_pair_sharded_closure(tmp_path):
         print(rank, res)
         for key in ("stats_means", "stats_covariances", "stats_second_moments", "stats_oas_absent_class"):
             assert res[key] < 1e-5, (rank, key, res[key])
+        assert res["peer_path_used"] == 1.0, res["peer_why"]
+        for key in ("peer_means", "peer_covariances", "peer_second_moments", "peer_oas", "peer_vs_nccl"):
+            assert res[key] < 1e-5, (rank, key, res[key])
+        assert res["peer_reproducible"] == 1.0 and res["peer_two_streams"] == 1.0
+        assert res["peer_one_class_rows"] == 1.0 and res.get("peer_one_class", 0.0) < 1e-5
         assert res["closure_bad"] == 0
         assert res["closure_loss_rel"] < 1e-6 and res["closure_grad_rel"] < 1e-5, res
         assert res["fit_loss_rel"] < 1e-4 and res["fit_filter_rel"] < 1e-3, res

@@ -17,7 +17,7 @@ def gram_with(X, perm, offsets, means, C, ks):
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     st = _lib.stream_ptr()
     _lib.check(lib.sqfa_class_gram(_lib.ptr(X), X.stride(0), _lib.ptr(perm), _lib.ptr(offsets), _lib.ptr(means),
-                                   n, D, C, _lib.ptr(g), 0, ks, _lib.ptr(ws), wsb, st), "gram")
+                                   n, D, C, _lib.ptr(g), 0, ks, None, 0, 0, 0, _lib.ptr(ws), wsb, st), "gram")
     return g
 
 def time_it(fn, reps=5):
