@@ -40,7 +40,9 @@ METRIC = "class_statistics samples/sec"
 # ours, per step at this size (n <= 65536 rows: single-block bucketing): label_max, bucket_small, class sums +
 # finalize, means, gram_plan, gram_tf32x3, stats_epilogue
 KERNELS_PER_STEP = 8
-PARALLELISM_NOTE = "samples sharded over {world} GPU(s); statistics of the union combined with NCCL"
+PARALLELISM_NOTE = ("samples sharded over {world} GPUs; statistics of the union, every rank finalising its share of the "
+                    "classes: reduce-scatter by class fused into the Gram kernel (copy-engine pushes over NVLink into "
+                    "peer-mapped slots) and the epilogue; 3 small NCCL all-reduces (max label, sums + counts, barrier)")
 
 
 def synth(n, d, c, device, seed):
@@ -263,7 +265,7 @@ def time_closure(plan, n_eval):
     return e0.elapsed_time(e1) / n_eval
 
 
-def closure_kernel_times(stats, model, dist_id, reps=5):
+def closure_kernel_times(stats, model, dist_id, reps=7):
     """The stages of one closure evaluation timed one by one through the step-by-step entry points (the
     fused call runs the same kernels back to back): projection (stream + finish), per-class
     factorisation, the pair kernel, the projection adjoint. ms each."""
@@ -279,8 +281,11 @@ def closure_kernel_times(stats, model, dist_id, reps=5):
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    out = {"project_fwd": 0.0, "class_factor": 0.0, "pair": 0.0, "project_bwd": 0.0}
-    for it in range(reps + 1):
+    # the wrappers allocate their outputs and workspaces between the events (host time, sometimes a cudaMalloc
+    # of hundreds of MB): two warm-up rounds, then the MEDIAN over the repetitions, not the mean
+    keys = ("project_fwd", "class_factor", "pair", "project_bwd")
+    samples = {key: [] for key in keys}
+    for it in range(reps + 2):
         marks = [ev() for _ in range(5)]
         marks[0].record()
         T, Psi, Mu = _ops.project_fwd_raw(S_, M_, F)
@@ -296,11 +301,11 @@ def closure_kernel_times(stats, model, dist_id, reps=5):
         _ops.project_bwd_raw(gPsi, gMu, T, M_)
         marks[4].record()
         torch.cuda.synchronize()
-        if it == 0:
+        if it < 2:
             continue  # warm-up
-        for key, a, b in zip(out, marks[:-1], marks[1:]):
-            out[key] += a.elapsed_time(b) / reps
-    return out
+        for key, a, b in zip(keys, marks[:-1], marks[1:]):
+            samples[key].append(a.elapsed_time(b))
+    return {key: sorted(v)[len(v) // 2] for key, v in samples.items()}
 
 
 def fit_leg(stats, d, c, k, dev, group, world, peaks, n_eval, epochs, label, cpu_evals=0, kernels=False):
@@ -472,7 +477,9 @@ def run_ours(args):
     ops = S._cuda_ops()
 
     def step():
-        return S.class_statistics(X, y, group=group)
+        # N > 1: the result of the job is sharded by class over the ranks ("ReduceScatter by
+        # class"); `value_replicated_output` below is the same job with the full result on every rank
+        return S.class_statistics(X, y, group=group, shard_output=world > 1)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -500,6 +507,19 @@ def run_ours(args):
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ms_rep = None
+    if world > 1:  # the same K steps with replicated output (NCCL all-reduce of the packed Gram partials)
+        for _ in range(3):
+            S.class_statistics(X, y, group=group)
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            rep_stats = S.class_statistics(X, y, group=group)
+        e1.record()
+        sync_all()
+        ms_rep = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms_rep, op=dist.ReduceOp.MAX)
+        del rep_stats
     # the same K steps once more with CUDA events around the Gram launch (on the launching stream);
     # the instrumented repetition takes the step-by-step entry points, the timed one above the
     # single-call sqfa_class_statistics when there is one GPU
@@ -524,7 +544,8 @@ def run_ours(args):
     Xh, yh = X.cpu().pin_memory(), y.cpu().pin_memory()
     nbuf = int(os.environ.get("SQFA_BENCH_E2E_BUFS", "3"))  # buffer sets / streams in flight
     streams = [torch.cuda.Stream(device=dev) for _ in range(nbuf)]
-    stats_full = stats  # full statistics on the device: input of the fit leg below
+    # full statistics on the device: input of the fit leg below (rank 0's own shard when the job's are sharded)
+    stats_full = stats if world == 1 else (S.class_statistics(X, y) if rank == 0 else None)
     # with several ranks every rank finalises and downloads ITS share of the classes (shard_output): the
     # ranks' host buffers together hold the job's result, nothing is computed or copied twice
     sharded = world > 1
@@ -655,6 +676,11 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "fit": fit, "fit_c4": fit_c4,
         "hp1_table": table, "tf32_peak_measured_tflops": tf32_cublas,
     }
+    if ms_rep is not None:
+        line["value_replicated_output"] = {
+            "value": n * world * args.steps / (float(ms_rep) * 1e-3), "unit": "samples/s",
+            "ms_per_step": float(ms_rep) / args.steps,
+            "note": "full statistics on every rank: NCCL all-reduce of the packed Gram partials behind the kernel"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

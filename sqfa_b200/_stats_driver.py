@@ -237,7 +237,7 @@ class CudaStatsOps:
         return gram
 
     # ---- reduce-scatter by class fused into the Gram kernel and the epilogue (peer-mapped memory) ----
-    PEER_SETS = 2  # receive-slot sets, used alternately by consecutive calls
+    PEER_SETS = 3  # receive-slot sets, used in turn by consecutive calls (callers pipeline steps over streams)
 
     def peer_acquire(self, D, C, group):
         """Receive slots for the Gram partials of this rank's classes, one per source rank, mapped into
