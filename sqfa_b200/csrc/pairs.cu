@@ -20,6 +20,7 @@
 // computes all C*C pairs and then reads the lower triangle (_optim.py:94).
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "../../include/sqfa_b200.h"
@@ -821,6 +822,377 @@ static cudaError_t launch_pair_reg(const PairArgs& A, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// pair kernel, affine-invariant family, COLUMN-PAIR variant for m <= 34 (MJ = m rounded up to even).
+//
+// A lane owns TWO adjacent columns of A = (L_j^-1 L_i)^T in registers (positions 2 lg and 2 lg + 1),
+// so a problem occupies LP = MJ / 2 lanes and a warp works on NP = 32 / LP problems side by side
+// (m = 17: 3, m = 9: 6, m = 4: 16, m = 33: 1) -- the pairs of one ROW of its R x R tile, which share L_i.
+// The Jacobi pairing is the odd-even transposition ordering: in an odd step a lane rotates its own two
+// columns (no data movement at all: one dot product, one set of rotation parameters, both columns
+// updated -- nothing is computed twice), in an even step the pairs (2 lg + 1, 2 lg + 2) straddle
+// neighbouring lanes: the left lane fetches the neighbour's column with MJ shuffles, rotates, and sends
+// the neighbour's half back. Every rotation also swaps the two columns, which is what makes MJ steps
+// meet every pair of columns exactly once (and reverses the column order: the zero padding column of an
+// odd m is at position MJ - 1 after an even number of sweeps, at 0 after an odd number).
+// Against one column per lane (round-robin pairing, partner's column by shuffle, dot product and
+// rotation parameters computed by both lanes, 18 of 32 lanes busy at m = 17) this executes about a
+// third of the warp instructions per pair.
+// ------------------------------------------------------------------------------------------------
+template <int MJ>
+struct CpGeom {
+  static constexpr int LP = MJ / 2;          // lanes per problem
+  static constexpr int NP = 32 / LP;         // problems per warp
+  static constexpr int MP4 = (MJ + 3) & ~3;  // row length in shared memory (16-byte loads)
+  static constexpr int MH = MP4 / 2;         // packed register pairs per column
+  static constexpr int LDJ = MP4 + 1;        // odd row stride of Linv_j (lane-varying scalar reads)
+};
+
+// floats of shared memory per warp: [L_i rows | per problem: Linv_j rows, Y rows, coefficients, column accumulator]
+__host__ __device__ inline int cp_group_floats(int MJ, int m) {
+  const int MP4 = (MJ + 3) & ~3;
+  return ((MJ * (MP4 + 1) + 3) & ~3) + m * MP4 + 2 * MP4 + ((m * m + 3) & ~3);
+}
+__host__ __device__ inline int cp_warp_floats(int MJ, int m) {
+  const int MP4 = (MJ + 3) & ~3;
+  return m * MP4 + (32 / (MJ / 2)) * cp_group_floats(MJ, m);
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Rotation of the column pair (x at position p, y at position p + 1) with squared norms alpha, beta and
+// x . y = ab, FOLLOWED BY THE SWAP: position p receives s x + c y (norm n0), position p + 1 receives
+// c x - s y (norm n1). has_pair = false (the end of the line in an even step): x stays where it is.
+__device__ __forceinline__ void cp_rotation(float alpha, float beta, float ab, bool has_pair, float& c, float& s,
+                                            float& n0, float& n1, bool& rotated) {
+  c = 1.f; s = 0.f; n0 = beta; n1 = alpha;
+  const float ab_sq = ab * ab, scale = alpha * beta;
+  if (has_pair && ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale) {
+    const float zeta = (beta - alpha) * rcp_approx(2.f * ab);
+    const float tt = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
+    c = rsqrt_approx(fmaf(tt, tt, 1.f));
+    s = c * tt;
+    n0 = fmaf(tt, ab, beta);
+    n1 = fmaf(-tt, ab, alpha);
+    rotated = rotated || ab_sq > (JACOBI_LAST * JACOBI_LAST) * scale;
+  }
+  if (!has_pair) { c = 0.f; s = 1.f; n0 = alpha; }
+}
+
+template <int MJ>
+__global__ void __launch_bounds__(PAIR_WARPS * 32, (MJ <= 12 ? 6 : (MJ <= 20 ? 4 : (MJ <= 28 ? 3 : 2))))
+pair_cp_kernel(const PairArgs A) {
+  using G = CpGeom<MJ>;
+  constexpr int LP = G::LP, NP = G::NP, MP4 = G::MP4, MH = G::MH, LDJ = G::LDJ;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) float smem[];
+  const int m = A.m, m2 = m * m, nB = A.nB, tri = A.tri, dist = A.dist, R = A.T.R;
+  const bool m_odd = m != MJ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= A.T.ntiles) return;  // no block-wide synchronisation below
+  const int szLi = m * MP4, szJ = (MJ * LDJ + 3) & ~3, szY = m * MP4, szCo = 2 * MP4;
+  const int per_group = cp_group_floats(MJ, m);
+  float* sLi = smem + (size_t)warp * cp_warp_floats(MJ, m);  // [m][MP4]: L_i, later Linv_i (shared by the problems)
+  const int g = lane / LP, lg = lane - g * LP;
+  const bool alive = g < NP;                // lanes beyond NP * LP only follow the instruction stream
+  float* sJ = sLi + szLi + (alive ? g : NP - 1) * per_group;  // [MJ][LDJ]: Linv_j of this problem's column class
+  float* sY = sJ + szJ;                     // [m][MP4]: generalized eigenvectors, row r = component, column = position
+  float* sCo = sY + szY;                    // [2][MP4]: coefficients ci | cj per position
+  float* sC = sCo + szCo;                   // [m][m]: dLoss/dE_j of this problem's column class
+  const bool want_grad = A.rowpart != nullptr;
+  auto div_m = [&](int idx) { return m_odd ? idx / (MJ - 1) : idx / MJ; };  // division by a compile-time constant
+
+  int bi, bj;
+  decode_tile(A.T, t, bi, bj);
+  for (int idx = lane; idx < NP * per_group; idx += 32) sLi[szLi + idx] = 0.f;  // padding rows / columns, accumulators
+  __syncwarp();
+  const int j = bj * R + g;
+  const bool jvalid = alive && g < R && j < nB;
+  if (jvalid) {
+    const float* Wj = A.Wb + (int64_t)j * 2 * m2 + m2;
+    for (int idx = lg; idx < m2; idx += LP) {
+      const int q = div_m(idx);
+      sJ[q * LDJ + (idx - q * m)] = Wj[idx];
+    }
+  }
+  float dsum = 0.f, badsum = 0.f;
+  for (int ii = 0; ii < R; ++ii) {
+    const int i = bi * R + ii;
+    const bool active = jvalid && pair_in_launch(i, j, A.nA, nB, tri, A.pair_begin, A.pair_end);
+    if (__ballot_sync(FULL, active) == 0u) {  // no pair of this row belongs to the launch: the slot is still written
+      if (want_grad) {
+        float* rp = A.rowpart + ((int64_t)t * R + ii) * m2;
+        for (int idx = lane; idx < m2; idx += 32) rp[idx] = 0.f;
+      }
+      continue;
+    }
+    const float* Wi = A.Wa + (int64_t)i * 2 * m2;
+    __syncwarp();
+    for (int idx = lane; idx < m * MP4; idx += 32) {
+      const int r = idx / MP4, c = idx - r * MP4;
+      sLi[idx] = c < m ? Wi[r * m + c] : 0.f;
+    }
+    __syncwarp();
+    // ---- columns 2 lg and 2 lg + 1 of A: a[s] = sum_r Linv_j[q][r] L_i[r][s]  (row MJ - 1 of sJ is zero for odd m)
+    float2 a[MH], b[MH];
+#pragma unroll
+    for (int s = 0; s < MH; ++s) { a[s] = make_float2(0.f, 0.f); b[s] = make_float2(0.f, 0.f); }
+    if (active) {
+      const float* ja = sJ + (2 * lg) * LDJ;
+      const float* jb = ja + LDJ;
+#pragma unroll
+      for (int r = 0; r < MJ; ++r) {
+        if (r < m) {
+          const float la = ja[r], lb = jb[r];
+          const float2 la2 = make_float2(la, la), lb2 = make_float2(lb, lb);
+#pragma unroll
+          for (int s4 = 0; s4 < MP4 / 4; ++s4) {
+            const float4 w = *reinterpret_cast<const float4*>(sLi + r * MP4 + 4 * s4);
+            const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
+            a[2 * s4] = __ffma2_rn(la2, w0, a[2 * s4]);
+            a[2 * s4 + 1] = __ffma2_rn(la2, w1, a[2 * s4 + 1]);
+            b[2 * s4] = __ffma2_rn(lb2, w0, b[2 * s4]);
+            b[2 * s4 + 1] = __ffma2_rn(lb2, w1, b[2 * s4 + 1]);
+          }
+        }
+      }
+    }
+    // ---- one-sided Jacobi, odd-even transposition ordering
+    const int up = (lane + 1) & 31, dn = (lane + 31) & 31;
+    const bool has_right = alive && lg < LP - 1;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
+      float2 na2 = make_float2(0.f, 0.f), nb2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < MJ / 2; ++s) {
+        na2 = __ffma2_rn(a[s], a[s], na2);
+        nb2 = __ffma2_rn(b[s], b[s], nb2);
+      }
+      float nA = na2.x + na2.y, nBq = nb2.x + nb2.y;  // carried along incrementally inside the sweep
+      bool rotated = false;
+#pragma unroll 1
+      for (int st = 0; st < LP; ++st) {
+        {  // odd step: this lane's own two columns
+          float2 ab2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int s = 0; s < MJ / 2; ++s) ab2 = __ffma2_rn(a[s], b[s], ab2);
+          float c, sn, n0, n1;
+          cp_rotation(nA, nBq, ab2.x + ab2.y, true, c, sn, n0, n1, rotated);
+          const float2 c2 = make_float2(c, c), s2 = make_float2(sn, sn), ms2 = make_float2(-sn, -sn);
+#pragma unroll
+          for (int s = 0; s < MJ / 2; ++s) {
+            const float2 x = a[s], y = b[s];
+            a[s] = __ffma2_rn(s2, x, __fmul2_rn(c2, y));
+            b[s] = __ffma2_rn(c2, x, __fmul2_rn(ms2, y));
+          }
+          nA = n0; nBq = n1;
+        }
+        {  // even step: (this lane's second column, the right neighbour's first column)
+          float2 x2[MJ / 2];
+          float2 ab2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int s = 0; s < MJ / 2; ++s) {
+            x2[s].x = __shfl_sync(FULL, a[s].x, up);
+            x2[s].y = __shfl_sync(FULL, a[s].y, up);
+            ab2 = __ffma2_rn(b[s], x2[s], ab2);
+          }
+          const float nX = __shfl_sync(FULL, nA, up);
+          float c, sn, n0, n1;
+          cp_rotation(nBq, nX, ab2.x + ab2.y, has_right, c, sn, n0, n1, rotated);
+          const float2 c2 = make_float2(c, c), s2 = make_float2(sn, sn), ms2 = make_float2(-sn, -sn);
+#pragma unroll
+          for (int s = 0; s < MJ / 2; ++s) {
+            const float2 x = b[s], y = x2[s];
+            b[s] = __ffma2_rn(s2, x, __fmul2_rn(c2, y));
+            x2[s] = __ffma2_rn(c2, x, __fmul2_rn(ms2, y));  // the neighbour's new first column
+          }
+          nBq = n0;
+#pragma unroll
+          for (int s = 0; s < MJ / 2; ++s) {
+            const float rx = __shfl_sync(FULL, x2[s].x, dn), ry = __shfl_sync(FULL, x2[s].y, dn);
+            if (lg > 0) a[s] = make_float2(rx, ry);
+          }
+          const float nr = __shfl_sync(FULL, n1, dn);
+          if (lg > 0) nA = nr;
+        }
+      }
+      ++sweeps;
+      // a sweep whose largest rotation was below JACOBI_LAST leaves off-diagonals of that size squared
+      if (!__any_sync(FULL, rotated)) break;
+    }
+    // ---- eigenvalues, distance. The padding column of an odd m sits at one end of the line.
+    float2 na2 = make_float2(0.f, 0.f), nb2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < MJ / 2; ++s) {
+      na2 = __ffma2_rn(a[s], a[s], na2);
+      nb2 = __ffma2_rn(b[s], b[s], nb2);
+    }
+    const float n2a = na2.x + na2.y, n2b = nb2.x + nb2.y;
+    const bool pad_first = m_odd && (sweeps & 1);
+    const bool real_a = active && !(pad_first && lg == 0);
+    const bool real_b = active && !(m_odd && !pad_first && lg == LP - 1);
+    const float lla = real_a ? logf(n2a) : 0.f, llb = real_b ? logf(n2b) : 0.f;
+    const int g0 = (g * LP) & 31;
+    float d2 = 0.f;
+    {
+      const float part = lla * lla + llb * llb;
+#pragma unroll
+      for (int u = 0; u < LP; ++u) d2 += __shfl_sync(FULL, part, (g0 + u) & 31);  // fixed order, same in every lane
+    }
+    if (A.eig_out != nullptr) {  // descending order (linalg.py:69-70); the padding column has norm 0 and ranks last
+      int ra = 0, rb = 0;
+#pragma unroll
+      for (int u = 0; u < LP; ++u) {
+        const float va = __shfl_sync(FULL, n2a, (g0 + u) & 31), vb = __shfl_sync(FULL, n2b, (g0 + u) & 31);
+        ra += (va > n2a || (va == n2a && 2 * u < 2 * lg)) ? 1 : 0;
+        ra += (vb > n2a || (vb == n2a && 2 * u + 1 < 2 * lg)) ? 1 : 0;
+        rb += (va > n2b || (va == n2b && 2 * u < 2 * lg + 1)) ? 1 : 0;
+        rb += (vb > n2b || (vb == n2b && 2 * u + 1 < 2 * lg + 1)) ? 1 : 0;
+      }
+      float* eo = A.eig_out + ((int64_t)i * nB + j) * m;
+      if (real_a) eo[ra] = n2a;
+      if (real_b) eo[rb] = n2b;
+    }
+    float dd_dd2;
+    const float dval = finish_distance(d2, dist, &dd_dd2);
+    if (active && lg == 0) {
+      dsum += dval;
+      if (!isfinite(dval)) badsum += 1.f;
+      if (A.dist_out != nullptr) {
+        A.dist_out[(int64_t)i * nB + j] = dval;
+        if (tri) A.dist_out[(int64_t)j * nB + i] = dval;
+      }
+    }
+    if (want_grad) {
+      float w = 0.f;
+      if (active) {
+        w = A.weight * dd_dd2;
+        if (A.gD != nullptr)
+          w *= tri ? (A.gD[(int64_t)i * nB + j] + A.gD[(int64_t)j * nB + i]) : A.gD[(int64_t)i * nB + j];
+      }
+      // ---- Y = L_i^-T A_f for this lane's two columns: y[r] = sum_s Linv_i[s][r] a[s]
+      __syncwarp();
+      for (int idx = lane; idx < m * MP4; idx += 32) {
+        const int r = idx / MP4, c = idx - r * MP4;
+        sLi[idx] = c < m ? Wi[m2 + r * m + c] : 0.f;
+      }
+      __syncwarp();
+      float2 ya[MH], yb[MH];
+#pragma unroll
+      for (int s = 0; s < MH; ++s) { ya[s] = make_float2(0.f, 0.f); yb[s] = make_float2(0.f, 0.f); }
+#pragma unroll
+      for (int s = 0; s < MJ; ++s) {
+        if (s < m) {
+          const float as = (s & 1) ? a[s / 2].y : a[s / 2].x, bs = (s & 1) ? b[s / 2].y : b[s / 2].x;
+          const float2 as2 = make_float2(as, as), bs2 = make_float2(bs, bs);
+#pragma unroll
+          for (int r4 = 0; r4 < MP4 / 4; ++r4) {
+            const float4 wv = *reinterpret_cast<const float4*>(sLi + s * MP4 + 4 * r4);
+            const float2 w0 = make_float2(wv.x, wv.y), w1 = make_float2(wv.z, wv.w);
+            ya[2 * r4] = __ffma2_rn(as2, w0, ya[2 * r4]);
+            ya[2 * r4 + 1] = __ffma2_rn(as2, w1, ya[2 * r4 + 1]);
+            yb[2 * r4] = __ffma2_rn(bs2, w0, yb[2 * r4]);
+            yb[2 * r4 + 1] = __ffma2_rn(bs2, w1, yb[2 * r4 + 1]);
+          }
+        }
+      }
+      // ---- Y -> shared memory (row = component r, column = position), coefficients of both matrices
+      if (alive) {
+#pragma unroll
+        for (int r = 0; r < MJ; ++r) {
+          if (r < m) {
+            const float y0 = (r & 1) ? ya[r / 2].y : ya[r / 2].x, y1 = (r & 1) ? yb[r / 2].y : yb[r / 2].x;
+            *reinterpret_cast<float2*>(sY + r * MP4 + 2 * lg) = make_float2(y0, y1);
+          }
+        }
+        const float cia = real_a ? w * 2.f * lla / n2a : 0.f, cib = real_b ? w * 2.f * llb / n2b : 0.f;
+        *reinterpret_cast<float2*>(sCo + 2 * lg) = make_float2(cia, cib);
+        *reinterpret_cast<float2*>(sCo + MP4 + 2 * lg) = make_float2(real_a ? -w * 2.f * lla : 0.f,
+                                                                     real_b ? -w * 2.f * llb : 0.f);
+      }
+      __syncwarp();
+      // ---- G_i[r][s'] = sum_q ci_q Y[r][q] Y[s'][q] and G_j with cj; a lane owns rows s' = lg and lg + LP.
+      // G_j goes to the problem's column accumulator (only its own lanes touch it); G_i of the NP problems
+      // of the row is summed across the problems in a fixed order (shuffles) and stored by the first one.
+      float* rp = A.rowpart + ((int64_t)t * R + ii) * m2;
+#pragma unroll 1
+      for (int u = 0; u < 2; ++u) {
+        const int sp = lg + LP * u;
+        const bool mine = alive && sp < m;
+        float2 cij[MP4];
+        {
+          const float* yrow = sY + (mine ? sp : 0) * MP4;
+#pragma unroll
+          for (int q4 = 0; q4 < MP4 / 4; ++q4) {
+            const float4 yy = *reinterpret_cast<const float4*>(yrow + 4 * q4);
+            const float4 c1 = *reinterpret_cast<const float4*>(sCo + 4 * q4);
+            const float4 c2 = *reinterpret_cast<const float4*>(sCo + MP4 + 4 * q4);
+            cij[4 * q4] = make_float2(yy.x * c1.x, yy.x * c2.x);
+            cij[4 * q4 + 1] = make_float2(yy.y * c1.y, yy.y * c2.y);
+            cij[4 * q4 + 2] = make_float2(yy.z * c1.z, yy.z * c2.z);
+            cij[4 * q4 + 3] = make_float2(yy.w * c1.w, yy.w * c2.w);
+          }
+        }
+#pragma unroll 1
+        for (int r = 0; r < m; ++r) {
+          float2 gab = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q4 = 0; q4 < MP4 / 4; ++q4) {
+            const float4 yr = *reinterpret_cast<const float4*>(sY + r * MP4 + 4 * q4);
+            gab = __ffma2_rn(make_float2(yr.x, yr.x), cij[4 * q4], gab);
+            gab = __ffma2_rn(make_float2(yr.y, yr.y), cij[4 * q4 + 1], gab);
+            gab = __ffma2_rn(make_float2(yr.z, yr.z), cij[4 * q4 + 2], gab);
+            gab = __ffma2_rn(make_float2(yr.w, yr.w), cij[4 * q4 + 3], gab);
+          }
+          const float gi = (active && mine) ? gab.x : 0.f;
+          float tot = 0.f;
+#pragma unroll
+          for (int gg = 0; gg < NP; ++gg) tot += __shfl_sync(FULL, gi, (gg * LP + lg) & 31);
+          if (g == 0 && mine) rp[r * m + sp] = tot;
+          if (active && mine) sC[r * m + sp] += gab.y;
+        }
+      }
+    }
+  }
+  if (want_grad) {  // column partials of the tile: every slot is written (zeros where a column had no pair)
+    __syncwarp();
+    float* cp = A.colpart + (int64_t)t * R * m2;
+    const float* sC0 = sLi + szLi + (per_group - ((m2 + 3) & ~3));
+    for (int gg = 0; gg < R; ++gg)
+      for (int idx = lane; idx < m2; idx += 32) cp[gg * m2 + idx] = sC0[gg * per_group + idx];
+  }
+  if (A.losspart != nullptr) {
+    float ds = 0.f, bs = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < NP; ++gg) {
+      ds += __shfl_sync(FULL, dsum, (gg * LP) & 31);
+      bs += __shfl_sync(FULL, badsum, (gg * LP) & 31);
+    }
+    if (lane == 0) {
+      A.losspart[2 * t] = ds;
+      A.losspart[2 * t + 1] = bs;
+    }
+  }
+}
+
+template <int MJ>
+static cudaError_t launch_pair_cp(const PairArgs& A, cudaStream_t st) {
+  const int smem = PAIR_WARPS * cp_warp_floats(MJ, A.m) * (int)sizeof(float);
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(pair_cp_kernel<MJ>, smem, smem_set);
+    if (e != cudaSuccess) return e;
+  }
+  const unsigned blocks = (unsigned)((A.T.ntiles + PAIR_WARPS - 1) / PAIR_WARPS);
+  pair_cp_kernel<MJ><<<blocks, PAIR_WARPS * 32, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // pair kernel, log-Euclidean: d^2 = |logE_i - logE_j|_F^2. Tiles are single pairs. The gradient
 // w.r.t. the matrix logarithms is sum_o pw(c, o) (logE_c - logE_o): this kernel stores the per-pair
 // factor pw = 2 w dd/d(d^2) and le_grad_kernel forms the sums class by class in a fixed order.
@@ -1119,11 +1491,24 @@ cudaError_t launch_class_prepare(const float* PsiPart, const float* MuPart, int 
   return cudaGetLastError();
 }
 
-// Tile edge: single pairs while the launch has few pairs (every pair gets its own warp: latency), 2 x 2
-// and 4 x 4 tiles for long pair lists (fewer, larger partials). The shared-memory variant (m > 32) and
-// log-Euclidean always use single pairs.
+// which AI-family kernel a launch takes (SQFA_PAIR_OLD=1: the one-column-per-lane kernel, for A/B runs)
+static bool pair_use_cp(int m, int dist) {
+  static const bool old_kernel = [] { const char* e = getenv("SQFA_PAIR_OLD"); return e != nullptr && atoi(e) != 0; }();
+  return (dist & 15) != SQFA_DIST_LOG_EUCLIDEAN && m <= 34 && !(old_kernel && m <= 32);
+}
+
+// Tile edge R (a warp owns R x R pairs). Column-pair kernel: the NP = 32 / (lanes per problem) pairs of a tile
+// row run side by side, so R goes up to NP as soon as there are enough tiles to fill the GPU a few times
+// over (R = 1 for short pair lists: every pair its own warp, latency). The shared-memory variant (m > 34)
+// and log-Euclidean always use single pairs.
 static int pair_tile_edge(int m, int dist, int64_t npairs) {
-  if ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN || m > 32) return 1;
+  if ((dist & 15) == SQFA_DIST_LOG_EUCLIDEAN || m > 34) return 1;
+  if (pair_use_cp(m, dist)) {
+    const int np = 32 / (((m + 1) & ~1) / 2);
+    int R = 1;
+    while (R < np && R < 8 && npairs / ((int64_t)(R + 1) * (R + 1)) >= 4096) ++R;
+    return R;
+  }
   int R = npairs <= 16384 ? 1 : (npairs <= 131072 ? 2 : 4);
   if (m > 24 && R > 2) R = 2;  // column accumulators are R m^2 floats of shared memory per warp
   return R;
@@ -1151,7 +1536,28 @@ static cudaError_t launch_pair_kernel(const PairArgs& A, cudaStream_t st) {
     pair_le_kernel<<<blocks, PAIR_WARPS * 32, 0, st>>>(A);
     return cudaGetLastError();
   }
-  if (m <= 32) {  // register-resident Jacobi
+  if (pair_use_cp(m, A.dist)) {  // two columns per lane, several problems per warp
+    switch ((m + 1) / 2) {
+      case 1: return launch_pair_cp<2>(A, st);
+      case 2: return launch_pair_cp<4>(A, st);
+      case 3: return launch_pair_cp<6>(A, st);
+      case 4: return launch_pair_cp<8>(A, st);
+      case 5: return launch_pair_cp<10>(A, st);
+      case 6: return launch_pair_cp<12>(A, st);
+      case 7: return launch_pair_cp<14>(A, st);
+      case 8: return launch_pair_cp<16>(A, st);
+      case 9: return launch_pair_cp<18>(A, st);
+      case 10: return launch_pair_cp<20>(A, st);
+      case 11: return launch_pair_cp<22>(A, st);
+      case 12: return launch_pair_cp<24>(A, st);
+      case 13: return launch_pair_cp<26>(A, st);
+      case 14: return launch_pair_cp<28>(A, st);
+      case 15: return launch_pair_cp<30>(A, st);
+      case 16: return launch_pair_cp<32>(A, st);
+      default: return launch_pair_cp<34>(A, st);
+    }
+  }
+  if (m <= 32) {  // register-resident Jacobi, one column per lane
 #define SQFA_PAIR_REG(MPV)                                                 \
   if (((m + 1) & ~1) < MPV) return launch_pair_reg<MPV, MPV - 2>(A, st); \
   return launch_pair_reg<MPV, MPV>(A, st)

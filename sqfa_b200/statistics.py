@@ -93,13 +93,14 @@ def class_statistics(points, labels, estimator="empirical", keep_on_device=False
         (extension) leave the result on the CUDA device even if `points` lives on the CPU.
     group : torch.distributed process group
         (extension) `points` / `labels` are this rank's shard of the samples; the statistics of the
-        union over all ranks are returned on every rank (three all-reduces, the large one overlapped
-        with the Gram kernel, see _stats_driver).
+        union over all ranks are returned on every rank (two small all-reduces and the all-reduce of
+        the packed Gram partials, see _stats_driver).
     shard_output : bool
         (extension, with `group`) every rank returns the means of all classes but the covariances and
         second moments of ITS share of the classes only -- rows `class_range[0]:class_range[1]`, the
         range is added to the dict as "class_range". The ranks' results together are the statistics;
-        nobody computes or moves the same matrix twice.
+        nobody computes or moves the same matrix twice: the Gram partials are reduce-scattered by class
+        inside the Gram kernel (copy-engine pushes into peer-mapped slots) and summed by the epilogue.
 
     Returns
     -------
