@@ -9,9 +9,9 @@
 //   closure loss + NaN/inf guard + autograd backward   _optim.py:16-30, 90-96
 //
 // Formulation. For a pair (i, j) the generalized eigenvalues of (E_i, E_j) are the squared singular
-// values of B = L_j^-1 L_i (E = L L^T Cholesky). One warp runs a one-sided (Hestenes) Jacobi on
-// the columns of A = B^T held in shared memory, one column per lane (two for 32 < m <= 64),
-// round-robin pairing, until all columns are mutually orthogonal: A_f = A V, |a_q|^2 = lambda_q.
+// values of B = L_j^-1 L_i (E = L L^T Cholesky). A one-sided (Hestenes) Jacobi orthogonalises the
+// columns of A = B^T: A_f = A V, |a_q|^2 = lambda_q. m <= 34: columns in registers, two per lane, several
+// problems per warp (pair_cp_kernel); 34 < m <= 64: columns in shared memory (pair_ai_kernel).
 // The generalized eigenvectors come for free as Y = L_i^-T A_f (y_q^T E_j y_q = 1), so
 //   d(d^2)/dE_i =  sum_q (2 log(lambda_q) / lambda_q) y_q y_q^T
 //   d(d^2)/dE_j = -sum_q (2 log(lambda_q))            y_q y_q^T
@@ -29,11 +29,11 @@
 namespace sqfa {
 
 // Deterministic accumulation. A warp owns a TILE of R x R pairs, (rows i = bi R + ii, columns
-// j = bj R + jj); it walks the tile row by row and keeps dLoss/dE_i of the current row in registers
-// and dLoss/dE_j of its R columns in shared memory, then stores both as per-tile PARTIALS (plain
-// stores, every slot written). A second kernel sums, for every class, the partials of the tiles in
-// its block row and block column in a fixed order. No floating-point atomics anywhere: loss and
-// gradient are bit-reproducible from run to run (L-BFGS amplifies gradient noise).
+// j = bj R + jj); it walks the tile row by row (the pairs of a row side by side in the column-pair
+// kernel), sums dLoss/dE_i over the row and keeps dLoss/dE_j of its R columns in shared memory, then
+// stores both as per-tile PARTIALS (plain stores, every slot written). A second kernel sums, for every
+// class, the partials of the tiles in its block row and block column in a fixed order. No floating-point
+// atomics anywhere: loss and gradient are bit-reproducible from run to run (L-BFGS amplifies noise).
 PairTiles make_pair_tiles(int nA, int nB, int tri, int64_t pair_begin, int64_t pair_end, int R) {
   PairTiles T;
   T.R = R < 1 ? 1 : R;
@@ -582,246 +582,6 @@ pair_ai_kernel(const PairArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// pair kernel, affine-invariant family, REGISTER-RESIDENT variant for m <= 32 (MP = m rounded up to
-// a multiple of 4): lane q keeps column q of A = (L_j^-1 L_i)^T in MP registers; a Jacobi round is
-// MP warp shuffles (the partner's column) + 3 MP FMAs; column norms are carried along incrementally
-// (alpha' = alpha - t gamma, beta' = beta + t gamma) and recomputed exactly once per sweep.
-// Shared memory only stages the triangular factors (broadcast reads) and the final
-// sum_q c_q y_q y_q^T. ~3x fewer issue slots per pair than the shared-memory variant above,
-// which stays in use for 32 < m <= 64.
-// ------------------------------------------------------------------------------------------------
-template <int MP, int MJ>  // MP: padded size (multiple of 4, shared-memory strides); MJ: even m, the Jacobi width
-// 6 blocks of 4 warps per SM: the kernel is issue-bound and needs the warps to hide shuffle / MUFU latency
-__global__ void __launch_bounds__(PAIR_WARPS * 32, 6)
-pair_ai_reg_kernel(const PairArgs A) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int LDT = MP + 1;                                  // odd stride: conflict-free transposed access
-  constexpr int PER_PAIR = MP * MP + ((MP * LDT + 3) & ~3);    // sL | sT, both 16-byte aligned
-  const int R = A.T.R;
-  const int m = A.m, nB = A.nB, tri = A.tri, dist = A.dist;
-  const int m2 = m * m;
-  const int per_warp = PER_PAIR + (((R + 1) * m2 + 3) & ~3);   // + row accumulator + R column accumulators
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
-  const int64_t t = (int64_t)blockIdx.x * nwarps + warp;
-  if (t >= A.T.ntiles) return;  // no block-wide synchronisation below
-  float* sL = smem + (size_t)warp * per_warp;  // [MP][MP]: L_i, then Linv_i, then Y
-  float* sT = sL + MP * MP;                    // [MP][MP+1]: Linv_j^T; later the coefficient vectors ci | cj
-  float* sRow = sL + PER_PAIR;                 // [m][m]: dLoss/dE_i of the current row of the tile
-  float* sC = sRow + m2;                       // [R][m][m]: dLoss/dE_j of the tile's columns
-  const int mp = (m + 1) & ~1;
-  const bool want_grad = A.rowpart != nullptr;
-  int bi, bj;
-  decode_tile(A.T, t, bi, bj);
-  if (want_grad) {
-    for (int idx = lane; idx < R * m2; idx += 32) sC[idx] = 0.f;
-  }
-  float dsum = 0.f, badsum = 0.f;
-  for (int ii = 0; ii < R; ++ii) {
-    const int i = bi * R + ii;
-    if (want_grad) {
-      __syncwarp();
-      for (int idx = lane; idx < m2; idx += 32) sRow[idx] = 0.f;
-    }
-    for (int jj = 0; jj < R; ++jj) {
-      const int j = bj * R + jj;
-      if (!pair_in_launch(i, j, A.nA, nB, tri, A.pair_begin, A.pair_end)) continue;  // warp-uniform
-      const float* Wi = A.Wa + (int64_t)i * 2 * m * m;
-      const float* Wj = A.Wb + (int64_t)j * 2 * m * m;
-      // ---- stage L_i (row-major, zero padded to MP) and Linv_j transposed
-      __syncwarp();
-      for (int idx = lane; idx < MP * MP; idx += 32) sL[idx] = 0.f;
-      __syncwarp();
-      for (int idx = lane; idx < m * m; idx += 32) {
-        const int r = idx / m, c = idx % m;
-        sL[r * MP + c] = Wi[idx];
-        sT[c * LDT + r] = Wj[m * m + idx];  // sT[r'][q] = Linv_j[q][r'], q < m <= MP
-      }
-      __syncwarp();
-      // ---- column `lane` of A: a[s] = sum_r Linv_j[lane][r] L_i[r][s]   (both factors lower triangular)
-      // The column lives in MP / 2 packed register pairs: dot products and rotations are packed-fp32
-      // instructions (fma.rn.f32x2 / mul.rn.f32x2), half the FMA issue slots of scalar code.
-      float2 a2[MP / 2];
-      float y[MP];
-#pragma unroll
-      for (int s = 0; s < MP / 2; ++s) a2[s] = make_float2(0.f, 0.f);
-      if (lane < m) {
-#pragma unroll
-        for (int r = 0; r < MP; ++r) {
-          if (r < m) {
-            const float l = sT[r * LDT + lane];
-            const float2 l2 = make_float2(l, l);
-#pragma unroll
-            for (int s4 = 0; s4 < MP / 4; ++s4) {
-              const float4 w = *reinterpret_cast<const float4*>(sL + r * MP + 4 * s4);
-              a2[2 * s4] = __ffma2_rn(l2, make_float2(w.x, w.y), a2[2 * s4]);
-              a2[2 * s4 + 1] = __ffma2_rn(l2, make_float2(w.z, w.w), a2[2 * s4 + 1]);
-            }
-          }
-        }
-      }
-      // ---- one-sided Jacobi, columns in registers (entries >= MJ are padding zeros and stay zero)
-      for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
-        float2 n2p = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int s = 0; s < MJ / 2; ++s) n2p = __ffma2_rn(a2[s], a2[s], n2p);
-        float nrm = n2p.x + n2p.y;
-        // a sweep whose largest rotation was below JACOBI_LAST leaves off-diagonals of that size
-        // squared (quadratic convergence): no verification sweep needed after it
-        bool rotated = false;
-        for (int r = 0; r < mp - 1; ++r) {
-          const int q = lane < mp ? rr_partner(lane, r, mp) : lane;
-          const float nq = __shfl_sync(0xffffffffu, nrm, q);
-          float2 y2[MJ / 2];
-          float2 ab2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int s = 0; s < MJ / 2; ++s) {
-            y2[s].x = __shfl_sync(0xffffffffu, a2[s].x, q);
-            y2[s].y = __shfl_sync(0xffffffffu, a2[s].y, q);
-            ab2 = __ffma2_rn(a2[s], y2[s], ab2);
-          }
-          const float ab = ab2.x + ab2.y;
-          const bool is_lo = lane < q;
-          const float alpha = is_lo ? nrm : nq, beta = is_lo ? nq : nrm;
-          float cs = 1.f, sn = 0.f;
-          const float ab_sq = ab * ab, scale = alpha * beta;
-          if (lane < mp && ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale && alpha > 0.f && beta > 0.f) {
-            // approximate reciprocal / square root (1 MUFU each): a Jacobi rotation only has to be
-            // orthogonal to fp32 precision (cs^2 + sn^2 = 1 from the same rsqrt as before); an angle
-            // off by 1e-7 relative leaves an off-diagonal of that size, far below the tolerance
-            const float zeta = (beta - alpha) * rcp_approx(2.f * ab);
-            const float tt = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
-            cs = rsqrtf(fmaf(tt, tt, 1.f));
-            sn = cs * tt;
-            nrm = is_lo ? alpha - tt * ab : beta + tt * ab;
-            rotated = rotated || ab_sq > (JACOBI_LAST * JACOBI_LAST) * scale;
-          }
-          const float other = is_lo ? -sn : sn;
-          const float2 cs2 = make_float2(cs, cs), ot2 = make_float2(other, other);
-#pragma unroll
-          for (int s = 0; s < MJ / 2; ++s) a2[s] = __ffma2_rn(cs2, a2[s], __fmul2_rn(ot2, y2[s]));
-        }
-        if (!__any_sync(0xffffffffu, rotated)) break;
-      }
-      float a[MP];
-#pragma unroll
-      for (int s = 0; s < MP / 2; ++s) { a[2 * s] = a2[s].x; a[2 * s + 1] = a2[s].y; }
-      // ---- eigenvalues, distance
-      float n2 = 0.f;
-#pragma unroll
-      for (int s = 0; s < MP; ++s) n2 += a[s] * a[s];
-      const float ll = lane < m ? logf(n2) : 0.f;
-      const float d2 = warp_sum(ll * ll);
-      if (A.eig_out != nullptr) {  // descending order (linalg.py:69-70)
-        int rank = 0;
-        for (int u = 0; u < m; ++u) {
-          const float v = __shfl_sync(0xffffffffu, n2, u);
-          rank += (v > n2 || (v == n2 && u < lane)) ? 1 : 0;
-        }
-        if (lane < m) A.eig_out[((int64_t)i * nB + j) * m + rank] = n2;
-      }
-      float dd_dd2;
-      const float dval = finish_distance(d2, dist, &dd_dd2);
-      dsum += dval;
-      if (!isfinite(dval)) badsum += 1.f;
-      if (A.dist_out != nullptr && lane == 0) {
-        A.dist_out[(int64_t)i * nB + j] = dval;
-        if (tri) A.dist_out[(int64_t)j * nB + i] = dval;
-      }
-      if (want_grad) {
-        float w = A.weight * dd_dd2;
-        if (A.gD != nullptr)
-          w *= tri ? (A.gD[(int64_t)i * nB + j] + A.gD[(int64_t)j * nB + i]) : A.gD[(int64_t)i * nB + j];
-        const float ci = lane < m ? w * 2.f * ll / n2 : 0.f, cj = lane < m ? -w * 2.f * ll : 0.f;
-        // ---- Y = L_i^-T A_f : y[r] = sum_{s >= r} Linv_i[s][r] a[s]
-        __syncwarp();
-        for (int idx = lane; idx < m * m; idx += 32) sL[(idx / m) * MP + idx % m] = Wi[m * m + idx];
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < MP; ++r) y[r] = 0.f;
-#pragma unroll
-        for (int s = 0; s < MP; ++s) {
-          if (s < m) {
-#pragma unroll
-            for (int r4 = 0; r4 < MP / 4; ++r4) {
-              const float4 wv = *reinterpret_cast<const float4*>(sL + s * MP + 4 * r4);
-              y[4 * r4 + 0] += wv.x * a[s]; y[4 * r4 + 1] += wv.y * a[s]; y[4 * r4 + 2] += wv.z * a[s]; y[4 * r4 + 3] += wv.w * a[s];
-            }
-          }
-        }
-        __syncwarp();
-        // ---- Y -> sL[r][q] (q = lane), coefficient vectors ci | cj -> sT (Linv_j^T is dead)
-        float* sCi = sT;
-        float* sCj = sT + MP;
-        if (lane < MP) {
-#pragma unroll
-          for (int r = 0; r < MP; ++r) sL[r * MP + lane] = lane < m ? y[r] : 0.f;
-          sCi[lane] = ci;
-          sCj[lane] = cj;
-        }
-        __syncwarp();
-        // ---- G_i[r][s'] = sum_q ci_q Y[r][q] Y[s'][q], G_j likewise with cj; lane = s': its row of Y,
-        // scaled by the coefficients, stays in registers; rows Y[r][:] are broadcast 16-byte loads.
-        // G_i is added to the row accumulator, G_j to this column's accumulator (shared memory;
-        // element (r, lane) is only ever touched by this lane).
-        if (lane < m) {
-          float yi[MP], yj[MP];
-#pragma unroll
-          for (int q4 = 0; q4 < MP / 4; ++q4) {
-            const float4 yy = *reinterpret_cast<const float4*>(sL + lane * MP + 4 * q4);
-            const float4 c1 = *reinterpret_cast<const float4*>(sCi + 4 * q4);
-            const float4 c2 = *reinterpret_cast<const float4*>(sCj + 4 * q4);
-            yi[4 * q4] = yy.x * c1.x; yi[4 * q4 + 1] = yy.y * c1.y; yi[4 * q4 + 2] = yy.z * c1.z; yi[4 * q4 + 3] = yy.w * c1.w;
-            yj[4 * q4] = yy.x * c2.x; yj[4 * q4 + 1] = yy.y * c2.y; yj[4 * q4 + 2] = yy.z * c2.z; yj[4 * q4 + 3] = yy.w * c2.w;
-          }
-          float* racc = sRow + lane;
-          float* cacc = sC + jj * m2 + lane;
-          for (int r = 0; r < m; ++r) {
-            float ga = 0.f, gb = 0.f;
-#pragma unroll
-            for (int q4 = 0; q4 < MP / 4; ++q4) {
-              const float4 yr = *reinterpret_cast<const float4*>(sL + r * MP + 4 * q4);
-              ga += yr.x * yi[4 * q4] + yr.y * yi[4 * q4 + 1] + yr.z * yi[4 * q4 + 2] + yr.w * yi[4 * q4 + 3];
-              gb += yr.x * yj[4 * q4] + yr.y * yj[4 * q4 + 1] + yr.z * yj[4 * q4 + 2] + yr.w * yj[4 * q4 + 3];
-            }
-            racc[r * m] += ga;
-            cacc[r * m] += gb;
-          }
-        }
-      }
-    }
-    if (want_grad) {  // row partial of (tile, ii): every slot is written (zeros if the row had no pair)
-      __syncwarp();
-      float* rp = A.rowpart + ((int64_t)t * R + ii) * m2;
-      for (int idx = lane; idx < m2; idx += 32) rp[idx] = sRow[idx];
-    }
-  }
-  if (want_grad) {
-    __syncwarp();
-    float* cp = A.colpart + (int64_t)t * R * m2;
-    for (int idx = lane; idx < R * m2; idx += 32) cp[idx] = sC[idx];
-  }
-  if (A.losspart != nullptr && lane == 0) {
-    A.losspart[2 * t] = dsum;
-    A.losspart[2 * t + 1] = badsum;
-  }
-}
-
-template <int MP, int MJ>
-static cudaError_t launch_pair_reg(const PairArgs& A, cudaStream_t st) {
-  constexpr int per_pair_floats = MP * MP + ((MP * (MP + 1) + 3) & ~3);
-  const int smem = PAIR_WARPS * (per_pair_floats + (((A.T.R + 1) * A.m * A.m + 3) & ~3)) * (int)sizeof(float);
-  static int smem_set[kMaxDevices] = {0};
-  {
-    cudaError_t e = ensure_dynamic_smem(pair_ai_reg_kernel<MP, MJ>, smem, smem_set);
-    if (e != cudaSuccess) return e;
-  }
-  const unsigned blocks = (unsigned)((A.T.ntiles + PAIR_WARPS - 1) / PAIR_WARPS);
-  pair_ai_reg_kernel<MP, MJ><<<blocks, PAIR_WARPS * 32, smem, st>>>(A);
-  return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
 // pair kernel, affine-invariant family, COLUMN-PAIR variant for m <= 34 (MJ = m rounded up to even).
 //
 // A lane owns TWO adjacent columns of A = (L_j^-1 L_i)^T in registers (positions 2 lg and 2 lg + 1),
@@ -871,8 +631,13 @@ __device__ __forceinline__ void cp_rotation(float alpha, float beta, float ab, b
   c = 1.f; s = 0.f; n0 = beta; n1 = alpha;
   const float ab_sq = ab * ab, scale = alpha * beta;
   if (has_pair && ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale) {
-    const float zeta = (beta - alpha) * rcp_approx(2.f * ab);
-    const float tt = copysignf(rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f))), zeta);
+    // t = sign(zeta) / (|zeta| + sqrt(zeta^2 + 1)) with zeta = d / h, d = beta - alpha, h = 2 ab, written as
+    // sign(d) h / (|d| + sqrt(d^2 + h^2)): one reciprocal less on the dependent chain, no division by a tiny ab.
+    // Approximate reciprocal / square roots: a rotation only has to be orthogonal to fp32 precision
+    // (c^2 + s^2 = 1 from the same rsqrt); an angle off by 1e-7 leaves an off-diagonal of that size.
+    const float d = beta - alpha, h = ab + ab;
+    const float hs = __uint_as_float(__float_as_uint(h) ^ (__float_as_uint(d) & 0x80000000u));  // sign(d) h
+    const float tt = hs * rcp_approx(fabsf(d) + sqrt_approx(fmaf(d, d, h * h)));
     c = rsqrt_approx(fmaf(tt, tt, 1.f));
     s = c * tt;
     n0 = fmaf(tt, ab, beta);
@@ -883,7 +648,7 @@ __device__ __forceinline__ void cp_rotation(float alpha, float beta, float ab, b
 }
 
 template <int MJ>
-__global__ void __launch_bounds__(PAIR_WARPS * 32, (MJ <= 12 ? 6 : (MJ <= 20 ? 4 : (MJ <= 28 ? 3 : 2))))
+__global__ void __launch_bounds__(PAIR_WARPS * 32, (MJ <= 12 ? 6 : (MJ <= 20 ? 4 : 3)))
 pair_cp_kernel(const PairArgs A) {
   using G = CpGeom<MJ>;
   constexpr int LP = G::LP, NP = G::NP, MP4 = G::MP4, MH = G::MH, LDJ = G::LDJ;
@@ -950,7 +715,7 @@ pair_cp_kernel(const PairArgs A) {
           const float la = ja[r], lb = jb[r];
           const float2 la2 = make_float2(la, la), lb2 = make_float2(lb, lb);
 #pragma unroll
-          for (int s4 = 0; s4 < MP4 / 4; ++s4) {
+          for (int s4 = 0; s4 <= r / 4; ++s4) {  // L_i is lower triangular: row r ends at column r
             const float4 w = *reinterpret_cast<const float4*>(sLi + r * MP4 + 4 * s4);
             const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
             a[2 * s4] = __ffma2_rn(la2, w0, a[2 * s4]);
@@ -1090,7 +855,7 @@ pair_cp_kernel(const PairArgs A) {
           const float as = (s & 1) ? a[s / 2].y : a[s / 2].x, bs = (s & 1) ? b[s / 2].y : b[s / 2].x;
           const float2 as2 = make_float2(as, as), bs2 = make_float2(bs, bs);
 #pragma unroll
-          for (int r4 = 0; r4 < MP4 / 4; ++r4) {
+          for (int r4 = 0; r4 <= s / 4; ++r4) {  // Linv_i is lower triangular
             const float4 wv = *reinterpret_cast<const float4*>(sLi + s * MP4 + 4 * r4);
             const float2 w0 = make_float2(wv.x, wv.y), w1 = make_float2(wv.z, wv.w);
             ya[2 * r4] = __ffma2_rn(as2, w0, ya[2 * r4]);
@@ -1491,11 +1256,8 @@ cudaError_t launch_class_prepare(const float* PsiPart, const float* MuPart, int 
   return cudaGetLastError();
 }
 
-// which AI-family kernel a launch takes (SQFA_PAIR_OLD=1: the one-column-per-lane kernel, for A/B runs)
-static bool pair_use_cp(int m, int dist) {
-  static const bool old_kernel = [] { const char* e = getenv("SQFA_PAIR_OLD"); return e != nullptr && atoi(e) != 0; }();
-  return (dist & 15) != SQFA_DIST_LOG_EUCLIDEAN && m <= 34 && !(old_kernel && m <= 32);
-}
+// AI family up to m = 34: the column-pair kernel; 34 < m <= 64: the shared-memory kernel
+static bool pair_use_cp(int m, int dist) { return (dist & 15) != SQFA_DIST_LOG_EUCLIDEAN && m <= 34; }
 
 // Tile edge R (a warp owns R x R pairs). Column-pair kernel: the NP = 32 / (lanes per problem) pairs of a tile
 // row run side by side, so R goes up to NP as soon as there are enough tiles to fill the GPU a few times
@@ -1509,9 +1271,7 @@ static int pair_tile_edge(int m, int dist, int64_t npairs) {
     while (R < np && R < 8 && npairs / ((int64_t)(R + 1) * (R + 1)) >= 4096) ++R;
     return R;
   }
-  int R = npairs <= 16384 ? 1 : (npairs <= 131072 ? 2 : 4);
-  if (m > 24 && R > 2) R = 2;  // column accumulators are R m^2 floats of shared memory per warp
-  return R;
+  return 1;
 }
 
 PairWorkspace pair_workspace(int nA, int nB, int m, int dist, int tri, int64_t pair_begin, int64_t pair_end) {
@@ -1556,22 +1316,6 @@ static cudaError_t launch_pair_kernel(const PairArgs& A, cudaStream_t st) {
       case 16: return launch_pair_cp<32>(A, st);
       default: return launch_pair_cp<34>(A, st);
     }
-  }
-  if (m <= 32) {  // register-resident Jacobi, one column per lane
-#define SQFA_PAIR_REG(MPV)                                                 \
-  if (((m + 1) & ~1) < MPV) return launch_pair_reg<MPV, MPV - 2>(A, st); \
-  return launch_pair_reg<MPV, MPV>(A, st)
-    switch ((m + 3) / 4) {
-      case 1: SQFA_PAIR_REG(4);
-      case 2: SQFA_PAIR_REG(8);
-      case 3: SQFA_PAIR_REG(12);
-      case 4: SQFA_PAIR_REG(16);
-      case 5: SQFA_PAIR_REG(20);
-      case 6: SQFA_PAIR_REG(24);
-      case 7: SQFA_PAIR_REG(28);
-      default: SQFA_PAIR_REG(32);
-    }
-#undef SQFA_PAIR_REG
   }
   const int per_warp = pair_smem_floats(m) * (int)sizeof(float);
   const int nw = warps_for(per_warp);
