@@ -104,18 +104,28 @@ struct GramParams {
 // job = ((rank * KS) + ks) * T + t
 __global__ void __launch_bounds__(256) gram_plan_kernel(const int64_t* __restrict__ offsets, int C, int TT, int KS,
                                                          int class_order, int first_class, int4* __restrict__ jobs) {
+  // one warp per class: its rank among the classes by descending size (lanes stride over the other classes),
+  // then its (K part, tile) jobs
   const int T = TT * (TT + 1) / 2;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-    const int64_t n_c = offsets[c + 1] - offsets[c];
-    int rank = class_order ? (c - first_class + C) % C : 0;
-    for (int o = 0; o < C && !class_order; ++o) {
-      const int64_t n_o = offsets[o + 1] - offsets[o];
-      rank += (n_o > n_c || (n_o == n_c && o < c)) ? 1 : 0;
+  const int lane = threadIdx.x & 31;
+  for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < C; c += gridDim.x * (blockDim.x >> 5)) {
+    int rank = 0;
+    if (class_order) {
+      rank = (c - first_class + C) % C;
+    } else {
+      const int64_t n_c = offsets[c + 1] - offsets[c];
+      for (int o = lane; o < C; o += 32) {
+        const int64_t n_o = offsets[o + 1] - offsets[o];
+        rank += (n_o > n_c || (n_o == n_c && o < c)) ? 1 : 0;
+      }
+      for (int sh = 16; sh > 0; sh >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, sh);
     }
-    int t = 0;
-    for (int tm = 0; tm < TT; ++tm)
-      for (int tn = tm; tn < TT; ++tn, ++t)
-        for (int ks = 0; ks < KS; ++ks) jobs[((int64_t)rank * KS + ks) * T + t] = make_int4(c, tm, tn, ks);
+    for (int e = lane; e < T * KS; e += 32) {
+      const int t = e / KS, ks = e - t * KS;
+      int tm = 0, rem = t;  // t -> (tm, tn), tm <= tn, row-major over the upper triangle
+      while (rem >= TT - tm) { rem -= TT - tm; ++tm; }
+      jobs[((int64_t)rank * KS + ks) * T + t] = make_int4(c, tm, tm + rem, ks);
+    }
   }
 }
 
@@ -727,7 +737,7 @@ cudaError_t launch_class_gram(const float* X, int64_t ldx, const int32_t* perm, 
     cudaError_t e = cudaMemsetAsync(gram, 0, floats * sizeof(float), stream);
     if (e != cudaSuccess) return e;
   }
-  gram_plan_kernel<<<(C + 255) / 256, 256, 0, stream>>>(offsets, C, TT, P.KS, P.class_order, P.first_class,
+  gram_plan_kernel<<<(C + 7) / 8, 256, 0, stream>>>(offsets, C, TT, P.KS, P.class_order, P.first_class,
                                                         reinterpret_cast<int4*>(ws));
   // reserve_sms SMs are left to other streams (the collective that runs while this kernel still computes)
   const int usable = num_sms - (reserve_sms > 0 ? reserve_sms : 0);

@@ -607,14 +607,15 @@ struct CpGeom {
   static constexpr int LDJ = MP4 + 1;        // odd row stride of Linv_j (lane-varying scalar reads)
 };
 
-// floats of shared memory per warp: [L_i rows | per problem: Linv_j rows, Y rows, coefficients, column accumulator]
-__host__ __device__ inline int cp_group_floats(int MJ, int m) {
+// floats of shared memory per warp: [L_i rows | per problem: Linv_j rows, Y rows, coefficients, column accumulator].
+// With single-pair tiles (R = 1) Linv_j is dead once the columns are formed and Y takes its place.
+__host__ __device__ inline int cp_group_floats(int MJ, int m, int R) {
   const int MP4 = (MJ + 3) & ~3;
-  return ((MJ * (MP4 + 1) + 3) & ~3) + m * MP4 + 2 * MP4 + ((m * m + 3) & ~3);
+  return ((MJ * (MP4 + 1) + 3) & ~3) + (R == 1 ? 0 : m * MP4) + 2 * MP4 + ((m * m + 3) & ~3);
 }
-__host__ __device__ inline int cp_warp_floats(int MJ, int m) {
+__host__ __device__ inline int cp_warp_floats(int MJ, int m, int R) {
   const int MP4 = (MJ + 3) & ~3;
-  return m * MP4 + (32 / (MJ / 2)) * cp_group_floats(MJ, m);
+  return m * MP4 + (32 / (MJ / 2)) * cp_group_floats(MJ, m, R);
 }
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -659,14 +660,15 @@ pair_cp_kernel(const PairArgs A) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (t >= A.T.ntiles) return;  // no block-wide synchronisation below
-  const int szLi = m * MP4, szJ = (MJ * LDJ + 3) & ~3, szY = m * MP4, szCo = 2 * MP4;
-  const int per_group = cp_group_floats(MJ, m);
-  float* sLi = smem + (size_t)warp * cp_warp_floats(MJ, m);  // [m][MP4]: L_i, later Linv_i (shared by the problems)
+  const bool y_over_j = R == 1;  // single-pair tiles: Y overwrites Linv_j
+  const int szLi = m * MP4, szJ = (MJ * LDJ + 3) & ~3, szY = y_over_j ? 0 : m * MP4, szCo = 2 * MP4;
+  const int per_group = cp_group_floats(MJ, m, R);
+  float* sLi = smem + (size_t)warp * cp_warp_floats(MJ, m, R);  // [m][MP4]: L_i, later Linv_i (shared by the problems)
   const int g = lane / LP, lg = lane - g * LP;
   const bool alive = g < NP;                // lanes beyond NP * LP only follow the instruction stream
   float* sJ = sLi + szLi + (alive ? g : NP - 1) * per_group;  // [MJ][LDJ]: Linv_j of this problem's column class
-  float* sY = sJ + szJ;                     // [m][MP4]: generalized eigenvectors, row r = component, column = position
-  float* sCo = sY + szY;                    // [2][MP4]: coefficients ci | cj per position
+  float* sY = y_over_j ? sJ : sJ + szJ;     // [m][MP4]: generalized eigenvectors, row r = component, column = position
+  float* sCo = sJ + szJ + szY;                  // [2][MP4]: coefficients ci | cj per position
   float* sC = sCo + szCo;                   // [m][m]: dLoss/dE_j of this problem's column class
   const bool want_grad = A.rowpart != nullptr;
   auto div_m = [&](int idx) { return m_odd ? idx / (MJ - 1) : idx / MJ; };  // division by a compile-time constant
@@ -866,6 +868,10 @@ pair_cp_kernel(const PairArgs A) {
         }
       }
       // ---- Y -> shared memory (row = component r, column = position), coefficients of both matrices
+      if constexpr (MP4 > MJ) {  // (two padding columns)
+        if (y_over_j)              // they lie on what was Linv_j: zero them
+          for (int idx = lg; idx < 2 * m; idx += LP) sY[(idx >> 1) * MP4 + MJ + (idx & 1)] = 0.f;
+      }
       if (alive) {
 #pragma unroll
         for (int r = 0; r < MJ; ++r) {
@@ -946,7 +952,7 @@ pair_cp_kernel(const PairArgs A) {
 
 template <int MJ>
 static cudaError_t launch_pair_cp(const PairArgs& A, cudaStream_t st) {
-  const int smem = PAIR_WARPS * cp_warp_floats(MJ, A.m) * (int)sizeof(float);
+  const int smem = PAIR_WARPS * cp_warp_floats(MJ, A.m, A.T.R) * (int)sizeof(float);
   static int smem_set[kMaxDevices] = {0};
   {
     cudaError_t e = ensure_dynamic_smem(pair_cp_kernel<MJ>, smem, smem_set);
