@@ -1041,19 +1041,20 @@ le_grad_kernel(const PairTiles T, const float* __restrict__ Wa, const float* __r
 }
 
 // fixed-order sum of the per-tile {sum of distances, non-finite count}: every thread sums a strided
-// subset in ascending tile order, then a fixed tree over the block
+// subset in ascending tile order, then a fixed tree over the block (any block size up to 1024)
 __device__ void reduce_loss_partials(const float* __restrict__ losspart, int64_t ntiles, float& sum, float& bad) {
-  __shared__ float red[2][256];
+  __shared__ float red[2][1024];
+  const int nt = blockDim.x;
   float a = 0.f, b = 0.f;
-  for (int64_t t = threadIdx.x; t < ntiles; t += 256) {
+  for (int64_t t = threadIdx.x; t < ntiles; t += nt) {
     a += losspart[2 * t];
     b += losspart[2 * t + 1];
   }
   red[0][threadIdx.x] = a;
   red[1][threadIdx.x] = b;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o && (int)threadIdx.x + o < nt) {
       red[0][threadIdx.x] += red[0][threadIdx.x + o];
       red[1][threadIdx.x] += red[1][threadIdx.x + o];
     }
@@ -1065,13 +1066,14 @@ __device__ void reduce_loss_partials(const float* __restrict__ losspart, int64_t
 
 // dLoss/dE of class c = its row partials (tiles of block row c / R, ascending block column) + its
 // column partials (tiles of block column c / R, ascending block row): blocks 0 .. max(nA, nB) - 1.
-// The last block reduces the loss partials. 256 threads.
+// The last block reduces the loss partials. Block size: pair_reduce_threads(m) (one matrix element per thread
+// and pass; m = 17 has 289 elements: 256 threads would run a second, almost empty pass of the same latency).
 //   CLOSURE = false: gEa[c] += rows, gEb[c] += columns (gEa == gEb: one sum); loss[0..1] += {sum d, #bad}
 //   CLOSURE = true : the closure's tail fused in: (gPsi, gMu) = adjoint of the embedding applied to the
 //                    reduced dLoss/dE (reference model.py:216-217 / 537-538, distances.py:162-174) and
 //                    loss = {weight * sum d, #bad, 0}
 template <bool CLOSURE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 pair_reduce_kernel(const PairTiles T, int nA, int nB, int m, const float* __restrict__ rowpart,
                    const float* __restrict__ colpart, const float* __restrict__ losspart, float* gEa, float* gEb,
                    float* loss, float weight, const float* __restrict__ Mu, int k, int fr, float* __restrict__ gPsi,
@@ -1099,17 +1101,20 @@ pair_reduce_kernel(const PairTiles T, int nA, int nB, int m, const float* __rest
   const int R = T.R, m2 = m * m;
   const int slot = c % R, bc = c / R;
   const int64_t pstride = (int64_t)R * m2;
-  for (int e = threadIdx.x; e < m2; e += 256) {
+  for (int e = threadIdx.x; e < m2; e += blockDim.x) {
     float a = 0.f, b = 0.f;
     if (c < nA && bc >= T.bi0 && bc <= T.bi1) {
       const int nb = T.tri ? bc + 1 : T.nbj;
       const float* p = rowpart + ((T.tri ? (int64_t)bc * (bc + 1) / 2 : (int64_t)bc * T.nbj) - T.tile0) * pstride +
                        (int64_t)slot * m2 + e;
       int bj = 0;
-      for (; bj + 4 <= nb; bj += 4) {  // four loads in flight, added in order
-        const float v0 = p[0], v1 = p[pstride], v2 = p[2 * pstride], v3 = p[3 * pstride];
-        a += v0; a += v1; a += v2; a += v3;
-        p += 4 * pstride;
+      for (; bj + 8 <= nb; bj += 8) {  // eight loads in flight, added in order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[u * pstride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a += v[u];
+        p += 8 * pstride;
       }
       for (; bj < nb; ++bj, p += pstride) a += *p;
     }
@@ -1120,9 +1125,12 @@ pair_reduce_kernel(const PairTiles T, int nA, int nB, int m, const float* __rest
         const int64_t tt = (T.tri ? (int64_t)bi_ * (bi_ + 1) / 2 + bc : (int64_t)bi_ * T.nbj + bc) - T.tile0;
         return colpart[tt * pstride + (int64_t)slot * m2 + e];
       };
-      for (; bi + 4 <= T.bi1 + 1; bi += 4) {
-        const float v0 = cp(bi), v1 = cp(bi + 1), v2 = cp(bi + 2), v3 = cp(bi + 3);
-        b += v0; b += v1; b += v2; b += v3;
+      for (; bi + 8 <= T.bi1 + 1; bi += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = cp(bi + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) b += v[u];
       }
       for (; bi <= T.bi1; ++bi) b += cp(bi);
     }
@@ -1138,7 +1146,7 @@ pair_reduce_kernel(const PairTiles T, int nA, int nB, int m, const float* __rest
   if (CLOSURE) {
     __syncthreads();
     // gPsi = gE[:k,:k];  gMu[r] = sum_s (gE[r][s] + gE[s][r]) mu[s] + gE[r][k] + gE[k][r]   (Fisher-Rao)
-    for (int idx = threadIdx.x; idx < k * (k + 1); idx += 256) {
+    for (int idx = threadIdx.x; idx < k * (k + 1); idx += blockDim.x) {
       const int r = idx / (k + 1), s = idx % (k + 1);
       if (s < k) {
         gPsi[(int64_t)c * k * k + r * k + s] = sg[r * m + s];
@@ -1280,6 +1288,13 @@ static int pair_tile_edge(int m, int dist, int64_t npairs) {
   return 1;
 }
 
+// threads of pair_reduce_kernel: the m^2 elements in as few, evenly filled passes as possible
+static int pair_reduce_threads(int m) {
+  const int m2 = m * m, passes = (m2 + 1023) / 1024;
+  int nt = (((m2 + passes - 1) / passes) + 31) & ~31;
+  return nt < 128 ? 128 : nt;
+}
+
 PairWorkspace pair_workspace(int nA, int nB, int m, int dist, int tri, int64_t pair_begin, int64_t pair_end) {
   PairWorkspace w;
   const int64_t npairs = pair_end > pair_begin ? pair_end - pair_begin : 0;
@@ -1373,7 +1388,7 @@ cudaError_t launch_pair_distances(const float* Wa, const float* Wb, int nA, int 
   const int nC = nA > nB ? nA : nB;
   const bool le = (dist & 15) == SQFA_DIST_LOG_EUCLIDEAN;
   if (le && want_grad) le_grad_kernel<<<nC, 256, 0, st>>>(L.T, Wa, Wb, nA, nB, m, A.rowpart, gEa, gEb);
-  pair_reduce_kernel<false><<<nC + 1, 256, 0, st>>>(L.T, nA, nB, m, le ? nullptr : A.rowpart, A.colpart, A.losspart,
+  pair_reduce_kernel<false><<<nC + 1, pair_reduce_threads(m), 0, st>>>(L.T, nA, nB, m, le ? nullptr : A.rowpart, A.colpart, A.losspart,
                                                     gEa, gEb, loss, 1.f, nullptr, 0, 0, nullptr, nullptr);
   return cudaGetLastError();
 }
@@ -1395,11 +1410,11 @@ cudaError_t launch_pair_closure(const float* W, int C, int m, int dist, int64_t 
   if (le) {
     if ((e = cudaMemsetAsync(gLog, 0, (size_t)C * m * m * sizeof(float), st)) != cudaSuccess) return e;
     if (L.T.ntiles > 0) le_grad_kernel<<<C, 256, 0, st>>>(L.T, W, W, C, C, m, A.rowpart, gLog, gLog);
-    pair_reduce_kernel<true><<<C + 1, 256, 0, st>>>(L.T, C, C, m, nullptr, nullptr, A.losspart, nullptr, nullptr, out,
+    pair_reduce_kernel<true><<<C + 1, pair_reduce_threads(m), 0, st>>>(L.T, C, C, m, nullptr, nullptr, A.losspart, nullptr, nullptr, out,
                                                     weight, nullptr, k, 0, nullptr, nullptr);
     return cudaGetLastError();
   }
-  pair_reduce_kernel<true><<<C + 1, 256, m * m * sizeof(float), st>>>(L.T, C, C, m, A.rowpart, A.colpart, A.losspart,
+  pair_reduce_kernel<true><<<C + 1, pair_reduce_threads(m), m * m * sizeof(float), st>>>(L.T, C, C, m, A.rowpart, A.colpart, A.losspart,
                                                                      nullptr, nullptr, out, weight, Mu, k, fr ? 1 : 0,
                                                                      gPsi, gMu);
   return cudaGetLastError();

@@ -131,3 +131,22 @@ def test_direct_closure_plan_only_for_closed_form_constraints():
         assert model._fused_direct_plan(stats) is None  # CPU parameter
     model = SecondMomentsSQFA(n_dim=6, n_filters=2, feature_noise=0.01)
     assert model._fused_direct_plan(stats["covariances"]) is None
+
+
+def test_odd_even_transposition_meets_every_column_pair_once():
+    """The pairing of the column-pair Jacobi kernel (pairs.cu, pair_cp_kernel): n alternating steps of
+    adjacent pairs, every rotation followed by a swap of the two columns. One sweep must bring every pair
+    of columns together exactly once and leave the columns in reversed order (the kernel locates the zero
+    padding column of an odd m from the parity of the sweep count)."""
+    for n in (2, 4, 6, 10, 18, 34):
+        pos = list(range(n))
+        met = set()
+        for step in range(n):
+            for p in range(step % 2, n - 1, 2):
+                a, b = pos[p], pos[p + 1]
+                key = (min(a, b), max(a, b))
+                assert key not in met
+                met.add(key)
+                pos[p], pos[p + 1] = b, a
+        assert len(met) == n * (n - 1) // 2
+        assert pos == list(range(n))[::-1]
