@@ -607,15 +607,16 @@ struct CpGeom {
   static constexpr int LDJ = MP4 + 1;        // odd row stride of Linv_j (lane-varying scalar reads)
 };
 
-// floats of shared memory per warp: [L_i rows | per problem: Linv_j rows, Y rows, coefficients, column accumulator].
-// With single-pair tiles (R = 1) Linv_j is dead once the columns are formed and Y takes its place.
-__host__ __device__ inline int cp_group_floats(int MJ, int m, int R) {
+// floats of shared memory per warp: [L_i rows | per problem: Linv_j rows (later Y rows), coefficients, column
+// accumulator]. Linv_j is dead once the columns of a pair are formed and Y takes its place (Linv_j is staged
+// again for the next row of the tile): 11 KB per warp at m = 17, which is what lets 20 warps share an SM.
+__host__ __device__ inline int cp_group_floats(int MJ, int m) {
   const int MP4 = (MJ + 3) & ~3;
-  return ((MJ * (MP4 + 1) + 3) & ~3) + (R == 1 ? 0 : m * MP4) + 2 * MP4 + ((m * m + 3) & ~3);
+  return ((MJ * (MP4 + 1) + 3) & ~3) + 2 * MP4 + ((m * m + 3) & ~3);
 }
-__host__ __device__ inline int cp_warp_floats(int MJ, int m, int R) {
+__host__ __device__ inline int cp_warp_floats(int MJ, int m) {
   const int MP4 = (MJ + 3) & ~3;
-  return m * MP4 + (32 / (MJ / 2)) * cp_group_floats(MJ, m, R);
+  return m * MP4 + (32 / (MJ / 2)) * cp_group_floats(MJ, m);
 }
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -649,7 +650,7 @@ __device__ __forceinline__ void cp_rotation(float alpha, float beta, float ab, b
 }
 
 template <int MJ>
-__global__ void __launch_bounds__(PAIR_WARPS * 32, (MJ <= 12 ? 6 : (MJ <= 20 ? 4 : 3)))
+__global__ void __launch_bounds__(PAIR_WARPS * 32, (MJ <= 12 ? 6 : (MJ <= 20 ? 5 : 3)))
 pair_cp_kernel(const PairArgs A) {
   using G = CpGeom<MJ>;
   constexpr int LP = G::LP, NP = G::NP, MP4 = G::MP4, MH = G::MH, LDJ = G::LDJ;
@@ -660,15 +661,14 @@ pair_cp_kernel(const PairArgs A) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (t >= A.T.ntiles) return;  // no block-wide synchronisation below
-  const bool y_over_j = R == 1;  // single-pair tiles: Y overwrites Linv_j
-  const int szLi = m * MP4, szJ = (MJ * LDJ + 3) & ~3, szY = y_over_j ? 0 : m * MP4, szCo = 2 * MP4;
-  const int per_group = cp_group_floats(MJ, m, R);
-  float* sLi = smem + (size_t)warp * cp_warp_floats(MJ, m, R);  // [m][MP4]: L_i, later Linv_i (shared by the problems)
+  const int szLi = m * MP4, szJ = (MJ * LDJ + 3) & ~3, szCo = 2 * MP4;
+  const int per_group = cp_group_floats(MJ, m);
+  float* sLi = smem + (size_t)warp * cp_warp_floats(MJ, m);  // [m][MP4]: L_i, later Linv_i (shared by the problems)
   const int g = lane / LP, lg = lane - g * LP;
   const bool alive = g < NP;                // lanes beyond NP * LP only follow the instruction stream
   float* sJ = sLi + szLi + (alive ? g : NP - 1) * per_group;  // [MJ][LDJ]: Linv_j of this problem's column class
-  float* sY = y_over_j ? sJ : sJ + szJ;     // [m][MP4]: generalized eigenvectors, row r = component, column = position
-  float* sCo = sJ + szJ + szY;                  // [2][MP4]: coefficients ci | cj per position
+  float* sY = sJ;                           // [m][MP4]: generalized eigenvectors (over Linv_j), row = component, column = position
+  float* sCo = sJ + szJ;                        // [2][MP4]: coefficients ci | cj per position
   float* sC = sCo + szCo;                   // [m][m]: dLoss/dE_j of this problem's column class
   const bool want_grad = A.rowpart != nullptr;
   auto div_m = [&](int idx) { return m_odd ? idx / (MJ - 1) : idx / MJ; };  // division by a compile-time constant
@@ -679,13 +679,6 @@ pair_cp_kernel(const PairArgs A) {
   __syncwarp();
   const int j = bj * R + g;
   const bool jvalid = alive && g < R && j < nB;
-  if (jvalid) {
-    const float* Wj = A.Wb + (int64_t)j * 2 * m2 + m2;
-    for (int idx = lg; idx < m2; idx += LP) {
-      const int q = div_m(idx);
-      sJ[q * LDJ + (idx - q * m)] = Wj[idx];
-    }
-  }
   float dsum = 0.f, badsum = 0.f;
   for (int ii = 0; ii < R; ++ii) {
     const int i = bi * R + ii;
@@ -702,6 +695,13 @@ pair_cp_kernel(const PairArgs A) {
     for (int idx = lane; idx < m * MP4; idx += 32) {
       const int r = idx / MP4, c = idx - r * MP4;
       sLi[idx] = c < m ? Wi[r * m + c] : 0.f;
+    }
+    if (active) {  // Linv_j of this problem's column class (row MJ - 1 of sJ stays zero: Y never reaches it)
+      const float* Wj = A.Wb + (int64_t)j * 2 * m2 + m2;
+      for (int idx = lg; idx < m2; idx += LP) {
+        const int q = div_m(idx);
+        sJ[q * LDJ + (idx - q * m)] = Wj[idx];
+      }
     }
     __syncwarp();
     // ---- columns 2 lg and 2 lg + 1 of A: a[s] = sum_r Linv_j[q][r] L_i[r][s]  (row MJ - 1 of sJ is zero for odd m)
@@ -868,9 +868,8 @@ pair_cp_kernel(const PairArgs A) {
         }
       }
       // ---- Y -> shared memory (row = component r, column = position), coefficients of both matrices
-      if constexpr (MP4 > MJ) {  // (two padding columns)
-        if (y_over_j)              // they lie on what was Linv_j: zero them
-          for (int idx = lg; idx < 2 * m; idx += LP) sY[(idx >> 1) * MP4 + MJ + (idx & 1)] = 0.f;
+      if constexpr (MP4 > MJ) {  // the two padding columns of Y lie on what was Linv_j: zero them
+        for (int idx = lg; idx < 2 * m; idx += LP) sY[(idx >> 1) * MP4 + MJ + (idx & 1)] = 0.f;
       }
       if (alive) {
 #pragma unroll
@@ -952,7 +951,7 @@ pair_cp_kernel(const PairArgs A) {
 
 template <int MJ>
 static cudaError_t launch_pair_cp(const PairArgs& A, cudaStream_t st) {
-  const int smem = PAIR_WARPS * cp_warp_floats(MJ, A.m, A.T.R) * (int)sizeof(float);
+  const int smem = PAIR_WARPS * cp_warp_floats(MJ, A.m) * (int)sizeof(float);
   static int smem_set[kMaxDevices] = {0};
   {
     cudaError_t e = ensure_dynamic_smem(pair_cp_kernel<MJ>, smem, smem_set);
