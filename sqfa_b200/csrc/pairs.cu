@@ -626,27 +626,25 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 }
 
 // Rotation of the column pair (x at position p, y at position p + 1) with squared norms alpha, beta and
-// x . y = ab, FOLLOWED BY THE SWAP: position p receives s x + c y (norm n0), position p + 1 receives
-// c x - s y (norm n1). has_pair = false (the end of the line in an even step): x stays where it is.
-__device__ __forceinline__ void cp_rotation(float alpha, float beta, float ab, bool has_pair, float& c, float& s,
+// x . y = ab, FOLLOWED BY THE SWAP: position p receives c (y + t x) (squared norm n0), position p + 1 receives
+// c (x - t y) (n1). No rotation (converged pair, or has_pair false): t = 0, c = 1 -- the swap alone.
+__device__ __forceinline__ void cp_rotation(float alpha, float beta, float ab, bool has_pair, float& t, float& c,
                                             float& n0, float& n1, bool& rotated) {
-  c = 1.f; s = 0.f; n0 = beta; n1 = alpha;
+  t = 0.f; c = 1.f; n0 = beta; n1 = alpha;
   const float ab_sq = ab * ab, scale = alpha * beta;
   if (has_pair && ab_sq > (JACOBI_TOL * JACOBI_TOL) * scale) {
     // t = sign(zeta) / (|zeta| + sqrt(zeta^2 + 1)) with zeta = d / h, d = beta - alpha, h = 2 ab, written as
     // sign(d) h / (|d| + sqrt(d^2 + h^2)): one reciprocal less on the dependent chain, no division by a tiny ab.
     // Approximate reciprocal / square roots: a rotation only has to be orthogonal to fp32 precision
-    // (c^2 + s^2 = 1 from the same rsqrt); an angle off by 1e-7 leaves an off-diagonal of that size.
+    // (an angle off by 1e-7 leaves an off-diagonal of that size, far below the tolerance).
     const float d = beta - alpha, h = ab + ab;
     const float hs = __uint_as_float(__float_as_uint(h) ^ (__float_as_uint(d) & 0x80000000u));  // sign(d) h
-    const float tt = hs * rcp_approx(fabsf(d) + sqrt_approx(fmaf(d, d, h * h)));
-    c = rsqrt_approx(fmaf(tt, tt, 1.f));
-    s = c * tt;
-    n0 = fmaf(tt, ab, beta);
-    n1 = fmaf(-tt, ab, alpha);
+    t = hs * rcp_approx(fabsf(d) + sqrt_approx(fmaf(d, d, h * h)));
+    c = rsqrt_approx(fmaf(t, t, 1.f));
+    n0 = fmaf(t, ab, beta);
+    n1 = fmaf(-t, ab, alpha);
     rotated = rotated || ab_sq > (JACOBI_LAST * JACOBI_LAST) * scale;
   }
-  if (!has_pair) { c = 0.f; s = 1.f; n0 = alpha; }
 }
 
 template <int MJ>
@@ -728,18 +726,29 @@ pair_cp_kernel(const PairArgs A) {
         }
       }
     }
-    // ---- one-sided Jacobi, odd-even transposition ordering
+    // ---- one-sided Jacobi, odd-even transposition ordering, scaled ("fast") rotations: a column is kept as
+    // scale * vector, a rotation c [[1, t], [-t, 1]] updates the vectors with ONE packed FMA per element pair
+    // and column (y + tau1 x, x - tau2 y; tau1 = t s_x / s_y, tau2 = t s_y / s_x) and multiplies the two
+    // scales by c, instead of two multiplies and two FMAs. The scales are folded back once per sweep (they
+    // shrink by at most 2^-1/2 per rotation).
     const int up = (lane + 1) & 31, dn = (lane + 31) & 31;
     const bool has_right = alive && lg < LP - 1;
+    float sA = 1.f, sB = 1.f;
     int sweeps = 0;
     for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; ++sweep) {
       float2 na2 = make_float2(0.f, 0.f), nb2 = make_float2(0.f, 0.f);
+      {
+        const float2 sa2 = make_float2(sA, sA), sb2 = make_float2(sB, sB);
 #pragma unroll
-      for (int s = 0; s < MJ / 2; ++s) {
-        na2 = __ffma2_rn(a[s], a[s], na2);
-        nb2 = __ffma2_rn(b[s], b[s], nb2);
+        for (int s = 0; s < MJ / 2; ++s) {
+          a[s] = __fmul2_rn(sa2, a[s]);
+          b[s] = __fmul2_rn(sb2, b[s]);
+          na2 = __ffma2_rn(a[s], a[s], na2);
+          nb2 = __ffma2_rn(b[s], b[s], nb2);
+        }
+        sA = 1.f; sB = 1.f;
       }
-      float nA = na2.x + na2.y, nBq = nb2.x + nb2.y;  // carried along incrementally inside the sweep
+      float nA = na2.x + na2.y, nBq = nb2.x + nb2.y;  // squared norms of the columns, carried incrementally
       bool rotated = false;
 #pragma unroll 1
       for (int st = 0; st < LP; ++st) {
@@ -747,15 +756,20 @@ pair_cp_kernel(const PairArgs A) {
           float2 ab2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int s = 0; s < MJ / 2; ++s) ab2 = __ffma2_rn(a[s], b[s], ab2);
-          float c, sn, n0, n1;
-          cp_rotation(nA, nBq, ab2.x + ab2.y, true, c, sn, n0, n1, rotated);
-          const float2 c2 = make_float2(c, c), s2 = make_float2(sn, sn), ms2 = make_float2(-sn, -sn);
+          const float sab = sA * sB;
+          float t, c, n0, n1;
+          cp_rotation(nA, nBq, sab * (ab2.x + ab2.y), true, t, c, n0, n1, rotated);
+          const float tq = t * rcp_approx(sab);
+          const float tau1 = tq * sA * sA, tau2 = -tq * sB * sB;
+          const float2 t1 = make_float2(tau1, tau1), t2 = make_float2(tau2, tau2);
 #pragma unroll
           for (int s = 0; s < MJ / 2; ++s) {
             const float2 x = a[s], y = b[s];
-            a[s] = __ffma2_rn(s2, x, __fmul2_rn(c2, y));
-            b[s] = __ffma2_rn(c2, x, __fmul2_rn(ms2, y));
+            a[s] = __ffma2_rn(t1, x, y);
+            b[s] = __ffma2_rn(t2, y, x);
           }
+          const float sa_old = sA;
+          sA = c * sB; sB = c * sa_old;
           nA = n0; nBq = n1;
         }
         {  // even step: (this lane's second column, the right neighbour's first column)
@@ -767,29 +781,42 @@ pair_cp_kernel(const PairArgs A) {
             x2[s].y = __shfl_sync(FULL, a[s].y, up);
             ab2 = __ffma2_rn(b[s], x2[s], ab2);
           }
-          const float nX = __shfl_sync(FULL, nA, up);
-          float c, sn, n0, n1;
-          cp_rotation(nBq, nX, ab2.x + ab2.y, has_right, c, sn, n0, n1, rotated);
-          const float2 c2 = make_float2(c, c), s2 = make_float2(sn, sn), ms2 = make_float2(-sn, -sn);
+          const float nX = __shfl_sync(FULL, nA, up), sX = __shfl_sync(FULL, sA, up);
+          const float sbx = sB * sX;
+          float t, c, n0, n1;
+          cp_rotation(nBq, nX, sbx * (ab2.x + ab2.y), has_right, t, c, n0, n1, rotated);
+          const float tq = t * rcp_approx(sbx);
+          // the end of the line has no partner: its column stays (1 * b + 0 * x)
+          const float keep = has_right ? tq * sB * sB : 1.f, take = has_right ? 1.f : 0.f, tau2 = -tq * sX * sX;
+          const float2 k2 = make_float2(keep, keep), m2v = make_float2(take, take), t2 = make_float2(tau2, tau2);
 #pragma unroll
           for (int s = 0; s < MJ / 2; ++s) {
             const float2 x = b[s], y = x2[s];
-            b[s] = __ffma2_rn(s2, x, __fmul2_rn(c2, y));
-            x2[s] = __ffma2_rn(c2, x, __fmul2_rn(ms2, y));  // the neighbour's new first column
+            b[s] = __ffma2_rn(k2, x, __fmul2_rn(m2v, y));
+            x2[s] = __ffma2_rn(t2, y, x);  // the neighbour's new first column
           }
-          nBq = n0;
+          const float sT = c * sB;  // scale of the column that goes back
+          if (has_right) { sB = c * sX; nBq = n0; }
 #pragma unroll
           for (int s = 0; s < MJ / 2; ++s) {
             const float rx = __shfl_sync(FULL, x2[s].x, dn), ry = __shfl_sync(FULL, x2[s].y, dn);
             if (lg > 0) a[s] = make_float2(rx, ry);
           }
-          const float nr = __shfl_sync(FULL, n1, dn);
-          if (lg > 0) nA = nr;
+          const float nr = __shfl_sync(FULL, n1, dn), sr = __shfl_sync(FULL, sT, dn);
+          if (lg > 0) { nA = nr; sA = sr; }
         }
       }
       ++sweeps;
       // a sweep whose largest rotation was below JACOBI_LAST leaves off-diagonals of that size squared
       if (!__any_sync(FULL, rotated)) break;
+    }
+    {
+      const float2 sa2 = make_float2(sA, sA), sb2 = make_float2(sB, sB);
+#pragma unroll
+      for (int s = 0; s < MJ / 2; ++s) {
+        a[s] = __fmul2_rn(sa2, a[s]);
+        b[s] = __fmul2_rn(sb2, b[s]);
+      }
     }
     // ---- eigenvalues, distance. The padding column of an odd m sits at one end of the line.
     float2 na2 = make_float2(0.f, 0.f), nb2 = make_float2(0.f, 0.f);
