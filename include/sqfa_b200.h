@@ -297,13 +297,15 @@ int sqfa_fused_loss(const float* S, const float* M, const float* F, int32_t n_cl
  * (constraints.py:17-141): F = W / |W| row-wise (SQFA_CONSTRAINT_SPHERE) or F = W
  * (SQFA_CONSTRAINT_NONE); grad = d out[0] / dW through the constraint's adjoint, with zero rows for
  * the first n_fixed filters (FixedFilters of the pairwise curriculum); out[2] = max |grad|, the
- * quantity L-BFGS tests first. One call per closure evaluation of the fitting loop. */
+ * quantity L-BFGS tests first. out_host (may be NULL): MAPPED PINNED HOST memory [3] that receives a copy
+ * of out from the last kernel, so the host needs an event wait and no device-to-host copy. One call per
+ * closure evaluation of the fitting loop. */
 #define SQFA_CONSTRAINT_NONE 0
 #define SQFA_CONSTRAINT_SPHERE 1
 int sqfa_closure_eval(const float* S, const float* M, const float* raw_filters, int32_t n_classes, int32_t n_dim,
                       int32_t n_filters, float noise, int32_t dist, int32_t constraint, int32_t n_fixed,
-                      int64_t pair_begin, int64_t pair_end, float* out, float* grad, void* ws, size_t ws_bytes,
-                      sqfa_stream_t stream);
+                      int64_t pair_begin, int64_t pair_end, float* out, float* out_host, float* grad, void* ws,
+                      size_t ws_bytes, sqfa_stream_t stream);
 
 /* Plug-in distances between Gaussians that use the mean covariance of the pair (distances.py:240-432),
  * one warp per pair (Cholesky of (Sigma_a + Sigma_b) / 2 in shared memory), all n_a * n_b pairs:
@@ -336,15 +338,19 @@ int sqfa_gauss_pair_distances(const float* mu_a, const float* sigma_a, const flo
  *   oldest..newest: r += (al_i - ro_i y_i.r) s_i;   d = r;  prev_g = g      (first: d = -g, H = 1)
  * State owned by the caller, all device memory: prev_g, d [n]; S, Y [(history + 1) * n] (ring with
  * one spare row); ro [history + 1]; hdiag [1]; meta int32 [2] = {ring head, pairs held}.
- * out_scalars [5] = {ys, g.d, max|d|, sum|g|, pairs held} may be device or MAPPED PINNED HOST
- * memory (the host then needs only an event wait to apply the optimiser's stopping rules).
+ * param (may be NULL): the optimiser's fixed step is applied in the same launch, x += t d with
+ * t = min(1, 1 / sum|g|) lr on the first iteration and lr afterwards, UNLESS g.d > -tolerance_change (the
+ * test on which torch.optim.LBFGS stops before stepping) -- so a caller can enqueue the next loss /
+ * gradient evaluation right behind this launch and wait once for both.
+ * out_scalars [8] = {ys, g.d, max|d|, sum|g|, pairs held, t, step applied (0/1), -} may be device or
+ * MAPPED PINNED HOST memory (the host then needs only an event wait to apply the stopping rules).
  * n <= sqfa_lbfgs_max_n() (the vector lives in the registers of one 8-CTA cluster),
  * history <= sqfa_lbfgs_max_history(); otherwise SQFA_E_UNSUPPORTED. */
 int64_t sqfa_lbfgs_max_n(void);
 int32_t sqfa_lbfgs_max_history(void);
 int sqfa_lbfgs_direction(const float* g, float* prev_g, float* d, float* S, float* Y, float* ro, float* hdiag,
-                         int32_t* meta, int64_t n, int32_t history, float t_prev, int first, float* out_scalars,
-                         sqfa_stream_t stream);
+                         int32_t* meta, int64_t n, int32_t history, float t_prev, int first, float* param, float lr,
+                         float tolerance_change, float* out_scalars, sqfa_stream_t stream);
 
 #ifdef __cplusplus
 }

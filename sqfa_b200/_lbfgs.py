@@ -3,8 +3,9 @@
 `LBFGS` is `torch.optim.LBFGS` -- the optimiser the reference's `fitting_loop` uses
 (reference _optim.py:78-79) -- with one change: when there is a single float32 CUDA parameter and no
 line search (the reference's configuration), the "update memory + two-loop recursion" block of
-`step` runs as ONE kernel (`sqfa_lbfgs_direction`) instead of 4 tiny torch kernels and 2 implicit
-host synchronisations per history entry. Same algorithm, same update rule and stopping tests, same
+`step` -- and the fixed step `x += t d` that follows it -- runs as ONE kernel (`sqfa_lbfgs_direction`)
+instead of 4 tiny torch kernels and 2 implicit host synchronisations per history entry; a closure that
+can be launched without a host wait is enqueued right behind it (one host wait per iteration). Same algorithm, same update rule and stopping tests, same
 order of floating-point operations up to the summation order inside each dot product. Every other
 configuration falls through to `torch.optim.LBFGS.step` unchanged.
 """
@@ -47,21 +48,27 @@ class LBFGS(torch.optim.LBFGS):
             state["sqfa_native"] = nat
         return nat
 
-    def _direction(self, nat, g, history, first):
-        """Launch the update; returns (ys, g.d, max|d|, sum|g|, pairs held) as Python numbers."""
+    def _direction(self, nat, g, history, first, param, lr, tolerance_change, then=None):
+        """Launch the update AND the optimiser's fixed step on `param` (skipped by the kernel when the
+        directional derivative is above -tolerance_change), then `then()` -- the next loss / gradient
+        evaluation, enqueued behind it --, and wait once. Returns (ys, g.d, max|d|, sum|g|, pairs held, t,
+        step applied) as Python numbers."""
         lib, dev = _lib.load(), g.device
         _lib.check(
             lib.sqfa_lbfgs_direction(
                 _lib.ptr(g), _lib.ptr(nat["prev_g"]), _lib.ptr(nat["d"]), _lib.ptr(nat["S"]), _lib.ptr(nat["Y"]),
                 _lib.ptr(nat["ro"]), _lib.ptr(nat["hdiag"]), _lib.ptr(nat["meta"]), g.numel(), history,
-                float(nat["t"]), 1 if first else 0, _lib.ptr(nat["out"]), _lib.stream_ptr(dev),
+                float(nat["t"]), 1 if first else 0, _lib.ptr(param), float(lr), float(tolerance_change),
+                _lib.ptr(nat["out"]), _lib.stream_ptr(dev),
             ),
             "sqfa_lbfgs_direction",
         )
+        if then is not None:
+            then()
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
-        ev.synchronize()  # the kernel stored the scalars in pinned host memory itself: no copy
-        return nat["out"][:5].tolist()
+        ev.synchronize()  # the kernels stored their scalars in pinned host memory themselves: no copy
+        return nat["out"][:7].tolist()
 
     def _grad_and_absmax(self, p):
         """Flat gradient (a view when possible: the kernel copies what it keeps) and max|grad|; a
@@ -79,6 +86,11 @@ class LBFGS(torch.optim.LBFGS):
         if nat is None:
             return super().step(closure)
 
+        # A closure may offer its evaluation in two halves, `launch()` (enqueue, no host wait) and `collect()`
+        # (read the result once the stream has been waited for): the evaluation at the new iterate is then
+        # enqueued right behind the direction kernel and ONE host wait per iteration serves both.
+        launch_eval, collect_eval = getattr(closure, "launch", None), getattr(closure, "collect", None)
+        pipelined = launch_eval is not None and collect_eval is not None
         closure = torch.enable_grad()(closure)
         group = self.param_groups[0]
         lr = float(group["lr"])
@@ -100,23 +112,27 @@ class LBFGS(torch.optim.LBFGS):
                 return orig_loss
 
             prev_loss = state.get("prev_loss")
-            t = nat["t"]
             n_iter = 0
             while n_iter < max_iter:
                 n_iter += 1
                 state["n_iter"] += 1
                 first = state["n_iter"] == 1
-                _ys, gtd, dmax, g_l1, _held = self._direction(nat, flat_grad, history, first)
+                evaluate = n_iter != max_iter
+                # direction + fixed step (no line search) in one launch; the evaluation at the new point
+                # right behind it. If the kernel finds the directional derivative above -tolerance_change it
+                # leaves the parameter alone (torch.optim.LBFGS stops before stepping) and the evaluation
+                # that was enqueued is not collected.
+                _ys, _gtd, dmax, _g_l1, _held, t, stepped = self._direction(
+                    nat, flat_grad, history, first, p, lr, tolerance_change,
+                    then=launch_eval if (pipelined and evaluate) else None)
                 prev_loss = loss
-                t = min(1.0, 1.0 / g_l1) * lr if first else lr
                 nat["t"] = t
-                if gtd > -tolerance_change:  # directional derivative is below tolerance
+                if not stepped:  # directional derivative is below tolerance
                     break
-                p.add_(nat["d"].view_as(p), alpha=t)  # fixed step, no line search
                 ls_func_evals = 0
                 opt_cond = False
-                if n_iter != max_iter:
-                    loss = float(closure())
+                if evaluate:
+                    loss = float(collect_eval()) if pipelined else float(closure())
                     flat_grad, grad_absmax = self._grad_and_absmax(p)
                     opt_cond = grad_absmax <= tolerance_grad
                     ls_func_evals = 1

@@ -74,7 +74,8 @@ SIGNATURES = {
     "sqfa_lbfgs_max_history": (c_i32, []),
     "sqfa_lbfgs_direction": (
         c_int,
-        [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i32, ctypes.c_float, c_int, c_ptr, c_ptr],
+        [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_f32, c_int, c_ptr, c_f32, c_f32, c_ptr,
+         c_ptr],
     ),
     "sqfa_project_workspace_bytes": (c_size, [c_i32, c_i32, c_i32]),
     "sqfa_project_fwd": (
@@ -111,7 +112,7 @@ SIGNATURES = {
     "sqfa_closure_eval": (
         c_int,
         [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, c_i32, c_i32, c_i32, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
-         c_size, c_ptr],
+         c_ptr, c_size, c_ptr],
     ),
 }
 

@@ -367,10 +367,11 @@ def fused_loss_raw(F, S, M, noise, dist, group=None, ws=None):
     return packed
 
 
-def closure_eval_raw(W, S, M, noise, dist, sphere, n_fixed, out, grad, ws):
+def closure_eval_raw(W, S, M, noise, dist, sphere, n_fixed, out, grad, ws, out_host=None):
     """One closure evaluation of the fitting loop at the RAW filter parameter W, constraint included:
     out <- [loss, #non-finite pair distances, max|grad|], grad <- dLoss/dW. Everything preallocated by
-    the caller (the call is capturable in a CUDA graph)."""
+    the caller (the call is capturable in a CUDA graph). `out_host`: pinned host tensor [3] that the last
+    kernel fills with a copy of `out` (pinned memory is mapped into the device's address space)."""
     lib = _lib.load()
     C, D, _ = S.shape
     k = W.shape[0]
@@ -378,7 +379,7 @@ def closure_eval_raw(W, S, M, noise, dist, sphere, n_fixed, out, grad, ws):
     _lib.check(
         lib.sqfa_closure_eval(
             _lib.ptr(S), _lib.ptr(M), _lib.ptr(W), C, D, k, float(noise), dist, 1 if sphere else 0, int(n_fixed), 0, P,
-            _lib.ptr(out), _lib.ptr(grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(S.device),
+            _lib.ptr(out), _lib.ptr(out_host), _lib.ptr(grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(S.device),
         ),
         "sqfa_closure_eval",
     )

@@ -133,6 +133,19 @@ def fitting_loop(
         epoch_loss.backward()
         return epoch_loss
 
+    if direct is not None and getattr(direct, "enqueue", None) is not None:
+        # the two halves of an evaluation for an optimiser that pipelines them (sqfa_b200._lbfgs.LBFGS)
+        def collect():
+            nonlocal evaluations
+            evaluations += 1
+            loss_value, bad, grad_absmax = direct.host_out.tolist()
+            if bad != 0 or loss_value != loss_value:
+                raise ValueError(_NAN_MSG if loss_value != loss_value else _INF_MSG)
+            optimizer._last_grad_absmax = grad_absmax
+            return loss_value
+
+        closure.launch, closure.collect = direct.enqueue, collect
+
     stop_rule = _PlateauStop(atol)
     history = _EpochHistory()
     with tqdm(total=max_epochs, desc="Epochs", unit="epoch", disable=not show_progress) as bar:

@@ -332,8 +332,8 @@ size_t sqfa_fused_loss_workspace_bytes(int32_t n_classes, int32_t n_dim, int32_t
 
 static int closure_common(const char* fn, const float* S_, const float* M, const float* filters, int32_t n_classes,
                           int32_t n_dim, int32_t n_filters, float noise, int32_t dist, int constraint, int n_fixed,
-                          int64_t pair_begin, int64_t pair_end, float* out, float* grad, void* ws, size_t ws_bytes,
-                          sqfa_stream_t stream) {
+                          int64_t pair_begin, int64_t pair_end, float* out, float* out_host, float* grad, void* ws,
+                          size_t ws_bytes, sqfa_stream_t stream) {
   const int base = dist & 15;
   if (!dist_ok(dist) || S_ == nullptr || filters == nullptr || out == nullptr || grad == nullptr || ws == nullptr ||
       n_classes <= 0 || n_dim <= 0 || n_filters <= 0 || (base == SQFA_DIST_FISHER_RAO_LB && M == nullptr) ||
@@ -346,25 +346,25 @@ static int closure_common(const char* fn, const float* S_, const float* M, const
   if (ws_bytes < sqfa_fused_loss_workspace_bytes(n_classes, n_dim, n_filters, dist, pair_begin, pair_end))
     return fail_arg(fn, "workspace too small", SQFA_E_WORKSPACE);
   return wrap(fn, sqfa::launch_fused_loss(S_, M, filters, n_classes, n_dim, n_filters, noise, dist, constraint,
-                                          n_fixed, pair_begin, pair_end, out, grad, static_cast<float*>(ws),
-                                          S(stream)));
+                                          n_fixed, pair_begin, pair_end, out, out_host, grad,
+                                          static_cast<float*>(ws), S(stream)));
 }
 
 int sqfa_fused_loss(const float* S_, const float* M, const float* F, int32_t n_classes, int32_t n_dim,
                     int32_t n_filters, float noise, int32_t dist, int64_t pair_begin, int64_t pair_end, float* out,
                     float* dF, void* ws, size_t ws_bytes, sqfa_stream_t stream) {
   return closure_common(__func__, S_, M, F, n_classes, n_dim, n_filters, noise, dist, -1, 0, pair_begin, pair_end,
-                        out, dF, ws, ws_bytes, stream);
+                        out, nullptr, dF, ws, ws_bytes, stream);
 }
 
 int sqfa_closure_eval(const float* S_, const float* M, const float* raw_filters, int32_t n_classes, int32_t n_dim,
                       int32_t n_filters, float noise, int32_t dist, int32_t constraint, int32_t n_fixed,
-                      int64_t pair_begin, int64_t pair_end, float* out, float* grad, void* ws, size_t ws_bytes,
-                      sqfa_stream_t stream) {
+                      int64_t pair_begin, int64_t pair_end, float* out, float* out_host, float* grad, void* ws,
+                      size_t ws_bytes, sqfa_stream_t stream) {
   if (constraint != SQFA_CONSTRAINT_NONE && constraint != SQFA_CONSTRAINT_SPHERE)
     return fail_arg(__func__, "constraint must be SQFA_CONSTRAINT_NONE or SQFA_CONSTRAINT_SPHERE");
   return closure_common(__func__, S_, M, raw_filters, n_classes, n_dim, n_filters, noise, dist, constraint, n_fixed,
-                        pair_begin, pair_end, out, grad, ws, ws_bytes, stream);
+                        pair_begin, pair_end, out, out_host, grad, ws, ws_bytes, stream);
 }
 
 }  // extern "C"
@@ -427,15 +427,16 @@ int64_t sqfa_lbfgs_max_n(void) { return sqfa::lbfgs_max_n(); }
 int32_t sqfa_lbfgs_max_history(void) { return sqfa::lbfgs_max_history(); }
 
 int sqfa_lbfgs_direction(const float* g, float* prev_g, float* d, float* S_, float* Y, float* ro, float* hdiag,
-                         int32_t* meta, int64_t n, int32_t history, float t_prev, int first, float* out_scalars,
-                         sqfa_stream_t stream) {
+                         int32_t* meta, int64_t n, int32_t history, float t_prev, int first, float* param, float lr,
+                         float tolerance_change, float* out_scalars, sqfa_stream_t stream) {
   if (g == nullptr || prev_g == nullptr || d == nullptr || S_ == nullptr || Y == nullptr || ro == nullptr ||
       hdiag == nullptr || meta == nullptr || out_scalars == nullptr || n <= 0 || history < 1)
     return fail_arg(__func__, "bad argument");
   if (n > sqfa::lbfgs_max_n() || history > sqfa::lbfgs_max_history())
     return fail_arg(__func__, "vector or history too large for the single-cluster kernel", SQFA_E_UNSUPPORTED);
   return wrap(__func__, sqfa::launch_lbfgs_direction(g, prev_g, d, S_, Y, ro, hdiag, meta, n, history, t_prev,
-                                                     first ? 1 : 0, out_scalars, S(stream)));
+                                                     first ? 1 : 0, param, lr, tolerance_change, out_scalars,
+                                                     S(stream)));
 }
 
 }  // extern "C"

@@ -62,10 +62,11 @@ size_t fused_loss_workspace_bytes(int C, int D, int k, int dist, int64_t pair_be
 }
 
 // filters: the constrained filters F (constraint < 0), or the raw parameter (constraint 0 = none,
-// 1 = sphere). grad: d out[0] / d filters.  out: {loss, #non-finite distances, max |grad|}.
+// 1 = sphere). grad: d out[0] / d filters.  out: {loss, #non-finite distances, max |grad|}; out_host (optional):
+// the same three numbers in mapped pinned host memory, written by the last kernel.
 cudaError_t launch_fused_loss(const float* S, const float* M, const float* filters, int C, int D, int k, float noise,
                               int dist, int constraint, int n_fixed, int64_t pair_begin, int64_t pair_end, float* out,
-                              float* grad, float* ws, cudaStream_t st) {
+                              float* out_host, float* grad, float* ws, cudaStream_t st) {
   const int base = dist & 15;
   const bool fr = base == SQFA_DIST_FISHER_RAO_LB;
   const bool le = base == SQFA_DIST_LOG_EUCLIDEAN;
@@ -111,7 +112,7 @@ cudaError_t launch_fused_loss(const float* S, const float* M, const float* filte
     if ((e = launch_embed_bwd(gE, Mu, C, k, 0, gPsi, gMu, st)) != cudaSuccess) return e;
   }
   return launch_project_bwd_constrained(gPsi, fr ? gMu : nullptr, T, Mfr, C, D, k, F, inv_norm, sphere, n_fixed, grad,
-                                        out, proj, st);
+                                        out, out_host, reinterpret_cast<unsigned int*>(flag + 1), proj, st);
 }
 
 }  // namespace sqfa

@@ -80,7 +80,8 @@ template <int EPT>
 __global__ void __cluster_dims__(LB_CTAS, 1, 1) __launch_bounds__(LB_THREADS, 1)
 lbfgs_direction_kernel(const float* __restrict__ g, float* __restrict__ prev_g, float* __restrict__ d,
                        float* __restrict__ S, float* __restrict__ Y, float* __restrict__ ro, float* hdiag,
-                       int32_t* meta, int n, int rows, float t_prev, int first, float* out) {
+                       int32_t* meta, int n, int rows, float t_prev, int first, float* param, float lr,
+                       float tol_change, float* out) {
   __shared__ float s_part[3][32];
   __shared__ float s_slots[2][LB_CTAS][4];
   __shared__ float s_al[LB_MAX_HISTORY + 1];
@@ -186,6 +187,19 @@ lbfgs_direction_kernel(const float* __restrict__ g, float* __restrict__ prev_g, 
     }
   }
   v = cluster_reduce3(v, s_part, s_slots, parity, rank);
+  // The fixed step of the optimiser (no line search), applied here when the caller passes the parameter:
+  // x += t d with t = min(1, 1 / |g|_1) lr on the first iteration, lr afterwards -- unless the directional
+  // derivative is above -tolerance_change, the test on which the optimiser stops BEFORE stepping. Every
+  // thread holds the same reduced scalars, so the decision is uniform.
+  const float t_step = first ? fminf(1.f, 1.f / v.b) * lr : lr;
+  const bool apply = param != nullptr && !(v.a > -tol_change);
+  if (apply) {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int j = j0 + e * LB_STRIDE;
+      if (j < n) param[j] = fmaf(t_step, r[e], param[j]);
+    }
+  }
   if (rank == 0 && threadIdx.x == 0) {
     if (first) {
       hdiag[0] = 1.f;
@@ -198,6 +212,8 @@ lbfgs_direction_kernel(const float* __restrict__ g, float* __restrict__ prev_g, 
     o[2] = v.c;          // max |d|
     o[3] = v.b;          // sum |g|
     o[4] = (float)count;  // pairs in the history
+    o[5] = t_step;        // the step length of this iteration
+    o[6] = apply ? 1.f : 0.f;  // whether the step was applied to `param`
     __threadfence_system();
   }
 }
@@ -208,14 +224,14 @@ int lbfgs_max_n() { return LB_STRIDE * 16; }
 int lbfgs_max_history() { return LB_MAX_HISTORY; }
 
 cudaError_t launch_lbfgs_direction(const float* g, float* prev_g, float* d, float* S, float* Y, float* ro, float* hdiag,
-                                   int32_t* meta, int64_t n, int history, float t_prev, int first, float* out,
-                                   cudaStream_t stream) {
+                                   int32_t* meta, int64_t n, int history, float t_prev, int first, float* param,
+                                   float lr, float tol_change, float* out, cudaStream_t stream) {
   if (n <= 0 || n > lbfgs_max_n() || history < 1 || history > LB_MAX_HISTORY) return cudaErrorInvalidValue;
   const int rows = history + 1;
   const int ept = (int)((n + LB_STRIDE - 1) / LB_STRIDE);
 #define SQFA_LBFGS(E)                                                                                          \
   lbfgs_direction_kernel<E><<<LB_CTAS, LB_THREADS, 0, stream>>>(g, prev_g, d, S, Y, ro, hdiag, meta, (int)n, rows, \
-                                                                t_prev, first, out)
+                                                                t_prev, first, param, lr, tol_change, out)
   if (ept <= 1) SQFA_LBFGS(1);
   else if (ept <= 2) SQFA_LBFGS(2);
   else if (ept <= 4) SQFA_LBFGS(4);

@@ -1289,7 +1289,7 @@ cudaError_t launch_class_prepare(const float* PsiPart, const float* MuPart, int 
     cudaError_t e = ensure_dynamic_smem(class_prepare_kernel, smem, smem_set);
     if (e != cudaSuccess) return e;
   }
-  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
+  cudaError_t e = cudaMemsetAsync(flag, 0, 2 * sizeof(int32_t), st);  // flag[1]: closure_finish's arrival ticket
   if (e != cudaSuccess) return e;
   class_prepare_kernel<<<(C + nw - 1) / nw, nw * 32, smem, st>>>(PsiPart, MuPart, nchunk, noise, C, k, dist, Mu, E, W,
                                                                   flag);

@@ -251,7 +251,7 @@ __device__ __forceinline__ float block_reduce_1024(float v, float* red, bool tak
 __global__ void __launch_bounds__(CF_THREADS)
 closure_finish_kernel(const float* __restrict__ partial, int D, int k, int csplit, const float* __restrict__ F,
                       const float* __restrict__ inv_norm, int sphere, int n_fixed, float* __restrict__ grad,
-                      float* __restrict__ out) {
+                      float* out, float* out_host, unsigned int* ticket) {
   __shared__ float red[CF_THREADS];
   const int f = blockIdx.x;
   float* g = grad + (int64_t)f * D;
@@ -284,7 +284,23 @@ closure_finish_kernel(const float* __restrict__ partial, int D, int k, int cspli
   }
   amax = block_reduce_1024(amax, red, true);
   // NaN gradients: fmaxf drops NaN, the loss / non-finite counter carry that information
-  if (threadIdx.x == 0 && out != nullptr) atomicMax(reinterpret_cast<unsigned int*>(out + 2), __float_as_uint(amax));
+  if (threadIdx.x == 0 && out != nullptr) {
+    atomicMax(reinterpret_cast<unsigned int*>(out + 2), __float_as_uint(amax));
+    if (out_host != nullptr) {
+      // the last block to arrive publishes {loss, #non-finite, max |grad|} in the caller's mapped host
+      // memory: the host then needs an event wait and no copy (`ticket` is zeroed by class_prepare's memset)
+      __threadfence();
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        __threadfence();
+        volatile float* o = out;
+        volatile float* h = out_host;
+        h[0] = o[0];
+        h[1] = o[1];
+        h[2] = o[2];
+        __threadfence_system();
+      }
+    }
+  }
 }
 
 // dF[f][j] = sum_c ( sum_g (gPsi[c][f][g] + gPsi[c][g][f]) T[c][g][j] + gMu[c][f] M[c][j] )
@@ -706,11 +722,13 @@ cudaError_t launch_project_bwd(const float* gPsi, const float* gMu, const float*
 // adjoint of the projection followed by the adjoint of the filter constraint (closure tail)
 cudaError_t launch_project_bwd_constrained(const float* gPsi, const float* gMu, const float* T, const float* M, int C,
                                            int D, int k, const float* F, const float* inv_norm, int sphere,
-                                           int n_fixed, float* grad, float* out, float* ws, cudaStream_t st) {
+                                           int n_fixed, float* grad, float* out, float* out_host,
+                                           unsigned int* ticket, float* ws, cudaStream_t st) {
   const int csplit = project_bwd_csplit(C, D);
   cudaError_t e = launch_project_bwd_partials(gPsi, gMu, T, M, C, D, k, ws, csplit, st);
   if (e != cudaSuccess) return e;
-  closure_finish_kernel<<<k, CF_THREADS, 0, st>>>(ws, D, k, csplit, F, inv_norm, sphere, n_fixed, grad, out);
+  closure_finish_kernel<<<k, CF_THREADS, 0, st>>>(ws, D, k, csplit, F, inv_norm, sphere, n_fixed, grad, out, out_host,
+                                                  ticket);
   return cudaGetLastError();
 }
 

@@ -74,7 +74,8 @@ cudaError_t launch_project_bwd(const float* gPsi, const float* gMu, const float*
                                int k, float* dF, float* ws, cudaStream_t st);
 cudaError_t launch_project_bwd_constrained(const float* gPsi, const float* gMu, const float* T, const float* M, int C,
                                            int D, int k, const float* F, const float* inv_norm, int sphere,
-                                           int n_fixed, float* grad, float* out, float* ws, cudaStream_t st);
+                                           int n_fixed, float* grad, float* out, float* out_host,
+                                           unsigned int* ticket, float* ws, cudaStream_t st);
 cudaError_t launch_constraint_fwd(const float* Wraw, int D, int k, float* F, float* inv_norm, cudaStream_t st);
 cudaError_t launch_transform(const float* X, int64_t ldx, const float* F, int64_t n, int D, int k, float* Z,
                              cudaStream_t st);
@@ -130,7 +131,7 @@ namespace sqfa {
 size_t fused_loss_workspace_bytes(int C, int D, int k, int dist, int64_t pair_begin, int64_t pair_end);
 cudaError_t launch_fused_loss(const float* S, const float* M, const float* filters, int C, int D, int k, float noise,
                               int dist, int constraint, int n_fixed, int64_t pair_begin, int64_t pair_end, float* out,
-                              float* grad, float* ws, cudaStream_t st);
+                              float* out_host, float* grad, float* ws, cudaStream_t st);
 }  // namespace sqfa
 
 
@@ -139,8 +140,8 @@ namespace sqfa {
 int lbfgs_max_n();
 int lbfgs_max_history();
 cudaError_t launch_lbfgs_direction(const float* g, float* prev_g, float* d, float* S, float* Y, float* ro, float* hdiag,
-                                   int32_t* meta, int64_t n, int history, float t_prev, int first, float* out,
-                                   cudaStream_t stream);
+                                   int32_t* meta, int64_t n, int history, float t_prev, int first, float* param,
+                                   float lr, float tol_change, float* out, cudaStream_t stream);
 }  // namespace sqfa
 
 namespace sqfa {

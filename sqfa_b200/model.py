@@ -354,14 +354,17 @@ class SecondMomentsSQFA(nn.Module):
         ws = torch.empty(max(int(lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist, 0, P)), 1), dtype=torch.uint8,
                          device=S.device)
         out = torch.zeros(_ops.N_OUT, dtype=torch.float32, device=S.device)
+        out_host = torch.zeros(_ops.N_OUT, dtype=torch.float32).pin_memory()  # mirror, filled by every evaluation
         grad = torch.zeros(k, D, dtype=torch.float32, device=S.device)
         state = {"calls": 0, "graph": None, "param_ptr": None}
 
         def launch():
-            _ops.closure_eval_raw(p.detach(), S, M, noise, dist, sphere, n_fixed, out, grad, ws)
+            _ops.closure_eval_raw(p.detach(), S, M, noise, dist, sphere, n_fixed, out, grad, ws, out_host)
 
         @torch.no_grad()
-        def run():
+        def enqueue():
+            """One evaluation enqueued on the current stream, no host wait: the result lands in `out`
+            (device) and `host_out` (pinned host memory, valid once the stream has been waited for)."""
             if not p.is_contiguous():
                 raise RuntimeError("filter parameter must be contiguous")
             state["calls"] += 1
@@ -372,8 +375,12 @@ class SecondMomentsSQFA(nn.Module):
                 if state["calls"] == 2 and _GRAPH_CLOSURE and state["graph"] is None:
                     state["graph"], state["param_ptr"] = _capture_graph(launch, S.device), p.data_ptr()
             p.grad = grad  # static buffer: the optimiser reads it before the next evaluation overwrites it
+
+        def run():
+            enqueue()
             return out
 
+        run.enqueue, run.host_out = enqueue, out_host
         return run
 
     # ------------------------------------------------------------------ training
