@@ -7,6 +7,7 @@ backward` sequence is ONE fused native evaluation (`_ops.FusedLoss`), for any ot
 `distance_fun` the projection is native and the user's function runs on device tensors.
 """
 
+import os
 import time
 
 import torch
@@ -133,7 +134,8 @@ def fitting_loop(
         epoch_loss.backward()
         return epoch_loss
 
-    if direct is not None and getattr(direct, "enqueue", None) is not None:
+    if (direct is not None and getattr(direct, "enqueue", None) is not None
+            and os.environ.get("SQFA_LBFGS_PIPELINE", "1") == "1"):
         # the two halves of an evaluation for an optimiser that pipelines them (sqfa_b200._lbfgs.LBFGS)
         def collect():
             nonlocal evaluations

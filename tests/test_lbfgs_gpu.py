@@ -145,3 +145,35 @@ def test_closure_and_fit_are_bit_reproducible(c, k, kind):
                             max_iter=7)
         fits.append((loss, model.filters.detach().clone()))
     assert torch.equal(fits[0][0], fits[1][0]) and torch.equal(fits[0][1], fits[1][1])
+
+
+def test_pipelined_iterations_equal_waited_ones(monkeypatch):
+    """The fitting loop enqueues the evaluation at the new iterate behind the direction kernel (which
+    applies the step itself) and waits once per iteration; with SQFA_LBFGS_PIPELINE=0 it waits after each
+    kernel. Same kernels on the same data in the same order: identical losses, filters and evaluation counts."""
+    from conftest import make_class_data
+    from sqfa_b200.model import SQFA
+    from sqfa_b200.statistics import class_statistics
+
+    d, c, k = 64, 15, 5
+    X, y = make_class_data(50 * c, d, c, seed=21)
+    stats = class_statistics(X.cuda(), y.cuda())
+    F0 = torch.randn(k, d, generator=torch.Generator().manual_seed(2))
+    runs = []
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("SQFA_LBFGS_PIPELINE", pipe)
+        model = SQFA(n_dim=d, feature_noise=0.01, n_filters=k, filters=F0.clone())
+        loss, _ = model.fit(data_statistics=stats, max_epochs=4, atol=0.0, show_progress=False, return_loss=True,
+                            max_iter=9)
+        runs.append((loss, model.filters.detach().clone(), model._last_fit_evaluations))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    assert runs[0][2] == runs[1][2]
+    # a fit that converges inside an epoch (the optimiser's own stopping tests fire): same again
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("SQFA_LBFGS_PIPELINE", pipe)
+        model = SQFA(n_dim=d, feature_noise=0.01, n_filters=k, filters=F0.clone())
+        loss, _ = model.fit(data_statistics=stats, max_epochs=40, atol=1e-7, show_progress=False, return_loss=True,
+                            tolerance_change=1e-7, tolerance_grad=1e-5)
+        runs.append((loss, model.filters.detach().clone(), model._last_fit_evaluations))
+    assert torch.equal(runs[2][0], runs[3][0]) and torch.equal(runs[2][1], runs[3][1])
+    assert runs[2][2] == runs[3][2]
