@@ -40,6 +40,11 @@ METRIC = "class_statistics samples/sec"
 # ours, per step at this size (n <= 65536 rows: single-block bucketing): label_max, bucket_small, class sums +
 # finalize, means, gram_plan, gram_tf32x3, stats_epilogue
 KERNELS_PER_STEP = 8
+# N > 1 (step-by-step entry points + the fused reduce-scatter): label_max x 2 (the second publishes the
+# all-reduced maximum to the host), bucket_small, class sums + finalize, means, gram_plan, gram_tf32x3,
+# stats_epilogue (reduce) -- torch's element-wise kernels that pack the counts, NCCL's kernels and the
+# copy-engine pushes are not counted
+KERNELS_PER_STEP_MULTI = 9
 PARALLELISM_NOTE = ("samples sharded over {world} GPUs; statistics of the union, every rank finalising its share of the "
                     "classes: reduce-scatter by class fused into the Gram kernel (copy-engine pushes over NVLink into "
                     "peer-mapped slots) and the epilogue; 3 small NCCL all-reduces (max label, sums + counts, barrier)")
@@ -672,7 +677,7 @@ def run_ours(args):
                 "steps": e2e_steps, "repetitions_ms": [round(x, 2) for x in e2e_ms], "reported": "median repetition",
                 "overlap": f"{nbuf} CUDA streams / buffer sets, inputs of step i+1 uploaded while step i computes and downloads",
                 "bytes": "whole job (all ranks); with N > 1 every rank downloads its share of the classes"},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "gpu_launches": (KERNELS_PER_STEP if world == 1 else KERNELS_PER_STEP_MULTI) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "fit": fit, "fit_c4": fit_c4,
         "hp1_table": table, "tf32_peak_measured_tflops": tf32_cublas,
     }

@@ -176,6 +176,81 @@ def test_packed_gram_exchange_layout(n, d, c):
     assert rel_err(cov_o, ref["covariances"]) < TOL and rel_err(sm_o, ref["second_moments"]) < TOL
 
 
+@pytest.mark.parametrize("n,d,c,world", [(6000, 512, 10, 8), (5000, 784, 3, 4), (9000, 520, 7, 2)])
+def test_reduce_scatter_building_blocks_on_one_device(n, d, c, world):
+    """The pieces of the fused reduce-scatter by class (multi-GPU class_statistics with sharded output),
+    exercised on ONE device with `world` emulated ranks that each hold a slice of the rows:
+    * sqfa_class_gram with completion counters: classes run owner group by owner group, rotated so that a
+      rank's own classes come last; the tiles equal those of the default job order and every group's counter
+      ends at sqfa_class_gram_group_signals;
+    * sqfa_peer_push copies a finished group into the owner's slot [source rank];
+    * sqfa_stats_epilogue_reduce sums the ranks' partials in rank order: statistics of the union."""
+    import ctypes
+
+    from sqfa_b200 import _lib
+    from sqfa_b200._stats_driver import CudaStatsOps, class_share, peer_push_schedule
+
+    lib = _lib.load()
+    X, y = make_class_data(n, d, c, seed=3 * d)
+    X, y = X.cuda(), y.cuda()
+    ops = CudaStatsOps()
+    perm_all, off_all, cnt_all = ops.bucket(y, c)
+    counts = cnt_all[:c].clone()
+    means = ops.class_means(ops.class_sums(X, perm_all, off_all, c), counts)
+    shares = [class_share(c, r, world) for r in range(world)]
+    per_class = lib.sqfa_gram_packed_floats(d, c) // c
+    stride = max(hi - lo for lo, hi in shares) * per_class
+    cuts = [(n * r) // world for r in range(world + 1)]
+    # every "rank": packed partial Gram of its rows, centred by the global means
+    slots = torch.full((world, world, stride), float("nan"), device="cuda")  # [owner][source][share]
+    partials = []
+    for r in range(world):
+        Xr, yr = X[cuts[r]:cuts[r + 1]], y[cuts[r]:cuts[r + 1]]
+        perm, offsets, _ = ops.bucket(yr, c)
+        plain = ops.class_gram(Xr, perm, offsets, means, c, packed=True)
+        done = torch.zeros(world, dtype=torch.int32, device="cuda")
+        own_hi = shares[r][1]
+        rotated = ops.class_gram(Xr, perm, offsets, means, c, packed=True, done=done, n_groups=world,
+                                 first_class=own_hi % c)
+        # same tiles in another job order (entries of edge tiles beyond D are never written: compare through
+        # the epilogue; K parts of small problems are summed with red.add, hence a tolerance)
+        ca = ops.finalize(plain, means, counts, 0, 1, False, packed=True)[0]
+        cb = ops.finalize(rotated, means, counts, 0, 1, False, packed=True)[0]
+        both = torch.isfinite(ca) & torch.isfinite(cb)  # classes absent from this slice divide 0 by n - 1 < 0
+        assert float((ca[both] - cb[both]).norm()) <= 1e-6 * float(ca[both].norm())
+        expected = [lib.sqfa_class_gram_group_signals(Xr.shape[0], d, c, world, g) for g in range(world)]
+        assert done.tolist() == expected
+        partials.append(rotated)
+        for g, lo, hi in peer_push_schedule(r, world, shares):
+            dst = slots[g, r].data_ptr()
+            src = rotated.data_ptr() + 4 * lo * per_class
+            _lib.check(lib.sqfa_peer_push(ctypes.c_void_p(dst), ctypes.c_void_p(src), 4 * (hi - lo) * per_class,
+                                          _lib.stream_ptr()), "sqfa_peer_push")
+    ref = O.class_statistics(X.double().cpu(), y.cpu())
+    for r in range(world):
+        lo, hi = shares[r]
+        nc = hi - lo
+        if nc == 0:
+            continue
+        cov = torch.empty(nc, d, d, device="cuda")
+        sm = torch.empty(nc, d, d, device="cuda")
+        ws = torch.empty(lib.sqfa_stats_epilogue_workspace_bytes(nc), dtype=torch.uint8, device="cuda")
+        own = partials[r].data_ptr() + 4 * lo * per_class
+        _lib.check(lib.sqfa_stats_epilogue_reduce(
+            ctypes.c_void_p(own), _lib.ptr(slots[r]), stride, world, r, _lib.ptr(means[lo:hi]), None,
+            _lib.ptr(counts[lo:hi]), d, nc, 0, 1, _lib.ptr(cov), _lib.ptr(sm), _lib.ptr(ws), ws.numel(),
+            _lib.stream_ptr()), "sqfa_stats_epilogue_reduce")
+        assert rel_err(cov, ref["covariances"][lo:hi]) < TOL
+        assert rel_err(sm, ref["second_moments"][lo:hi]) < TOL
+        # the same sum formed on the host side in rank order, through the ordinary epilogue: identical bits
+        total = torch.zeros(nc * per_class, device="cuda")
+        for q in range(world):
+            total += partials[q][lo * per_class:hi * per_class]
+        total = torch.nan_to_num(total)  # (never-written padding of edge tiles)
+        cov2, _ = ops.finalize(total, means[lo:hi], counts[lo:hi], 0, 1, True, packed=True)
+        assert torch.equal(cov, cov2)
+
+
 @pytest.mark.parametrize("n,d,c,est", [(5000, 512, 6, "empirical"), (3000, 203, 4, "oas"), (2000, 1027, 3, "empirical")])
 def test_single_call_entry_matches_stepwise(n, d, c, est):
     """sqfa_class_statistics (one host call) enqueues exactly the step-by-step sequence: identical bits."""
