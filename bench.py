@@ -316,7 +316,7 @@ def closure_kernel_times(stats, model, dist_id, reps=7):
 def fit_leg(stats, d, c, k, dev, group, world, peaks, n_eval, epochs, label, cpu_evals=0, kernels=False):
     """Closure evaluations/s and LBFGS epochs/s of SQFA.fit (Fisher-Rao lower bound, PCA init,
     feature_noise 0.01, lr 0.1, default L-BFGS, atol 0) on the given class statistics; with a process
-    group the pair list of every evaluation is sharded over the ranks."""
+    group the pair list of every evaluation AND the classes of the projection are sharded over the ranks."""
     import torch
 
     from sqfa_b200 import _ops
@@ -354,8 +354,8 @@ def fit_leg(stats, d, c, k, dev, group, world, peaks, n_eval, epochs, label, cpu
         "closure_evals_in_fit": evals, "loss_first_last": [float(losses[0]), float(losses[-1])],
         "algorithmic_bytes_per_closure": 4 * c * d * d,
         "closure_hbm_gbs": 4 * c * d * d / (closure_ms * 1e-3) / 1e9,
-        "pair_list": f"sharded over {world} ranks, one all-reduce of [loss, flag, dF] per evaluation" if world > 1
-        else "single GPU",
+        "pair_list": (f"pairs AND the projection's classes sharded over {world} ranks; three small all-reduces per "
+                      "evaluation ([Psi | mu'] partials, [gPsi | gMu | loss, flag], dF)") if world > 1 else "single GPU",
     }
     if kernels:
         kt = closure_kernel_times(stats, model, _ops.DIST_FR)

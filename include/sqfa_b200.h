@@ -293,6 +293,27 @@ int sqfa_fused_loss(const float* S, const float* M, const float* F, int32_t n_cl
                     int32_t n_filters, float noise, int32_t dist, int64_t pair_begin, int64_t pair_end, float* out,
                     float* dF, void* ws, size_t ws_bytes, sqfa_stream_t stream);
 
+/* sqfa_fused_loss with the CLASSES and the PAIRS sharded over the ranks of a multi-device caller (AI and
+ * FR; S, M hold all classes on every rank, a rank reads only its own), in three phases on the SAME
+ * workspace with one small all-reduce (the caller's) after each of the first two:
+ *   phase 0: projection of classes [class_begin, class_end): T_c and their slices of exchange span 0 =
+ *            [per-chunk partials of Psi | of mu'] (zero elsewhere)          -> all-reduce span 0 (sum)
+ *   phase 1: embedding + factorisation of all classes, pair kernel on [pair_begin, pair_end), per-class
+ *            reduction and embedding adjoint: partial (gPsi, gMu) of all classes and
+ *            {weight * sum d, #non-finite} in exchange span 1               -> all-reduce span 1 (sum)
+ *   phase 2: projection adjoint over classes [class_begin, class_end) -> dF (k x D), the caller's share of
+ *            d loss / dF                                                     -> all-reduce dF (sum)
+ * After the second all-reduce the last 64 floats of span 1 start with {loss, #non-finite distances}.
+ * The projection -- the only part that reads C D^2 floats -- and its adjoint shard with the classes, the
+ * pair stage with the pairs; sqfa_fused_loss_exchange_span gives a span's byte offset and size in ws. */
+int sqfa_fused_loss_exchange_span(int32_t n_classes, int32_t n_dim, int32_t n_filters, int32_t dist,
+                                  int64_t pair_begin, int64_t pair_end, int32_t which, size_t* offset_bytes,
+                                  size_t* bytes);
+int sqfa_fused_loss_sharded(int32_t phase, const float* S, const float* M, const float* F, int32_t n_classes,
+                            int32_t n_dim, int32_t n_filters, float noise, int32_t dist, int32_t class_begin,
+                            int32_t class_end, int64_t pair_begin, int64_t pair_end, float* dF, void* ws,
+                            size_t ws_bytes, sqfa_stream_t stream);
+
 /* The same evaluation at the RAW filter parameter W of a constrained model, constraint included
  * (constraints.py:17-141): F = W / |W| row-wise (SQFA_CONSTRAINT_SPHERE) or F = W
  * (SQFA_CONSTRAINT_NONE); grad = d out[0] / dW through the constraint's adjoint, with zero rows for

@@ -109,6 +109,12 @@ SIGNATURES = {
         c_int,
         [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, c_i32, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr],
     ),
+    "sqfa_fused_loss_exchange_span": (c_int, [c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_i32, c_ptr, c_ptr]),
+    "sqfa_fused_loss_sharded": (
+        c_int,
+        [c_i32, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, c_i32, c_i32, c_i32, c_i64, c_i64, c_ptr, c_ptr,
+         c_size, c_ptr],
+    ),
     "sqfa_closure_eval": (
         c_int,
         [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, c_i32, c_i32, c_i32, c_i64, c_i64, c_ptr, c_ptr, c_ptr,

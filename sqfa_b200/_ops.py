@@ -367,6 +367,51 @@ def fused_loss_raw(F, S, M, noise, dist, group=None, ws=None):
     return packed
 
 
+def fused_loss_sharded_raw(F, S, M, noise, dist, group, ws=None):
+    """`fused_loss_raw` with the classes AND the pairs sharded over the ranks of `group` (AI / FR): every
+    rank projects only its share of the classes (the part that reads C D^2 floats) and evaluates only its
+    share of the pairs; three small all-reduces -- the per-chunk partials of (Psi, mu') [assembles all classes
+    on every rank], the partial (gPsi, gMu, loss, flag), and dF. Returns the same packed vector."""
+    import torch.distributed as dist_mod
+
+    from ._stats_driver import class_share
+
+    lib = _lib.load()
+    dev = S.device
+    Fc = f32c(F, dev)
+    C, D, _ = S.shape
+    k = Fc.shape[0]
+    P = C * (C - 1) // 2
+    rank, world = dist_mod.get_rank(group), dist_mod.get_world_size(group)
+    p0, p1 = shard_pairs(P, C, rank, world)
+    c0, c1 = class_share(C, rank, world)
+    ws = _closure_workspace(lib, C, D, k, dist, p0, p1, dev, ws)
+    spans = []
+    for which in (0, 1):
+        off, nbytes = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        _lib.check(lib.sqfa_fused_loss_exchange_span(C, D, k, dist, p0, p1, which, ctypes.byref(off), ctypes.byref(nbytes)),
+                   "sqfa_fused_loss_exchange_span")
+        spans.append(ws[off.value : off.value + nbytes.value].view(torch.float32))
+    packed = torch.empty(4 + k * D, dtype=torch.float32, device=dev)
+    dF = ctypes.c_void_p(packed.data_ptr() + 16)
+
+    def phase(i):
+        _lib.check(
+            lib.sqfa_fused_loss_sharded(i, _lib.ptr(S), _lib.ptr(M), _lib.ptr(Fc), C, D, k, float(noise), dist, c0, c1, p0,
+                                        p1, dF, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+            "sqfa_fused_loss_sharded",
+        )
+
+    phase(0)
+    dist_mod.all_reduce(spans[0], group=group)
+    phase(1)
+    dist_mod.all_reduce(spans[1], group=group)
+    phase(2)
+    dist_mod.all_reduce(packed[4:], group=group)
+    packed[:4] = spans[1][-64:-60]  # {loss, #non-finite, -, -} summed over the ranks
+    return packed
+
+
 def closure_eval_raw(W, S, M, noise, dist, sphere, n_fixed, out, grad, ws, out_host=None):
     """One closure evaluation of the fitting loop at the RAW filter parameter W, constraint included:
     out <- [loss, #non-finite pair distances, max|grad|], grad <- dLoss/dW. Everything preallocated by

@@ -357,6 +357,39 @@ int sqfa_fused_loss(const float* S_, const float* M, const float* F, int32_t n_c
                         out, nullptr, dF, ws, ws_bytes, stream);
 }
 
+int sqfa_fused_loss_exchange_span(int32_t n_classes, int32_t n_dim, int32_t n_filters, int32_t dist,
+                                  int64_t pair_begin, int64_t pair_end, int32_t which, size_t* offset_bytes,
+                                  size_t* bytes) {
+  if (n_classes <= 0 || n_dim <= 0 || n_filters <= 0 || !dist_ok(dist) || (which != 0 && which != 1) ||
+      offset_bytes == nullptr || bytes == nullptr)
+    return fail_arg(__func__, "bad argument");
+  sqfa::fused_loss_exchange_span(n_classes, n_dim, n_filters, dist, pair_begin, pair_end, which, offset_bytes, bytes);
+  return 0;
+}
+
+int sqfa_fused_loss_sharded(int32_t phase, const float* S_, const float* M, const float* F, int32_t n_classes,
+                            int32_t n_dim, int32_t n_filters, float noise, int32_t dist, int32_t class_begin,
+                            int32_t class_end, int64_t pair_begin, int64_t pair_end, float* dF, void* ws,
+                            size_t ws_bytes, sqfa_stream_t stream) {
+  const int base = dist & 15;
+  if (!dist_ok(dist) || S_ == nullptr || F == nullptr || ws == nullptr || n_classes <= 0 || n_dim <= 0 ||
+      n_filters <= 0 || (base == SQFA_DIST_FISHER_RAO_LB && M == nullptr) || phase < 0 || phase > 2 ||
+      (phase == 2 && dF == nullptr) || class_begin < 0 || class_end > n_classes || class_begin > class_end ||
+      (reinterpret_cast<uintptr_t>(ws) & 15) != 0)
+    return fail_arg(__func__, "bad argument");
+  if (base == SQFA_DIST_LOG_EUCLIDEAN)
+    return fail_arg(__func__, "log-Euclidean closures shard their pairs only (sqfa_fused_loss)", SQFA_E_UNSUPPORTED);
+  const int m = base == SQFA_DIST_FISHER_RAO_LB ? n_filters + 1 : n_filters;
+  if (n_filters > 32 || m > SQFA_MAX_M) return fail_arg(__func__, "n_filters must be <= 32", SQFA_E_UNSUPPORTED);
+  const int64_t P = (int64_t)n_classes * (n_classes - 1) / 2;
+  if (pair_begin < 0 || pair_end > P || pair_begin > pair_end) return fail_arg(__func__, "bad pair range");
+  if (ws_bytes < sqfa_fused_loss_workspace_bytes(n_classes, n_dim, n_filters, dist, pair_begin, pair_end))
+    return fail_arg(__func__, "workspace too small", SQFA_E_WORKSPACE);
+  return wrap(__func__, sqfa::launch_fused_loss_sharded(phase, S_, M, F, n_classes, n_dim, n_filters, noise, dist,
+                                                        class_begin, class_end, pair_begin, pair_end, dF,
+                                                        static_cast<float*>(ws), S(stream)));
+}
+
 int sqfa_closure_eval(const float* S_, const float* M, const float* raw_filters, int32_t n_classes, int32_t n_dim,
                       int32_t n_filters, float noise, int32_t dist, int32_t constraint, int32_t n_fixed,
                       int64_t pair_begin, int64_t pair_end, float* out, float* out_host, float* grad, void* ws,

@@ -129,6 +129,11 @@ cudaError_t launch_class_factor_bwd(const float* W, const float* gLog, int C, in
 namespace sqfa {
 // ---- closure.cu ----
 size_t fused_loss_workspace_bytes(int C, int D, int k, int dist, int64_t pair_begin, int64_t pair_end);
+void fused_loss_exchange_span(int C, int D, int k, int dist, int64_t pair_begin, int64_t pair_end, int which,
+                              size_t* offset_bytes, size_t* bytes);
+cudaError_t launch_fused_loss_sharded(int phase, const float* S, const float* M, const float* F, int C, int D, int k,
+                                      float noise, int dist, int c0, int c1, int64_t pair_begin, int64_t pair_end,
+                                      float* dF, float* ws, cudaStream_t st);
 cudaError_t launch_fused_loss(const float* S, const float* M, const float* filters, int C, int D, int k, float noise,
                               int dist, int constraint, int n_fixed, int64_t pair_begin, int64_t pair_end, float* out,
                               float* out_host, float* grad, float* ws, cudaStream_t st);

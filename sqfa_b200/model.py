@@ -329,6 +329,11 @@ class SecondMomentsSQFA(nn.Module):
             p0, p1 = _ops.shard_pairs(C * (C - 1) // 2, C, rank, world)
             ws = torch.empty(max(int(lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist, p0, p1)), 1),
                              dtype=torch.uint8, device=S.device)
+            # AI / FR with at least one class per rank: the projection shards with the classes as well
+            # (three small all-reduces per evaluation instead of one; SQFA_SHARD_CLASSES=0: pairs only)
+            shard_classes = ((dist & 15) != _ops.DIST_LE and C >= world
+                             and os.environ.get("SQFA_SHARD_CLASSES", "1") == "1")
+            eval_sharded = _ops.fused_loss_sharded_raw if shard_classes else _ops.fused_loss_raw
 
             @torch.no_grad()
             def run_sharded():
@@ -338,7 +343,7 @@ class SecondMomentsSQFA(nn.Module):
                     F = W / nrm
                 else:
                     F = W
-                packed = _ops.fused_loss_raw(F, S, M, noise, dist, group, ws)
+                packed = eval_sharded(F, S, M, noise, dist, group, ws)
                 dF = packed[4:].view(k, D)
                 if n_fixed:
                     dF[:n_fixed] = 0.0  # frozen rows are detached in FixedFilters.forward

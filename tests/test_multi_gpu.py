@@ -1,8 +1,8 @@
 """GPU, 2 ranks over NCCL (skipped on a single-GPU box): the two places where the hot paths shard.
 
 * class_statistics with the samples sharded over the ranks == the single-GPU result
-* the closure with the class-pair list sharded over the ranks == the replicated closure: loss and
-  gradient to 1e-6, and a short fit produces the same losses
+* the closure with the class-pair list (and the projection's classes) sharded over the ranks == the
+  replicated closure: loss and gradient to 1e-6, and a short fit produces the same losses
 Each rank is a spawned process (`torch.multiprocessing`), rendezvous on 127.0.0.1.
 """
 
@@ -112,7 +112,14 @@ def _worker(rank, world, port, out_dir):
         model._process_group = dist.group.WORLD
         sh = model._fused_direct_plan(stats)().clone()
         g_sh = model.parametrizations.filters.original.grad.clone()
+        # the same with only the pairs sharded (every rank projects all classes)
+        os.environ["SQFA_SHARD_CLASSES"] = "0"
+        sh_p = model._fused_direct_plan(stats)().clone()
+        g_sh_p = model.parametrizations.filters.original.grad.clone()
+        os.environ["SQFA_SHARD_CLASSES"] = "1"
         model._process_group = None
+        res["closure_pairs_only_loss_rel"] = abs(float(sh_p[0]) - float(rep[0])) / abs(float(rep[0]))
+        res["closure_pairs_only_grad_rel"] = float((g_sh_p - g_rep).norm() / g_rep.norm())
         res["closure_loss_rel"] = abs(float(sh[0]) - float(rep[0])) / abs(float(rep[0]))
         res["closure_grad_rel"] = float((g_sh - g_rep).norm() / g_rep.norm())
         res["closure_bad"] = float(sh[1])
@@ -152,5 +159,6 @@ def test_sharded_statistics_and_pair_sharded_closure(tmp_path):
         assert res["peer_one_class_rows"] == 1.0 and res.get("peer_one_class", 0.0) < 1e-5
         assert res["closure_bad"] == 0
         assert res["closure_loss_rel"] < 1e-6 and res["closure_grad_rel"] < 1e-5, res
+        assert res["closure_pairs_only_loss_rel"] < 1e-6 and res["closure_pairs_only_grad_rel"] < 1e-5, res
         assert res["fit_loss_rel"] < 1e-4 and res["fit_filter_rel"] < 1e-3, res
         assert res["fit_rank_divergence"] == 0.0
