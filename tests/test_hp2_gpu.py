@@ -174,6 +174,67 @@ def test_fused_loss_and_gradient_match_oracle(kind, n, d, c, k, distance):
     assert rel_err(g2, grad64) < GRAD_TOL
 
 
+@pytest.mark.parametrize("kind,d,c,k,world", [("full", 96, 37, 6, 4), ("second_moments", 200, 12, 4, 3),
+                                              ("full", 64, 5, 16, 8)])
+def test_class_and_pair_sharded_closure_phases_on_one_device(kind, d, c, k, world):
+    """sqfa_fused_loss_sharded (multi-GPU fits: classes of the projection AND pairs sharded over ranks) with
+    `world` emulated ranks on one device: every rank runs the three phases on its own workspace, the two
+    exchange spans and dF are summed over the ranks the way the all-reduces would. Loss and dLoss/dF must
+    equal the unsharded sqfa_fused_loss and the oracle (also with more ranks than classes)."""
+    import ctypes
+
+    from sqfa_b200 import _lib, _ops
+    from sqfa_b200._stats_driver import class_share
+
+    lib = _lib.load()
+    stats = stats_for(60 * c, d, c, seed=c)
+    sc = to_f32_cuda(stats)
+    F = torch.randn(k, d, generator=torch.Generator().manual_seed(5)).cuda()
+    F = (F / F.norm(dim=1, keepdim=True)).contiguous()
+    model = _models(kind, d, k, F.cpu()).cuda()
+    S, M, dist = model._fused_inputs(sc)
+    noise = model._noise_scalar()
+    ref = _ops.fused_loss_raw(F, S, M, noise, dist)
+    P = c * (c - 1) // 2
+    ranks = []
+    for r in range(world):
+        p0, p1 = _ops.shard_pairs(P, c, r, world)
+        c0, c1 = class_share(c, r, world)
+        ws = torch.empty(lib.sqfa_fused_loss_workspace_bytes(c, d, k, dist, p0, p1), dtype=torch.uint8, device="cuda")
+        spans = []
+        for which in (0, 1):
+            off, nb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+            _lib.check(lib.sqfa_fused_loss_exchange_span(c, d, k, dist, p0, p1, which, ctypes.byref(off),
+                                                         ctypes.byref(nb)), "span")
+            spans.append(ws[off.value:off.value + nb.value].view(torch.float32))
+        ranks.append({"p": (p0, p1), "c": (c0, c1), "ws": ws, "spans": spans,
+                      "dF": torch.empty(k, d, device="cuda")})
+
+    def phase(i):
+        for q in ranks:
+            _lib.check(lib.sqfa_fused_loss_sharded(i, _lib.ptr(S), _lib.ptr(M), _lib.ptr(F), c, d, k, float(noise), dist,
+                                                   q["c"][0], q["c"][1], q["p"][0], q["p"][1], _lib.ptr(q["dF"]),
+                                                   _lib.ptr(q["ws"]), q["ws"].numel(), _lib.stream_ptr()), "sharded")
+
+    def all_reduce(which):
+        total = torch.stack([q["spans"][which] for q in ranks]).sum(0)
+        for q in ranks:
+            q["spans"][which].copy_(total)
+
+    phase(0)
+    all_reduce(0)
+    phase(1)
+    all_reduce(1)
+    phase(2)
+    dF = torch.stack([q["dF"] for q in ranks]).sum(0)
+    loss, bad = ranks[0]["spans"][1][-64:-62].tolist()
+    assert bad == 0.0
+    assert abs(loss - float(ref[0])) <= 1e-6 * abs(float(ref[0]))
+    assert rel_err(dF, ref[4:].view(k, d)) < 1e-5
+    loss64, _, _ = O.loss_and_grad(kind, stats, F.double().cpu(), noise=0.01)
+    assert abs(loss - float(loss64)) <= DIST_TOL * abs(float(loss64))
+
+
 def test_fit_matches_oracle_trajectory():
     """Filters after ONE epoch (well conditioned) and the converged loss."""
     n, d, c, k = 4000, 32, 6, 4
