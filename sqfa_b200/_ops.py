@@ -309,8 +309,8 @@ N_OUT = 3  # [loss, number of non-finite pair distances, max |gradient|]
 
 def shard_pairs(n_pairs, n_classes, rank, world):
     """Slice [begin, end) of the linearised lower-triangle pair list (p = i (i - 1) / 2 + j) owned by
-    `rank`: whole rows i, cut where the pair count is balanced and at multiples of 4 rows (the pair
-    kernel works on 4 x 4 tiles, so tiles are never split between ranks)."""
+    `rank`: whole rows i, cut where the pair count is balanced and at multiples of 4 rows (a tile of the
+    pair kernel that straddles a cut is evaluated by both ranks, each masking the other's pairs)."""
     if world <= 1:
         return 0, n_pairs
 

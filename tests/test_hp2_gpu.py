@@ -130,9 +130,9 @@ CASES = [
     ("full", 3000, 64, 10, 4, None),
     ("full", 4000, 104, 19, 8, None),
     ("second_moments", 3000, 48, 6, 8, "log_euclidean"),
-    ("full", 3000, 40, 5, 32, None),      # m = 33: two Jacobi columns per lane
+    ("full", 3000, 40, 5, 32, None),      # m = 33: one problem per warp, 17 lanes
     ("second_moments", 2000, 784, 10, 4, None),
-    ("full", 10000, 32, 200, 4, None),    # 19 900 pairs: 2 x 2 pair tiles
+    ("full", 10000, 32, 200, 4, None),    # 19 900 pairs, m = 5: 2 x 2 pair tiles, two of the ten problems a warp could hold
     ("second_moments", 10000, 24, 190, 6, "log_euclidean"),
 ]
 
