@@ -37,14 +37,13 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = {"name": "configs[1] CIFAR-10-shaped synthetic", "N": 50000, "D": 3072, "C": 10, "k": 8}
 METRIC = "class_statistics samples/sec"
-# ours, per step at this size (n <= 65536 rows: single-block bucketing): label_max, bucket_small, class sums +
-# finalize, means, gram_plan, gram_tf32x3, stats_epilogue
-KERNELS_PER_STEP = 8
-# N > 1 (step-by-step entry points + the fused reduce-scatter): label_max x 2 (the second publishes the
-# all-reduced maximum to the host), bucket_small, class sums + finalize, means, gram_plan, gram_tf32x3,
-# stats_epilogue (reduce) -- torch's element-wise kernels that pack the counts, NCCL's kernels and the
-# copy-engine pushes are not counted
-KERNELS_PER_STEP_MULTI = 9
+# ours, per step at this size (one 8-bit bucketing pass): label_max, radix_hist, scan_offsets, radix_scatter,
+# class sums + finalize, means, gram_plan, gram_tf32x3, stats_epilogue
+KERNELS_PER_STEP = 10
+# N > 1 (step-by-step entry points + the fused reduce-scatter): one more label_max (publishes the all-reduced
+# maximum to the host) and the epilogue in its multi-source form -- torch's element-wise kernels that pack the
+# counts, NCCL's kernels and the copy-engine pushes are not counted
+KERNELS_PER_STEP_MULTI = 11
 PARALLELISM_NOTE = ("samples sharded over {world} GPUs; statistics of the union, every rank finalising its share of the "
                     "classes: reduce-scatter by class fused into the Gram kernel (copy-engine pushes over NVLink into "
                     "peer-mapped slots) and the epilogue; 3 small NCCL all-reduces (max label, sums + counts, barrier)")

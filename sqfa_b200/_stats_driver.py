@@ -49,6 +49,14 @@ class CudaStatsOps:
         if getattr(self, "_host_mx", None) is None:
             self._host_mx = torch.empty(self._HOST_SLOTS, dtype=torch.int64).pin_memory()
             self._host_next = 0
+        return self.label_max_wait(self.label_max_begin(y))
+
+    def label_max_begin(self, y):
+        """Launch the label maximum; `label_max_wait(token)` returns it. Host work done between the two
+        (allocating the outputs for the expected number of classes) overlaps the kernel and the wake-up."""
+        if getattr(self, "_host_mx", None) is None:
+            self._host_mx = torch.empty(self._HOST_SLOTS, dtype=torch.int64).pin_memory()
+            self._host_next = 0
         k = self._host_next
         self._host_next = (k + 1) % self._HOST_SLOTS
         slot = self._host_mx[k : k + 1]
@@ -58,6 +66,11 @@ class CudaStatsOps:
         )
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(y.device))
+        return ev, slot
+
+    @staticmethod
+    def label_max_wait(token):
+        ev, slot = token
         ev.synchronize()
         return int(slot[0])
 
@@ -377,18 +390,27 @@ class CudaStatsOps:
         )
         return cov, sm
 
-    def fused(self, X, y, C, estimator_id, ddof, want_sm):
-        """All local steps from ONE C call (sqfa_class_statistics): no host work between kernels."""
+    def fused_prepare(self, X, C, want_sm):
+        """Outputs and workspace of `fused` for C classes (allocated while the label maximum is in flight)."""
         lib, dev = self.lib, X.device
         n, D = X.shape
         means = torch.empty(C, D, dtype=torch.float32, device=dev)
         cov = torch.empty(C, D, D, dtype=torch.float32, device=dev)
         sm = torch.empty(C, D, D, dtype=torch.float32, device=dev) if want_sm else None
         meta = torch.empty(2 * C + 4, dtype=torch.int64, device=dev)  # counts [C+1] | offsets [C+2]
-        counts, offsets = meta[: C + 1], meta[C + 1 : 2 * C + 3]
         perm = torch.empty(n, dtype=torch.int32, device=dev)
         ws_bytes = lib.sqfa_class_statistics_workspace_bytes(n, D, C)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        return C, want_sm, means, cov, sm, meta, perm, ws, ws_bytes
+
+    def fused(self, X, y, C, estimator_id, ddof, want_sm, prepared=None):
+        """All local steps from ONE C call (sqfa_class_statistics): no host work between kernels."""
+        lib, dev = self.lib, X.device
+        n, D = X.shape
+        if prepared is None or prepared[0] != C or prepared[1] != want_sm:
+            prepared = self.fused_prepare(X, C, want_sm)
+        _, _, means, cov, sm, meta, perm, ws, ws_bytes = prepared
+        counts, offsets = meta[: C + 1], meta[C + 1 : 2 * C + 3]
         _lib.check(
             lib.sqfa_class_statistics(
                 _lib.ptr(X), X.stride(0), _lib.ptr(y), n, D, C, estimator_id, ddof, _lib.ptr(means), _lib.ptr(cov),
@@ -406,6 +428,7 @@ class CudaStatsOps64(CudaStatsOps):
 
     supports_packed = False
     fused = None
+    fused_prepare = None
     class_gram_overlapped = None
     peer_acquire = None
 
@@ -493,10 +516,18 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
     Two passes over the local rows, like the reference (mean first, then the Gram of the centred
     rows, statistics.py:118-120). `centre` (C, D) overrides the centring vectors.
     """
+    prepared = None
     if n_classes is None:
         # the one host read the reference also does (statistics.py:29)
         if group is None and getattr(ops, "label_max_host", None) is not None:
-            n_classes = ops.label_max_host(y) + 1
+            token = ops.label_max_begin(y)
+            guess = getattr(ops, "_last_n_classes", None)
+            if (guess and centre is None and y.numel() > 0 and getattr(ops, "fused_prepare", None) is not None
+                    and getattr(ops, "gram_events", None) is None):
+                # while the kernel runs and the host wakes up: allocate for as many classes as the last call had
+                prepared = ops.fused_prepare(X, guess, want_sm)
+            n_classes = ops.label_max_wait(token) + 1
+            ops._last_n_classes = n_classes
         else:
             mx = ops.label_max(y)
             if group is not None:
@@ -512,7 +543,7 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
         group is None and centre is None and C > 0 and y.numel() > 0
         and getattr(ops, "fused", None) is not None and getattr(ops, "gram_events", None) is None
     ):
-        return ops.fused(X, y, C, estimator_id, ddof, want_sm)
+        return ops.fused(X, y, C, estimator_id, ddof, want_sm, prepared)
     perm, offsets, counts = ops.bucket(y, C)
     D = X.shape[1]
     lease = None

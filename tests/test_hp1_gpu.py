@@ -42,7 +42,8 @@ def test_umma_operand_layout(K, N):
     assert _probe(K, N) == 0.0
 
 
-@pytest.mark.parametrize("n,c", [(1000, 3), (5000, 10), (4099, 300), (70000, 1000)])
+@pytest.mark.parametrize("n,c", [(1000, 3), (5000, 10), (8193, 7), (50000, 10), (200000, 19), (300000, 255), (4099, 300),
+                                 (70000, 1000)])
 def test_bucket_labels_bit_exact(n, c):
     from sqfa_b200.statistics import bucket_labels
 
