@@ -673,9 +673,13 @@ size_t project_workspace_bytes(int C, int D, int k) {
 cudaError_t launch_project_partials(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
                                     float* partial, float* PsiPart, float* MuPart, cudaStream_t st) {
   if (C <= 0) return cudaSuccess;
-  const int rows = project_rows_per_split(C, D, k), nsplit = project_nsplit_actual(C, D, k);
+  const int rows = project_rows_per_split(C, D, k);
+  int nsplit = project_nsplit_actual(C, D, k);
   cudaError_t e;
-  if (k <= 4) e = run_project_stream<4>(S, F, C, D, k, rows, nsplit, partial, st);
+  if (project_tc_applicable(S, F, D, k)) {  // k > 8: tensor cores (the SIMT pass is FP32-FMA bound there)
+    e = launch_project_tc(S, F, C, D, k, partial, st);
+    nsplit = 1;  // the finish kernel finds T itself in the first "row split"
+  } else if (k <= 4) e = run_project_stream<4>(S, F, C, D, k, rows, nsplit, partial, st);
   else if (k <= 8) e = run_project_stream<8>(S, F, C, D, k, rows, nsplit, partial, st);
   else if (k <= 16) e = run_project_stream<16>(S, F, C, D, k, rows, nsplit, partial, st);
   else e = run_project_stream<32>(S, F, C, D, k, rows, nsplit, partial, st);

@@ -66,6 +66,9 @@ int project_nchunk(int D);
 size_t project_workspace_bytes(int C, int D, int k);
 size_t project_psipart_floats(int C, int D, int k);
 size_t project_mupart_floats(int C, int D, int k);
+// ---- project_tc.cu (K4 on the tensor cores for 8 < k <= 32) ----
+bool project_tc_applicable(const float* S, const float* F, int D, int k);
+cudaError_t launch_project_tc(const float* S, const float* F, int C, int D, int k, float* T, cudaStream_t st);
 cudaError_t launch_project_partials(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
                                     float* partial, float* PsiPart, float* MuPart, cudaStream_t st);
 cudaError_t launch_project_fwd(const float* S, const float* M, const float* F, int C, int D, int k, float* T,
