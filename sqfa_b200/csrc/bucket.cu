@@ -244,10 +244,10 @@ __global__ void class_counts_kernel(const int64_t* __restrict__ offsets, int32_t
 }
 
 // One 8-bit pass (at most 255 classes) with a histogram of at most MID_MAX_ENTRIES entries: the exclusive scan
-// of the digit-major histogram in ONE block (a contiguous run of entries per thread), which also writes the
+// of the digit-major histogram in ONE block (coalesced chunks of 8192 entries with a running carry), which also writes the
 // class offsets and counts -- class c is digit c, its first row sits at the scanned entry of (digit c, tile 0).
 // Replaces the three scan launches and the two offset launches of the general path.
-constexpr int MID_MAX_ENTRIES = 1 << 18;  // 1024 tiles = about a million rows
+constexpr int MID_MAX_ENTRIES = 1 << 16;  // 256 tiles = 262 144 rows (8 chunks: beyond that the parallel scan wins)
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int32_t* __restrict__ hist, int total, int ntiles,
                                                                      int32_t C, int64_t n,
@@ -255,16 +255,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int32_t* __r
                                                                      int64_t* __restrict__ offsets) {
   __shared__ int32_t s_warp[33];
   const int tid = threadIdx.x;
-  const int per = (total + SCAN_THREADS - 1) / SCAN_THREADS;
-  const int lo = tid * per, hi = min(total, lo + per);
-  int32_t sum = 0;
-  for (int i = lo; i < hi; ++i) sum += hist[i];
-  int32_t tot;
-  int32_t run = block_exclusive_scan(sum, s_warp, &tot);
-  for (int i = lo; i < hi; ++i) {
-    const int32_t t = hist[i];
-    hist[i] = run;
-    run += t;
+  int32_t carry = 0;
+  for (int base = 0; base < total; base += SCAN_CHUNK) {  // chunks of 8192 entries, 8 consecutive ones per thread
+    const int64_t i0 = (int64_t)base + tid * SCAN_PER_THREAD;
+    int32_t v[8];
+    scan_load8(hist, total, i0, v);
+    int32_t t = 0, chunk_total;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += v[j];
+    int32_t run = carry + block_exclusive_scan(t, s_warp, &chunk_total);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int32_t x = v[j];
+      v[j] = run;
+      run += x;
+    }
+    if (i0 + 8 <= total) {
+      *reinterpret_cast<int4*>(hist + i0) = make_int4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<int4*>(hist + i0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + j < total) hist[i0 + j] = v[j];
+    }
+    carry += chunk_total;
   }
   __syncthreads();  // (block-wide visibility of the global writes above)
   for (int c = tid; c <= C + 1; c += SCAN_THREADS) offsets[c] = (c <= C) ? (int64_t)hist[(int64_t)c * ntiles] : n;

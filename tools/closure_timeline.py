@@ -10,7 +10,7 @@ hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
 h = rows[hi]
 kn, mn, mv = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value")
 seq = [(r[kn], float(r[mv].replace(",", ""))) for r in rows[hi + 1:] if len(r) > mv and r[mn] == "gpu__time_duration.sum"]
-starts = [i for i, (k, v) in enumerate(seq) if "project_stream" in k or "project_partial" in k]
+starts = [i for i, (k, v) in enumerate(seq) if "project_stream" in k or "project_partial" in k or "project_tc" in k]
 i0 = starts[-1]
 tot = 0.0
 for k, v in seq[i0:]:

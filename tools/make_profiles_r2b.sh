@@ -5,7 +5,8 @@ python - <<'PY'
 import json, subprocess, os
 caps = [("r2b_gram_c2", "gram_tf32x3_kernel", "c2 class_statistics (N=50000, D=3072, C=10): tcgen05 cta_group::2 3xTF32 Gram"),
         ("r2b_pair_c4", "pair_cp_kernel", "c4 closure (C=1000, m=17, 499500 pairs): column-pair Jacobi, 3 problems per warp, 3x3 pair tiles"),
-        ("r2b_pair_c5", "pair_cp_kernel", "c5 closure (C=100, m=33, 4950 pairs): column-pair Jacobi, one problem per warp")]
+        ("r2b_pair_c5", "pair_cp_kernel", "c5 closure (C=100, m=33, 4950 pairs): column-pair Jacobi, one problem per warp"),
+        ("r2b_ptc_c5", "project_tc", "c5 closure (C=100, D=1024, k=32): tcgen05 projection T_c^T = S_c F^T, 3xTF32")]
 out = []
 for rep, regex, what in caps:
     path = f"gpurun_out/{rep}.ncu-rep"
@@ -30,7 +31,7 @@ if "r2b_pair_c4" in by:
                "issue_active_pct": p["issue_active_pct"], "warp_instructions": p["warp_instructions"],
                "duration_ms": p["duration_ms"]}, open("profiles/pair_issue.json", "w"), indent=1)
 PY
-for f in bench_launches cl_c1 cl_c2 cl_c3 cl_c4 cl_c5; do
+for f in bench_launches cl_c1 cl_c2 cl_c3 cl_c4 cl_c5 st_c1 st_c3 st_c4; do
   [ -f gpurun_out/r2b_$f.csv ] && cp gpurun_out/r2b_$f.csv profiles/r02b_${f}_ncu.csv
 done
 {
