@@ -143,6 +143,12 @@ int64_t sqfa_class_gram_group_signals(int64_t n, int32_t n_dim, int32_t n_classe
  * collective on the counters above. No kernel is launched, no SM is occupied while waiting. */
 int sqfa_stream_wait_geq(sqfa_stream_t stream, const int32_t* flag, int32_t value);
 
+/* Class counts as two exact float32 words, out[c] = counts[c] / 2^20 and out[n_classes + c] = counts[c] mod
+ * 2^20, so that a multi-device caller sums [class sums | counts] of its ranks in ONE float32 all-reduce;
+ * sqfa_counts_unpack turns the summed words back into int64 (exact below 2^44 rows). */
+int sqfa_counts_pack(const int64_t* counts, int32_t n_classes, float* out, sqfa_stream_t stream);
+int sqfa_counts_unpack(const float* in, int32_t n_classes, int64_t* counts, sqfa_stream_t stream);
+
 /* Statistics epilogue (statistics.py:43-47, 84-93, 116, 120-122):
  *   cov[c] = (gram[c] - n_c d d^T) / (n_c - ddof),  d = means[c] - shift[c]  (shift NULL -> d = 0)
  *   ddof = 1: unbiased estimate; ddof = 0: `assume_centered` (statistics.py:116)

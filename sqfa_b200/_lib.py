@@ -48,6 +48,8 @@ SIGNATURES = {
     "sqfa_stream_wait_geq": (c_int, [c_ptr, c_ptr, c_i32]),
     "sqfa_gram_packed_floats": (c_size, [c_i32, c_i32]),
     "sqfa_gram_executed_tile_area": (c_i64, [c_i32]),
+    "sqfa_counts_pack": (c_int, [c_ptr, c_i32, c_ptr, c_ptr]),
+    "sqfa_counts_unpack": (c_int, [c_ptr, c_i32, c_ptr, c_ptr]),
     "sqfa_stats_epilogue_workspace_bytes": (c_size, [c_i32]),
     "sqfa_stats_epilogue": (
         c_int,

@@ -121,6 +121,18 @@ class CudaStatsOps:
         )
         return sums
 
+    def counts_pack(self, counts, out):
+        """counts (int64 [C]) -> out (float32 [2 C]) = [count / 2^20 | count mod 2^20], one launch."""
+        _lib.check(self.lib.sqfa_counts_pack(_lib.ptr(counts), counts.numel(), _lib.ptr(out),
+                                             _lib.stream_ptr(counts.device)), "sqfa_counts_pack")
+
+    def counts_unpack(self, words):
+        C = words.numel() // 2
+        counts = torch.empty(C, dtype=torch.int64, device=words.device)
+        _lib.check(self.lib.sqfa_counts_unpack(_lib.ptr(words), C, _lib.ptr(counts), _lib.stream_ptr(words.device)),
+                   "sqfa_counts_unpack")
+        return counts
+
     def class_means(self, sums, counts):
         C, D = sums.shape
         means = torch.empty_like(sums)
@@ -319,10 +331,14 @@ class CudaStatsOps:
         gram.record_stream(side)
         done.record_stream(side)
         set_base = k * W * stride
-        for g, lo, hi in peer_push_schedule(r, W, shares):
-            expected = lib.sqfa_class_gram_group_signals(n, D, C, W, g)
+        plan = st.setdefault("plans", {}).get(n)
+        if plan is None:  # push order and the counter value that says "group g is final", per row count
+            plan = [(g, lo, hi, int(lib.sqfa_class_gram_group_signals(n, D, C, W, g)))
+                    for g, lo, hi in peer_push_schedule(r, W, shares)]
+            st["plans"][n] = plan
+        for g, lo, hi, expected in plan:
             _lib.check(lib.sqfa_stream_wait_geq(ctypes.c_void_p(side.cuda_stream),
-                                                ctypes.c_void_p(done.data_ptr() + 4 * g), int(expected)),
+                                                ctypes.c_void_p(done.data_ptr() + 4 * g), expected),
                        "sqfa_stream_wait_geq")
             dst = st["peers"][g].data_ptr() + 4 * (set_base + r * stride)
             src = gram.data_ptr() + 4 * lo * per_class
@@ -429,6 +445,7 @@ class CudaStatsOps64(CudaStatsOps):
     supports_packed = False
     fused = None
     fused_prepare = None
+    counts_pack = None
     class_gram_overlapped = None
     peer_acquire = None
 
@@ -559,11 +576,18 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
         if local_sums is not sums:  # ops without an `out` argument
             sums.copy_(local_sums)
         local = counts[:C]
-        small[C * D : C * D + C] = torch.div(local, _COUNT_BASE, rounding_mode="floor").to(X.dtype)
-        small[C * D + C :] = torch.remainder(local, _COUNT_BASE).to(X.dtype)
+        native_words = X.dtype == torch.float32 and getattr(ops, "counts_pack", None) is not None
+        if native_words:  # one launch each way instead of a dozen element-wise torch kernels
+            ops.counts_pack(local, small[C * D :])
+        else:
+            small[C * D : C * D + C] = torch.div(local, _COUNT_BASE, rounding_mode="floor").to(X.dtype)
+            small[C * D + C :] = torch.remainder(local, _COUNT_BASE).to(X.dtype)
         _all_reduce(small, group)
-        class_counts = (small[C * D : C * D + C].round().to(torch.int64) * _COUNT_BASE
-                        + small[C * D + C :].round().to(torch.int64))
+        if native_words:
+            class_counts = ops.counts_unpack(small[C * D :])
+        else:
+            class_counts = (small[C * D : C * D + C].round().to(torch.int64) * _COUNT_BASE
+                            + small[C * D + C :].round().to(torch.int64))
     else:
         sums = ops.class_sums(X, perm, offsets, C)
         class_counts = counts[:C].clone()

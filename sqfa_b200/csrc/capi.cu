@@ -165,6 +165,15 @@ int sqfa_stream_wait_geq(sqfa_stream_t stream, const int32_t* flag, int32_t valu
   return 0;
 }
 
+int sqfa_counts_pack(const int64_t* counts, int32_t n_classes, float* out, sqfa_stream_t stream) {
+  if (n_classes < 0 || (n_classes > 0 && (counts == nullptr || out == nullptr))) return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_counts_pack(counts, n_classes, out, S(stream)));
+}
+int sqfa_counts_unpack(const float* in, int32_t n_classes, int64_t* counts, sqfa_stream_t stream) {
+  if (n_classes < 0 || (n_classes > 0 && (counts == nullptr || in == nullptr))) return fail_arg(__func__, "bad argument");
+  return wrap(__func__, sqfa::launch_counts_unpack(in, n_classes, counts, S(stream)));
+}
+
 size_t sqfa_stats_epilogue_workspace_bytes(int32_t n_classes) {
   return sqfa::stats_epilogue_workspace_bytes(n_classes);
 }

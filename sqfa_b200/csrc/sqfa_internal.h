@@ -34,6 +34,8 @@ cudaError_t launch_class_sums(const float* X, int64_t ldx, const int32_t* perm, 
                               float* partial_ws, int nsplit, cudaStream_t stream);
 cudaError_t launch_class_means(const float* sums, const int64_t* counts, const float* shift, int D, int C,
                                float* means, cudaStream_t stream);
+cudaError_t launch_counts_pack(const int64_t* counts, int C, float* out, cudaStream_t stream);
+cudaError_t launch_counts_unpack(const float* in, int C, int64_t* counts, cudaStream_t stream);
 size_t stats_epilogue_workspace_bytes(int C);
 // Partial Grams of the same classes held in several buffers (a rank's own packed tiles + the slots its
 // peers pushed theirs into): source s is `gram` for s == self, else peers + s * stride. Summed in order.

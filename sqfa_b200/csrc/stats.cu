@@ -382,7 +382,33 @@ oas_apply_kernel(const double* __restrict__ partial, const float* __restrict__ m
   }
 }
 
+// Class counts as two exact float32 words (count / 2^20, count mod 2^20) behind the class sums: ONE small
+// all-reduce carries both (a multi-device caller), and back to int64 afterwards. Exact below 2^44 rows.
+__global__ void counts_pack_kernel(const int64_t* __restrict__ counts, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int64_t n = counts[c];
+  out[c] = (float)(n >> 20);
+  out[C + c] = (float)(n & ((1 << 20) - 1));
+}
+__global__ void counts_unpack_kernel(const float* __restrict__ in, int C, int64_t* __restrict__ counts) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  counts[c] = ((int64_t)llrintf(in[c]) << 20) + (int64_t)llrintf(in[C + c]);
+}
+
 }  // namespace
+
+cudaError_t launch_counts_pack(const int64_t* counts, int C, float* out, cudaStream_t stream) {
+  if (C <= 0) return cudaSuccess;
+  counts_pack_kernel<<<(C + 255) / 256, 256, 0, stream>>>(counts, C, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_counts_unpack(const float* in, int C, int64_t* counts, cudaStream_t stream) {
+  if (C <= 0) return cudaSuccess;
+  counts_unpack_kernel<<<(C + 255) / 256, 256, 0, stream>>>(in, C, counts);
+  return cudaGetLastError();
+}
 
 int class_sums_splits(int64_t n, int C, int D, int num_sms) {
   const int tpr = sums_threads_per_row(D);
