@@ -539,12 +539,21 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
         if group is None and getattr(ops, "label_max_host", None) is not None:
             token = ops.label_max_begin(y)
             guess = getattr(ops, "_last_n_classes", None)
+            speculative = None
             if (guess and centre is None and y.numel() > 0 and getattr(ops, "fused_prepare", None) is not None
-                    and getattr(ops, "gram_events", None) is None):
-                # while the kernel runs and the host wakes up: allocate for as many classes as the last call had
+                    and getattr(ops, "fused", None) is not None and getattr(ops, "gram_events", None) is None):
+                # Do not idle while the label maximum travels to the host: run the whole call for as many
+                # classes as the last call had, enqueued right behind the label_max kernel, and check afterwards.
+                # A different class count (first call on new data) discards it and runs again below -- any
+                # guess is safe to execute: labels beyond it fall into the "dropped" bucket, classes without
+                # rows are empty.
                 prepared = ops.fused_prepare(X, guess, want_sm)
+                speculative = ops.fused(X, y, guess, estimator_id, ddof, want_sm, prepared)
             n_classes = ops.label_max_wait(token) + 1
             ops._last_n_classes = n_classes
+            if speculative is not None and n_classes == guess:
+                return speculative
+            prepared = None
         else:
             mx = ops.label_max(y)
             if group is not None:
