@@ -540,8 +540,12 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
             token = ops.label_max_begin(y)
             guess = getattr(ops, "_last_n_classes", None)
             speculative = None
-            if (guess and centre is None and y.numel() > 0 and getattr(ops, "fused_prepare", None) is not None
-                    and getattr(ops, "fused", None) is not None and getattr(ops, "gram_events", None) is None):
+            fusable = (guess and centre is None and y.numel() > 0 and getattr(ops, "fused_prepare", None) is not None
+                       and getattr(ops, "fused", None) is not None and getattr(ops, "gram_events", None) is None)
+            if fusable and getattr(ops, "_n_classes_streak", 0) < 1:
+                # the class count has not repeated yet: only allocate for it while the kernel runs
+                prepared = ops.fused_prepare(X, guess, want_sm)
+            elif fusable:
                 # Do not idle while the label maximum travels to the host: run the whole call for as many
                 # classes as the last call had, enqueued right behind the label_max kernel, and check afterwards.
                 # A different class count (first call on new data) discards it and runs again below -- any
@@ -550,10 +554,12 @@ def run_class_statistics(ops, X, y, estimator_id, group=None, n_classes=None, dd
                 prepared = ops.fused_prepare(X, guess, want_sm)
                 speculative = ops.fused(X, y, guess, estimator_id, ddof, want_sm, prepared)
             n_classes = ops.label_max_wait(token) + 1
+            ops._n_classes_streak = getattr(ops, "_n_classes_streak", 0) + 1 if n_classes == guess else 0
             ops._last_n_classes = n_classes
-            if speculative is not None and n_classes == guess:
-                return speculative
-            prepared = None
+            if speculative is not None:
+                if n_classes == guess:
+                    return speculative
+                prepared = None
         else:
             mx = ops.label_max(y)
             if group is not None:

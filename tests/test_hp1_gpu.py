@@ -271,6 +271,26 @@ def test_single_call_entry_matches_stepwise(n, d, c, est):
     assert rel_err(cov1, ref["covariances"]) < TOL
 
 
+def test_class_count_change_between_calls():
+    """Once the class count has repeated, a call is enqueued for that count before the label maximum has reached
+    the host; a call whose labels have another maximum must notice and run again with the right count."""
+    from sqfa_b200.statistics import class_statistics
+
+    d = 96
+    Xa, ya = make_class_data(3000, d, 5, seed=1)
+    Xb, yb = make_class_data(3000, d, 8, seed=2)
+    Xc, yc = make_class_data(3000, d, 3, seed=3)
+    for _ in range(3):
+        got = class_statistics(Xa.cuda(), ya.cuda())
+    assert got["means"].shape[0] == 5
+    for X, y, c in ((Xb, yb, 8), (Xc, yc, 3), (Xa, ya, 5), (Xa, ya, 5), (Xa, ya, 5), (Xb, yb, 8)):
+        got = class_statistics(X.cuda(), y.cuda())
+        ref = O.class_statistics(X.double(), y)
+        assert got["covariances"].shape == (c, d, d)
+        for key in ref:
+            assert rel_err(got[key], ref[key]) < TOL
+
+
 def test_label_max_published_to_mapped_host_memory():
     """The label maximum lands in pinned host memory without a device-to-host copy, also when calls
     from several streams are in flight and for empty / all-negative labels."""
