@@ -4,7 +4,7 @@
 //  distances.py -> linalg.py and the autograd backward of all of it, including the filter
 //  constraint constraints.py:37).
 // It sequences the kernels of project.cu and pairs.cu on the caller's stream inside a caller-provided
-// workspace -- 8 launches, no memsets, no atomics on floating-point sums:
+// workspace -- 8 kernel launches (and one 8-byte memset of the flags), no atomics on floating-point sums:
 //   constraint_fwd          F = W / |W|                                  (sphere constraint only)
 //   project_stream          row-split partials of T_c = F S_c            (the one pass over C D^2 floats)
 //   project_finish          T_c, per-chunk partials of Psi_c = T_c F^T and mu'_c = F m_c
