@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "ptx.cuh"
@@ -295,6 +296,282 @@ project_tc_kernel(const float* __restrict__ S, const float* __restrict__ F, int 
   if (warp == PT_MMA_WARP) tmem_dealloc<G::TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Variant with the raw tile staged by TMA: ONE cp.async.bulk.tensor.2d per stage brings the 128 x 32 box of
+// S_c (and one the KP x 32 box of F) into a raw ring of four stages -- 66 KB per SM in flight without holding
+// a register -- and reports the bytes to an mbarrier; the eight splitter warps read the raw rows back
+// (a quarter warp reads the 8 chunks of one row: 128 contiguous bytes), split them and store hi / lo into a
+// two-stage operand ring (conflict-free thanks to the padded LBO); MMA issuer and epilogue as above. Rows
+// and columns beyond the matrix are zero-filled by the copy unit or zeroed by the splitters. Costs one more
+// write and one more read of every byte in shared memory (the trade DESIGN.md section 4 describes for the
+// Gram). MEASURED (B200, SQFA_PROJECT_TC_BULK=1): c4 (k = 16) 391 us, c5 shape (k = 32) 210 us against 297 /
+// 155 us for the register-staged producers above and 274 / 261 us for the SIMT pass -- the second pass through
+// shared memory and the two-stage operand ring cost more than the deeper prefetch gains, so this variant is
+// opt-in; it is what DESIGN.md section 4 argues for the Gram, here as a measured A/B. (A first version with
+// one 1-D bulk copy per ROW, 160 copies of 128 bytes per stage, took 2.0 ms at c4: the copy unit needs ~70
+// cycles per copy -- small bulk copies are not a substitute for a tensor map.)
+// ------------------------------------------------------------------------------------------------
+constexpr int PB_RAW_STAGES = 4, PB_OP_STAGES = 2;
+constexpr int PB_RAW_ROW = PT_BK * 4;                // dense 128-byte rows, as the copy unit writes a box
+constexpr int PB_THREADS = PT_THREADS + 32;          // + the copy warp
+constexpr int PB_COPY_WARP = PT_PROD_WARPS + 1 + PT_EPI_WARPS;
+
+template <int KP>
+struct PbGeom {
+  static constexpr int RAW_A_BYTES = PT_ROWS * PB_RAW_ROW, RAW_B_BYTES = KP * PB_RAW_ROW;
+  static constexpr int RAW_BYTES = RAW_A_BYTES + RAW_B_BYTES;  // rows of the tile, then the filters
+  static constexpr int SMEM = PB_OP_STAGES * PtGeom<KP>::STAGE_BYTES + PB_RAW_STAGES * RAW_BYTES + 1024;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int KP>
+__global__ void __launch_bounds__(PB_THREADS, 1)
+project_tcb_kernel(const __grid_constant__ CUtensorMap map_S, const __grid_constant__ CUtensorMap map_F, int C, int D,
+                   int k, float* __restrict__ T) {
+  using G = PtGeom<KP>;
+  using GB = PbGeom<KP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* raw = smem + PB_OP_STAGES * G::STAGE_BYTES;
+  __shared__ __align__(8) uint64_t raw_full_bar[PB_RAW_STAGES];   // copy warp (expect_tx) + the copies' bytes
+  __shared__ __align__(8) uint64_t raw_empty_bar[PB_RAW_STAGES];  // splitters (8 warp arrivals) -> copy warp
+  __shared__ __align__(8) uint64_t full_bar[PB_OP_STAGES];        // splitters -> MMA
+  __shared__ __align__(8) uint64_t empty_bar[PB_OP_STAGES];       // MMA (commit) -> splitters
+  __shared__ __align__(8) uint64_t acc_full_bar[2];
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < PB_RAW_STAGES; ++s) {
+      mbar_init(&raw_full_bar[s], 1);
+      mbar_init(&raw_empty_bar[s], PT_PROD_WARPS);
+    }
+    for (int s = 0; s < PB_OP_STAGES; ++s) {
+      mbar_init(&full_bar[s], PT_PROD_WARPS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full_bar[b], 1);
+      mbar_init(&acc_empty_bar[b], PT_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == PT_MMA_WARP) tmem_alloc<G::TMEM_COLS>(&s_tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = s_tmem_base;
+
+  const int row_tiles = (D + PT_ROWS - 1) / PT_ROWS;
+  const int njobs = C * row_tiles;
+  const int nstages = (D + PT_BK - 1) / PT_BK;  // per job
+  const int nchains = (nstages + PT_CHAIN - 1) / PT_CHAIN;
+
+  if (warp == PB_COPY_WARP) {
+    // =========================== TMA issuer (one thread) ===========================
+    if (lane == 0) {
+      uint32_t rs = 0, rphase = 0;
+      for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        const int c = job / row_tiles, r0 = (job - c * row_tiles) * PT_ROWS;
+        for (int st = 0; st < nstages; ++st) {
+          mbar_wait(&raw_empty_bar[rs], rphase ^ 1);
+          mbar_arrive_expect_tx(&raw_full_bar[rs], (uint32_t)GB::RAW_BYTES);  // a box counts in full, zero fill included
+          const uint32_t dst = smem_u32(raw + rs * GB::RAW_BYTES);
+          tma_load_2d(dst, &map_S, st * PT_BK, c * D + r0, &raw_full_bar[rs]);
+          tma_load_2d(dst + GB::RAW_A_BYTES, &map_F, st * PT_BK, 0, &raw_full_bar[rs]);
+          if (++rs == PB_RAW_STAGES) { rs = 0; rphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < PT_PROD_WARPS) {
+    // =========================== splitters ===========================
+    // lane l: chunk l % 8 of row l / 8 of a group of four rows; warp w takes the row groups w, w + 8, w + 16,
+    // w + 24. A quarter warp reads 128 contiguous bytes and writes the 8 chunks of one row (padded LBO).
+    const int chunk = lane & 7, row_lane = lane >> 3;
+    const bool has_b = tid < KP * 8;
+    const int brow = tid >> 3;  // tid < 8 KP: filter row, chunk tid % 8 = lane % 8
+    const bool b_row_ok = has_b && brow < k;
+    const uint32_t bh_off = op_offset(brow, chunk, G::B_LBO), bl_off = op_offset(KP + brow, chunk, G::B_LBO);
+    auto split = [](float4 v, float4& h, float4& l) {
+      h.x = to_tf32(v.x); l.x = v.x - h.x;
+      h.y = to_tf32(v.y); l.y = v.y - h.y;
+      h.z = to_tf32(v.z); l.z = v.z - h.z;
+      h.w = to_tf32(v.w); l.w = v.w - h.w;
+    };
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t rs = 0, rphase = 0, stage = 0, phase = 0;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+      const int r0 = (job % row_tiles) * PT_ROWS;
+      for (int st = 0; st < nstages; ++st) {
+        mbar_wait(&raw_full_bar[rs], rphase);
+        const uint32_t src = smem_u32(raw + rs * GB::RAW_BYTES) + 16u * chunk;
+        float4 va[4], vb = z;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = 4 * (warp + 8 * u) + row_lane;
+          va[u] = ld_shared_v4(src + row * PB_RAW_ROW);
+          if (r0 + row >= D) va[u] = z;  // rows of the next class (or zero fill behind the last one)
+        }
+        if (has_b) {
+          vb = ld_shared_v4(src + GB::RAW_A_BYTES + brow * PB_RAW_ROW);
+          if (!b_row_ok) vb = z;
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t sa = smem_u32(smem + stage * G::STAGE_BYTES);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = 4 * (warp + 8 * u) + row_lane;
+          float4 h, l;
+          split(va[u], h, l);
+          const uint32_t off = sa + op_offset(row, chunk, PT_A_LBO);
+          st_shared_v4(off, h);
+          st_shared_v4(off + PT_A_BYTES, l);
+        }
+        if (has_b) {
+          float4 h, l;
+          split(vb, h, l);
+          st_shared_v4(sa + 2 * PT_A_BYTES + bh_off, h);
+          st_shared_v4(sa + 2 * PT_A_BYTES + bl_off, l);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&full_bar[stage]);
+          mbar_arrive(&raw_empty_bar[rs]);  // every value of the raw stage has been consumed
+        }
+        if (++stage == PB_OP_STAGES) { stage = 0; phase ^= 1; }
+        if (++rs == PB_RAW_STAGES) { rs = 0; rphase ^= 1; }
+      }
+    }
+  } else if (warp == PT_MMA_WARP) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc_wide = make_idesc_tf32(PT_ROWS, 2 * KP, 0, 0), idesc_narrow = make_idesc_tf32(PT_ROWS, KP, 0, 0);
+    uint32_t stage = 0, phase = 0, chain = 0;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+      for (int ch = 0; ch < nchains; ++ch, ++chain) {
+        const uint32_t buf = chain & 1u;
+        mbar_wait(&acc_empty_bar[buf], ((chain >> 1) & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + buf * G::ACC_COLS;
+        const int s_end = min(nstages, (ch + 1) * PT_CHAIN);
+        for (int st = ch * PT_CHAIN; st < s_end; ++st) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * G::STAGE_BYTES);
+            const uint32_t a_hi = sa, a_lo = sa + PT_A_BYTES, b = sa + 2 * PT_A_BYTES;
+#pragma unroll
+            for (int k8 = 0; k8 < PT_BK / 8; ++k8) {
+              const uint64_t dA_hi = make_smem_desc(a_hi + k8 * 2 * PT_A_LBO, PT_A_LBO, PT_SBO, 0);
+              const uint64_t dA_lo = make_smem_desc(a_lo + k8 * 2 * PT_A_LBO, PT_A_LBO, PT_SBO, 0);
+              const uint64_t dB = make_smem_desc(b + k8 * 2 * G::B_LBO, G::B_LBO, PT_SBO, 0);
+              const uint32_t accumulate = (st > ch * PT_CHAIN || k8 > 0) ? 1u : 0u;
+              umma_tf32_ss(acc, dA_hi, dB, idesc_wide, accumulate);
+              umma_tf32_ss(acc + 2 * KP, dA_lo, dB, idesc_narrow, accumulate);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (st == s_end - 1) umma_commit(&acc_full_bar[buf]);
+          }
+          __syncwarp();
+          if (++stage == PB_OP_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int q = warp & 3;
+    const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16);
+    uint32_t chain = 0;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+      const int c = job / row_tiles, r0 = (job - c * row_tiles) * PT_ROWS;
+      float run[KP];
+#pragma unroll
+      for (int f = 0; f < KP; ++f) run[f] = 0.f;
+      for (int ch = 0; ch < nchains; ++ch, ++chain) {
+        const uint32_t buf = chain & 1u;
+        mbar_wait(&acc_full_bar[buf], (chain >> 1) & 1u);
+        tc_fence_after_sync();
+        const uint32_t acc = tq + buf * G::ACC_COLS;
+#pragma unroll
+        for (int f0 = 0; f0 < KP; f0 += 16) {
+          uint32_t hh[16], hl[16], lh[16];
+          tmem_ld_32x32b_x16(acc + f0, hh);
+          tmem_ld_32x32b_x16(acc + KP + f0, hl);
+          tmem_ld_32x32b_x16(acc + 2 * KP + f0, lh);
+          tmem_ld_wait();
+#pragma unroll
+          for (int f = 0; f < 16; ++f)
+            run[f0 + f] += __uint_as_float(hh[f]) + (__uint_as_float(hl[f]) + __uint_as_float(lh[f]));
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty_bar[buf]);
+      }
+      const int r = r0 + 32 * q + lane;
+      if (r < D) {
+        float* out = T + (size_t)c * k * D + r;
+#pragma unroll
+        for (int f = 0; f < KP; ++f)
+          if (f < k) out[(size_t)f * D] = run[f];
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == PT_MMA_WARP) tmem_dealloc<G::TMEM_COLS>(tmem_base);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link dependency on libcuda):
+// a 2-D float32 tensor of `rows` x `cols` (row-major), boxes of box_rows x box_cols, no swizzle, zero fill
+static cudaError_t encode_map_2d(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                                 uint32_t box_rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || p == nullptr || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    fn = reinterpret_cast<encode_fn>(p);
+  }
+  const cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols * sizeof(float)};
+  const cuuint32_t box[2] = {box_cols, box_rows}, estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int KP>
+cudaError_t run_project_tcb(const float* S, const float* F, int C, int D, int k, float* T, cudaStream_t st) {
+  using GB = PbGeom<KP>;
+  static int smem_set[kMaxDevices] = {0};
+  {
+    cudaError_t e = ensure_dynamic_smem(project_tcb_kernel<KP>, GB::SMEM, smem_set);
+    if (e != cudaSuccess) return e;
+  }
+  CUtensorMap map_S, map_F;
+  cudaError_t e = encode_map_2d(&map_S, S, (uint64_t)D, (uint64_t)C * D, PT_BK, PT_ROWS);
+  if (e != cudaSuccess) return e;
+  if ((e = encode_map_2d(&map_F, F, (uint64_t)D, (uint64_t)k, PT_BK, KP)) != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int njobs = C * ((D + PT_ROWS - 1) / PT_ROWS);
+  const int grid = njobs < sms ? njobs : sms;
+  project_tcb_kernel<KP><<<grid, PB_THREADS, GB::SMEM, st>>>(map_S, map_F, C, D, k, T);
+  return cudaGetLastError();
+}
+
 template <int KP>
 cudaError_t run_project_tc(const float* S, const float* F, int C, int D, int k, float* T, cudaStream_t st) {
   using G = PtGeom<KP>;
@@ -329,6 +606,11 @@ bool project_tc_applicable(const float* S, const float* F, int D, int k) {
 
 cudaError_t launch_project_tc(const float* S, const float* F, int C, int D, int k, float* T, cudaStream_t st) {
   if (C <= 0) return cudaSuccess;
+  const char* env = getenv("SQFA_PROJECT_TC_BULK");  // 1: raw tile staged by TMA (A/B switch)
+  if (env != nullptr && atoi(env) != 0) {
+    if (k <= 16) return run_project_tcb<16>(S, F, C, D, k, T, st);
+    return run_project_tcb<32>(S, F, C, D, k, T, st);
+  }
   if (k <= 16) return run_project_tc<16>(S, F, C, D, k, T, st);
   return run_project_tc<32>(S, F, C, D, k, T, st);
 }

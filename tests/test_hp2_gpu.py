@@ -302,17 +302,22 @@ def test_error_types_match_reference():
         SQFA(n_dim=8, n_filters=2).get_class_distances(stats["second_moments"])
 
 
-@pytest.mark.parametrize("tc", ["default", "0", "1"])
+@pytest.mark.parametrize("tc", ["default", "0", "1", "tma"])
 @pytest.mark.parametrize("C,D,k", [(3, 1027, 5), (7, 40, 3), (2, 3072, 8), (130, 96, 16), (5, 520, 32), (3, 1024, 24),
                                    (40, 512, 16), (2, 132, 9), (6, 300, 31)])
 def test_project_forward_shapes(C, D, k, tc, monkeypatch):
     """T = F S, Psi = T F^T, mu' = F m for row splits, partial column strips, D % 4 != 0, every KT -- through
     the SIMT pass (SQFA_PROJECT_TC=0), the tcgen05 pass forced for every 8 < k <= 32 (=1: ragged row tiles and
-    column stages, k not a multiple of 16) and the default choice (tensor cores for k > 16)."""
+    column stages, k not a multiple of 16), its TMA-staged variant, and the default choice (tensor cores, register
+    staging, for k > 16)."""
     from sqfa_b200 import _ops
 
+    monkeypatch.delenv("SQFA_PROJECT_TC_BULK", raising=False)
     if tc == "default":
         monkeypatch.delenv("SQFA_PROJECT_TC", raising=False)
+    elif tc == "tma":  # the tcgen05 pass with the raw tile staged by TMA (cp.async.bulk.tensor), for every 8 < k <= 32
+        monkeypatch.setenv("SQFA_PROJECT_TC", "1")
+        monkeypatch.setenv("SQFA_PROJECT_TC_BULK", "1")
     else:
         monkeypatch.setenv("SQFA_PROJECT_TC", tc)
 
