@@ -150,3 +150,62 @@ def test_odd_even_transposition_meets_every_column_pair_once():
                 pos[p], pos[p + 1] = b, a
         assert len(met) == n * (n - 1) // 2
         assert pos == list(range(n))[::-1]
+
+
+def test_column_pair_jacobi_model_matches_lapack():
+    """float32 numpy model of the pair kernel's Jacobi (pairs.cu, pair_cp_kernel): one-sided rotations in the
+    odd-even transposition ordering, every rotation followed by the swap, columns kept as scale * vector
+    ("fast" rotations: y + tau1 x, x - tau2 y, scales multiplied by c and folded back once per sweep), carried
+    norms, the same convergence rules. The squared column norms must be the generalized eigenvalues that
+    LAPACK finds, and the zero padding column of an odd m must sit where the sweep parity says."""
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    tol, last = 1e-6, 3e-4
+    for m in (4, 9, 17, 33):
+        n = m + (m & 1)
+        a = rng.standard_normal((m, m + 4))
+        b = rng.standard_normal((m, m + 4))
+        Ei, Ej = a @ a.T / (m + 4) + 0.05 * np.eye(m), b @ b.T / (m + 4) + 0.05 * np.eye(m)
+        Li, Lj = np.linalg.cholesky(Ei), np.linalg.cholesky(Ej)
+        A = np.zeros((n, n), np.float32)
+        A[:m, :m] = (np.linalg.solve(Lj, Li)).T.astype(np.float32)  # columns of (L_j^-1 L_i)^T
+        scale = np.ones(n, np.float32)
+        sweeps = 0
+        for _ in range(24):
+            A *= scale
+            scale[:] = 1
+            norms = (A * A).sum(0)
+            rotated = False
+            for step in range(n):
+                for p in range(step % 2, n - 1, 2):
+                    x, y = A[:, p].copy(), A[:, p + 1].copy()
+                    al, be = norms[p], norms[p + 1]
+                    ab = np.float32(scale[p] * scale[p + 1] * np.dot(x, y))
+                    t, c, n0, n1 = np.float32(0), np.float32(1), be, al
+                    if ab * ab > tol * tol * al * be:
+                        d, h = be - al, ab + ab
+                        hs = h if not np.signbit(d) else -h
+                        t = np.float32(hs / (abs(d) + np.sqrt(d * d + h * h)))
+                        c = np.float32(1 / np.sqrt(t * t + 1))
+                        n0, n1 = be + t * ab, al - t * ab
+                        rotated = rotated or ab * ab > last * last * al * be
+                    tq = t / (scale[p] * scale[p + 1])
+                    A[:, p] = y + (tq * scale[p] * scale[p]) * x          # position p <- c (y + t x)
+                    A[:, p + 1] = x - (tq * scale[p + 1] * scale[p + 1]) * y  # position p + 1 <- c (x - t y)
+                    scale[p], scale[p + 1] = c * scale[p + 1], c * scale[p]
+                    norms[p], norms[p + 1] = n0, n1
+            sweeps += 1
+            if not rotated:
+                break
+        A *= scale
+        lam = (A.astype(np.float64) ** 2).sum(0)
+        if m & 1:  # the padding column: last position after an even number of sweeps, first after an odd number
+            pad = 0 if sweeps & 1 else n - 1
+            assert lam[pad] == 0.0
+            lam = np.delete(lam, pad)
+        ref = np.linalg.eigvalsh(np.linalg.solve(Lj, Ei) @ np.linalg.inv(Lj).T)
+        assert sweeps <= 10
+        assert np.allclose(np.sort(lam), ref, rtol=2e-5)
+        d2 = (np.log(lam) ** 2).sum()
+        assert abs(d2 - (np.log(ref) ** 2).sum()) <= 1e-4 * (np.log(ref) ** 2).sum()
