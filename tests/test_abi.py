@@ -87,3 +87,30 @@ def test_header_is_plain_c(tmp_path):
         res = subprocess.run([gcc, *args, "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
                              capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
+
+
+def test_integration_stub_matches_the_abi():
+    """The ctypes stub a maintainer is told to add declares the same number of
+    arguments as the header for every entry point it binds, and its calls pass that many."""
+    import re
+
+    from sqfa_b200 import _lib
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("# sqfa/_native.py"):]
+    block = block[: block.index("```")]
+    decls = re.findall(r'\("(sqfa_\w+)",\s*ctypes\.\w+,\s*\[(.*?)\]\)', block, flags=re.S)
+    assert len(decls) >= 8
+    for name, args in decls:
+        n_args = len([a for a in args.replace("\n", " ").split(",") if a.strip()])
+        assert n_args == len(_lib.SIGNATURES[name][1]), (name, n_args, len(_lib.SIGNATURES[name][1]))
+    for name, _ in decls:
+        for hit in re.finditer(r"_lib\." + name + r"\(", block):
+            depth, n, i = 1, 1, hit.end()
+            while depth:
+                ch = block[i]
+                depth += ch in "(["
+                depth -= ch in ")]"
+                n += ch == "," and depth == 1
+                i += 1
+            assert n == len(_lib.SIGNATURES[name][1]), (name, n, block[hit.start():i])
