@@ -152,7 +152,8 @@ def fitting_loop(
     history = _EpochHistory()
     with tqdm(total=max_epochs, desc="Epochs", unit="epoch", disable=not show_progress) as bar:
         while history.epochs < max_epochs and not stop_rule.met:
-            history.add(float(optimizer.step(closure)))
+            epoch_loss = optimizer.step(closure)
+            history.add(epoch_loss.item() if isinstance(epoch_loss, torch.Tensor) else float(epoch_loss))
             stop_rule.observe(history.losses[-1])
             bar.update(1)
     if stop_rule.met:

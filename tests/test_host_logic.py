@@ -101,7 +101,7 @@ def test_lbfgs_on_cpu_parameters_is_torch_lbfgs():
             loss.backward()
             return loss
 
-        losses = [float(opt.step(closure)) for _ in range(3)]
+        losses = [opt.step(closure).item() for _ in range(3)]
         return x.detach().clone(), losses, opt.state[opt._params[0]]
 
     for kw in ({}, {"line_search_fn": "strong_wolfe"}):
@@ -209,3 +209,63 @@ def test_column_pair_jacobi_model_matches_lapack():
         assert np.allclose(np.sort(lam), ref, rtol=2e-5)
         d2 = (np.log(lam) ** 2).sum()
         assert abs(d2 - (np.log(ref) ** 2).sum()) <= 1e-4 * (np.log(ref) ** 2).sum()
+
+
+class _ToyModel(torch.nn.Module):
+    """A model with the one method `fitting_loop` needs, in plain CPU torch: distances between the rows of
+    `stats` seen through a learnable diagonal scaling (bounded, so L-BFGS converges to a plateau)."""
+
+    def __init__(self, n_dim, poison=None):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.linspace(-0.5, 0.5, n_dim))
+        self.poison = poison
+
+    def get_class_distances(self, data_statistics, regularized=False):
+        z = data_statistics * torch.tanh(self.w)
+        d = (z[:, None, :] - z[None, :, :]).pow(2).sum(-1)
+        if self.poison is not None:
+            d = d + torch.tril(torch.full_like(d, self.poison), -1)
+        return d
+
+
+@pytest.mark.parametrize("max_epochs,atol", [(30, 1e-6), (2, 1e-6), (0, 1e-6), (6, 1e3)])
+def test_fitting_loop_host_semantics_match_reference(max_epochs, atol, capsys):
+    """Epoch loop, stopping rule, history and messages of `fitting_loop` against the REAL reference's
+    (_optim.py:78-145) on a toy CPU model: same losses, same epoch count, same final message."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference sources not present")
+    from sqfa_b200._optim import fitting_loop
+
+    R = ref_loader.load()
+    stats = torch.randn(5, 7, generator=torch.Generator().manual_seed(3))
+    out = {}
+    for name, loop in (("ref", R._optim.fitting_loop), ("ours", fitting_loop)):
+        model = _ToyModel(7)
+        loss, seconds = loop(model, stats, max_epochs=max_epochs, lr=0.1, atol=atol, show_progress=False,
+                             return_loss=True)
+        captured = capsys.readouterr()
+        out[name] = (loss, seconds, model.w.detach().clone(), captured.out + captured.err)
+    (l_ref, t_ref, w_ref, msg_ref), (l_got, t_got, w_got, msg_got) = out["ref"], out["ours"]
+    assert l_got.shape == l_ref.shape == t_got.shape and torch.equal(l_got, l_ref)
+    assert torch.equal(w_got, w_ref)
+    assert msg_got.strip() == msg_ref.strip()
+    assert fitting_loop(_ToyModel(7), stats, max_epochs=1, show_progress=False) is None
+
+
+@pytest.mark.parametrize("poison,word", [(float("nan"), "NaN"), (float("inf"), "inf")])
+def test_fitting_loop_guard_messages_match_reference(poison, word):
+    """NaN / inf distances raise the reference's ValueError texts (_optim.py:16-30) on the generic path."""
+    from oracle import ref_loader
+
+    from sqfa_b200._optim import fitting_loop
+
+    stats = torch.randn(4, 3, generator=torch.Generator().manual_seed(1))
+    with pytest.raises(ValueError) as got:
+        fitting_loop(_ToyModel(3, poison), stats, max_epochs=2, show_progress=False)
+    assert word in str(got.value)
+    if ref_loader.available():
+        with pytest.raises(ValueError) as ref:
+            ref_loader.load()._optim.fitting_loop(_ToyModel(3, poison), stats, max_epochs=2, show_progress=False)
+        assert str(got.value) == str(ref.value)
