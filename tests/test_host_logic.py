@@ -269,3 +269,36 @@ def test_fitting_loop_guard_messages_match_reference(poison, word):
         with pytest.raises(ValueError) as ref:
             ref_loader.load()._optim.fitting_loop(_ToyModel(3, poison), stats, max_epochs=2, show_progress=False)
         assert str(got.value) == str(ref.value)
+
+
+@pytest.mark.parametrize("kind", ["SQFA", "SecondMomentsSQFA"])
+@pytest.mark.parametrize("constraint", ["sphere", "none", "orthogonal"])
+def test_state_dict_interchange_with_reference(kind, constraint):
+    """A model saved by the reference loads here and the other way round: same state-dict keys, shapes and
+    dtypes, same constrained filters from the same raw parameter (reference model.py:148-170, constraints.py)."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference sources not present")
+    import sqfa_b200
+
+    R = ref_loader.load()
+    F0 = torch.randn(3, 9, generator=torch.Generator().manual_seed(7))
+    kw = dict(n_dim=9, feature_noise=0.02, n_filters=3, filters=F0.clone(), constraint=constraint)
+    ref, ours = getattr(R.model, kind)(**kw), getattr(sqfa_b200.model, kind)(**kw)
+    sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
+    assert list(sd_ref) == list(sd_ours)
+    for key in sd_ref:
+        assert sd_ref[key].shape == sd_ours[key].shape and sd_ref[key].dtype == sd_ours[key].dtype, key
+    assert torch.allclose(ref.filters, ours.filters, atol=1e-6)
+    assert torch.equal(ref.noise_mat, ours.noise_mat)
+
+    # fresh models with other filters, then cross-load
+    kw["filters"] = torch.randn(3, 9, generator=torch.Generator().manual_seed(8))
+    ref2, ours2 = getattr(R.model, kind)(**kw), getattr(sqfa_b200.model, kind)(**kw)
+    ours2.load_state_dict(sd_ref)
+    ref2.load_state_dict(sd_ours)
+    assert torch.allclose(ours2.filters, ref.filters, atol=1e-6)
+    assert torch.allclose(ref2.filters, ours.filters, atol=1e-6)
+    assert type(ours.distance_fun).__name__ == type(ref.distance_fun).__name__
+    assert ours.distance_fun.__name__ == ref.distance_fun.__name__ and ours.constraint == ref.constraint
