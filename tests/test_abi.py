@@ -114,3 +114,91 @@ def test_integration_stub_matches_the_abi():
                 n += ch == "," and depth == 1
                 i += 1
             assert n == len(_lib.SIGNATURES[name][1]), (name, n, block[hit.start():i])
+
+
+def header_prototypes():
+    """name -> (return C type, [argument C types]) parsed from include/sqfa_b200.h."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = {}
+    for ret, name, args in re.findall(r"([A-Za-z_][\w \*]*?)\s*\b(sqfa_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        args = " ".join(args.split())
+        types = []
+        if args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                # drop the parameter name: everything up to the last '*' or the last space
+                t = a[: a.rindex("*") + 1] if "*" in a else a[: a.rindex(" ")]
+                types.append(" ".join(t.replace("*", " * ").split()))
+        protos[name] = (" ".join(ret.replace("*", " * ").split()), types)
+    return protos
+
+
+def _ctype_of(c_type):
+    """The ctypes class _lib.py must use for a C type of the header."""
+    from sqfa_b200 import _lib
+
+    if c_type == "const char *":
+        return ctypes.c_char_p
+    if c_type.endswith("*") or c_type == "sqfa_stream_t":
+        return _lib.c_ptr
+    return {"int": _lib.c_int, "int32_t": _lib.c_i32, "int64_t": _lib.c_i64, "float": _lib.c_f32,
+            "size_t": _lib.c_size}[c_type]
+
+
+def test_ctypes_argument_types_match_header_prototypes():
+    """Every argument of every entry point: the ctypes declaration in sqfa_b200/_lib.py has the width and
+    kind (pointer / int32 / int64 / float / size_t) of the C prototype -- a drifted binding would pass
+    garbage across the boundary without any error on the Python side."""
+    from sqfa_b200 import _lib
+
+    protos = header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, (ret, args) in protos.items():
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert restype is _ctype_of(ret), (name, ret, restype)
+        assert len(argtypes) == len(args), (name, len(argtypes), len(args))
+        for i, (c_type, ct) in enumerate(zip(args, argtypes)):
+            assert ct is _ctype_of(c_type), (name, i, c_type, ct)
+
+
+def test_pure_size_queries_are_consistent(lib):
+    """The host-only queries of the ABI (no GPU needed): executed tile area and packed Gram size follow the
+    tile shapes DESIGN.md section 4 states, workspaces grow with the problem, the exchange spans of the
+    sharded closure lie inside its workspace, 16-byte aligned and disjoint."""
+    # D <= 128: one 128 x 128 tile; larger: 256 x 256 upper-triangular tiles
+    assert lib.sqfa_gram_executed_tile_area(104) == 128 * 128
+    assert lib.sqfa_gram_executed_tile_area(128) == 128 * 128
+    for d in (129, 256, 784, 1024, 3072):
+        t = -(-d // 256)
+        assert lib.sqfa_gram_executed_tile_area(d) == t * (t + 1) // 2 * 256 * 256, d
+        assert lib.sqfa_gram_packed_floats(d, 7) == 7 * t * (t + 1) // 2 * 256 * 256, d
+    assert lib.sqfa_gram_executed_tile_area(0) == 0 and lib.sqfa_gram_packed_floats(0, 3) == 0
+    # the single-call workspace covers its parts
+    n, d, c = 50000, 3072, 10
+    total = lib.sqfa_class_statistics_workspace_bytes(n, d, c)
+    parts = (lib.sqfa_bucket_workspace_bytes(n, c) + lib.sqfa_class_sums_workspace_bytes(n, d, c) + c * d * 4
+             + lib.sqfa_class_gram_workspace_bytes(n, d, c) + lib.sqfa_stats_epilogue_workspace_bytes(c))
+    assert parts <= total <= parts + 5 * 256
+    # closure workspace: larger pair ranges need at least as much; spans inside, aligned, disjoint
+    C, D, k, dist = 1000, 512, 16, 1
+    P = C * (C - 1) // 2
+    full = lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist, 0, P)
+    half = lib.sqfa_fused_loss_workspace_bytes(C, D, k, dist, 0, P // 2)
+    assert 0 < half <= full
+    spans = []
+    for which in (0, 1):
+        off, nb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        assert lib.sqfa_fused_loss_exchange_span(C, D, k, dist, 0, P // 2, which, ctypes.byref(off), ctypes.byref(nb)) == 0
+        assert off.value % 16 == 0 and nb.value % 4 == 0 and nb.value > 0
+        assert off.value + nb.value <= half
+        spans.append((off.value, off.value + nb.value))
+    assert spans[0][1] <= spans[1][0] or spans[1][1] <= spans[0][0]
+    assert lib.sqfa_fused_loss_exchange_span(C, D, k, dist, 0, P, 2, None, None) == -1
+    # completion signals of the class groups add up to those of one group holding every class
+    n_groups = 4
+    per_group = [lib.sqfa_class_gram_group_signals(n, d, c, n_groups, g) for g in range(n_groups)]
+    assert all(s > 0 for s in per_group)
+    assert sum(per_group) == lib.sqfa_class_gram_group_signals(n, d, c, 1, 0)
+    assert lib.sqfa_lbfgs_max_n() >= 32 * 3072 and lib.sqfa_lbfgs_max_history() >= 100
