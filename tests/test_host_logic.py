@@ -302,3 +302,44 @@ def test_state_dict_interchange_with_reference(kind, constraint):
     assert torch.allclose(ref2.filters, ours.filters, atol=1e-6)
     assert type(ours.distance_fun).__name__ == type(ref.distance_fun).__name__
     assert ours.distance_fun.__name__ == ref.distance_fun.__name__ and ours.constraint == ref.constraint
+
+
+def test_tf32_split_model_keeps_the_gram_at_float32_accuracy():
+    """numpy model of the operand split of the tcgen05 Gram and projection kernels (ptx.cuh `to_tf32`,
+    gram.cu / project_tc.cu producers): hi = (bits + 0x1000) & 0xFFFFE000 (round to nearest on the 10-bit
+    TF32 mantissa, two integer instructions), lo = x - hi in float32. The split must be exact (hi + lo == x),
+    hi must be a TF32 number, |lo| <= 2^-11 |x|, and the three products the kernels issue
+    (hi hi + hi lo + lo hi, the tensor core reading only the TF32 part of lo) must reproduce the float64 Gram
+    to ~2^-21 -- well inside the 1e-5 the statistics are held to."""
+    import numpy as np
+
+    def to_tf32(x):
+        return ((x.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    def tf32_part(x):  # what kind::tf32 reads of an fp32 operand word: the low 13 mantissa bits are ignored
+        return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((4096, 48)) * np.exp(rng.uniform(-3, 3, (1, 48)))).astype(np.float32)
+    x[0, :4] = [0.0, -0.0, 1.0, -1.5]  # exactly representable values split into (x, 0)
+    hi = to_tf32(x)
+    lo = x - hi
+    assert hi.dtype == np.float32 and lo.dtype == np.float32
+    assert np.array_equal(hi + lo, x)  # exact split
+    assert not (hi.view(np.uint32) & np.uint32(0x1FFF)).any()
+    assert (np.abs(lo) <= np.abs(x) * 2.0**-11).all()
+    assert np.array_equal(lo[0, :4], np.zeros(4, np.float32))
+    # ties round away from zero (add half an ulp to the magnitude, then truncate)
+    tie = np.array([1.0 + 2.0**-11, -(1.0 + 2.0**-11)], dtype=np.float32)
+    assert np.array_equal(to_tf32(tie), np.array([1.0 + 2.0**-10, -(1.0 + 2.0**-10)], dtype=np.float32))
+    # non-finite inputs stay non-finite (the guard downstream reports them; nothing is silently zeroed)
+    bad = to_tf32(np.array([np.inf, -np.inf, np.nan], dtype=np.float32))
+    assert np.isinf(bad[:2]).all() and np.isnan(bad[2])
+
+    h, l = hi.astype(np.float64), tf32_part(lo).astype(np.float64)
+    model = h.T @ h + h.T @ l + l.T @ h
+    truth = x.astype(np.float64).T @ x.astype(np.float64)
+    scale = np.sqrt(np.outer(np.diag(truth), np.diag(truth)))  # entry-wise, relative to the diagonal scale
+    assert (np.abs(model - truth) / scale).max() < 2.0**-20
+    # one TF32 product alone would not do: 2^-11 operand rounding
+    assert (np.abs(h.T @ h - truth) / scale).max() > 2.0**-16
