@@ -1,5 +1,7 @@
-"""CPU, world_size 2, gloo: the sample-sharded class_statistics driver (three all-reduces) with
-the local kernels replaced by oracle-backed CPU ops. Checks that sharded == unsharded."""
+"""CPU, world_size 2 / 3, gloo: (i) the sample-sharded class_statistics driver (three all-reduces) with
+the local kernels replaced by oracle-backed CPU ops -- sharded == unsharded; (ii) the pair-sharded closure
+(shard_pairs slices, one all-reduce of [loss, flag, dF], constraint adjoint after it) with the oracle's
+arithmetic in place of the kernels -- equals the replicated closure, identical on every rank."""
 
 import os
 import sys
@@ -140,3 +142,68 @@ def test_peer_push_schedule_is_staggered_and_complete():
             for step in range(1, world):
                 dests = [(r + step) % world for r in range(world)]
                 assert len(set(dests)) == world
+
+
+def _closure_worker(rank, world, port, ret):
+    """One rank of the pair-sharded closure (model._fused_direct_plan.run_sharded) with the kernels replaced
+    by the oracle's float64 arithmetic: loss and dLoss/dF over THIS rank's slice of the linearised pair list
+    (p = i (i - 1) / 2 + j, weight 1 / P), ONE all-reduce of [loss, flag, -, -, dF], then the sphere adjoint."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import sqfa_oracle as O
+    from sqfa_b200._ops import shard_pairs
+
+    stats, W, noise = _closure_problem()
+    C, (k, D) = stats["means"].shape[0], W.shape
+    P = C * (C - 1) // 2
+    p0, p1 = shard_pairs(P, C, rank, world)
+    nrm = W.norm(dim=-1, keepdim=True)
+    F = (W / nrm).detach().requires_grad_(True)
+    d = O.class_distances_full(stats, F, noise)
+    i, j = torch.tril_indices(C, C, offset=-1)
+    p = i * (i - 1) // 2 + j
+    mine = (p >= p0) & (p < p1)
+    loss = -(d[i, j] * mine).sum() / P
+    loss.backward()
+    packed = torch.cat([loss.detach().view(1), torch.zeros(3, dtype=W.dtype), F.grad.reshape(-1)])
+    dist.all_reduce(packed)
+    dF = packed[4:].view(k, D)
+    Fd = F.detach()
+    dW = (dF - (dF * Fd).sum(dim=-1, keepdim=True) * Fd) / nrm
+    ret[rank] = (packed[0].clone(), dW.clone(), int(mine.sum()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _closure_problem():
+    from oracle import sqfa_oracle as O
+
+    g = torch.Generator().manual_seed(3)
+    C, D, k = 13, 10, 3
+    X = torch.randn(C * 40, D, generator=g, dtype=torch.float64) * (0.5 + torch.rand(D, generator=g, dtype=torch.float64))
+    y = torch.arange(C).repeat_interleave(40)
+    X = X + 0.3 * torch.randn(C, D, generator=g, dtype=torch.float64)[y]
+    stats = O.class_statistics(X, y)
+    W = torch.randn(k, D, generator=g, dtype=torch.float64)
+    return stats, W, 0.01
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pair_sharded_closure_sums_to_the_replicated_one(world):
+    from oracle import sqfa_oracle as O
+
+    port = 31500 + (os.getpid() % 2000) + world
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_closure_worker, args=(world, port, ret), nprocs=world, join=True)
+        got = [ret[r] for r in range(world)]
+    stats, W, noise = _closure_problem()
+    loss, grad, _ = O.loss_and_grad("full", stats, W, noise=noise, constraint="sphere")
+    C = stats["means"].shape[0]
+    assert sum(n for _, _, n in got) == C * (C - 1) // 2  # every pair evaluated by exactly one rank
+    for l, dW, _ in got:  # identical on every rank (the optimiser state stays replicated)
+        assert torch.equal(l, got[0][0]) and torch.equal(dW, got[0][1])
+    assert torch.allclose(got[0][0], loss, rtol=1e-12)
+    assert torch.allclose(got[0][1], grad, rtol=1e-9, atol=1e-13)
