@@ -207,3 +207,72 @@ def test_pair_sharded_closure_sums_to_the_replicated_one(world):
         assert torch.equal(l, got[0][0]) and torch.equal(dW, got[0][1])
     assert torch.allclose(got[0][0], loss, rtol=1e-12)
     assert torch.allclose(got[0][1], grad, rtol=1e-9, atol=1e-13)
+
+
+def _three_phase_worker(rank, world, port, ret):
+    """One rank of the class- AND pair-sharded closure (sqfa_fused_loss_sharded, _ops.fused_loss_sharded_raw) in
+    the oracle's float64 arithmetic: (0) project the rank's classes, all-reduce (Psi, mu') [zeros elsewhere];
+    (1) embedding + distances of the rank's pairs, all-reduce (gPsi, gmu, loss); (2) projection adjoint over
+    the rank's classes, all-reduce dF."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import sqfa_oracle as O
+    from sqfa_b200._ops import shard_pairs
+    from sqfa_b200._stats_driver import class_share
+
+    stats, W, noise = _closure_problem()
+    S, M = stats["covariances"], stats["means"]
+    C, (k, D) = M.shape[0], W.shape
+    P = C * (C - 1) // 2
+    p0, p1 = shard_pairs(P, C, rank, world)
+    c0, c1 = class_share(C, rank, world)
+    F = W / W.norm(dim=-1, keepdim=True)
+    # phase 0
+    psi = torch.zeros(C, k, k, dtype=W.dtype)
+    mu = torch.zeros(C, k, dtype=W.dtype)
+    T = F @ S[c0:c1]  # saved for the adjoint: (c1 - c0, k, D)
+    psi[c0:c1] = T @ F.T
+    mu[c0:c1] = M[c0:c1] @ F.T
+    dist.all_reduce(psi)
+    dist.all_reduce(mu)
+    # phase 1
+    psi.requires_grad_(True)
+    mu.requires_grad_(True)
+    cov = psi + noise * torch.eye(k, dtype=W.dtype)
+    fs = {"means": mu, "covariances": cov}
+    d = O.fisher_rao_lower_bound(fs, fs)
+    i, j = torch.tril_indices(C, C, offset=-1)
+    p = i * (i - 1) // 2 + j
+    mine = (p >= p0) & (p < p1)
+    loss = -(d[i, j] * mine).sum() / P
+    loss.backward()
+    g_psi, g_mu, loss = psi.grad.clone(), mu.grad.clone(), loss.detach().clone()
+    for t in (g_psi, g_mu, loss):
+        dist.all_reduce(t)
+    # phase 2: dF = sum over own classes of (gPsi + gPsi^T) T_c + gmu_c m_c^T
+    sym = g_psi[c0:c1] + g_psi[c0:c1].mT
+    dF = (sym @ T).sum(0) + g_mu[c0:c1].T @ M[c0:c1]
+    dist.all_reduce(dF)
+    ret[rank] = (loss, dF.clone())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_class_and_pair_sharded_closure_phases_sum_to_the_replicated_one(world):
+    from oracle import sqfa_oracle as O
+
+    port = 33500 + (os.getpid() % 2000) + world
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_three_phase_worker, args=(world, port, ret), nprocs=world, join=True)
+        got = [ret[r] for r in range(world)]
+    stats, W, noise = _closure_problem()
+    F = W / W.norm(dim=-1, keepdim=True)
+    loss, dF, _ = O.loss_and_grad("full", stats, F, noise=noise, constraint="none")  # gradient at the constrained filters
+    for l, g in got:
+        assert torch.equal(l, got[0][0]) and torch.equal(g, got[0][1])
+    assert torch.allclose(got[0][0], loss, rtol=1e-12)
+    assert torch.allclose(got[0][1], dF, rtol=1e-9, atol=1e-13)
