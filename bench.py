@@ -49,6 +49,14 @@ PARALLELISM_NOTE = ("samples sharded over {world} GPUs; statistics of the union,
                     "peer-mapped slots) and the epilogue; 3 small NCCL all-reduces (max label, sums + counts, barrier)")
 
 
+def workload_config(world):
+    """The `config` object of the JSON line: the same for both arms at the same N (the driver compares them)."""
+    w = WORKLOAD
+    return {"workload": w["name"], "N_per_gpu": w["N"], "D": w["D"], "classes": w["C"], "n_filters": w["k"],
+            "l2": "inputs (614 MB per GPU) exceed the 126 MB L2; no flush needed",
+            "parallelism": PARALLELISM_NOTE.format(world=world) if world > 1 else "single GPU"}
+
+
 def synth(n, d, c, device, seed):
     """Seeded synthetic class data: low-rank class-scaled signal + noise + means."""
     import torch
@@ -449,9 +457,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "N_per_gpu": w["N"], "D": w["D"], "classes": w["C"], "n_filters": w["k"],
-                   "l2": "host arm: not applicable",
-                   "parallelism": f"reference CPU path, {torch.get_num_threads()} host threads (rank 0 only)"},
+        "config": workload_config(max(int(args.gpus), 1)),  # this repo's arm's config at the same N
+        "host_arm": f"reference CPU path, {torch.get_num_threads()} host threads (rank 0 only); no device, l2 not applicable",
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"full workload, {args.steps} repetitions of N={w['N']} (warm-up on 5000 rows)"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -669,9 +676,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core split, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": w["name"], "N_per_gpu": n, "D": d, "classes": c, "n_filters": k,
-                   "l2": "inputs (614 MB per GPU) exceed the 126 MB L2; no flush needed",
-                   "parallelism": PARALLELISM_NOTE.format(world=world) if world > 1 else "single GPU"},
+        "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "repetitions_ms": [round(x, 2) for x in e2e_ms], "reported": "median repetition",
                 "overlap": f"{nbuf} CUDA streams / buffer sets, inputs of step i+1 uploaded while step i computes and downloads",
