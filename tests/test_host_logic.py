@@ -365,3 +365,41 @@ def test_design_document_cites_existing_tests_and_files():
         assert f in sources, f
     for f in set(re.findall(r"`((?:sqfa_b200|tools|oracle|profiles|include)/[\w/\.]+\.(?:py|cu|cuh|h|sh|json|txt|csv|md))`", text)):
         assert os.path.exists(os.path.join(root, f)), f
+
+
+def test_partitions_hold_for_arbitrary_sizes():
+    """Property test (hypothesis) of the three partitions the multi-GPU paths rest on, for arbitrary class
+    counts and world sizes: `shard_pairs` (pair list: contiguous, complete, whole rows at multiples of 4),
+    `class_share` (classes: contiguous, complete, equal to the Gram kernel's completion-counter groups
+    c * W / C) and `peer_push_schedule` (every foreign non-empty group once, distinct destinations per step)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from sqfa_b200._ops import shard_pairs
+    from sqfa_b200._stats_driver import class_share, peer_push_schedule
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(min_value=1, max_value=5000), st.integers(min_value=1, max_value=16))
+    def check(C, W):
+        P = C * (C - 1) // 2
+        cuts = [shard_pairs(P, C, r, W) for r in range(W)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == P
+        for (a0, a1), (b0, b1) in zip(cuts[:-1], cuts[1:]):
+            assert a0 <= a1 == b0 <= b1
+        for _, e in cuts[:-1]:  # a cut is the first pair of a row i with i % 4 == 0 (or an end of the list)
+            i = (1 + int(round((1 + 8 * e) ** 0.5))) // 2
+            assert i * (i - 1) // 2 == e and (i % 4 == 0 or e in (0, P))
+        shares = [class_share(C, r, W) for r in range(W)]
+        assert shares[0][0] == 0 and shares[-1][1] == C
+        assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(shares, shares[1:] + [(C, C)]))
+        owner = [c * W // C for c in range(C)]
+        for r, (lo, hi) in enumerate(shares):
+            assert owner[lo:hi] == [r] * (hi - lo)
+        for r in range(W):
+            sched = peer_push_schedule(r, W, shares)
+            groups = [g for g, _, _ in sched]
+            assert r not in groups and len(set(groups)) == len(groups)
+            assert set(groups) == {g for g in range(W) if g != r and shares[g][1] > shares[g][0]}
+            assert all((lo, hi) == shares[g] for g, lo, hi in sched)
+
+    check()
